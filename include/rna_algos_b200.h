@@ -254,10 +254,9 @@ int rna_durbin_algo(rna_handle *h, const uint8_t *seq_a, uint32_t len_a, const u
  * on `stream` (a cudaStream_t passed as void*; NULL = default stream) and NOT synchronised.  Inputs
  * must have been validated by the caller (or by rna_validate_bases).  Used for HBM-resident timing
  * and for pipelines that keep the BPPs on the GPU.
- *   d_order: optional device array of n_seqs sequence indices giving the launch order (the batch
- *            functions above pass a length-sorted order); NULL = identity.
  * ---------------------------------------------------------------------------------------------- */
 typedef struct {
+  const uint32_t *h_offsets;      /* HOST copy of the offsets [n_seqs+1]: the launcher buckets by length */
   const uint8_t *d_bases;
   const uint32_t *d_offsets;      /* [n_seqs+1] */
   const uint64_t *d_bpp_offsets;  /* [n_seqs+1], required when d_out_bpp != NULL */
@@ -279,6 +278,8 @@ typedef struct {
 int rna_mccaskill_centroid_batch_dev(rna_handle *h, const RnaFoldBatchDev *b, void *stream);
 
 typedef struct {
+  const uint32_t *h_offsets;       /* HOST copies: the launcher orders pairs by cost */
+  const uint32_t *h_pairs;
   const uint8_t *d_bases;
   const uint32_t *d_offsets;       /* [n_seqs+1] */
   const uint32_t *d_pairs;         /* [2*n_pairs] */
@@ -308,6 +309,11 @@ typedef struct {
 int rna_get_stats(const rna_handle *h, RnaCallStats *out);
 
 const char *rna_version(void);
+
+/* sizeof() of the blobs as compiled into the library (binding sanity checks). */
+size_t rna_sizeof_turner_tables(void);
+size_t rna_sizeof_contra_tables(void);
+size_t rna_sizeof_align_tables(void);
 
 #ifdef __cplusplus
 }

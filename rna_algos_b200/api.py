@@ -1,0 +1,319 @@
+"""Host-side mirror of the reference crate's public API for the hot path, over the C ABI.
+
+reference (Rust, heartsh/rna-algos 0.1.37)                     here
+-------------------------------------------------------------  ------------------------------------
+utils::bytes2seq                     src/utils.rs:562-577       bytes2seq
+mccaskill_algo::mccaskill_algo<T>    src/mccaskill_algo.rs:247  mccaskill_algo / Handle.mccaskill_batch
+centroid_fold::centroid_fold<T>      src/centroid_fold.rs:25    centroid_fold / Handle.centroid_batch
+bin centroid_fold (BPP + MEA sweep)  src/bin/centroid_fold.rs   Handle.fold_batch (fused on device)
+durbin_algo::durbin_algo             src/durbin_algo.rs:73      durbin_algo / Handle.durbin_batch
+
+Same argument meaning (``uses_contra_model``, ``allows_short_hairpins``, ``centroid_threshold``) and the
+same error behaviour translated to exceptions: the reference panics on a non-ACGU byte or an empty
+sequence; here ``RnaError`` is raised.  Everything computes on the GPU through
+``librna_algos_b200.so``; there is no CPU path in this package.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, Iterable, List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import _lib
+from . import tables as T
+
+UNPAIR, BASEPAIR_LEFT, BASEPAIR_RIGHT = ".", "(", ")"   # src/utils.rs:123-125
+PSEUDO_BASE = 4                                         # src/utils.rs:122
+MIN_POW_2, MAX_POW_2 = -7, 10                           # src/bin/centroid_fold.rs:9-10
+
+
+class RnaError(RuntimeError):
+    def __init__(self, code: int, detail: str = ""):
+        self.code = code
+        super().__init__(f"{_lib.STATUS.get(code, code)}{': ' + detail if detail else ''}")
+
+
+_CHAR2BASE = np.full(256, 255, dtype=np.uint8)
+for _c, _b in (("A", 0), ("C", 1), ("G", 2), ("U", 3)):
+    _CHAR2BASE[ord(_c)] = _b
+    _CHAR2BASE[ord(_c.lower())] = _b
+
+
+def bytes2seq(x) -> np.ndarray:
+    """ASCII a/c/g/u (either case) -> base codes 0..3; anything else is an error (the reference
+    panics: src/utils.rs:570-572; 'T' and 'N' are NOT accepted there either)."""
+    if isinstance(x, str):
+        x = x.encode()
+    a = np.frombuffer(bytes(x), dtype=np.uint8)
+    s = _CHAR2BASE[a]
+    if (s == 255).any():
+        raise RnaError(2, "non-ACGU byte in sequence")
+    return s
+
+
+def read_fasta(path: str) -> List[Tuple[str, np.ndarray]]:
+    recs: List[Tuple[str, List[str]]] = []
+    with open(path) as fh:
+        for line in fh:
+            line = line.strip()
+            if not line:
+                continue
+            if line.startswith(">"):
+                recs.append((line[1:].split()[0] if len(line) > 1 else "", []))
+            elif recs:
+                recs[-1][1].append(line)
+    return [(rid, bytes2seq("".join(parts))) for rid, parts in recs]
+
+
+def pack_seqs(seqs: Sequence[np.ndarray]) -> Tuple[np.ndarray, np.ndarray]:
+    """Concatenate sequences -> (bases u8, offsets u32[n+1])."""
+    lens = np.array([len(s) for s in seqs], dtype=np.int64)
+    offsets = np.zeros(len(seqs) + 1, dtype=np.uint32)
+    offsets[1:] = np.cumsum(lens)
+    bases = np.concatenate([np.asarray(s, dtype=np.uint8) for s in seqs]) if len(seqs) else np.zeros(0, np.uint8)
+    return np.ascontiguousarray(bases), offsets
+
+
+def bpp_offsets_of(offsets: np.ndarray) -> np.ndarray:
+    lens = np.diff(offsets.astype(np.int64))
+    o = np.zeros(len(lens) + 1, dtype=np.uint64)
+    o[1:] = np.cumsum(lens * (lens - 1) // 2)
+    return o
+
+
+def bpp_index(L: int, i: int, j: int) -> int:
+    return i * (2 * L - i - 1) // 2 + (j - i - 1)
+
+
+def sparse_prob_mat(bpp: np.ndarray, L: int) -> Dict[Tuple[int, int], float]:
+    """Packed BPP -> the reference's SparseProbMat<T> (HashMap<(i,j), Prob>): one key per closable pair,
+    INCLUDING keys whose probability is exactly 0.0 (expf flush), absent keys dropped."""
+    out = {}
+    for i in range(L):
+        base = i * (2 * L - i - 1) // 2
+        row = bpp[base: base + L - 1 - i]
+        for x in np.nonzero(row != T.BPP_ABSENT)[0]:
+            out[(i, i + 1 + int(x))] = float(row[x])
+    return out
+
+
+def _p(a: Optional[np.ndarray]):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def fold_cost(L) -> np.ndarray:
+    """Cost model of one McCaskill+centroid unit: cubic split-point loops + the
+    O(496 L^2) interior-loop enumeration."""
+    L = np.asarray(L, dtype=np.uint64)
+    return L * L * L + np.uint64(500) * L * L
+
+
+def partition_lpt(costs: np.ndarray, n_parts: int) -> np.ndarray:
+    """Longest-processing-time-first partition of work units over GPUs (no collective is needed: units
+    are independent — src/bin/centroid_fold.rs:119-132 fans them out over threads the same way)."""
+    lib = _lib.load()
+    costs = np.ascontiguousarray(costs, dtype=np.uint64)
+    part = np.zeros(costs.shape[0], dtype=np.uint32)
+    rc = lib.rna_partition_lpt(_p(costs), costs.shape[0], n_parts, _p(part))
+    if rc:
+        raise RnaError(rc)
+    return part
+
+
+class Handle:
+    """One GPU.  Owns the device copies of the table blobs and the scratch buffers."""
+
+    def __init__(self, device: int = 0, turner: Optional[T.TurnerTables] = None,
+                 contra: Optional[T.ContraTables] = None, align: Optional[T.AlignTables] = None):
+        self.lib = _lib.load()
+        h = C.c_void_p()
+        rc = self.lib.rna_create(device, C.byref(h))
+        if rc:
+            raise RnaError(rc, "rna_create: a CUDA device is required (no CPU fallback)")
+        self.h = h
+        self.set_tables(turner, contra, align)
+
+    def set_tables(self, turner=None, contra=None, align=None):
+        if turner is not None:
+            self._chk(self.lib.rna_set_turner_tables(self.h, C.byref(turner)))
+        if contra is not None:
+            self._chk(self.lib.rna_set_contra_tables(self.h, C.byref(contra)))
+        if align is not None:
+            self._chk(self.lib.rna_set_align_tables(self.h, C.byref(align)))
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.rna_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _chk(self, rc: int):
+        if rc:
+            raise RnaError(rc, (self.lib.rna_last_error(self.h) or b"").decode())
+
+    def stats(self) -> Dict[str, int]:
+        s = _lib.CallStats()
+        self.lib.rna_get_stats(self.h, C.byref(s))
+        return dict(kernel_launches=int(s.kernel_launches), h2d_bytes=int(s.h2d_bytes), d2h_bytes=int(s.d2h_bytes))
+
+    # ---- batched, host buffers ------------------------------------------------------------------
+    def fold_batch(self, bases: np.ndarray, offsets: np.ndarray, uses_contra_model: bool,
+                   allows_short_hairpins: bool = False, gammas: Iterable[float] = (),
+                   want_bpp: bool = True, out: Optional[dict] = None) -> dict:
+        """mccaskill_algo for every sequence (+ centroid_fold for every gamma), fused on the GPU.
+        `out` may carry preallocated (e.g. pinned) numpy arrays: logz, bpp, structs, expect_acc."""
+        bases = np.ascontiguousarray(bases, dtype=np.uint8)
+        offsets = np.ascontiguousarray(offsets, dtype=np.uint32)
+        n = offsets.shape[0] - 1
+        g = np.ascontiguousarray(np.array(list(gammas), dtype=np.float32))
+        ng = g.shape[0]
+        total = int(offsets[-1]) if n else 0
+        out = dict(out or {})
+        bpp_off = bpp_offsets_of(offsets)
+        logz = out.get("logz")
+        if logz is None:
+            logz = np.empty(n, dtype=np.float32)
+        bpp = out.get("bpp") if want_bpp else None
+        if want_bpp and bpp is None:
+            bpp = np.empty(int(bpp_off[-1]), dtype=np.float32)
+        structs = out.get("structs")
+        if structs is None:
+            structs = np.empty((ng, total), dtype=np.uint8)
+        ea = out.get("expect_acc")
+        if ea is None:
+            ea = np.empty((ng, n), dtype=np.float32)
+        self._chk(self.lib.rna_mccaskill_centroid_batch(
+            self.h, _p(bases), _p(offsets), n, _lib.MODEL_CONTRA if uses_contra_model else _lib.MODEL_TURNER,
+            int(allows_short_hairpins), _p(g) if ng else None, ng, _p(logz), _p(bpp),
+            _p(bpp_off) if want_bpp else None, _p(structs) if ng else None, _p(ea) if ng else None))
+        return dict(logz=logz, bpp=bpp, bpp_offsets=bpp_off, structs=structs, expect_acc=ea, gammas=g)
+
+    def mccaskill_batch(self, bases, offsets, uses_contra_model, allows_short_hairpins=False):
+        return self.fold_batch(bases, offsets, uses_contra_model, allows_short_hairpins, gammas=())
+
+    def centroid_batch(self, bpp: np.ndarray, offsets: np.ndarray, gammas: Iterable[float]) -> dict:
+        bpp = np.ascontiguousarray(bpp, dtype=np.float32)
+        offsets = np.ascontiguousarray(offsets, dtype=np.uint32)
+        n = offsets.shape[0] - 1
+        g = np.ascontiguousarray(np.array(list(gammas), dtype=np.float32))
+        structs = np.empty((g.shape[0], int(offsets[-1])), dtype=np.uint8)
+        ea = np.empty((g.shape[0], n), dtype=np.float32)
+        bpp_off = bpp_offsets_of(offsets)
+        self._chk(self.lib.rna_centroid_batch(self.h, _p(bpp), _p(bpp_off), _p(offsets), n, _p(g), g.shape[0],
+                                              _p(structs), _p(ea)))
+        return dict(structs=structs, expect_acc=ea)
+
+    def durbin_batch(self, bases: np.ndarray, offsets: np.ndarray, pairs: np.ndarray,
+                     out: Optional[np.ndarray] = None) -> dict:
+        bases = np.ascontiguousarray(bases, dtype=np.uint8)
+        offsets = np.ascontiguousarray(offsets, dtype=np.uint32)
+        pairs = np.ascontiguousarray(pairs, dtype=np.uint32).reshape(-1, 2)
+        lens = np.diff(offsets.astype(np.int64))
+        po = np.zeros(pairs.shape[0] + 1, dtype=np.uint64)
+        po[1:] = np.cumsum((lens[pairs[:, 0]] + 2) * (lens[pairs[:, 1]] + 2))
+        if out is None:
+            out = np.empty(int(po[-1]), dtype=np.float32)
+        self._chk(self.lib.rna_durbin_batch(self.h, _p(bases), _p(offsets), offsets.shape[0] - 1, _p(pairs),
+                                            pairs.shape[0], _p(out), _p(po)))
+        return dict(probs=out, prob_offsets=po)
+
+    # ---- single item (the reference's call granularity) ----------------------------------------
+    def mccaskill_algo(self, seq: np.ndarray, uses_contra_model: bool, allows_short_hairpins: bool = False):
+        seq = np.ascontiguousarray(seq, dtype=np.uint8)
+        L = seq.shape[0]
+        if L == 0:
+            raise RnaError(3, "empty sequence")
+        bpp = np.empty(L * (L - 1) // 2, dtype=np.float32)
+        logz = C.c_float()
+        self._chk(self.lib.rna_mccaskill_algo(self.h, _p(seq), L, int(uses_contra_model),
+                                              int(allows_short_hairpins), _p(bpp), C.byref(logz)))
+        return bpp, np.float32(logz.value)
+
+    def centroid_fold(self, bpp: np.ndarray, seq_len: int, centroid_threshold: float):
+        bpp = np.ascontiguousarray(bpp, dtype=np.float32)
+        s = np.empty(seq_len, dtype=np.uint8)
+        pairs = np.zeros((max(seq_len, 2), 2), dtype=np.uint16)
+        npairs = C.c_uint32()
+        ea = C.c_float()
+        self._chk(self.lib.rna_centroid_fold(self.h, _p(bpp), seq_len, C.c_float(centroid_threshold), _p(s),
+                                             _p(pairs), C.byref(npairs), C.byref(ea)))
+        return s.tobytes().decode(), pairs[: npairs.value].copy(), np.float32(ea.value)
+
+    def durbin_algo(self, seq_a: np.ndarray, seq_b: np.ndarray) -> np.ndarray:
+        a = np.ascontiguousarray(seq_a, dtype=np.uint8)
+        b = np.ascontiguousarray(seq_b, dtype=np.uint8)
+        out = np.empty((a.shape[0] + 2, b.shape[0] + 2), dtype=np.float32)
+        self._chk(self.lib.rna_durbin_algo(self.h, _p(a), a.shape[0], _p(b), b.shape[0], _p(out)))
+        return out
+
+
+_default: Optional[Handle] = None
+
+
+def default_handle() -> Handle:
+    global _default
+    if _default is None:
+        lib = _lib.load()
+        _default = Handle(0, T.turner_tables(), T.contra_tables(lib), T.contralign_tables())
+    return _default
+
+
+def mccaskill_algo(seq, uses_contra_model: bool, allows_short_hairpins: bool = False,
+                   fold_score_sets: Optional[T.ContraTables] = None, handle: Optional[Handle] = None):
+    """mccaskill_algo(seq, uses_contra_model, allows_short_hairpins, &fold_score_sets) ->
+    SparseProbMat (as a dict; FoldScores<T>, the second tuple element, is not produced: no in-tree
+    caller reads it — src/bin/centroid_fold.rs:129, tests/tests.rs:31)."""
+    h = handle or default_handle()
+    if fold_score_sets is not None:
+        h.set_tables(contra=fold_score_sets)
+    bpp, _ = h.mccaskill_algo(seq, uses_contra_model, allows_short_hairpins)
+    return sparse_prob_mat(bpp, len(seq))
+
+
+def centroid_fold(basepair_probs, seq_len: int, centroid_threshold: float, handle: Optional[Handle] = None):
+    """centroid_fold(&basepair_probs, seq_len, centroid_threshold) -> (basepair_pos_pairs, expect_accuracy).
+    `basepair_probs` is a packed array or the dict form returned by mccaskill_algo."""
+    h = handle or default_handle()
+    if isinstance(basepair_probs, dict):
+        bpp = np.full(seq_len * (seq_len - 1) // 2, T.BPP_ABSENT, dtype=np.float32)
+        for (i, j), p in basepair_probs.items():
+            bpp[bpp_index(seq_len, i, j)] = p
+    else:
+        bpp = basepair_probs
+    _, pairs, ea = h.centroid_fold(bpp, seq_len, centroid_threshold)
+    return [tuple(int(v) for v in p) for p in pairs], float(ea)
+
+
+def get_fold_str(pairs, seq_len: int) -> str:
+    """src/bin/centroid_fold.rs:197-207"""
+    s = [UNPAIR] * seq_len
+    for i, j in pairs:
+        s[int(i)] = BASEPAIR_LEFT
+        s[int(j)] = BASEPAIR_RIGHT
+    return "".join(s)
+
+
+def durbin_algo(seq_pair, align_scores: Optional[T.AlignTables] = None, handle: Optional[Handle] = None):
+    """durbin_algo(&(seq_a, seq_b), &align_scores) -> ProbMat.  The reference's callers pad both
+    sequences with PSEUDO_BASE first (src/bin/durbin_algo.rs:48-50); pass them either way — sentinels
+    are stripped and re-added by the library, and the result is the same sentinel-indexed matrix."""
+    h = handle or default_handle()
+    if align_scores is not None:
+        h.set_tables(align=align_scores)
+    a, b = (np.asarray(s, dtype=np.uint8) for s in seq_pair)
+    if len(a) >= 2 and a[0] == PSEUDO_BASE and a[-1] == PSEUDO_BASE:
+        a = a[1:-1]
+    if len(b) >= 2 and b[0] == PSEUDO_BASE and b[-1] == PSEUDO_BASE:
+        b = b[1:-1]
+    return h.durbin_algo(a, b)
+
+
+def centroid_threshold_sweep() -> List[float]:
+    """The default threshold range of the reference's binary: 2^-7 .. 2^10 (src/bin/centroid_fold.rs:148-149)."""
+    return [float(np.float32(2.0) ** p) for p in range(MIN_POW_2, MAX_POW_2 + 1)]

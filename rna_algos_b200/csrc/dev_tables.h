@@ -1,0 +1,77 @@
+// dev_tables.h — packed device images of the table blobs (SURVEY.md §8 "table packing").
+// Built on the host from RnaTurnerTables / RnaContraTables / RnaAlignTables (rna_abi.cu) with plain
+// IEEE f32 operations, so every precomputed entry has the bits the reference would compute in-line.
+#pragma once
+#include <stdint.h>
+
+namespace rna {
+
+// Base-indexed Turner tables that the kernels gather with per-lane indices (staged in shared memory).
+struct TurnerSmall {
+  float tm_hairpin[256];   // TERMINAL_MISMATCH_SCORES_HAIRPIN[i][j][i+1][j-1]
+  float stack[256];        // STACK_SCORES[i][j][k][l]
+  float tm_1xmany[256];
+  float tm_2x3[256];
+  float tm_interior[256];
+  float tm_multi[256];     // TERMINAL_MISMATCH_SCORES_MULTIBRANCH
+  float d5[64];            // DANGLING_SCORES_5PRIME[i][j][i-1]
+  float d3[64];            // DANGLING_SCORES_3PRIME[i][j][j+1]
+};
+
+#define RNA_HAIRPIN_EXT_LEN 65536
+
+struct DevTurner {
+  int max_2loop_len;
+  int min_span;
+  int min_hairpin_len;
+  int num_special;
+  unsigned special_len_mask;        // bit n set <=> some special hairpin has slice length n (n < 32)
+  float augu_pen;
+  float init_mb_base;
+  float coeff_num_branches;
+  float bulge_init[31];
+  float interior_init_ninio[31 * 31];   // [a][b] = INTERIOR_SCORES_INIT[a+b] + max(NINIO_COEFF*|a-b|, NINIO_MAX)
+  unsigned special_key[128];        // 2 bits per base, base p at bits 2p (slice incl. closing pair)
+  unsigned char special_len[128];
+  float special_score[128];
+  TurnerSmall small;
+  // device-global arrays
+  const float* hairpin_init_ext;    // [RNA_HAIRPIN_EXT_LEN]: INIT[len] or the ln-extrapolation (src/utils.rs:178-184)
+  const float* int11;               // [4^6]
+  const float* int12;               // [4^7]
+  const float* int22;               // [4^8]
+};
+
+struct ContraSmall {
+  float stack[256];
+  float tm[256];          // terminal_mismatch_scores
+  float dl[64];           // dangling_scores_left
+  float dr[64];           // dangling_scores_right
+  float hc[16];           // helix_close_scores
+  float bp[16];           // basepair_scores
+  float bulge0x1[4];
+  float int1x1[16];
+};
+
+struct DevContra {
+  int max_loop_len;
+  int min_span;
+  int max_explicit;
+  float mb_base, mb_bp, mb_unpair, ext_bp, ext_unpair;
+  float mb_base_plus_bp;            // multibranch_score_base + multibranch_score_basepair (src/mccaskill_algo.rs:437-438)
+  float hairpin_cum[31];
+  float bulge_cum[30];
+  float interior_cum[29];
+  float sym_cum[15];
+  float asym_cum[28];
+  float explicit_[16];
+  ContraSmall small;
+};
+
+struct DevAlign {
+  float m2m, m2i, iex, inm, ini;
+  float insert[4];
+  float match[16];
+};
+
+}  // namespace rna

@@ -1,0 +1,695 @@
+// fold_kernel.cuh — McCaskill inside/outside + BPP + centroid estimator as an anti-diagonal wavefront.
+//
+// One thread per DP cell of the current diagonal ("span"); every cell's fold over split points /
+// interior loops is evaluated sequentially IN THE REFERENCE'S ORDER with the reference's polynomial
+// logsumexp, so all values are bit-identical to the reference algorithm.
+// All matrices are stored DIAGONAL-MAJOR (index(i,j) = off(j-i) + i): the cells of one diagonal are
+// contiguous, so for every operand of every recurrence the 32 lanes of a warp (cells i..i+31 of the same
+// diagonal) touch 32 consecutive words — conflict-free in shared memory, fully coalesced in HBM/L2.
+// Loop-type branches (stack / bulge / 1x1 / ... / generic interior) depend only on the offsets
+// (a,b) = (k-i-1, j-l-1), which are identical for all lanes: the scoring code is warp-uniform.
+//
+// Three storage/synchronisation modes share this one body:
+//   MODE_SMEM   one CTA per sequence, matrices resident in shared memory      (tRNA .. ~145 nt)
+//   MODE_GLOBAL one CTA per sequence, matrices in an HBM/L2 workspace slot    (Rfam-length batches)
+//   MODE_COOP   the whole grid works on one sequence, grid-wide barrier per diagonal (1k-4k nt)
+//
+// Reference recurrences: src/mccaskill_algo.rs:282-378 (Turner inside), :380-516 (CONTRAfold inside),
+// :518-610 / :612-723 (outside + BPP), src/centroid_fold.rs:25-105 (centroid + traceback),
+// scorers src/utils.rs:166-556.
+#pragma once
+#include <cooperative_groups.h>
+
+#include "dev_tables.h"
+#include "numerics.cuh"
+
+namespace rna {
+namespace cg = cooperative_groups;
+
+enum { MODE_SMEM = 0, MODE_GLOBAL = 1, MODE_COOP = 2 };
+
+struct FoldArgs {
+  const uint8_t* bases;
+  const uint32_t* offsets;
+  const uint32_t* order;     // sequence indices handled by this launch (length n_launch)
+  uint32_t n_launch;
+  uint32_t n_seqs;           // whole batch (stride of the per-gamma outputs)
+  uint32_t total_len;
+  int allows_short;
+  const void* tables;        // DevTurner* / DevContra*
+  const float* gammas;
+  uint32_t n_gammas;
+  float* out_logz;
+  float* out_bpp;
+  const uint64_t* bpp_offsets;
+  uint8_t* out_structs;
+  float* out_ea;
+  uint16_t* out_pairs;
+  uint32_t* out_npairs;
+  float* workspace;          // MODE_GLOBAL / MODE_COOP
+  unsigned long long ws_stride;   // floats per workspace slot
+  int* work_counter;         // MODE_SMEM / MODE_GLOBAL: dynamic work queue
+  int Lcap;                  // capacity the shared-memory carve-up was sized for
+};
+
+template <int MODE>
+struct Ctx {
+  typedef typename std::conditional<MODE == MODE_SMEM, int, long long>::type ofs_t;
+  __device__ __forceinline__ static void sync() {
+    if (MODE == MODE_COOP) cg::this_grid().sync(); else __syncthreads();
+  }
+  __device__ __forceinline__ static int first() {
+    return MODE == MODE_COOP ? (int)(blockIdx.x * blockDim.x + threadIdx.x) : (int)threadIdx.x;
+  }
+  __device__ __forceinline__ static int stride() {
+    return MODE == MODE_COOP ? (int)(gridDim.x * blockDim.x) : (int)blockDim.x;
+  }
+  // In MODE_COOP other SMs produce the data: read through L2 (ld.global.cg), never a stale L1 line.
+  __device__ __forceinline__ static float ld(const float* p) { return MODE == MODE_COOP ? __ldcg(p) : *p; }
+  __device__ __forceinline__ static ofs_t off(int d, int L) {
+    return (ofs_t)d * (ofs_t)L - (((ofs_t)d * (ofs_t)(d - 1)) >> 1);
+  }
+};
+
+__device__ __forceinline__ int idx4(int a, int b, int c, int d) { return ((a * 4 + b) * 4 + c) * 4 + d; }
+__device__ __forceinline__ int idx3(int a, int b, int c) { return (a * 4 + b) * 4 + c; }
+
+// ---------------------------------------------------------------------------------------------------
+// Turner 2004 scorers (src/utils.rs:166-411).  `s` = sequence bytes (shared memory), T = staged tables.
+// ---------------------------------------------------------------------------------------------------
+struct TurnerView {
+  const DevTurner* g;        // global (uniform reads)
+  const TurnerSmall* sm;     // shared copy (per-lane gathers)
+};
+
+__device__ __forceinline__ float t_pen(const TurnerView& T, int x, int y) {
+  return augu_pair(x, y) ? T.g->augu_pen : 0.f;
+}
+
+// get_hairpin_score, src/utils.rs:166-196 (special-loop scan :198-205 via packed keys)
+__device__ float t_hairpin(const TurnerView& T, const uint8_t* s, int i, int j) {
+  const int span = j - i + 1;
+  if (span < 32 && ((T.g->special_len_mask >> span) & 1u)) {
+    unsigned key = 0;
+    for (int p = 0; p < span; p++) key |= (unsigned)s[i + p] << (2 * p);
+    const int n = T.g->num_special;
+    for (int x = 0; x < n; x++) {
+      if ((int)T.g->special_len[x] == span && T.g->special_key[x] == key) return T.g->special_score[x];
+    }
+  }
+  const int len = j - i - 1;
+  const int si = s[i], sj = s[j];
+  float hs;
+  if (len == T.g->min_hairpin_len) {
+    hs = __ldg(&T.g->hairpin_init_ext[len]);
+  } else {
+    hs = __fadd_rn(__ldg(&T.g->hairpin_init_ext[len]), T.sm->tm_hairpin[idx4(si, sj, s[i + 1], s[j - 1])]);
+  }
+  return __fadd_rn(hs, t_pen(T, si, sj));
+}
+
+// get_2loop_score, src/utils.rs:207-366.  (i,j) closes, (k,l) is enclosed; a = k-i-1, b = j-l-1 (warp-uniform).
+__device__ __forceinline__ float t_twoloop(const TurnerView& T, const uint8_t* s, int i, int j, int k, int l,
+                                           int a, int b) {
+  const int si = s[i], sj = s[j], sk = s[k], sl = s[l];
+  if (a == 0 && b == 0) return T.sm->stack[idx4(si, sj, sk, sl)];
+  if (a == 0 || b == 0) {
+    const int len = a + b;
+    const float bi = T.g->bulge_init[len];
+    if (len == 1) return __fadd_rn(bi, T.sm->stack[idx4(si, sj, sk, sl)]);
+    return __fadd_rn(__fadd_rn(bi, t_pen(T, si, sj)), t_pen(T, sk, sl));
+  }
+  if (a <= 2 && b <= 2) {
+    const int i1 = s[i + 1], j1 = s[j - 1];
+    if (a == 1 && b == 1) return __ldg(&T.g->int11[idx4(si, sj, i1, j1) * 16 + sk * 4 + sl]);
+    if (a == 1 && b == 2) return __ldg(&T.g->int12[(idx4(si, sj, i1, j1) * 4 + s[j - 2]) * 16 + sk * 4 + sl]);
+    if (a == 2 && b == 1)
+      return __ldg(&T.g->int12[(idx4(sl, sk, j1, s[i + 2]) * 4 + i1) * 16 + sj * 4 + si]);
+    return __ldg(&T.g->int22[(idx4(si, sj, i1, j1) * 16 + s[i + 2] * 4 + s[j - 2]) * 16 + sk * 4 + sl]);
+  }
+  const float* tm = (a == 1 || b == 1) ? T.sm->tm_1xmany
+                    : ((a == 2 && b == 3) || (a == 3 && b == 2)) ? T.sm->tm_2x3 : T.sm->tm_interior;
+  const float mm = __fadd_rn(tm[idx4(si, sj, s[i + 1], s[j - 1])], tm[idx4(sl, sk, s[l + 1], s[k - 1])]);
+  float v = __fadd_rn(T.g->interior_init_ninio[a * 31 + b], mm);
+  v = __fadd_rn(v, t_pen(T, si, sj));
+  return __fadd_rn(v, t_pen(T, sk, sl));
+}
+
+// get_multibranch_close_score, src/utils.rs:368-382
+__device__ __forceinline__ float t_mbclose(const TurnerView& T, const uint8_t* s, int i, int j) {
+  const int si = s[i], sj = s[j];
+  const float tm = T.sm->tm_multi[idx4(sj, si, s[j - 1], s[i + 1])];
+  return __fadd_rn(__fadd_rn(T.g->init_mb_base, tm), t_pen(T, si, sj));
+}
+
+// get_accessible_score (uses_sentinel_bases = false), src/utils.rs:384-411
+__device__ __forceinline__ float t_acc(const TurnerView& T, const uint8_t* s, int L, int i, int j) {
+  const int si = s[i], sj = s[j];
+  float sc;
+  if (i > 0 && j < L - 1) sc = T.sm->tm_multi[idx4(si, sj, s[i - 1], s[j + 1])];
+  else if (i > 0) sc = T.sm->d5[idx3(si, sj, s[i - 1])];
+  else if (j < L - 1) sc = T.sm->d3[idx3(si, sj, s[j + 1])];
+  else sc = 0.f;
+  return __fadd_rn(sc, t_pen(T, si, sj));
+}
+
+// ---------------------------------------------------------------------------------------------------
+// CONTRAfold v2.02 scorers (src/utils.rs:413-556)
+// ---------------------------------------------------------------------------------------------------
+struct ContraView {
+  const DevContra* g;
+  const ContraSmall* sm;
+};
+
+// get_junction_score_single, src/utils.rs:545-556
+__device__ __forceinline__ float c_jsingle(const ContraView& T, const uint8_t* s, int p0, int p1) {
+  const int x = s[p0], y = s[p1];
+  return __fadd_rn(T.sm->hc[x * 4 + y], T.sm->tm[idx4(x, y, s[p0 + 1], s[p1 - 1])]);
+}
+
+// get_junction_score (uses_sentinel_bases = false), src/utils.rs:522-543
+__device__ __forceinline__ float c_junction(const ContraView& T, const uint8_t* s, int L, int p0, int p1) {
+  const int x = s[p0], y = s[p1];
+  float v = __fadd_rn(T.sm->hc[x * 4 + y], (p0 < L - 1) ? T.sm->dl[idx3(x, y, s[min(p0 + 1, L - 1)])] : 0.f);
+  return __fadd_rn(v, (p1 > 0) ? T.sm->dr[idx3(x, y, s[max(p1 - 1, 0)])] : 0.f);
+}
+
+// get_hairpin_score_contra, src/utils.rs:413-421
+__device__ __forceinline__ float c_hairpin(const ContraView& T, const uint8_t* s, int i, int j) {
+  const int len = j - i - 1;
+  return __fadd_rn(T.g->hairpin_cum[min(len, T.g->max_loop_len)], c_jsingle(T, s, i, j));
+}
+
+// get_2loop_score_contra, src/utils.rs:423-520
+__device__ __forceinline__ float c_twoloop(const ContraView& T, const uint8_t* s, int i, int j, int k, int l,
+                                           int a, int b) {
+  const int sk = s[k], sl = s[l];
+  float sc;
+  if (a == 0 && b == 0) {
+    sc = T.sm->stack[idx4(s[i], s[j], sk, sl)];
+  } else if (a == 0 || b == 0) {
+    const int len = a + b;
+    const float s0 = (len == 1) ? T.sm->bulge0x1[(a == 1) ? s[i + 1] : s[j - 1]] : 0.f;
+    sc = __fadd_rn(s0, T.g->bulge_cum[len - 1]);
+    sc = __fadd_rn(sc, c_jsingle(T, s, i, j));
+    sc = __fadd_rn(sc, c_jsingle(T, s, l, k));
+  } else {
+    const int len = a + b;
+    float v;
+    if (a == b) {
+      const float s11 = (len == 2) ? T.sm->int1x1[s[i + 1] * 4 + s[j - 1]] : 0.f;
+      v = __fadd_rn(s11, T.g->sym_cum[a - 1]);
+    } else {
+      v = T.g->asym_cum[(a > b ? a - b : b - a) - 1];
+    }
+    const float ex = (a <= T.g->max_explicit && b <= T.g->max_explicit) ? T.g->explicit_[(a - 1) * 4 + (b - 1)] : 0.f;
+    v = __fadd_rn(v, ex);
+    v = __fadd_rn(v, T.g->interior_cum[len - 2]);
+    v = __fadd_rn(v, c_jsingle(T, s, i, j));
+    sc = __fadd_rn(v, c_jsingle(T, s, l, k));
+  }
+  return __fadd_rn(sc, T.sm->bp[sk * 4 + sl]);
+}
+
+template <bool CONTRA> struct ModelTraits;
+template <> struct ModelTraits<false> { typedef DevTurner Dev; typedef TurnerSmall Small; typedef TurnerView View; };
+template <> struct ModelTraits<true> { typedef DevContra Dev; typedef ContraSmall Small; typedef ContraView View; };
+
+template <bool CONTRA>
+__device__ __forceinline__ float m_twoloop(const typename ModelTraits<CONTRA>::View& T, const uint8_t* s, int i,
+                                           int j, int k, int l, int a, int b) {
+  if constexpr (CONTRA) return c_twoloop(T, s, i, j, k, l, a, b);
+  else return t_twoloop(T, s, i, j, k, l, a, b);
+}
+template <bool CONTRA>
+__device__ __forceinline__ float m_mbclose(const typename ModelTraits<CONTRA>::View& T, const uint8_t* s, int L,
+                                           int i, int j) {
+  if constexpr (CONTRA) return __fadd_rn(T.g->mb_base_plus_bp, c_junction(T, s, L, i, j));
+  else return t_mbclose(T, s, i, j);
+}
+template <bool CONTRA>
+__device__ __forceinline__ float m_acc(const typename ModelTraits<CONTRA>::View& T, const uint8_t* s, int L, int i,
+                                       int j) {
+  if constexpr (CONTRA) return __fadd_rn(c_junction(T, s, L, j, i), T.sm->bp[s[i] * 4 + s[j]]);
+  else return t_acc(T, s, L, i, j);
+}
+
+// Shared-memory footprint (bytes) of the fixed part and of the SMEM-mode matrices for capacity Lcap.
+template <bool CONTRA>
+__host__ __device__ inline size_t fold_smem_fixed_bytes(int Lcap) {
+  size_t b = 128;                                            // LSE coefficient LUT
+  b += (sizeof(typename ModelTraits<CONTRA>::Small) + 15) / 16 * 16;
+  b += ((size_t)Lcap + 8 + 15) / 16 * 16;                    // sequence bytes (+ guard)
+  return b;
+}
+template <bool CONTRA>
+__host__ __device__ inline size_t fold_ws_floats(int L) {
+  const size_t T = (size_t)L * ((size_t)L + 1) / 2;
+  const size_t nm = CONTRA ? 6 : 5;
+  // matrices | Mroll 3L | E0 L | EL L | traceback stack 2(L+2) ints
+  return nm * T + 3 * (size_t)L + 2 * (size_t)L + 2 * ((size_t)L + 2) + 8;
+}
+template <bool CONTRA>
+__host__ __device__ inline size_t fold_smem_bytes(int Lcap, bool smem_mats) {
+  size_t b = fold_smem_fixed_bytes<CONTRA>(Lcap);
+  if (smem_mats) b += fold_ws_floats<CONTRA>(Lcap) * 4;
+  return b;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// centroid_fold: src/centroid_fold.rs:25-105.  W (max_expect_accuracies) is diagonal-major in `W`;
+// getp(d, i) returns the base-pairing probability of (i, i+d) or -1 when the key is absent.
+// ---------------------------------------------------------------------------------------------------
+template <int MODE, class PF>
+__device__ __forceinline__ void centroid_run(const FoldArgs& a, uint32_t sidx, uint32_t sbeg, int L, float* W,
+                                             int* tstack, PF getp) {
+  typedef Ctx<MODE> X;
+  typedef typename X::ofs_t ofs_t;
+  const int tid = threadIdx.x;
+  const int c0 = X::first(), cs = X::stride();
+  const ofs_t TRI = (ofs_t)L * (ofs_t)(L + 1) / 2;
+  for (uint32_t g = 0; g < a.n_gammas; g++) {
+    const float gamma = a.gammas[g];
+    for (ofs_t x = c0; x < TRI; x += cs) W[x] = 0.f;
+    uint8_t* ostr = a.out_structs ? a.out_structs + (size_t)g * a.total_len + sbeg : nullptr;
+    if (ostr) for (int x = c0; x < L; x += cs) ostr[x] = '.';
+    X::sync();
+    for (int d = 1; d < L; d++) {
+      const int ncell = L - d;
+      const ofs_t od = X::off(d, L);
+      const ofs_t od1 = X::off(d - 1, L);
+      for (int i = c0; i < ncell; i += cs) {
+        float wv = X::ld(&W[od1 + i + 1]);
+        float e = X::ld(&W[od1 + i]);
+        if (e > wv) wv = e;
+        const float p = getp(d, i);
+        if (p != -1.0f) {
+          const float inner = (d >= 2) ? X::ld(&W[X::off(d - 2, L) + i + 1]) : 0.f;
+          e = __fsub_rn(__fadd_rn(inner, __fmul_rn(gamma, p)), 1.0f);
+          if (e > wv) wv = e;
+        }
+        for (int m = 1; m < d; m++) {
+          e = __fadd_rn(X::ld(&W[X::off(m, L) + i]), X::ld(&W[X::off(d - m - 1, L) + i + m]));
+          if (e > wv) wv = e;
+        }
+        W[od + i] = wv;
+      }
+      X::sync();
+    }
+    // traceback by the first warp of the (first) CTA; the k-scan is lane-parallel (first match wins)
+    if ((MODE != MODE_COOP || blockIdx.x == 0) && tid < 32) {
+      const int lane = tid;
+      int sp = 0;
+      uint32_t np = 0;
+      uint16_t* opairs = a.out_pairs ? a.out_pairs + 2 * ((size_t)g * a.total_len + sbeg) : nullptr;
+      if (lane == 0) { tstack[0] = 0; tstack[1] = L - 1; }
+      sp = 1;
+      __syncwarp();
+      while (sp > 0) {
+        sp--;
+        const int i = tstack[2 * sp], j = tstack[2 * sp + 1];
+        __syncwarp();
+        if (j <= i) continue;
+        const int d = j - i;
+        const float wv = X::ld(&W[X::off(d, L) + i]);
+        if (wv == 0.f) continue;
+        const float wi1 = X::ld(&W[X::off(d - 1, L) + i + 1]);
+        const float wj1 = X::ld(&W[X::off(d - 1, L) + i]);
+        const float p = getp(d, i);
+        const float inner = (d >= 2) ? X::ld(&W[X::off(d - 2, L) + i + 1]) : 0.f;
+        if (wv == wi1) {
+          if (lane == 0) { tstack[2 * sp] = i + 1; tstack[2 * sp + 1] = j; }
+          sp++;
+        } else if (wv == wj1) {
+          if (lane == 0) { tstack[2 * sp] = i; tstack[2 * sp + 1] = j - 1; }
+          sp++;
+        } else if (p != -1.0f && wv == __fsub_rn(__fadd_rn(inner, __fmul_rn(gamma, p)), 1.0f)) {
+          if (lane == 0) {
+            tstack[2 * sp] = i + 1; tstack[2 * sp + 1] = j - 1;
+            if (ostr) { ostr[i] = '('; ostr[j] = ')'; }
+            if (opairs) { opairs[2 * np] = (uint16_t)i; opairs[2 * np + 1] = (uint16_t)j; }
+          }
+          sp++;
+          np++;
+        } else {
+          for (int m0 = 1; m0 < d; m0 += 32) {
+            const int m = m0 + lane;
+            bool hit = false;
+            if (m < d) {
+              hit = (wv == __fadd_rn(X::ld(&W[X::off(m, L) + i]), X::ld(&W[X::off(d - m - 1, L) + i + m])));
+            }
+            const unsigned bal = __ballot_sync(0xffffffffu, hit);
+            if (bal) {
+              const int k = i + m0 + (__ffs(bal) - 1);
+              if (lane == 0) {
+                tstack[2 * sp] = i; tstack[2 * sp + 1] = k;
+                tstack[2 * sp + 2] = k + 1; tstack[2 * sp + 3] = j;
+              }
+              sp += 2;
+              break;
+            }
+          }
+        }
+        __syncwarp();
+      }
+      if (lane == 0) {
+        if (a.out_ea) a.out_ea[(size_t)g * a.n_seqs + sidx] = X::ld(&W[X::off(L - 1, L)]);
+        if (a.out_npairs) a.out_npairs[(size_t)g * a.n_seqs + sidx] = np;
+      }
+    }
+    X::sync();
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// The kernel
+// ---------------------------------------------------------------------------------------------------
+template <bool CONTRA, int MODE>
+__global__ void __launch_bounds__(MODE == MODE_SMEM ? 256 : 512) fold_kernel(const FoldArgs a) {
+  typedef Ctx<MODE> X;
+  typedef typename X::ofs_t ofs_t;
+  typedef typename ModelTraits<CONTRA>::Dev Dev;
+  typedef typename ModelTraits<CONTRA>::Small Small;
+  typedef typename ModelTraits<CONTRA>::View View;
+
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float4* lut = reinterpret_cast<float4*>(smem_raw);
+  Small* small = reinterpret_cast<Small*>(smem_raw + 128);
+  uint8_t* sseq = smem_raw + 128 + (sizeof(Small) + 15) / 16 * 16;
+  float* smats = reinterpret_cast<float*>(smem_raw + fold_smem_fixed_bytes<CONTRA>(a.Lcap));
+  __shared__ int s_work;
+
+  const Dev* dev = reinterpret_cast<const Dev*>(a.tables);
+  const int tid = threadIdx.x;
+  load_lse_lut(lut);
+  for (int x = tid; x < (int)(sizeof(Small) / 4); x += blockDim.x)
+    reinterpret_cast<float*>(small)[x] = reinterpret_cast<const float*>(&dev->small)[x];
+  View T;
+  T.g = dev;
+  T.sm = small;
+  __syncthreads();
+
+  const float NEG = RNA_NEG_INF;
+  const int MINSPAN = dev->min_span;
+  int MAX2;
+  if constexpr (CONTRA) MAX2 = dev->max_loop_len; else MAX2 = dev->max_2loop_len;
+
+  for (uint32_t wloop = 0;; wloop++) {
+    uint32_t w;
+    if (MODE == MODE_COOP) {
+      w = wloop;
+    } else {
+      __syncthreads();
+      if (tid == 0) s_work = atomicAdd(a.work_counter, 1);
+      __syncthreads();
+      w = (uint32_t)s_work;
+    }
+    if (w >= a.n_launch) break;
+    const uint32_t sidx = a.order ? a.order[w] : w;
+    const uint32_t sbeg = a.offsets[sidx];
+    const int L = (int)(a.offsets[sidx + 1] - sbeg);
+    const ofs_t TRI = (ofs_t)L * (ofs_t)(L + 1) / 2;
+
+    float* base;
+    if (MODE == MODE_SMEM) base = smats;
+    else if (MODE == MODE_GLOBAL) base = a.workspace + (size_t)blockIdx.x * a.ws_stride;
+    else base = a.workspace;
+    float* mC = base;
+    float* mR = mC + TRI;       // R -> PM -> W (centroid)
+    float* mE = mR + TRI;       // E -> P (log) -> prob
+    float* mM1 = mE + TRI;
+    float* mX = mM1 + TRI;      // Turner: PM2 (outside only); CONTRAfold: Rm -> PM2
+    float* mA = mX + TRI;       // CONTRAfold only: A
+    float* Mroll = CONTRA ? mA + TRI : mX + TRI;   // sums_multibranch: only diagonals d, d-1, d-2 are live
+    float* E0 = Mroll + 3 * (size_t)L;             // sums_external[0][x]
+    float* EL = E0 + L;                            // sums_external[x][L-1]
+    int* tstack = reinterpret_cast<int*>(EL + L);
+
+    uint8_t* s = sseq + 4;
+    for (int x = tid; x < L; x += blockDim.x) s[x] = a.bases[sbeg + x];
+    if (tid < 4) { sseq[tid] = 0; s[L + tid] = 0; }
+
+    const int c0 = X::first(), cs = X::stride();
+    // ---- init (FoldSums::new, src/mccaskill_algo.rs:213-226) ---------------------------------------
+    for (ofs_t x = c0; x < TRI; x += cs) {
+      mC[x] = NEG; mR[x] = NEG; mE[x] = 0.f; mM1[x] = NEG; mX[x] = NEG;
+      if (CONTRA) mA[x] = NEG;
+    }
+    for (int x = c0; x < 3 * L; x += cs) Mroll[x] = NEG;
+    X::sync();
+
+    // ================================ inside =======================================================
+    const int d_in0 = CONTRA ? 0 : (MINSPAN - 1);
+    for (int d = d_in0; d < L; d++) {
+      const int ncell = L - d;
+      const ofs_t od = X::off(d, L);
+      float* Mcur = Mroll + (size_t)(d % 3) * L;
+      const float* Mm2 = Mroll + (size_t)((d + 1) % 3) * L;   // diagonal d-2
+      for (int i = c0; i < ncell; i += cs) {
+        const int j = i + d;
+        const int si = s[i], sj = s[j];
+        bool pairable = canonical_pair(si, sj);
+        if (CONTRA) pairable = pairable && (a.allows_short || d + 1 >= MINSPAN);
+        float sumC = NEG;
+        // (1) sums_close
+        if (__any_sync(__activemask(), pairable)) {
+          if (pairable) {
+            if constexpr (CONTRA) {
+              if (d - 1 <= MAX2) sumC = lse(sumC, c_hairpin(T, s, i, j), lut);
+            } else {
+              sumC = lse(sumC, t_hairpin(T, s, i, j), lut);
+            }
+          }
+          const int amax = min(MAX2, d - 3);
+          for (int aa = 0; aa <= amax; aa++) {
+            const int k = i + 1 + aa;
+            const int bmax = min(MAX2 - aa, d - 3 - aa);
+            for (int bb = 0; bb <= bmax; bb++) {
+              const int l = j - 1 - bb;
+              const float c = X::ld(&mC[X::off(d - 2 - aa - bb, L) + k]);
+              const bool on = pairable && (c > NEG);
+              if (__any_sync(__activemask(), on)) {
+                const float y = __fadd_rn(c, m_twoloop<CONTRA>(T, s, i, j, k, l, aa, bb));
+                sumC = lse_if(on, sumC, y, lut);
+              }
+            }
+          }
+          if (pairable) {
+            const float mbc = m_mbclose<CONTRA>(T, s, L, i, j);
+            const float mb = (d >= 2) ? X::ld(&Mm2[i + 1]) : NEG;
+            sumC = lse(sumC, __fadd_rn(mb, mbc), lut);
+          }
+        }
+        float accv = NEG;
+        if (sumC > NEG) {
+          mC[od + i] = sumC;
+          accv = __fadd_rn(sumC, m_acc<CONTRA>(T, s, L, i, j));
+          if (CONTRA) mA[od + i] = accv;
+        }
+        // (2) sums_rightmost_basepairs_external (/ _multibranch)
+        float Rij, Rmij = NEG;
+        if constexpr (!CONTRA) {
+          // prefix property of the left-to-right fold: R[i][j] = R[i][j-1] (+) A(i,j)
+          const float prev = (d >= 1) ? X::ld(&mR[X::off(d - 1, L) + i]) : NEG;
+          Rij = lse(prev, accv, lut);
+        } else {
+          Rij = NEG;
+          for (int m = 1; m <= d; m++) {
+            const float av = (m == d) ? accv : X::ld(&mA[X::off(m, L) + i]);
+            const float n = (float)(d - m);
+            Rij = lse(Rij, __fadd_rn(__fadd_rn(av, dev->ext_bp), __fmul_rn(dev->ext_unpair, n)), lut);
+            Rmij = lse(Rmij, __fadd_rn(__fadd_rn(av, dev->mb_bp), __fmul_rn(dev->mb_unpair, n)), lut);
+          }
+          mX[od + i] = Rmij;
+        }
+        mR[od + i] = Rij;
+        // (3) sums_external, (4) sums_multibranch / sums_1ormore_basepairs — three independent chains
+        float sE, sM1, sM = NEG;
+        if constexpr (CONTRA) {
+          sE = __fmul_rn(dev->ext_unpair, (float)(d + 1));
+          sM1 = Rmij;
+        } else {
+          sE = 0.f;
+          sM1 = __fadd_rn(Rij, dev->coeff_num_branches);
+        }
+        sE = lse(sE, __fadd_rn(Rij, 0.f), lut);   // k = i: E[i][i-1] = 0 (lower triangle / literal 0)
+        for (int m = 1; m < d; m++) {
+          const float r = X::ld(&mR[X::off(d - m, L) + i + m]);
+          const float e = X::ld(&mE[X::off(m - 1, L) + i]);
+          const float m1 = X::ld(&mM1[X::off(m - 1, L) + i]);
+          sE = lse(sE, __fadd_rn(r, e), lut);
+          if constexpr (CONTRA) {
+            const float rm = X::ld(&mX[X::off(d - m, L) + i + m]);
+            sM1 = lse(sM1, __fadd_rn(rm, __fmul_rn(dev->mb_unpair, (float)m)), lut);
+            sM = lse(sM, __fadd_rn(m1, rm), lut);
+          } else {
+            const float xx = __fadd_rn(r, dev->coeff_num_branches);
+            sM1 = lse(sM1, xx, lut);
+            sM = lse(sM, __fadd_rn(m1, xx), lut);
+          }
+        }
+        mE[od + i] = sE;
+        Mcur[i] = sM;
+        sM1 = lse(sM1, sM, lut);
+        mM1[od + i] = sM1;
+      }
+      X::sync();
+    }
+
+    // ================================ outside ======================================================
+    // keep sums_external[0][*] and [*][L-1], then recycle: E -> P, R -> PM, X -> PM2
+    for (int x = c0; x < L; x += cs) {
+      E0[x] = X::ld(&mE[X::off(x, L)]);
+      EL[x] = X::ld(&mE[X::off(L - 1 - x, L) + x]);
+    }
+    X::sync();
+    const float Z = X::ld(&E0[L - 1]);
+    for (ofs_t x = c0; x < TRI; x += cs) { mE[x] = NEG; mR[x] = NEG; mX[x] = NEG; }
+    if (c0 == 0 && a.out_logz) a.out_logz[sidx] = Z;
+    X::sync();
+
+    const int d_out0 = CONTRA ? (a.allows_short ? 1 : MINSPAN - 1) : (MINSPAN - 1);
+    for (int d = L - 1; d >= d_out0; d--) {
+      const int ncell = L - d;
+      const ofs_t od = X::off(d, L);
+      for (int i = c0; i < ncell; i += cs) {
+        const int j = i + d;
+        // (1) probs_multibranch / probs_multibranch2  (src/mccaskill_algo.rs:540-557, 641-661)
+        float pm = NEG, pm2 = NEG;
+        const int mmax = L - 1 - d;   // largest k - j over the diagonal (lane i = 0)
+        for (int m = 1; m <= mmax; m++) {
+          const int k = j + m;
+          const bool inr = k < L;
+          const ofs_t q = X::off(d + m, L) + i;
+          const float c = inr ? X::ld(&mC[q]) : NEG;
+          const bool on = c > NEG;
+          if (__any_sync(__activemask(), on)) {
+            const int kk = inr ? k : j;
+            const float p = inr ? X::ld(&mE[q]) : NEG;
+            const float x = __fsub_rn(__fadd_rn(p, m_mbclose<CONTRA>(T, s, L, i, kk)), c);
+            const float m1 = (m >= 2 && inr) ? X::ld(&mM1[X::off(m - 2, L) + j + 1]) : NEG;
+            pm = lse_if(on, pm, __fadd_rn(x, m1), lut);
+            if constexpr (CONTRA) pm2 = lse_if(on, pm2, __fadd_rn(x, __fmul_rn(dev->mb_unpair, (float)(m - 1))), lut);
+            else pm2 = lse_if(on, pm2, x, lut);
+          }
+        }
+        mR[od + i] = pm;
+        mX[od + i] = pm2;
+        // (2) the pair (i,j) itself
+        const float Cij = X::ld(&mC[od + i]);
+        const bool has = Cij > NEG;
+        if (__any_sync(__activemask(), has)) {
+          const float Aij = has ? __fadd_rn(Cij, m_acc<CONTRA>(T, s, L, i, j)) : NEG;
+          const float El = (i < 1) ? 0.f : X::ld(&E0[i - 1]);
+          const float Er = (j > L - 2) ? 0.f : X::ld(&EL[j + 1]);
+          float sm;
+          if constexpr (CONTRA) {
+            sm = __fsub_rn(__fadd_rn(__fadd_rn(__fadd_rn(El, Er), Aij), dev->ext_bp), Z);
+          } else {
+            sm = __fsub_rn(__fadd_rn(__fadd_rn(El, Aij), Er), Z);
+          }
+          if (!has) sm = NEG;
+          // enclosing two-loops: k descending from i-1, l ascending from j+1
+          const int cap = min(MAX2, L - d - 3);
+          for (int aa = 0; aa <= cap; aa++) {
+            const int k = i - 1 - aa;
+            for (int bb = 0; aa + bb <= cap; bb++) {
+              const int l = j + 1 + bb;
+              const bool inr = (k >= 0) && (l < L);
+              const ofs_t q = X::off(d + 2 + aa + bb, L) + k;
+              const float c = inr ? X::ld(&mC[q]) : NEG;
+              const bool on = has && (c > NEG);
+              if (__any_sync(__activemask(), on)) {
+                const int kk = inr ? k : i, ll = inr ? l : j;
+                const float p = inr ? X::ld(&mE[q]) : NEG;
+                const float tl = on ? m_twoloop<CONTRA>(T, s, kk, ll, i, j, aa, bb) : 0.f;
+                const float y = __fadd_rn(__fsub_rn(__fadd_rn(p, Cij), c), tl);
+                sm = lse_if(on, sm, y, lut);
+              }
+            }
+          }
+          // enclosing multiloops: k ascending 0..i-1  <=>  m = i-1-k descending
+          float sa;
+          if constexpr (CONTRA) sa = __fadd_rn(Aij, dev->mb_bp); else sa = __fadd_rn(Aij, dev->coeff_num_branches);
+          for (int m = ncell - 2; m >= 0; m--) {
+            const bool on = has && (m <= i - 1);
+            const int k = on ? (i - 1 - m) : 0;
+            const ofs_t q = X::off(d + 1 + m, L) + k;
+            const float x = (on && m >= 1) ? X::ld(&mM1[X::off(m - 1, L) + k + 1]) : NEG;
+            const float p2 = on ? X::ld(&mX[q]) : NEG;
+            const float y = on ? X::ld(&mR[q]) : NEG;
+            sm = lse_if(on, sm, __fadd_rn(__fadd_rn(sa, p2), x), lut);
+            if constexpr (CONTRA) sm = lse_if(on, sm, __fadd_rn(__fadd_rn(sa, y), __fmul_rn(dev->mb_unpair, (float)m)), lut);
+            else sm = lse_if(on, sm, __fadd_rn(sa, y), lut);
+            sm = lse_if(on, sm, __fadd_rn(__fadd_rn(sa, x), y), lut);
+          }
+          if (has && sm > NEG) mE[od + i] = sm;
+        }
+      }
+      X::sync();
+    }
+
+    // ================================ BPP = expf(P) ================================================
+    for (ofs_t x = c0; x < TRI; x += cs) {
+      const float v = X::ld(&mE[x]);
+      mE[x] = (v > NEG) ? approx_expf(v) : -1.0f;
+    }
+    X::sync();
+    if (a.out_bpp) {
+      float* ob = a.out_bpp + a.bpp_offsets[sidx];
+      for (int i = 0; i < L - 1; i++) {
+        const size_t rowoff = (size_t)i * (size_t)(2 * L - i - 1) / 2;
+        for (int x = c0; x < L - 1 - i; x += cs) ob[rowoff + x] = X::ld(&mE[X::off(x + 1, L) + i]);
+      }
+    }
+
+    // ================================ centroid (src/centroid_fold.rs:25-105) =======================
+    {
+      const float* P = mE;
+      auto getp = [=](int d, int i) -> float { return X::ld(&P[X::off(d, L) + i]); };
+      centroid_run<MODE>(a, sidx, sbeg, L, mR, tstack, getp);
+    }
+  }
+}
+
+// centroid_fold over packed BPP matrices that already live in device memory (rna_centroid_batch).
+// Workspace layout per slot: W (L(L+1)/2 floats) | traceback stack.
+template <int MODE>
+__global__ void __launch_bounds__(MODE == MODE_SMEM ? 256 : 512) centroid_kernel(const FoldArgs a, const float* bpp_in) {
+  typedef Ctx<MODE> X;
+  typedef typename X::ofs_t ofs_t;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ int s_work;
+  const int tid = threadIdx.x;
+  for (uint32_t wloop = 0;; wloop++) {
+    uint32_t w;
+    if (MODE == MODE_COOP) {
+      w = wloop;
+    } else {
+      __syncthreads();
+      if (tid == 0) s_work = atomicAdd(a.work_counter, 1);
+      __syncthreads();
+      w = (uint32_t)s_work;
+    }
+    if (w >= a.n_launch) break;
+    const uint32_t sidx = a.order ? a.order[w] : w;
+    const uint32_t sbeg = a.offsets[sidx];
+    const int L = (int)(a.offsets[sidx + 1] - sbeg);
+    const ofs_t TRI = (ofs_t)L * (ofs_t)(L + 1) / 2;
+    float* W;
+    if (MODE == MODE_SMEM) W = reinterpret_cast<float*>(smem_raw);
+    else if (MODE == MODE_GLOBAL) W = a.workspace + (size_t)blockIdx.x * a.ws_stride;
+    else W = a.workspace;
+    int* tstack = reinterpret_cast<int*>(W + TRI);
+    const float* P = bpp_in + a.bpp_offsets[sidx];
+    auto getp = [=](int d, int i) -> float {
+      return __ldg(&P[(size_t)i * (size_t)(2 * L - i - 1) / 2 + (size_t)(d - 1)]);
+    };
+    centroid_run<MODE>(a, sidx, sbeg, L, W, tstack, getp);
+  }
+}
+__host__ __device__ inline size_t centroid_ws_floats(int L) {
+  return (size_t)L * ((size_t)L + 1) / 2 + 2 * ((size_t)L + 2) + 8;
+}
+
+}  // namespace rna

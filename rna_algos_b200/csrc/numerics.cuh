@@ -1,0 +1,101 @@
+// numerics.cuh — device versions of the reference's approximate log-sum-exp / exp
+// (reference src/utils.rs:579-655).  Bit-exact by construction: every product and sum is a separate
+// IEEE f32 operation (__fmul_rn/__fadd_rn never contract to FMA), evaluated in the reference's order,
+// with the reference's f32 coefficient literals.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace rna {
+
+#define RNA_NEG_INF (__int_as_float(0xff800000))
+#define RNA_LSE_THRESHOLD 11.862479f
+
+// Coefficient table of ln_exp_1p: 8 segments x {a, b, c, d}, poly = ((a*x + b)*x + c)*x + d.
+// Staged into shared memory once per CTA (per-lane segment index => LDS.128, conflict-free: each
+// 16-byte row lives in its own 4 banks, equal rows broadcast).
+__device__ __constant__ float4 kLnExp1pCoef[8] = {
+    {-0.0065591595f, 0.12764427f, 0.49965546f, 0.6931542f},     // x < 0.66153675
+    {-0.015515756f, 0.14467756f, 0.48829398f, 0.6958093f},      // x < 1.6320158
+    {-0.012890925f, 0.13010283f, 0.51503986f, 0.6795586f},      // x < 2.4912589
+    {-0.0072142647f, 0.087754086f, 0.6208708f, 0.5909676f},     // x < 3.37925
+    {-0.0031455354f, 0.046722945f, 0.7592532f, 0.43487945f},    // x < 4.426169
+    {-0.0010110698f, 0.018594341f, 0.88317305f, 0.25236955f},   // x < 5.789071
+    {-0.000196278f, 0.0046084408f, 0.9634432f, 0.09831489f},    // x < 7.8162727
+    {-0.0000113994f, 0.0003734731f, 0.9959107f, 0.0149855051f}  // else
+};
+
+__device__ __forceinline__ void load_lse_lut(float4* lut_smem) {
+  if (threadIdx.x < 8) lut_smem[threadIdx.x] = kLnExp1pCoef[threadIdx.x];
+}
+
+// Segment index of the reference's comparison tree (src/utils.rs:604-626), branch-free.
+__device__ __forceinline__ int ln_exp_1p_segment(float x) {
+  const bool p1 = x < 3.37925f;
+  const float t2 = p1 ? 1.6320158f : 5.789071f;
+  const bool p2 = x < t2;
+  const float t3 = p1 ? (p2 ? 0.66153675f : 2.4912589f) : (p2 ? 4.426169f : 7.8162727f);
+  const bool p3 = x < t3;
+  return (p1 ? 0 : 4) + (p2 ? 0 : 2) + (p3 ? 0 : 1);
+}
+
+__device__ __forceinline__ float ln_exp_1p(float x, const float4* __restrict__ lut) {
+  const float4 c = lut[ln_exp_1p_segment(x)];
+  float r = __fadd_rn(__fmul_rn(c.x, x), c.y);
+  r = __fadd_rn(__fmul_rn(r, x), c.z);
+  r = __fadd_rn(__fmul_rn(r, x), c.w);
+  return r;
+}
+
+__device__ __forceinline__ bool is_finite(float x) { return fabsf(x) < __int_as_float(0x7f800000); }
+
+// logsumexp(&mut sum, x): src/utils.rs:580-596.  Returns the new sum.
+__device__ __forceinline__ float lse(float sum, float x, const float4* __restrict__ lut) {
+  const float y = fminf(sum, x);
+  const float z = __fsub_rn(fmaxf(sum, x), y);
+  // z is NaN/inf when either operand is not finite; the LUT index stays in range (all compares false => 7).
+  const float r = ln_exp_1p(z, lut);
+  const float v = __fadd_rn(y, (z >= RNA_LSE_THRESHOLD) ? z : r);
+  const float w = is_finite(sum) ? v : x;
+  return is_finite(x) ? w : sum;
+}
+
+// lse with a per-lane enable predicate (disabled lanes keep `sum`).
+__device__ __forceinline__ float lse_if(bool on, float sum, float x, const float4* __restrict__ lut) {
+  return lse(sum, on ? x : RNA_NEG_INF, lut);
+}
+
+// expf: src/utils.rs:631-655.  For x >= 0 the reference calls libm expf; here exp is evaluated in f64
+// and rounded once to f32, which equals the correctly rounded f32 result (and glibc's <1-ULP expf)
+// except for ~1e-8 of inputs (DESIGN.md "numerics").
+__device__ __forceinline__ float approx_expf(float x) {
+  if (x < -2.4915035f) {
+    if (x < -5.8622823f) {
+      if (x < -9.91152f) return 0.f;
+      return __fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(0.0000803850f, x), 0.002162743f), x), 0.019470856f), x), 0.058808003f);
+    } else if (x < -3.839663f) {
+      return __fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(0.0013889414f, x), 0.024467647f), x), 0.14712906f), x), 0.30427578f);
+    } else {
+      return __fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(0.0072335607f, x), 0.09060027f), x), 0.39831114f), x), 0.62459594f);
+    }
+  } else if (x < -0.6725053f) {
+    if (x < -1.4805375f) {
+      return __fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(0.023241036f, x), 0.2085646f), x), 0.6906368f), x), 0.86823225f);
+    } else {
+      return __fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(0.057378277f, x), 0.35802585f), x), 0.9121133f), x), 0.9793092f);
+    }
+  } else if (x < 0.f) {
+    return __fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(0.119917594f, x), 0.48156682f), x), 0.9975992f), x), 0.9999505f);
+  }
+  return (float)exp((double)x);
+}
+
+__device__ __forceinline__ bool canonical_pair(int x, int y) {
+  // AU CG GC GU UA UG with A=0 C=1 G=2 U=3: bitmask over x*4+y
+  return (0x5a48u >> (x * 4 + y)) & 1u;   // bits 3(AU) 6(CG) 9(GC) 11(GU) 12(UA) 14(UG)
+}
+__device__ __forceinline__ bool augu_pair(int x, int y) {
+  return (0x5808u >> (x * 4 + y)) & 1u;   // bits 3(AU) 11(GU) 12(UA) 14(UG)
+}
+
+}  // namespace rna

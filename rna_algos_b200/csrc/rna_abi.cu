@@ -1,0 +1,788 @@
+// rna_abi.cu — C ABI (include/rna_algos_b200.h) over the CUDA kernels: handle, table packing,
+// length bucketing, launches, host<->device copies.  No CPU fallback: every entry point that computes
+// needs a CUDA device and reports RNA_ERR_NO_DEVICE / RNA_ERR_CUDA otherwise.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <queue>
+#include <string>
+#include <vector>
+
+#include "../../include/rna_algos_b200.h"
+#include "dev_tables.h"
+#include "durbin_kernel.cuh"
+#include "fold_kernel.cuh"
+
+using namespace rna;
+
+// ---------------------------------------------------------------------------------------------------
+// handle
+// ---------------------------------------------------------------------------------------------------
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+};
+
+struct rna_handle {
+  int device = 0;
+  int sm_count = 0;
+  size_t smem_optin = 0;
+  cudaStream_t stream = nullptr;
+  std::string err;
+  bool has_turner = false, has_contra = false, has_align = false;
+  DevTurner* d_turner = nullptr;
+  DevContra* d_contra = nullptr;
+  DevAlign* d_align = nullptr;
+  float *d_hp_ext = nullptr, *d_int11 = nullptr, *d_int12 = nullptr, *d_int22 = nullptr;
+  DevBuf ws, counters, order;                                      // kernel scratch
+  DevBuf b_bases, b_offsets, b_bppoff, b_gammas, b_logz, b_bpp, b_structs, b_ea, b_pairs, b_probs, b_proboff;
+  RnaCallStats stats{};
+  bool attrs_set = false;
+};
+
+#define CU(h, call)                                                                                  \
+  do {                                                                                               \
+    cudaError_t e__ = (call);                                                                        \
+    if (e__ != cudaSuccess) {                                                                        \
+      (h)->err = std::string(#call) + ": " + cudaGetErrorString(e__);                                \
+      return RNA_ERR_CUDA;                                                                           \
+    }                                                                                                \
+  } while (0)
+
+static int ensure(rna_handle* h, DevBuf& b, size_t bytes) {
+  if (bytes <= b.cap && b.p) return RNA_OK;
+  if (b.p) { cudaFree(b.p); b.p = nullptr; b.cap = 0; }
+  size_t want = std::max<size_t>(bytes, 256);
+  cudaError_t e = cudaMalloc(&b.p, want);
+  if (e != cudaSuccess) {
+    h->err = std::string("cudaMalloc(") + std::to_string(want) + "): " + cudaGetErrorString(e);
+    cudaGetLastError();
+    return RNA_ERR_NOMEM;
+  }
+  b.cap = want;
+  return RNA_OK;
+}
+#define TRY(x) do { int rc__ = (x); if (rc__ != RNA_OK) return rc__; } while (0)
+
+extern "C" const char* rna_version(void) { return "rna_algos_b200 0.1.0 (sm_100a)"; }
+extern "C" size_t rna_sizeof_turner_tables(void) { return sizeof(RnaTurnerTables); }
+extern "C" size_t rna_sizeof_contra_tables(void) { return sizeof(RnaContraTables); }
+extern "C" size_t rna_sizeof_align_tables(void) { return sizeof(RnaAlignTables); }
+
+extern "C" int rna_create(int device, rna_handle** out) {
+  if (!out) return RNA_ERR_BAD_ARG;
+  *out = nullptr;
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0) { cudaGetLastError(); return RNA_ERR_NO_DEVICE; }
+  if (device < 0 || device >= n) return RNA_ERR_BAD_ARG;
+  rna_handle* h = new rna_handle();
+  h->device = device;
+  if (cudaSetDevice(device) != cudaSuccess) { delete h; return RNA_ERR_NO_DEVICE; }
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { delete h; return RNA_ERR_NO_DEVICE; }
+  h->sm_count = prop.multiProcessorCount;
+  h->smem_optin = prop.sharedMemPerBlockOptin;
+  if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) { delete h; return RNA_ERR_CUDA; }
+  *out = h;
+  return RNA_OK;
+}
+
+static void free_buf(DevBuf& b) { if (b.p) cudaFree(b.p); b.p = nullptr; b.cap = 0; }
+
+extern "C" int rna_destroy(rna_handle* h) {
+  if (!h) return RNA_OK;
+  cudaSetDevice(h->device);
+  cudaStreamSynchronize(h->stream);
+  DevBuf* bufs[] = {&h->ws, &h->counters, &h->order, &h->b_bases, &h->b_offsets, &h->b_bppoff, &h->b_gammas,
+                    &h->b_logz, &h->b_bpp, &h->b_structs, &h->b_ea, &h->b_pairs, &h->b_probs, &h->b_proboff};
+  for (DevBuf* b : bufs) free_buf(*b);
+  cudaFree(h->d_turner); cudaFree(h->d_contra); cudaFree(h->d_align);
+  cudaFree(h->d_hp_ext); cudaFree(h->d_int11); cudaFree(h->d_int12); cudaFree(h->d_int22);
+  cudaStreamDestroy(h->stream);
+  delete h;
+  return RNA_OK;
+}
+
+extern "C" const char* rna_last_error(const rna_handle* h) { return h ? h->err.c_str() : "null handle"; }
+extern "C" int rna_device(const rna_handle* h) { return h ? h->device : -1; }
+extern "C" int rna_get_stats(const rna_handle* h, RnaCallStats* out) {
+  if (!h || !out) return RNA_ERR_BAD_ARG;
+  *out = h->stats;
+  return RNA_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// table packing (host, plain IEEE f32 — compiled with -ffp-contract=off)
+// ---------------------------------------------------------------------------------------------------
+extern "C" void rna_contra_tables_accumulate(RnaContraTables* t) {
+  // FoldScoreSets::accumulate, reference src/mccaskill_algo.rs:60-86
+  struct { const float* src; float* dst; int n; } jobs[] = {
+      {t->hairpin_scores_len, t->hairpin_scores_len_cumulative, RNA_CONTRA_MAX_LOOP_LEN + 1},
+      {t->bulge_scores_len, t->bulge_scores_len_cumulative, RNA_CONTRA_MAX_LOOP_LEN},
+      {t->interior_scores_len, t->interior_scores_len_cumulative, RNA_CONTRA_MAX_LOOP_LEN - 1},
+      {t->interior_scores_symmetric, t->interior_scores_symmetric_cumulative, RNA_CONTRA_MAX_INTERIOR_SYMMETRIC},
+      {t->interior_scores_asymmetric, t->interior_scores_asymmetric_cumulative, RNA_CONTRA_MAX_INTERIOR_ASYMMETRIC}};
+  for (auto& j : jobs) {
+    volatile float sum = 0.f;
+    for (int i = 0; i < j.n; i++) { sum = sum + j.src[i]; j.dst[i] = sum; }
+  }
+}
+
+extern "C" void rna_align_tables_contralign_v201(RnaAlignTables* t) {
+  // reference src/compiled_align_scores.rs:2-19
+  static const float m[4][4] = {{0.5256508867f, -0.40906402f, -0.2502759109f, -0.3252306723f},
+                                {-0.40906402f, 0.6665219366f, -0.3289391181f, -0.1326088918f},
+                                {-0.2502759109f, -0.3289391181f, 0.6684676551f, -0.3565888168f},
+                                {-0.3252306723f, -0.1326088918f, -0.3565888168f, 0.459052045f}};
+  static const float ins[4] = {-0.002521927159f, -0.08313891561f, -0.07443970653f, -0.01290054598f};
+  memcpy(t->match_scores, m, sizeof m);
+  memcpy(t->insert_scores, ins, sizeof ins);
+  t->init_match_score = 0.3959924457f;
+  t->init_insert_score = -0.3488104904f;
+  t->match2match_score = 2.50575671f;
+  t->match2insert_score = 0.1970448791f;
+  t->insert_extend_score = 1.014026583f;
+  t->insert_switch_score = -7.346968782f;
+}
+
+extern "C" int rna_set_turner_tables(rna_handle* h, const RnaTurnerTables* t) {
+  if (!h || !t) return RNA_ERR_BAD_ARG;
+  if (t->max_2loop_len < 0 || t->max_2loop_len > 30 || t->min_span_hairpin_close < 2 ||
+      t->min_hairpin_len < 0 || t->min_hairpin_len > 30 || t->max_hairpin_len_extrapolation > 30 ||
+      t->max_hairpin_len_extrapolation < t->min_hairpin_len || t->min_hairpin_len_extrapolation < 2 ||
+      t->min_hairpin_len_extrapolation > 31 || t->num_special_hairpins < 0 ||
+      t->num_special_hairpins > RNA_MAX_SPECIAL_HAIRPINS) {
+    h->err = "Turner blob: caps out of range";
+    return RNA_ERR_BAD_TABLES;
+  }
+  CU(h, cudaSetDevice(h->device));
+  DevTurner d;
+  memset(&d, 0, sizeof d);
+  d.max_2loop_len = t->max_2loop_len;
+  d.min_span = t->min_span_hairpin_close;
+  d.min_hairpin_len = t->min_hairpin_len;
+  d.num_special = t->num_special_hairpins;
+  d.augu_pen = t->helix_augu_end_penalty;
+  d.init_mb_base = t->init_multibranch_base;
+  d.coeff_num_branches = t->coeff_num_branches;
+  memcpy(d.bulge_init, t->bulge_scores_init, sizeof d.bulge_init);
+  for (int a = 0; a < 31; a++)
+    for (int b = 0; b < 31; b++) {
+      float v = 0.f;
+      if (a + b <= 30) {
+        const int diff = a > b ? a - b : b - a;
+        volatile float nin = t->ninio_coeff * (float)diff;          // NINIO_COEFF * diff as Score
+        float nn = fmaxf(nin, t->ninio_max);                        // .max(NINIO_MAX), src/utils.rs:307
+        volatile float s = t->interior_scores_init[a + b] + nn;
+        v = s;
+      }
+      d.interior_init_ninio[a * 31 + b] = v;
+    }
+  for (int x = 0; x < t->num_special_hairpins; x++) {
+    const RnaSpecialHairpin& e = t->hairpin_scores_special[x];
+    if (e.len < 2 || e.len > RNA_MAX_SPECIAL_HAIRPIN_LEN) { h->err = "Turner blob: special hairpin length"; return RNA_ERR_BAD_TABLES; }
+    unsigned key = 0;
+    for (int p = 0; p < e.len; p++) {
+      if (e.seq[p] > 3) { h->err = "Turner blob: special hairpin base"; return RNA_ERR_BAD_TABLES; }
+      key |= (unsigned)e.seq[p] << (2 * p);
+    }
+    d.special_key[x] = key;
+    d.special_len[x] = e.len;
+    d.special_score[x] = e.score;
+    d.special_len_mask |= 1u << e.len;
+  }
+  memcpy(d.small.tm_hairpin, t->terminal_mismatch_scores_hairpin, 1024);
+  memcpy(d.small.stack, t->stack_scores, 1024);
+  memcpy(d.small.tm_1xmany, t->terminal_mismatch_scores_1xmany, 1024);
+  memcpy(d.small.tm_2x3, t->terminal_mismatch_scores_2x3, 1024);
+  memcpy(d.small.tm_interior, t->terminal_mismatch_scores_interior, 1024);
+  memcpy(d.small.tm_multi, t->terminal_mismatch_scores_multibranch, 1024);
+  memcpy(d.small.d5, t->dangling_scores_5prime, 256);
+  memcpy(d.small.d3, t->dangling_scores_3prime, 256);
+  // hairpin initiation for every loop length: table, or the f32 ln-extrapolation of src/utils.rs:178-184
+  std::vector<float> hp(RNA_HAIRPIN_EXT_LEN);
+  const int mex = t->min_hairpin_len_extrapolation - 1;
+  for (int len = 0; len < RNA_HAIRPIN_EXT_LEN; len++) {
+    if (len <= t->max_hairpin_len_extrapolation) {
+      hp[len] = t->hairpin_scores_init[len];
+    } else {
+      volatile float ratio = (float)len / (float)mex;
+      volatile float lg = logf(ratio);
+      volatile float pr = t->coeff_hairpin_len_extrapolation * lg;
+      volatile float s = t->hairpin_scores_init[mex] + pr;
+      hp[len] = s;
+    }
+  }
+  if (!h->d_turner) {
+    CU(h, cudaMalloc(&h->d_turner, sizeof(DevTurner)));
+    CU(h, cudaMalloc(&h->d_hp_ext, sizeof(float) * RNA_HAIRPIN_EXT_LEN));
+    CU(h, cudaMalloc(&h->d_int11, sizeof t->interior_scores_1x1));
+    CU(h, cudaMalloc(&h->d_int12, sizeof t->interior_scores_1x2));
+    CU(h, cudaMalloc(&h->d_int22, sizeof t->interior_scores_2x2));
+  }
+  d.hairpin_init_ext = h->d_hp_ext;
+  d.int11 = h->d_int11;
+  d.int12 = h->d_int12;
+  d.int22 = h->d_int22;
+  CU(h, cudaMemcpy(h->d_hp_ext, hp.data(), sizeof(float) * RNA_HAIRPIN_EXT_LEN, cudaMemcpyHostToDevice));
+  CU(h, cudaMemcpy(h->d_int11, t->interior_scores_1x1, sizeof t->interior_scores_1x1, cudaMemcpyHostToDevice));
+  CU(h, cudaMemcpy(h->d_int12, t->interior_scores_1x2, sizeof t->interior_scores_1x2, cudaMemcpyHostToDevice));
+  CU(h, cudaMemcpy(h->d_int22, t->interior_scores_2x2, sizeof t->interior_scores_2x2, cudaMemcpyHostToDevice));
+  CU(h, cudaMemcpy(h->d_turner, &d, sizeof d, cudaMemcpyHostToDevice));
+  h->has_turner = true;
+  return RNA_OK;
+}
+
+extern "C" int rna_set_contra_tables(rna_handle* h, const RnaContraTables* t) {
+  if (!h || !t) return RNA_ERR_BAD_ARG;
+  if (t->max_loop_len != RNA_CONTRA_MAX_LOOP_LEN || t->min_span_hairpin_close < 2 ||
+      t->max_interior_explicit < 0 || t->max_interior_explicit > RNA_CONTRA_MAX_INTERIOR_EXPLICIT) {
+    h->err = "CONTRAfold blob: caps out of range";
+    return RNA_ERR_BAD_TABLES;
+  }
+  CU(h, cudaSetDevice(h->device));
+  DevContra d;
+  memset(&d, 0, sizeof d);
+  d.max_loop_len = t->max_loop_len;
+  d.min_span = t->min_span_hairpin_close;
+  d.max_explicit = t->max_interior_explicit;
+  d.mb_base = t->multibranch_score_base;
+  d.mb_bp = t->multibranch_score_basepair;
+  d.mb_unpair = t->multibranch_score_unpair;
+  d.ext_bp = t->external_score_basepair;
+  d.ext_unpair = t->external_score_unpair;
+  { volatile float s = t->multibranch_score_base + t->multibranch_score_basepair; d.mb_base_plus_bp = s; }
+  memcpy(d.hairpin_cum, t->hairpin_scores_len_cumulative, sizeof d.hairpin_cum);
+  memcpy(d.bulge_cum, t->bulge_scores_len_cumulative, sizeof d.bulge_cum);
+  memcpy(d.interior_cum, t->interior_scores_len_cumulative, sizeof d.interior_cum);
+  memcpy(d.sym_cum, t->interior_scores_symmetric_cumulative, sizeof d.sym_cum);
+  memcpy(d.asym_cum, t->interior_scores_asymmetric_cumulative, sizeof d.asym_cum);
+  memcpy(d.explicit_, t->interior_scores_explicit, sizeof d.explicit_);
+  memcpy(d.small.stack, t->stack_scores, 1024);
+  memcpy(d.small.tm, t->terminal_mismatch_scores, 1024);
+  memcpy(d.small.dl, t->dangling_scores_left, 256);
+  memcpy(d.small.dr, t->dangling_scores_right, 256);
+  memcpy(d.small.hc, t->helix_close_scores, 64);
+  memcpy(d.small.bp, t->basepair_scores, 64);
+  memcpy(d.small.bulge0x1, t->bulge_scores_0x1, 16);
+  memcpy(d.small.int1x1, t->interior_scores_1x1, 64);
+  if (!h->d_contra) CU(h, cudaMalloc(&h->d_contra, sizeof(DevContra)));
+  CU(h, cudaMemcpy(h->d_contra, &d, sizeof d, cudaMemcpyHostToDevice));
+  h->has_contra = true;
+  return RNA_OK;
+}
+
+extern "C" int rna_set_align_tables(rna_handle* h, const RnaAlignTables* t) {
+  if (!h || !t) return RNA_ERR_BAD_ARG;
+  CU(h, cudaSetDevice(h->device));
+  DevAlign d;
+  d.m2m = t->match2match_score;
+  d.m2i = t->match2insert_score;
+  d.iex = t->insert_extend_score;
+  d.inm = t->init_match_score;
+  d.ini = t->init_insert_score;
+  memcpy(d.insert, t->insert_scores, 16);
+  memcpy(d.match, t->match_scores, 64);
+  if (!h->d_align) CU(h, cudaMalloc(&h->d_align, sizeof(DevAlign)));
+  CU(h, cudaMemcpy(h->d_align, &d, sizeof d, cudaMemcpyHostToDevice));
+  h->has_align = true;
+  return RNA_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// validation + partition (pure host)
+// ---------------------------------------------------------------------------------------------------
+extern "C" int rna_validate_bases(const uint8_t* bases, const uint32_t* offsets, uint32_t n_seqs) {
+  if (!offsets || (n_seqs && !bases)) return RNA_ERR_BAD_ARG;
+  for (uint32_t s = 0; s < n_seqs; s++) {
+    if (offsets[s + 1] < offsets[s]) return RNA_ERR_BAD_ARG;
+    const uint32_t L = offsets[s + 1] - offsets[s];
+    if (L == 0) return RNA_ERR_EMPTY_SEQ;
+    if (L > RNA_MAX_SEQ_LEN) return RNA_ERR_TOO_LONG;
+  }
+  const uint32_t tot = n_seqs ? offsets[n_seqs] : 0, beg = n_seqs ? offsets[0] : 0;
+  for (uint32_t x = beg; x < tot; x++)
+    if (bases[x] > 3) return RNA_ERR_INVALID_BASE;
+  return RNA_OK;
+}
+
+extern "C" int rna_partition_lpt(const uint64_t* costs, uint32_t n_units, uint32_t n_parts, uint32_t* part_of) {
+  if (!costs || !part_of || n_parts == 0) return RNA_ERR_BAD_ARG;
+  std::vector<uint32_t> idx(n_units);
+  for (uint32_t i = 0; i < n_units; i++) idx[i] = i;
+  std::stable_sort(idx.begin(), idx.end(), [&](uint32_t a, uint32_t b) { return costs[a] > costs[b]; });
+  typedef std::pair<uint64_t, uint32_t> LP;   // (load, part): least-loaded part first, ties -> lowest index
+  std::priority_queue<LP, std::vector<LP>, std::greater<LP>> pq;
+  for (uint32_t p = 0; p < n_parts; p++) pq.push(LP(0, p));
+  for (uint32_t u : idx) {
+    LP t = pq.top();
+    pq.pop();
+    part_of[u] = t.second;
+    pq.push(LP(t.first + costs[u], t.second));
+  }
+  return RNA_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// fold launcher
+// ---------------------------------------------------------------------------------------------------
+template <class K>
+static int set_smem_attr(rna_handle* h, K kernel, size_t bytes) {
+  CU(h, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+  return RNA_OK;
+}
+
+struct Bucket {
+  int mode;
+  int Lcap;
+  uint32_t begin, end;   // range in the sorted order array
+};
+
+template <bool CONTRA>
+static int launch_fold_model(rna_handle* h, const RnaFoldBatchDev* b, cudaStream_t st, bool centroid_only,
+                             const float* d_bpp_in) {
+  const uint32_t n = b->n_seqs;
+  const uint32_t* ho = b->h_offsets;
+  // sort by length, longest first (LPT inside each launch's work queue)
+  std::vector<uint32_t> order(n);
+  for (uint32_t i = 0; i < n; i++) order[i] = i;
+  std::stable_sort(order.begin(), order.end(),
+                   [&](uint32_t x, uint32_t y) { return ho[x + 1] - ho[x] > ho[y + 1] - ho[y]; });
+  auto len_of = [&](uint32_t pos) { return (int)(ho[order[pos] + 1] - ho[order[pos]]); };
+  const size_t smem_cap = h->smem_optin;
+  auto smem_need = [&](int Lcap) -> size_t {
+    return centroid_only ? centroid_ws_floats(Lcap) * 4 : fold_smem_bytes<CONTRA>(Lcap, true);
+  };
+  // largest L whose matrices fit in shared memory
+  int Lsmem = 0;
+  for (int L = 16; L <= 1024; L += 8) { if (smem_need(L) + 1024 <= smem_cap) Lsmem = L; else break; }
+  const int Lcoop_min = 1025;   // longer sequences get the whole grid (one at a time)
+  std::vector<Bucket> buckets;
+  uint32_t pos = 0;
+  while (pos < n) {
+    const int L = len_of(pos);
+    Bucket bk;
+    bk.begin = pos;
+    if (L >= Lcoop_min) {
+      bk.mode = MODE_COOP; bk.Lcap = L; bk.end = pos + 1;
+    } else if (L > Lsmem) {
+      bk.mode = MODE_GLOBAL; bk.Lcap = L;
+      uint32_t e = pos;
+      while (e < n && len_of(e) > Lsmem) e++;
+      bk.end = e;
+    } else {
+      bk.mode = MODE_SMEM;
+      bk.Lcap = std::max(16, (L + 7) / 8 * 8);
+      const int lo = bk.Lcap - 8;          // bucket = lengths in (Lcap-8, Lcap]
+      uint32_t e = pos;
+      while (e < n && len_of(e) > lo) e++;
+      bk.end = e;
+    }
+    buckets.push_back(bk);
+    pos = bk.end;
+  }
+  TRY(ensure(h, h->order, sizeof(uint32_t) * (size_t)std::max<uint32_t>(n, 1)));
+  TRY(ensure(h, h->counters, sizeof(int) * buckets.size()));
+  CU(h, cudaMemcpyAsync(h->order.p, order.data(), sizeof(uint32_t) * n, cudaMemcpyHostToDevice, st));
+  CU(h, cudaMemsetAsync(h->counters.p, 0, sizeof(int) * buckets.size(), st));
+  h->stats.h2d_bytes += sizeof(uint32_t) * n;
+
+  // workspace for the GLOBAL / COOP buckets
+  size_t ws_floats = 0;
+  std::vector<int> grid_of(buckets.size(), 0);
+  std::vector<size_t> stride_of(buckets.size(), 0);
+  for (size_t k = 0; k < buckets.size(); k++) {
+    const Bucket& bk = buckets[k];
+    if (bk.mode == MODE_SMEM) continue;
+    const size_t per = (centroid_only ? centroid_ws_floats(bk.Lcap) : fold_ws_floats<CONTRA>(bk.Lcap)) + 32;
+    stride_of[k] = per;
+    if (bk.mode == MODE_COOP) {
+      ws_floats = std::max(ws_floats, per);
+    } else {
+      size_t freeb = 0, totb = 0;
+      cudaMemGetInfo(&freeb, &totb);
+      const size_t budget = (freeb + h->ws.cap) / 2;
+      int g = (int)std::min<size_t>(bk.end - bk.begin, (size_t)h->sm_count * 2);
+      while (g > 1 && (size_t)g * per * 4 > budget) g--;
+      if ((size_t)g * per * 4 > budget) { h->err = "sequence too long for device memory"; return RNA_ERR_NOMEM; }
+      grid_of[k] = g;
+      ws_floats = std::max(ws_floats, (size_t)g * per);
+    }
+  }
+  if (ws_floats) TRY(ensure(h, h->ws, ws_floats * 4));
+
+  FoldArgs a;
+  memset(&a, 0, sizeof a);
+  a.bases = b->d_bases;
+  a.offsets = b->d_offsets;
+  a.n_seqs = n;
+  a.total_len = b->total_len;
+  a.allows_short = b->allows_short_hairpins;
+  a.tables = CONTRA ? (const void*)h->d_contra : (const void*)h->d_turner;
+  a.gammas = b->d_gammas;
+  a.n_gammas = b->n_gammas;
+  a.out_logz = b->d_out_logz;
+  a.out_bpp = b->d_out_bpp;
+  a.bpp_offsets = b->d_bpp_offsets;
+  a.out_structs = b->d_out_structs;
+  a.out_ea = b->d_out_expect_acc;
+  a.out_pairs = b->d_out_pairs;
+  a.out_npairs = b->d_out_num_pairs;
+  a.workspace = (float*)h->ws.p;
+
+  for (size_t k = 0; k < buckets.size(); k++) {
+    const Bucket& bk = buckets[k];
+    a.order = (const uint32_t*)h->order.p + bk.begin;
+    a.n_launch = bk.end - bk.begin;
+    a.work_counter = (int*)h->counters.p + k;
+    a.Lcap = bk.Lcap;
+    a.ws_stride = stride_of[k];
+    if (bk.mode == MODE_SMEM) {
+      const int nt = std::min(256, std::max(32, (bk.Lcap + 31) / 32 * 32));
+      const size_t smem = smem_need(bk.Lcap);
+      int occ = 1;
+      if (centroid_only) {
+        TRY(set_smem_attr(h, centroid_kernel<MODE_SMEM>, smem));
+        CU(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, centroid_kernel<MODE_SMEM>, nt, smem));
+      } else {
+        TRY(set_smem_attr(h, fold_kernel<CONTRA, MODE_SMEM>, smem));
+        CU(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fold_kernel<CONTRA, MODE_SMEM>, nt, smem));
+      }
+      const int grid = (int)std::min<size_t>(a.n_launch, (size_t)std::max(1, occ) * h->sm_count);
+      if (centroid_only) centroid_kernel<MODE_SMEM><<<grid, nt, smem, st>>>(a, d_bpp_in);
+      else fold_kernel<CONTRA, MODE_SMEM><<<grid, nt, smem, st>>>(a);
+    } else if (bk.mode == MODE_GLOBAL) {
+      const int nt = std::min(512, std::max(32, (bk.Lcap + 31) / 32 * 32));
+      const size_t smem = centroid_only ? 16 : fold_smem_bytes<CONTRA>(bk.Lcap, false);
+      if (centroid_only) {
+        centroid_kernel<MODE_GLOBAL><<<grid_of[k], nt, smem, st>>>(a, d_bpp_in);
+      } else {
+        TRY(set_smem_attr(h, fold_kernel<CONTRA, MODE_GLOBAL>, smem));
+        fold_kernel<CONTRA, MODE_GLOBAL><<<grid_of[k], nt, smem, st>>>(a);
+      }
+    } else {
+      const int nt = 128;
+      const size_t smem = centroid_only ? 16 : fold_smem_bytes<CONTRA>(bk.Lcap, false);
+      int occ = 1;
+      void* kern;
+      if (centroid_only) {
+        kern = (void*)centroid_kernel<MODE_COOP>;
+        CU(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, centroid_kernel<MODE_COOP>, nt, smem));
+      } else {
+        kern = (void*)fold_kernel<CONTRA, MODE_COOP>;
+        TRY(set_smem_attr(h, fold_kernel<CONTRA, MODE_COOP>, smem));
+        CU(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fold_kernel<CONTRA, MODE_COOP>, nt, smem));
+      }
+      const int maxg = std::max(1, occ) * h->sm_count;
+      const int grid = std::max(1, std::min(maxg, (bk.Lcap + nt - 1) / nt));
+      void* params_fold[] = {(void*)&a};
+      void* params_cent[] = {(void*)&a, (void*)&d_bpp_in};
+      CU(h, cudaLaunchCooperativeKernel(kern, dim3(grid), dim3(nt), centroid_only ? params_cent : params_fold, smem, st));
+    }
+    CU(h, cudaGetLastError());
+    h->stats.kernel_launches++;
+  }
+  return RNA_OK;
+}
+
+static int check_fold_args(rna_handle* h, const RnaFoldBatchDev* b) {
+  if (!h || !b) return RNA_ERR_BAD_ARG;
+  if (b->n_seqs == 0) return RNA_OK;
+  if (!b->h_offsets || !b->d_bases || !b->d_offsets) { h->err = "null input pointer"; return RNA_ERR_BAD_ARG; }
+  if (b->model != RNA_MODEL_TURNER && b->model != RNA_MODEL_CONTRA) { h->err = "bad model"; return RNA_ERR_BAD_ARG; }
+  if (b->model == RNA_MODEL_TURNER && !h->has_turner) { h->err = "Turner tables not set"; return RNA_ERR_NO_TABLES; }
+  if (b->model == RNA_MODEL_CONTRA && !h->has_contra) { h->err = "CONTRAfold tables not set"; return RNA_ERR_NO_TABLES; }
+  if (b->d_out_bpp && !b->d_bpp_offsets) { h->err = "d_bpp_offsets required"; return RNA_ERR_BAD_ARG; }
+  if (b->n_gammas && !b->d_gammas) { h->err = "d_gammas required"; return RNA_ERR_BAD_ARG; }
+  return RNA_OK;
+}
+
+extern "C" int rna_mccaskill_centroid_batch_dev(rna_handle* h, const RnaFoldBatchDev* b, void* stream) {
+  TRY(check_fold_args(h, b));
+  if (b->n_seqs == 0) return RNA_OK;
+  CU(h, cudaSetDevice(h->device));
+  cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
+  if (b->model == RNA_MODEL_CONTRA) return launch_fold_model<true>(h, b, st, false, nullptr);
+  return launch_fold_model<false>(h, b, st, false, nullptr);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// host-buffer entry points
+// ---------------------------------------------------------------------------------------------------
+static int h2d(rna_handle* h, DevBuf& buf, const void* src, size_t bytes, cudaStream_t st) {
+  TRY(ensure(h, buf, bytes));
+  if (bytes) CU(h, cudaMemcpyAsync(buf.p, src, bytes, cudaMemcpyHostToDevice, st));
+  h->stats.h2d_bytes += bytes;
+  return RNA_OK;
+}
+static int d2h(rna_handle* h, void* dst, const DevBuf& buf, size_t bytes, cudaStream_t st) {
+  if (bytes) CU(h, cudaMemcpyAsync(dst, buf.p, bytes, cudaMemcpyDeviceToHost, st));
+  h->stats.d2h_bytes += bytes;
+  return RNA_OK;
+}
+
+extern "C" int rna_mccaskill_centroid_batch(rna_handle* h, const uint8_t* bases, const uint32_t* offsets,
+                                            uint32_t n_seqs, int model, int allows_short_hairpins,
+                                            const float* gammas, uint32_t n_gammas, float* out_logz,
+                                            float* out_bpp, const uint64_t* bpp_offsets, uint8_t* out_structs,
+                                            float* out_expect_acc) {
+  if (!h) return RNA_ERR_BAD_ARG;
+  h->stats = RnaCallStats{};
+  if (n_seqs == 0) return RNA_OK;
+  int rc = rna_validate_bases(bases, offsets, n_seqs);
+  if (rc != RNA_OK) { h->err = "input validation failed"; return rc; }
+  if (offsets[0] != 0) { h->err = "offsets[0] must be 0"; return RNA_ERR_BAD_ARG; }
+  if (n_gammas && !gammas) return RNA_ERR_BAD_ARG;
+  CU(h, cudaSetDevice(h->device));
+  cudaStream_t st = h->stream;
+  const uint32_t total = offsets[n_seqs];
+  std::vector<uint64_t> own_off;
+  uint32_t maxlen = 0;
+  for (uint32_t s = 0; s < n_seqs; s++) maxlen = std::max(maxlen, offsets[s + 1] - offsets[s]);
+  if (out_bpp && !bpp_offsets) {
+    own_off.resize((size_t)n_seqs + 1);
+    own_off[0] = 0;
+    for (uint32_t s = 0; s < n_seqs; s++) own_off[s + 1] = own_off[s] + rna_bpp_len(offsets[s + 1] - offsets[s]);
+    bpp_offsets = own_off.data();
+  }
+  RnaFoldBatchDev b;
+  memset(&b, 0, sizeof b);
+  b.h_offsets = offsets;
+  TRY(h2d(h, h->b_bases, bases, total, st));
+  TRY(h2d(h, h->b_offsets, offsets, sizeof(uint32_t) * ((size_t)n_seqs + 1), st));
+  b.d_bases = (const uint8_t*)h->b_bases.p;
+  b.d_offsets = (const uint32_t*)h->b_offsets.p;
+  size_t bpp_total = 0;
+  if (out_bpp) {
+    bpp_total = bpp_offsets[n_seqs];
+    TRY(h2d(h, h->b_bppoff, bpp_offsets, sizeof(uint64_t) * ((size_t)n_seqs + 1), st));
+    TRY(ensure(h, h->b_bpp, bpp_total * 4));
+    b.d_bpp_offsets = (const uint64_t*)h->b_bppoff.p;
+    b.d_out_bpp = (float*)h->b_bpp.p;
+  }
+  if (n_gammas) {
+    TRY(h2d(h, h->b_gammas, gammas, sizeof(float) * n_gammas, st));
+    b.d_gammas = (const float*)h->b_gammas.p;
+    if (out_structs) { TRY(ensure(h, h->b_structs, (size_t)n_gammas * total)); b.d_out_structs = (uint8_t*)h->b_structs.p; }
+    if (out_expect_acc) { TRY(ensure(h, h->b_ea, sizeof(float) * (size_t)n_gammas * n_seqs)); b.d_out_expect_acc = (float*)h->b_ea.p; }
+  }
+  if (out_logz) { TRY(ensure(h, h->b_logz, sizeof(float) * n_seqs)); b.d_out_logz = (float*)h->b_logz.p; }
+  b.n_seqs = n_seqs;
+  b.total_len = total;
+  b.max_len = maxlen;
+  b.model = model;
+  b.allows_short_hairpins = allows_short_hairpins;
+  b.n_gammas = n_gammas;
+  TRY(rna_mccaskill_centroid_batch_dev(h, &b, st));
+  if (out_logz) TRY(d2h(h, out_logz, h->b_logz, sizeof(float) * n_seqs, st));
+  if (out_bpp) TRY(d2h(h, out_bpp, h->b_bpp, bpp_total * 4, st));
+  if (n_gammas && out_structs) TRY(d2h(h, out_structs, h->b_structs, (size_t)n_gammas * total, st));
+  if (n_gammas && out_expect_acc) TRY(d2h(h, out_expect_acc, h->b_ea, sizeof(float) * (size_t)n_gammas * n_seqs, st));
+  CU(h, cudaStreamSynchronize(st));
+  return RNA_OK;
+}
+
+extern "C" int rna_mccaskill_batch(rna_handle* h, const uint8_t* bases, const uint32_t* offsets, uint32_t n_seqs,
+                                   int model, int allows_short_hairpins, float* out_logz, float* out_bpp,
+                                   const uint64_t* bpp_offsets) {
+  return rna_mccaskill_centroid_batch(h, bases, offsets, n_seqs, model, allows_short_hairpins, nullptr, 0,
+                                      out_logz, out_bpp, bpp_offsets, nullptr, nullptr);
+}
+
+static int centroid_host(rna_handle* h, const float* bpp, const uint64_t* bpp_offsets, const uint32_t* offsets,
+                         uint32_t n_seqs, const float* gammas, uint32_t n_gammas, uint8_t* out_structs,
+                         float* out_expect_acc, uint16_t* out_pairs, uint32_t* out_num_pairs) {
+  if (!h) return RNA_ERR_BAD_ARG;
+  h->stats = RnaCallStats{};
+  if (n_seqs == 0 || n_gammas == 0) return RNA_OK;
+  if (!bpp || !offsets || !gammas) return RNA_ERR_BAD_ARG;
+  if (offsets[0] != 0) { h->err = "offsets[0] must be 0"; return RNA_ERR_BAD_ARG; }
+  for (uint32_t s = 0; s < n_seqs; s++) {
+    if (offsets[s + 1] <= offsets[s]) return RNA_ERR_EMPTY_SEQ;
+    if (offsets[s + 1] - offsets[s] > RNA_MAX_SEQ_LEN) return RNA_ERR_TOO_LONG;
+  }
+  CU(h, cudaSetDevice(h->device));
+  cudaStream_t st = h->stream;
+  const uint32_t total = offsets[n_seqs];
+  std::vector<uint64_t> own_off;
+  if (!bpp_offsets) {
+    own_off.resize((size_t)n_seqs + 1);
+    own_off[0] = 0;
+    for (uint32_t s = 0; s < n_seqs; s++) own_off[s + 1] = own_off[s] + rna_bpp_len(offsets[s + 1] - offsets[s]);
+    bpp_offsets = own_off.data();
+  }
+  const size_t bpp_total = bpp_offsets[n_seqs];
+  RnaFoldBatchDev b;
+  memset(&b, 0, sizeof b);
+  b.h_offsets = offsets;
+  TRY(h2d(h, h->b_offsets, offsets, sizeof(uint32_t) * ((size_t)n_seqs + 1), st));
+  TRY(h2d(h, h->b_bppoff, bpp_offsets, sizeof(uint64_t) * ((size_t)n_seqs + 1), st));
+  TRY(h2d(h, h->b_bpp, bpp, bpp_total * 4, st));
+  TRY(h2d(h, h->b_gammas, gammas, sizeof(float) * n_gammas, st));
+  b.d_offsets = (const uint32_t*)h->b_offsets.p;
+  b.d_bpp_offsets = (const uint64_t*)h->b_bppoff.p;
+  b.d_gammas = (const float*)h->b_gammas.p;
+  b.n_seqs = n_seqs;
+  b.total_len = total;
+  b.n_gammas = n_gammas;
+  if (out_structs) { TRY(ensure(h, h->b_structs, (size_t)n_gammas * total)); b.d_out_structs = (uint8_t*)h->b_structs.p; }
+  if (out_expect_acc) { TRY(ensure(h, h->b_ea, sizeof(float) * (size_t)n_gammas * n_seqs)); b.d_out_expect_acc = (float*)h->b_ea.p; }
+  if (out_pairs) { TRY(ensure(h, h->b_pairs, sizeof(uint16_t) * 2 * (size_t)n_gammas * total)); b.d_out_pairs = (uint16_t*)h->b_pairs.p; }
+  if (out_num_pairs) { TRY(ensure(h, h->b_logz, sizeof(uint32_t) * (size_t)n_gammas * n_seqs)); b.d_out_num_pairs = (uint32_t*)h->b_logz.p; }
+  TRY(launch_fold_model<false>(h, &b, st, true, (const float*)h->b_bpp.p));
+  if (out_structs) TRY(d2h(h, out_structs, h->b_structs, (size_t)n_gammas * total, st));
+  if (out_expect_acc) TRY(d2h(h, out_expect_acc, h->b_ea, sizeof(float) * (size_t)n_gammas * n_seqs, st));
+  if (out_pairs) TRY(d2h(h, out_pairs, h->b_pairs, sizeof(uint16_t) * 2 * (size_t)n_gammas * total, st));
+  if (out_num_pairs) TRY(d2h(h, out_num_pairs, h->b_logz, sizeof(uint32_t) * (size_t)n_gammas * n_seqs, st));
+  CU(h, cudaStreamSynchronize(st));
+  return RNA_OK;
+}
+
+extern "C" int rna_centroid_batch(rna_handle* h, const float* bpp, const uint64_t* bpp_offsets,
+                                  const uint32_t* offsets, uint32_t n_seqs, const float* gammas, uint32_t n_gammas,
+                                  uint8_t* out_structs, float* out_expect_acc) {
+  return centroid_host(h, bpp, bpp_offsets, offsets, n_seqs, gammas, n_gammas, out_structs, out_expect_acc, nullptr,
+                       nullptr);
+}
+
+extern "C" int rna_mccaskill_algo(rna_handle* h, const uint8_t* seq, uint32_t seq_len, int uses_contra_model,
+                                  int allows_short_hairpins, float* out_bpp, float* out_logz) {
+  const uint32_t off[2] = {0, seq_len};
+  return rna_mccaskill_centroid_batch(h, seq, off, 1, uses_contra_model ? RNA_MODEL_CONTRA : RNA_MODEL_TURNER,
+                                      allows_short_hairpins, nullptr, 0, out_logz, out_bpp, nullptr, nullptr, nullptr);
+}
+
+extern "C" int rna_centroid_fold(rna_handle* h, const float* bpp, uint32_t seq_len, float centroid_threshold,
+                                 uint8_t* out_fold_str, uint16_t* out_pairs, uint32_t* out_num_pairs,
+                                 float* out_expect_accuracy) {
+  const uint32_t off[2] = {0, seq_len};
+  return centroid_host(h, bpp, nullptr, off, 1, &centroid_threshold, 1, out_fold_str, out_expect_accuracy, out_pairs,
+                       out_num_pairs);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Durbin
+// ---------------------------------------------------------------------------------------------------
+extern "C" int rna_durbin_batch_dev(rna_handle* h, const RnaDurbinBatchDev* b, void* stream) {
+  if (!h || !b) return RNA_ERR_BAD_ARG;
+  if (b->n_pairs == 0) return RNA_OK;
+  if (!h->has_align) { h->err = "align tables not set"; return RNA_ERR_NO_TABLES; }
+  if (!b->h_offsets || !b->h_pairs || !b->d_bases || !b->d_offsets || !b->d_pairs || !b->d_prob_offsets ||
+      !b->d_out_probs) { h->err = "null pointer"; return RNA_ERR_BAD_ARG; }
+  CU(h, cudaSetDevice(h->device));
+  cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
+  const uint32_t np = b->n_pairs;
+  const uint32_t* ho = b->h_offsets;
+  std::vector<uint32_t> order(np);
+  int ncap = 0, mcap = 0;
+  for (uint32_t p = 0; p < np; p++) {
+    order[p] = p;
+    const uint32_t sa = b->h_pairs[2 * p], sb = b->h_pairs[2 * p + 1];
+    if (sa >= b->n_seqs || sb >= b->n_seqs) { h->err = "pair index out of range"; return RNA_ERR_BAD_ARG; }
+    ncap = std::max(ncap, (int)(ho[sa + 1] - ho[sa]) + 2);
+    mcap = std::max(mcap, (int)(ho[sb + 1] - ho[sb]) + 2);
+  }
+  auto cost = [&](uint32_t p) {
+    const uint32_t sa = b->h_pairs[2 * p], sb = b->h_pairs[2 * p + 1];
+    return (uint64_t)(ho[sa + 1] - ho[sa] + 2) * (uint64_t)(ho[sb + 1] - ho[sb] + 2);
+  };
+  std::stable_sort(order.begin(), order.end(), [&](uint32_t x, uint32_t y) { return cost(x) > cost(y); });
+  TRY(ensure(h, h->order, sizeof(uint32_t) * np));
+  TRY(ensure(h, h->counters, sizeof(int)));
+  CU(h, cudaMemcpyAsync(h->order.p, order.data(), sizeof(uint32_t) * np, cudaMemcpyHostToDevice, st));
+  CU(h, cudaMemsetAsync(h->counters.p, 0, sizeof(int), st));
+  h->stats.h2d_bytes += sizeof(uint32_t) * np;
+  DurbinArgs a;
+  memset(&a, 0, sizeof a);
+  a.bases = b->d_bases;
+  a.offsets = b->d_offsets;
+  a.pairs = b->d_pairs;
+  a.order = (const uint32_t*)h->order.p;
+  a.n_pairs = np;
+  a.prob_offsets = b->d_prob_offsets;
+  a.out_probs = b->d_out_probs;
+  a.tables = h->d_align;
+  a.work_counter = (int*)h->counters.p;
+  a.ncap = ncap;
+  a.mcap = mcap;
+  a.roll_in_smem = durbin_smem_bytes(ncap, mcap, true) + 1024 <= h->smem_optin;
+  const size_t smem = durbin_smem_bytes(ncap, mcap, a.roll_in_smem != 0);
+  if (smem + 1024 > h->smem_optin) { h->err = "sequence too long for the Durbin kernel"; return RNA_ERR_TOO_LONG; }
+  const int nt = std::min(256, std::max(32, (ncap + 31) / 32 * 32));
+  TRY(set_smem_attr(h, durbin_kernel, smem));
+  int occ = 1;
+  CU(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, durbin_kernel, nt, smem));
+  const int grid = (int)std::min<size_t>(np, (size_t)std::max(1, occ) * h->sm_count);
+  if (!a.roll_in_smem) {
+    a.ws_stride = (size_t)9 * ncap + 32;
+    TRY(ensure(h, h->ws, (size_t)grid * a.ws_stride * 4));
+    a.workspace = (float*)h->ws.p;
+  }
+  durbin_kernel<<<grid, nt, smem, st>>>(a);
+  CU(h, cudaGetLastError());
+  h->stats.kernel_launches++;
+  return RNA_OK;
+}
+
+extern "C" int rna_durbin_batch(rna_handle* h, const uint8_t* bases, const uint32_t* offsets, uint32_t n_seqs,
+                                const uint32_t* pairs, uint32_t n_pairs, float* out_probs,
+                                const uint64_t* prob_offsets) {
+  if (!h) return RNA_ERR_BAD_ARG;
+  h->stats = RnaCallStats{};
+  if (n_pairs == 0) return RNA_OK;
+  int rc = rna_validate_bases(bases, offsets, n_seqs);
+  if (rc != RNA_OK) { h->err = "input validation failed"; return rc; }
+  if (!pairs || !out_probs) return RNA_ERR_BAD_ARG;
+  if (offsets[0] != 0) { h->err = "offsets[0] must be 0"; return RNA_ERR_BAD_ARG; }
+  for (uint32_t p = 0; p < 2 * n_pairs; p++)
+    if (pairs[p] >= n_seqs) { h->err = "pair index out of range"; return RNA_ERR_BAD_ARG; }
+  CU(h, cudaSetDevice(h->device));
+  cudaStream_t st = h->stream;
+  std::vector<uint64_t> own;
+  if (!prob_offsets) {
+    own.resize((size_t)n_pairs + 1);
+    own[0] = 0;
+    for (uint32_t p = 0; p < n_pairs; p++) {
+      const uint64_t la = offsets[pairs[2 * p] + 1] - offsets[pairs[2 * p]];
+      const uint64_t lb = offsets[pairs[2 * p + 1] + 1] - offsets[pairs[2 * p + 1]];
+      own[p + 1] = own[p] + (la + 2) * (lb + 2);
+    }
+    prob_offsets = own.data();
+  }
+  const size_t tot = prob_offsets[n_pairs];
+  TRY(h2d(h, h->b_bases, bases, offsets[n_seqs], st));
+  TRY(h2d(h, h->b_offsets, offsets, sizeof(uint32_t) * ((size_t)n_seqs + 1), st));
+  TRY(h2d(h, h->b_pairs, pairs, sizeof(uint32_t) * 2 * (size_t)n_pairs, st));
+  TRY(h2d(h, h->b_proboff, prob_offsets, sizeof(uint64_t) * ((size_t)n_pairs + 1), st));
+  TRY(ensure(h, h->b_probs, tot * 4));
+  RnaDurbinBatchDev b;
+  memset(&b, 0, sizeof b);
+  b.h_offsets = offsets;
+  b.h_pairs = pairs;
+  b.d_bases = (const uint8_t*)h->b_bases.p;
+  b.d_offsets = (const uint32_t*)h->b_offsets.p;
+  b.d_pairs = (const uint32_t*)h->b_pairs.p;
+  b.d_prob_offsets = (const uint64_t*)h->b_proboff.p;
+  b.n_seqs = n_seqs;
+  b.n_pairs = n_pairs;
+  b.d_out_probs = (float*)h->b_probs.p;
+  TRY(rna_durbin_batch_dev(h, &b, st));
+  TRY(d2h(h, out_probs, h->b_probs, tot * 4, st));
+  CU(h, cudaStreamSynchronize(st));
+  return RNA_OK;
+}
+
+extern "C" int rna_durbin_algo(rna_handle* h, const uint8_t* seq_a, uint32_t len_a, const uint8_t* seq_b,
+                               uint32_t len_b, float* out_probs) {
+  if (!seq_a || !seq_b) return RNA_ERR_BAD_ARG;
+  if (len_a == 0 || len_b == 0) return RNA_ERR_EMPTY_SEQ;
+  std::vector<uint8_t> cat((size_t)len_a + len_b);
+  memcpy(cat.data(), seq_a, len_a);
+  memcpy(cat.data() + len_a, seq_b, len_b);
+  const uint32_t off[3] = {0, len_a, len_a + len_b};
+  const uint32_t pr[2] = {0, 1};
+  return rna_durbin_batch(h, cat.data(), off, 2, pr, 1, out_probs, nullptr);
+}

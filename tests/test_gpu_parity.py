@@ -1,0 +1,171 @@
+"""Parity of the CUDA path (through the C ABI) against the CPU oracle: BIT-EXACT for partition
+functions, base-pairing probabilities, expected accuracies, dot-bracket structures and match
+probabilities (all f32; tolerance 0 ULP)."""
+import numpy as np
+import pytest
+
+from common import assert_bits_equal, default_tables, load_trnas, pack, random_seqs
+from oracle_lib import Oracle
+from rna_algos_b200 import tables as T
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def handle():
+    from rna_algos_b200.api import Handle
+    tt, ct, at = default_tables()
+    h = Handle(0, tt, ct, at)
+    yield h
+    h.close()
+
+
+@pytest.fixture(scope="module")
+def oracle():
+    return Oracle()
+
+
+SWEEP = [float(np.float32(2.0) ** p) for p in range(-7, 11)]
+
+
+def check_fold(handle, oracle, seqs, contra, allows_short, gammas, tt, ct, threads=8):
+    bases, offsets = pack(seqs)
+    got = handle.fold_batch(bases, offsets, contra, allows_short, gammas)
+    want = oracle.fold_batch(bases, offsets, contra, allows_short, tt, ct, gammas, n_threads=threads)
+    assert_bits_equal(got["logz"], want["logz"], "logZ")
+    assert_bits_equal(got["bpp"], want["bpp"], "BPP")
+    assert_bits_equal(got["expect_acc"], want["expect_acc"], "expect_accuracy")
+    assert (got["structs"] == want["structs"]).all(), "dot-bracket structures differ"
+    return got, want
+
+
+@pytest.mark.parametrize("contra", [False, True])
+def test_trnas_bit_exact(handle, oracle, contra):
+    """Config 1/2 parity set: the 6 bundled tRNAs, Turner and CONTRAfold, gamma = 1 and the sweep."""
+    tt, ct, _ = default_tables()
+    got, _ = check_fold(handle, oracle, load_trnas(), contra, False, [1.0] + SWEEP, tt, ct)
+    p = got["bpp"]
+    present = p != T.BPP_ABSENT
+    # the reference's own (only) assertion: tests/tests.rs:33,38
+    assert (p[present] >= -0.001).all() and (p[present] < 1.001).all()
+    assert (got["structs"] == ord("(")).sum() > 0
+
+
+@pytest.mark.parametrize("contra", [False, True])
+def test_edge_lengths(handle, oracle, contra):
+    """L = 1 .. 40: below / at / above MIN_SPAN_HAIRPIN_CLOSE, empty structures, ragged batch."""
+    tt, ct, _ = default_tables()
+    seqs = random_seqs(11, list(range(1, 41)))
+    check_fold(handle, oracle, seqs, contra, False, [0.5, 2.0, 1024.0], tt, ct)
+
+
+def test_allows_short_hairpins(handle, oracle):
+    tt, ct, _ = default_tables()
+    seqs = random_seqs(12, [2, 3, 4, 5, 9, 17, 33, 60])
+    check_fold(handle, oracle, seqs, True, True, [2.0, 16.0], tt, ct)
+
+
+@pytest.mark.parametrize("contra", [False, True])
+def test_random_batch_ragged(handle, oracle, contra):
+    """Ragged batch crossing several shared-memory buckets, incl. the 2-loop cap (spans > 32)."""
+    tt, ct, _ = default_tables()
+    rng = np.random.default_rng(5)
+    seqs = random_seqs(13, rng.integers(20, 140, size=48))
+    check_fold(handle, oracle, seqs, contra, False, [1.0, 4.0], tt, ct)
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3])
+@pytest.mark.parametrize("contra", [False, True])
+def test_random_tables_fuzz(oracle, seed, contra):
+    """Arbitrary tables (caps included): parity does not depend on the restated table values."""
+    from rna_algos_b200.api import Handle
+    tt = T.random_turner_tables(100 + seed)
+    ct = T.random_contra_tables(200 + seed)
+    h = Handle(0, tt, ct, None)
+    try:
+        seqs = random_seqs(20 + seed, [5, 8, 13, 21, 34, 55, 76, 89, 100])
+        # hairpin-prone sequences exercise the special-hairpin list and the interior tables
+        rng = np.random.default_rng(seed)
+        seqs += [rng.choice(4, size=64, p=[0.15, 0.35, 0.35, 0.15]).astype(np.uint8) for _ in range(4)]
+        check_fold(h, oracle, seqs, contra, False, [1.0, 8.0], tt, ct)
+    finally:
+        h.close()
+
+
+def test_mid_length_global_path(handle, oracle):
+    """Rfam-length sequences: matrices in the HBM/L2 workspace (one CTA per sequence)."""
+    tt, ct, _ = default_tables()
+    seqs = random_seqs(31, [150, 201, 333, 420])
+    for contra in (False, True):
+        check_fold(handle, oracle, seqs, contra, False, [2.0], tt, ct)
+
+
+def test_long_cooperative_path(handle, oracle):
+    """> 1024 nt: multi-CTA per-diagonal wavefront with a grid-wide barrier."""
+    tt, ct, _ = default_tables()
+    seqs = random_seqs(32, [1100])
+    check_fold(handle, oracle, seqs, False, False, [2.0], tt, ct)
+
+
+def test_single_item_api(handle, oracle):
+    """The reference's per-call granularity: mccaskill_algo / centroid_fold on one sequence."""
+    tt, ct, _ = default_tables()
+    seq = load_trnas()[4]
+    for contra in (False, True):
+        bpp, logz = handle.mccaskill_algo(seq, contra, False)
+        wbpp, wlogz = oracle.mccaskill(seq, contra, False, tt, ct)
+        assert_bits_equal(bpp, wbpp, "BPP")
+        assert_bits_equal(np.array([logz]), np.array([wlogz]), "logZ")
+        for g in (0.25, 1.0, 2.0, 64.0):
+            s, pairs, ea = handle.centroid_fold(bpp, len(seq), g)
+            ws, wpairs, wea = oracle.centroid(wbpp, len(seq), g)
+            assert s == ws
+            assert (pairs == wpairs).all(), "traceback order of basepair_pos_pairs differs"
+            assert_bits_equal(np.array([ea]), np.array([wea]), "expect_accuracy")
+
+
+def test_centroid_batch_from_host_bpp(handle, oracle):
+    tt, ct, _ = default_tables()
+    seqs = load_trnas() + random_seqs(40, [30, 200])
+    bases, offsets = pack(seqs)
+    want = oracle.fold_batch(bases, offsets, False, False, tt, ct, SWEEP, n_threads=8)
+    got = handle.centroid_batch(want["bpp"], offsets, SWEEP)
+    assert (got["structs"] == want["structs"]).all()
+    assert_bits_equal(got["expect_acc"], want["expect_acc"], "expect_accuracy")
+
+
+def test_durbin_trna_pairs(handle, oracle):
+    """Config 5 parity set: all 15 tRNA pairs with the genuine CONTRAlign v2.01 scores."""
+    _, _, at = default_tables()
+    seqs = load_trnas()
+    bases, offsets = pack(seqs)
+    pairs = np.array([(a, b) for a in range(6) for b in range(a + 1, 6)], dtype=np.uint32)
+    got = handle.durbin_batch(bases, offsets, pairs)
+    want = oracle.durbin_batch(bases, offsets, pairs, at, n_threads=8)
+    assert_bits_equal(got["probs"], want["probs"], "match probs")
+    p = got["probs"]
+    assert (p >= -0.001).all() and (p < 1.001).all()   # tests/tests.rs:74
+
+
+def test_durbin_random(handle, oracle):
+    rng = np.random.default_rng(9)
+    seqs = random_seqs(50, [1, 2, 3, 7, 40, 130, 300, 77])
+    bases, offsets = pack(seqs)
+    pairs = np.array([(a, b) for a in range(8) for b in range(8) if a != b], dtype=np.uint32)
+    at = T.random_align_tables(3)
+    from rna_algos_b200.api import Handle
+    h = Handle(0, None, None, at)
+    try:
+        got = h.durbin_batch(bases, offsets, pairs)
+    finally:
+        h.close()
+    want = oracle.durbin_batch(bases, offsets, pairs, at, n_threads=8)
+    assert_bits_equal(got["probs"], want["probs"], "match probs")
+
+
+def test_errors_do_not_abort(handle):
+    from rna_algos_b200.api import RnaError
+    with pytest.raises(RnaError):
+        handle.fold_batch(np.array([0, 1, 7], dtype=np.uint8), np.array([0, 3], dtype=np.uint32), False)
+    with pytest.raises(RnaError):
+        handle.fold_batch(np.zeros(0, dtype=np.uint8), np.array([0, 0], dtype=np.uint32), False)
