@@ -1,0 +1,407 @@
+#!/usr/bin/env python
+"""bench.py — McCaskill BPP + gamma-centroid throughput (sequences/s, DP cells/s) on N B200s.
+
+Contract (one JSON line on rank 0):
+  python bench.py --gpus N --steps K --warmup W            this repo's CUDA path
+  python bench.py --impl reference --gpus N ...            the reference algorithm's CPU path (oracle port,
+                                                           all host cores, bounded sample per step)
+
+A "step" is one pass of the hot path (rna_mccaskill_centroid_batch*: inside, outside, BPP, centroid
+fold + traceback for every sequence) over one batch.  Default workload = BASELINE.json configs[1]: the
+6 tRNAs of assets/sampled_trnas.fa (copied to tests/golden/) tiled to --nseq sequences per GPU, CONTRAfold
+v2.02 model, centroid threshold gamma = 1.  Per-GPU work is fixed as N grows ("weak" scaling); ranks are
+independent (no collective on the data path).
+
+  value      sequences/s with inputs and outputs resident in HBM (device pointers, *_dev entry point),
+             CUDA events on the launching stream, max over ranks.
+  e2e        sequences/s through the host-buffer C-ABI call (pinned host memory in, pinned host memory out;
+             H2D + kernels + D2H inside the timed region).
+  roofline   HBM roofline of the fold kernel (algorithmic bytes / measured kernel time / measured peak) —
+             plus the FP32-issue view that actually bounds this path ("compute").
+  cpu_baseline  the oracle port (tests-only code) on all host cores over a bounded sample.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "tests")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+METRIC = "mccaskill_bpp_centroid_sequences_per_s"
+UNIT = "sequences/s"
+FP32_INSTR_PER_LSE = 14          # FP32-pipe instructions per reference-exact LSE term
+
+
+# ----------------------------------------------------------------------------------------------------
+# workloads (synthetic / bundled; nothing is read from /root/reference)
+# ----------------------------------------------------------------------------------------------------
+def make_workload(name: str, nseq: int, seed: int = 20251018, length: int = 76):
+    from common import load_trnas
+    rng = np.random.default_rng(seed)
+    if name in ("trna_contra", "trna_turner"):
+        base = load_trnas()
+        seqs = [base[i % 6] for i in range(nseq)]
+        contra = name == "trna_contra"
+        desc = (f"6 tRNAs of assets/sampled_trnas.fa (L=84,74,73,73,68,89) tiled to {nseq} seqs/GPU, "
+                f"{'CONTRAfold v2.02' if contra else 'Turner 2004'}, BPP + centroid gamma=1")
+    elif name in ("random76_contra", "random76_turner"):
+        seqs = [rng.integers(0, 4, size=length).astype(np.uint8) for _ in range(nseq)]
+        contra = name.endswith("contra")
+        desc = f"{nseq} i.i.d. uniform ACGU sequences of L={length} per GPU, {'CONTRAfold' if contra else 'Turner'}"
+    elif name in ("rfam_synth_contra", "rfam_synth_turner"):
+        # stand-in for the missing Rfam seed file: log-uniform lengths in [50, 500]
+        lens = np.exp(rng.uniform(np.log(50), np.log(500), size=nseq)).astype(int)
+        seqs = [rng.integers(0, 4, size=int(L)).astype(np.uint8) for L in lens]
+        contra = name.endswith("contra")
+        desc = f"{nseq} synthetic Rfam-like sequences (log-uniform 50..500 nt) per GPU"
+    elif name in ("long_turner", "long_contra"):
+        seqs = [rng.integers(0, 4, size=length).astype(np.uint8) for _ in range(nseq)]
+        contra = name.endswith("contra")
+        desc = f"{nseq} random sequence(s) of L={length}, HBM-resident multi-CTA wavefront"
+    else:
+        raise SystemExit(f"unknown workload {name}")
+    return seqs, contra, desc
+
+
+def cells_of(lens: np.ndarray) -> int:
+    """DP cells of McCaskill+centroid = 3 triangular passes (inside, outside, MEA): SURVEY.md §8(d)."""
+    lens = lens.astype(np.int64)
+    return int((3 * lens * (lens + 1) // 2).sum())
+
+
+def algorithmic_bytes(lens: np.ndarray, n_gammas: int) -> int:
+    """Compulsory HBM traffic of one step: read bases + offsets, write packed BPP, logZ, structures, E[acc]."""
+    lens = lens.astype(np.int64)
+    return int((lens + 4 + 8 + 4 * lens * (lens - 1) // 2 + 4 + n_gammas * (lens + 4)).sum())
+
+
+# ----------------------------------------------------------------------------------------------------
+# clocks sampling (B200_PROFILING.md recipe)
+# ----------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.idx = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.idx), "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._pump, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self) -> dict:
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons, pw = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2])); pw.append(float(f[3]))
+            except ValueError:
+                continue
+            for k, nm in enumerate(names):
+                if f[5 + k].lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ----------------------------------------------------------------------------------------------------
+# CPU leg: the oracle port on all host cores over a bounded sample
+# ----------------------------------------------------------------------------------------------------
+def cpu_run(seqs, contra, gammas, n_threads):
+    from common import default_tables, pack
+    from oracle_lib import Oracle
+    tt, ct, _ = default_tables()
+    orc = cpu_run.orc = getattr(cpu_run, "orc", None) or Oracle()
+    bases, offsets = pack(seqs)
+    t0 = time.perf_counter()
+    r = orc.fold_batch(bases, offsets, contra, False, tt, ct, gammas, n_threads=n_threads)
+    return time.perf_counter() - t0, r
+
+
+def cpu_sample(seqs_all, contra, gammas, n_threads, target_s):
+    """Pick a prefix of the workload that takes about target_s on the host, run it, return (rate, n, dt, lse/seq)."""
+    k = min(len(seqs_all), 6 * max(1, n_threads))
+    while True:   # grow the probe until it is long enough to give a stable rate
+        probe = seqs_all[:k]
+        dt, r = cpu_run(probe, contra, gammas, n_threads)
+        if dt >= min(0.5, 0.25 * target_s) or k >= len(seqs_all):
+            break
+        k = min(len(seqs_all), 2 * k)
+    rate = len(probe) / dt
+    n = int(max(len(probe), min(len(seqs_all), rate * target_s)))
+    n = max(6, n // 6 * 6) if len(seqs_all) >= 6 else n
+    dt, r = cpu_run(seqs_all[:n], contra, gammas, n_threads)
+    return n / dt, n, dt, r["lse_terms"] / n
+
+
+def reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    seqs, contra, desc = make_workload(args.workload, args.nseq, length=args.length)
+    gammas = [float(g) for g in args.gammas.split(",")]
+    cores = os.cpu_count() or 1
+    lens = np.array([len(s) for s in seqs])
+    # bounded sample per step: ~args.ref_step_seconds of host work
+    rate, n, _, _ = cpu_sample(seqs, contra, gammas, cores, args.ref_step_seconds)
+    sample = seqs[:n]
+    for _ in range(args.warmup):
+        cpu_run(sample, contra, gammas, cores)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        cpu_run(sample, contra, gammas, cores)
+    dt = time.perf_counter() - t0
+    v = n * args.steps / dt
+    slens = lens[:n]
+    out = {
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic (bundled tRNAs tiled)",
+        "config": {"workload": desc, "gammas": gammas, "nseq_per_gpu": args.nseq},
+        "cells_per_s": cells_of(slens) * args.steps / dt,
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"first {n} sequences of the workload per step (oracle/oracle.c, one sequence per "
+                                   f"task on {cores} threads, like benches/benches.rs:24-41)"},
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(out), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------------
+# GPU arm
+# ----------------------------------------------------------------------------------------------------
+def gpu_arm(args):
+    import torch
+    import torch.distributed as dist
+    from common import default_tables, pack
+    from rna_algos_b200 import _lib
+    from rna_algos_b200.api import Handle, bpp_offsets_of, fold_cost, partition_lpt
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the product has no CPU path; use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    gammas = [float(g) for g in args.gammas.split(",")]
+    # global batch = world x nseq, length-balanced LPT partition over ranks (no collective on the data path)
+    seqs_all, contra, desc = make_workload(args.workload, args.nseq * world, length=args.length)
+    if world > 1:
+        part = partition_lpt(fold_cost([len(s) for s in seqs_all]), world)
+        seqs = [s for s, p in zip(seqs_all, part) if p == rank]
+    else:
+        seqs = seqs_all
+    bases, offsets = pack(seqs)
+    n = len(seqs)
+    lens = np.diff(offsets.astype(np.int64))
+    total = int(offsets[-1])
+    bpp_off = bpp_offsets_of(offsets)
+    bpp_total = int(bpp_off[-1])
+    ng = len(gammas)
+
+    tt, ct, at = default_tables()
+    h = Handle(local, tt, ct, at)
+    lib = h.lib
+
+    # ---- device-resident buffers (torch = device memory + streams only) -------------------------------
+    d_bases = torch.from_numpy(bases).to(dev)
+    d_offsets = torch.from_numpy(offsets.view(np.int32)).to(dev)
+    d_bppoff = torch.from_numpy(bpp_off.view(np.int64)).to(dev)
+    d_gammas = torch.tensor(gammas, dtype=torch.float32, device=dev)
+    d_logz = torch.empty(n, dtype=torch.float32, device=dev)
+    d_bpp = torch.empty(max(bpp_total, 1), dtype=torch.float32, device=dev)
+    d_structs = torch.empty(max(ng * total, 1), dtype=torch.uint8, device=dev)
+    d_ea = torch.empty(max(ng * n, 1), dtype=torch.float32, device=dev)
+    fb = _lib.FoldBatchDev()
+    fb.h_offsets = offsets.ctypes.data
+    fb.d_bases = d_bases.data_ptr(); fb.d_offsets = d_offsets.data_ptr(); fb.d_bpp_offsets = d_bppoff.data_ptr()
+    fb.n_seqs = n; fb.total_len = total; fb.max_len = int(lens.max())
+    fb.model = _lib.MODEL_CONTRA if contra else _lib.MODEL_TURNER
+    fb.allows_short_hairpins = 0
+    fb.d_gammas = d_gammas.data_ptr(); fb.n_gammas = ng
+    fb.d_out_logz = d_logz.data_ptr(); fb.d_out_bpp = d_bpp.data_ptr()
+    fb.d_out_structs = d_structs.data_ptr(); fb.d_out_expect_acc = d_ea.data_ptr()
+    stream = torch.cuda.current_stream()
+    sptr = C.c_void_p(stream.cuda_stream)
+
+    def step_dev():
+        rc = lib.rna_mccaskill_centroid_batch_dev(h.h, C.byref(fb), sptr)
+        if rc:
+            raise RuntimeError(f"rna_mccaskill_centroid_batch_dev rc={rc}: {lib.rna_last_error(h.h)}")
+
+    for _ in range(max(args.warmup, 3)):
+        step_dev()
+    barrier()
+    launches0 = h.stats()["kernel_launches"]
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record(stream)
+    for _ in range(args.steps):
+        step_dev()
+    ev1.record(stream)
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    clocks = sampler.stop() if rank == 0 else None
+    launches = h.stats()["kernel_launches"] - launches0
+    # quick self-check of the timed result (not timed): logZ finite, every structure byte is . ( or )
+    assert torch.isfinite(d_logz).all(), "non-finite logZ"
+    sb = d_structs[: ng * total]
+    assert bool(((sb == 46) | (sb == 40) | (sb == 41)).all()), "structure bytes corrupted"
+
+    # ---- end to end through the host-buffer C-ABI call: pinned host in / out ----------------------------
+    def pinned(shape, dtype):
+        return torch.empty(shape, dtype=dtype).pin_memory().numpy()
+    pb = pinned(bases.shape[0], torch.uint8); pb[:] = bases
+    out = {"logz": pinned(n, torch.float32), "bpp": pinned(max(bpp_total, 1), torch.float32)[:bpp_total],
+           "structs": pinned((ng, total), torch.uint8), "expect_acc": pinned((ng, n), torch.float32)}
+    e2e_steps = max(1, min(args.steps, args.e2e_steps))
+    for _ in range(2):
+        h.fold_batch(pb, offsets, contra, False, gammas, out=out)
+    st = h.stats()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        h.fold_batch(pb, offsets, contra, False, gammas, out=out)
+    torch.cuda.synchronize()
+    e2e_dt = time.perf_counter() - t0
+    barrier()
+
+    # ---- reduce over ranks: max time, sum of units ---------------------------------------------------------
+    red = torch.tensor([ms, e2e_dt], dtype=torch.float64, device=dev)
+    cnt = torch.tensor([n, cells_of(lens), algorithmic_bytes(lens, ng), launches, st["h2d_bytes"], st["d2h_bytes"]],
+                       dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(red, op=dist.ReduceOp.MAX)
+        dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
+    ms, e2e_dt = (float(x) for x in red.tolist())
+    n_all, cells_all, abytes_all, launches_all, h2d_all, d2h_all = (float(x) for x in cnt.tolist())
+
+    if rank == 0:
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+            hbm_peak, peak_src = float(peaks["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            hbm_peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+        sec_per_step = ms / 1e3 / args.steps
+        value = n_all * args.steps / (ms / 1e3)
+        # cpu baseline (rank 0, N = 1 only): oracle on all host cores over a bounded sample
+        cpu = None
+        lse_per_seq = None
+        if world == 1 and not args.no_cpu_baseline:
+            cores = os.cpu_count() or 1
+            crate, cn, cdt, lse_per_seq = cpu_sample(seqs, contra, gammas, cores, args.cpu_seconds)
+            cpu = {"value": crate, "unit": UNIT, "cores": cores, "kind": "port",
+                   "sample": f"first {cn} sequences of the same workload, {cdt:.1f} s wall (oracle/oracle.c port of the "
+                             f"reference algorithm, one sequence per task on {cores} threads)"}
+        per_gpu_bytes = abytes_all / world
+        achieved = per_gpu_bytes / sec_per_step / 1e9
+        roof = {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
+                "traffic": None, "peak_source": peak_src, "kernel": f"fold_kernel<{'CONTRA' if contra else 'TURNER'}>",
+                "note": "algorithmic bytes per step / CUDA-event time of the step's fold_kernel launches; the path is "
+                        "FP32-issue bound, see 'compute'"}
+        comp = None
+        if lse_per_seq is not None:
+            sm_mhz = (clocks or {}).get("sm_mhz") or 1965.0
+            peak_instr = 148 * 128 * sm_mhz * 1e6   # FP32 lanes x clock (thread-instructions/s)
+            ach = lse_per_seq * value / world * FP32_INSTR_PER_LSE
+            comp = {"lse_terms_per_seq": lse_per_seq, "lse_terms_per_s": lse_per_seq * value,
+                    "fp32_instr_per_lse": FP32_INSTR_PER_LSE, "achieved_ginstr_per_s_per_gpu": ach / 1e9,
+                    "peak_ginstr_per_s_per_gpu": peak_instr / 1e9, "frac": ach / peak_instr,
+                    "peak_source": f"nominal 148 SM x 128 FP32 lanes x {sm_mhz:.0f} MHz (median SM clock under load)"}
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic (bundled tRNAs tiled)",
+            "config": {"workload": desc, "gammas": gammas, "nseq_per_gpu": args.nseq, "numeric_mode": "reference-exact f32",
+                       "l2": f"per-step output working set {4 * bpp_total / 1e6:.0f} MB/GPU vs 126 MB L2 "
+                             f"({'exceeds L2, no flush needed' if 4 * bpp_total > 126e6 else 'smaller than L2'})",
+                       "partition": "LPT on L^3+500L^2 over ranks, no collective"},
+            "cells_per_s": cells_all * args.steps / (ms / 1e3),
+            "e2e": {"value": n_all * e2e_steps / e2e_dt, "unit": UNIT, "h2d_bytes_per_step": h2d_all,
+                    "d2h_bytes_per_step": d2h_all, "steps": e2e_steps,
+                    "path": "rna_mccaskill_centroid_batch (host buffers, pinned)"},
+            "gpu_launches": int(launches_all),
+            "clocks": clocks,
+            "roofline": roof,
+            "compute": comp,
+            "cpu_baseline": cpu,
+        }
+        print(json.dumps(line), flush=True)
+    h.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="trna_contra")
+    ap.add_argument("--nseq", type=int, default=24576, help="sequences per GPU per step")
+    ap.add_argument("--length", type=int, default=76)
+    ap.add_argument("--gammas", default="1.0")
+    ap.add_argument("--e2e-steps", type=int, default=5)
+    ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    ap.add_argument("--ref-step-seconds", type=float, default=3.0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        reference_arm(args)
+    else:
+        gpu_arm(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -289,7 +289,7 @@ __device__ __forceinline__ void centroid_run(const FoldArgs& a, uint32_t sidx, u
           if (e > wv) wv = e;
         }
         for (int m = 1; m < d; m++) {
-          e = __fadd_rn(X::ld(&W[X::off(m, L) + i]), X::ld(&W[X::off(d - m - 1, L) + i + m]));
+          e = __fadd_rn(X::ld(&W[X::off(m, L) + i]), X::ld(&W[X::off(d - m - 1, L) + i + m + 1]));
           if (e > wv) wv = e;
         }
         W[od + i] = wv;
@@ -336,7 +336,7 @@ __device__ __forceinline__ void centroid_run(const FoldArgs& a, uint32_t sidx, u
             const int m = m0 + lane;
             bool hit = false;
             if (m < d) {
-              hit = (wv == __fadd_rn(X::ld(&W[X::off(m, L) + i]), X::ld(&W[X::off(d - m - 1, L) + i + m])));
+              hit = (wv == __fadd_rn(X::ld(&W[X::off(m, L) + i]), X::ld(&W[X::off(d - m - 1, L) + i + m + 1])));
             }
             const unsigned bal = __ballot_sync(0xffffffffu, hit);
             if (bal) {

@@ -376,7 +376,7 @@ static int launch_fold_model(rna_handle* h, const RnaFoldBatchDev* b, cudaStream
     } else {
       bk.mode = MODE_SMEM;
       bk.Lcap = std::max(16, (L + 7) / 8 * 8);
-      const int lo = bk.Lcap - 8;          // bucket = lengths in (Lcap-8, Lcap]
+      const int lo = bk.Lcap > 16 ? bk.Lcap - 8 : 0;   // bucket = lengths in (Lcap-8, Lcap]; the smallest takes 1..16
       uint32_t e = pos;
       while (e < n && len_of(e) > lo) e++;
       bk.end = e;
