@@ -268,8 +268,12 @@ def gpu_arm(args):
     fb.d_gammas = d_gammas.data_ptr(); fb.n_gammas = ng
     fb.d_out_logz = d_logz.data_ptr(); fb.d_out_bpp = d_bpp.data_ptr()
     fb.d_out_structs = d_structs.data_ptr(); fb.d_out_expect_acc = d_ea.data_ptr()
-    stream = torch.cuda.current_stream()
+    # a dedicated non-default stream: the library treats a NULL stream as "use the handle's own stream", and
+    # CUDA events only see the stream they are recorded on
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
     sptr = C.c_void_p(stream.cuda_stream)
+    assert sptr.value, "expected a non-default stream"
 
     def step_dev():
         rc = lib.rna_mccaskill_centroid_batch_dev(h.h, C.byref(fb), sptr)

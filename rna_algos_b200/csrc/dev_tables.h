@@ -53,6 +53,20 @@ struct ContraSmall {
   float int1x1[16];
 };
 
+// v2 kernels (fold_phases.cuh): per-lane gathers.  js / b1 / i11 / ptab are host-precomputed combinations;
+// every entry is produced by the same f32 operations, in the same order, as the reference's scorer
+// (src/utils.rs:456-520, 545-548), so using them is bit-identical to evaluating the scorer in-line.
+struct ContraSmall2 {
+  float stack[256];
+  float js[256];          // helix_close[x][y] + terminal_mismatch[x][y][p][q]   (get_junction_score_single)
+  float dl[64];
+  float dr[64];
+  float hc[16];
+  float bp[16];
+  float b1[4];            // bulge_scores_0x1[x] + bulge_cum[0]                    (bulge of length 1)
+  float i11[16];          // ((interior_1x1[x][y] + sym_cum[0]) + explicit[0][0]) + interior_cum[0]   (1x1 interior)
+};
+
 struct DevContra {
   int max_loop_len;
   int min_span;
@@ -66,6 +80,9 @@ struct DevContra {
   float asym_cum[28];
   float explicit_[16];
   ContraSmall small;
+  ContraSmall2 small2;
+  // [a*31+b], a+b>=2: bulge (a==0 or b==0): 0 + bulge_cum[len-1]; interior (not 1x1): ((sym|asym) + explicit|0) + interior_cum[len-2]
+  float ptab[31 * 31];
 };
 
 struct DevAlign {

@@ -1,0 +1,179 @@
+// fold_kernel2.cuh — v2 batch kernel: one CTA per sequence, warp ROLES pipelined across anti-diagonals
+// (see fold_phases.cuh for the phases and their dependencies).  Storage modes:
+//   MODE_SMEM    matrices, bit matrix and cell lists resident in shared memory   (tRNA .. ~150 nt)
+//   MODE_GLOBAL  the same working set in an HBM/L2 workspace slot of the CTA     (Rfam-length batches)
+// Sequences longer than 1024 nt use the cooperative multi-CTA wavefront of fold_kernel.cuh.
+#pragma once
+#include "fold_kernel.cuh"
+#include "fold_phases.cuh"
+
+namespace rna {
+
+template <int MODE> struct PIdxOf { typedef uint16_t type; };
+template <> struct PIdxOf<MODE_SMEM> { typedef uint8_t type; };   // SMEM mode is only used for L <= 255
+
+__host__ __device__ inline size_t align16(size_t x) { return (x + 15) / 16 * 16; }
+
+// bytes of the table / sequence part that always lives in shared memory
+template <bool CONTRA>
+__host__ __device__ inline size_t fold2_fixed_bytes(int Lcap) {
+  return 128 + align16(sizeof(typename Model2<CONTRA>::Small)) + align16((size_t)Lcap + 8);
+}
+// bytes of one sequence's working set (SeqViewT) for capacity Lcap
+__host__ __device__ inline size_t fold2_seq_bytes(int Lcap, size_t pidx_size) {
+  const size_t T = (size_t)Lcap * ((size_t)Lcap + 1) / 2;
+  const size_t W2 = ((size_t)Lcap + 31) / 32 + 2;
+  size_t b = 5 * T * 4;                         // C R X E M1
+  b += (3 + 2) * (size_t)Lcap * 4;              // Mroll, E0, EL
+  b += align16(2 * ((size_t)Lcap + 2) * 4);     // traceback stack
+  b += align16((size_t)Lcap * W2 * 4);          // closable bit matrix
+  b += align16((size_t)Lcap * 2);               // pcnt
+  b += align16(T * pidx_size);                  // closable-cell lists
+  return align16(b);
+}
+
+struct Roles { int nX, nY, nZ; };   // warps per role
+__host__ __device__ inline Roles fold2_roles(int Lcap, bool contra, int max_warps) {
+  Roles r;
+  r.nX = (Lcap + 63) / 64;
+  r.nZ = (Lcap + 31) / 32;
+  r.nY = contra ? r.nZ : 0;
+  while (r.nX + r.nY + r.nZ > max_warps) {       // long sequences: strided roles
+    if (r.nZ > 1) r.nZ--;
+    if (r.nY > 1 && r.nX + r.nY + r.nZ > max_warps) r.nY--;
+    if (r.nX > 1 && r.nX + r.nY + r.nZ > max_warps) r.nX--;
+  }
+  return r;
+}
+
+template <bool CONTRA, int MODE>
+__global__ void __launch_bounds__(512) fold_kernel2(const FoldArgs a) {
+  typedef typename Model2<CONTRA>::Dev Dev;
+  typedef typename Model2<CONTRA>::Small Small;
+  typedef typename Model2<CONTRA>::View View;
+  typedef typename PIdxOf<MODE>::type PIdx;
+  typedef SeqViewT<PIdx> SV;
+
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float4* lut = reinterpret_cast<float4*>(smem_raw);
+  Small* small = reinterpret_cast<Small*>(smem_raw + 128);
+  uint8_t* sseq = smem_raw + 128 + align16(sizeof(Small));
+  unsigned char* sregion = smem_raw + fold2_fixed_bytes<CONTRA>(a.Lcap);
+  __shared__ int s_work;
+
+  const Dev* dev = reinterpret_cast<const Dev*>(a.tables);
+  const int tid = threadIdx.x, nt = blockDim.x;
+  load_lse_lut(lut);
+  {
+    const Small* gs = dev_small<CONTRA>(dev);
+    for (int x = tid; x < (int)(sizeof(Small) / 4); x += nt)
+      reinterpret_cast<float*>(small)[x] = reinterpret_cast<const float*>(gs)[x];
+  }
+  View T;
+  T.g = dev;
+  T.sm = small;
+  ModelParams P;
+  P.MINSPAN = dev->min_span;
+  if constexpr (CONTRA) P.MAX2 = dev->max_loop_len; else P.MAX2 = dev->max_2loop_len;
+  P.allows_short = a.allows_short;
+  const float NEG = RNA_NEG_INF;
+  const int warp = tid >> 5;
+  const int nXl = a.nXw * 32, nYl = a.nYw * 32, nZl = a.nZw * 32;
+  __syncthreads();
+
+  for (;;) {
+    __syncthreads();
+    if (tid == 0) s_work = atomicAdd(a.work_counter, 1);
+    __syncthreads();
+    const uint32_t w = (uint32_t)s_work;
+    if (w >= a.n_launch) break;
+    const uint32_t sidx = a.order ? a.order[w] : w;
+    const uint32_t sbeg = a.offsets[sidx];
+    const int L = (int)(a.offsets[sidx + 1] - sbeg);
+    const int TRI = L * (L + 1) / 2;
+
+    // ---- carve the working set (sizes by L: every pointer stays inside the Lcap-sized region) -----------
+    unsigned char* base = (MODE == MODE_SMEM) ? sregion
+                                              : reinterpret_cast<unsigned char*>(a.workspace) + (size_t)blockIdx.x * a.ws_stride * 4;
+    SV v;
+    v.L = L;
+    v.W2 = (L + 31) / 32 + 2;
+    uint8_t* s = sseq + 4;
+    v.s = s;
+    float* f = reinterpret_cast<float*>(base);
+    v.C = f; f += TRI;
+    v.R = f; f += TRI;
+    v.X = f; f += TRI;
+    v.E = f; f += TRI;
+    v.M1 = f; f += TRI;
+    v.Mroll = f; f += 3 * L;
+    v.E0 = f; f += L;
+    v.EL = f; f += L;
+    int* tstack = reinterpret_cast<int*>(f);
+    v.mask = reinterpret_cast<uint32_t*>(tstack + 2 * (L + 2));
+    v.pcnt = reinterpret_cast<uint16_t*>(v.mask + L * v.W2);
+    v.plist = reinterpret_cast<PIdx*>(v.pcnt + ((L + 1) & ~1));
+
+    for (int x = tid; x < L; x += nt) s[x] = a.bases[sbeg + x];
+    if (tid < 4) { sseq[tid] = 0; s[L + tid] = 0; }
+    for (int x = tid; x < TRI; x += nt) { v.C[x] = NEG; v.R[x] = NEG; v.X[x] = NEG; v.E[x] = 0.f; v.M1[x] = NEG; }
+    for (int x = tid; x < 3 * L; x += nt) v.Mroll[x] = NEG;
+    __syncthreads();
+    for (int x = tid; x < L * v.W2; x += nt) setup_mask_word<CONTRA>(v, P, x);
+    __syncthreads();
+    for (int d = tid; d < L; d += nt) setup_list_diag(v, d);
+    __syncthreads();
+
+    // ================================ inside: step t = X(t) | Y(t) | Z(t-1) ==============================
+    const int d_in0 = CONTRA ? 0 : (P.MINSPAN - 1);
+    for (int t = d_in0; t <= L; t++) {
+      if (warp < a.nXw) {
+        if (t < L) inside_X<CONTRA>(v, T, lut, P, t, tid, nXl);
+      } else if (warp < a.nXw + a.nYw) {
+        if constexpr (CONTRA) { if (t < L) inside_Y_contra(v, T, lut, t, tid - nXl, nYl); }
+      } else {
+        if (t - 1 >= d_in0) inside_Z<CONTRA>(v, T, lut, t - 1, tid - nXl - nYl, nZl);
+      }
+      __syncthreads();
+    }
+
+    // ================================ outside ===========================================================
+    for (int x = tid; x < L; x += nt) {
+      v.E0[x] = v.E[doff(x, L)];
+      v.EL[x] = v.E[doff(L - 1 - x, L) + x];
+    }
+    __syncthreads();
+    const float Z = v.E0[L - 1];
+    for (int x = tid; x < TRI; x += nt) { v.E[x] = NEG; v.R[x] = NEG; v.X[x] = NEG; }
+    if (tid == 0 && a.out_logz) a.out_logz[sidx] = Z;
+    __syncthreads();
+    const int d_out0 = CONTRA ? (a.allows_short ? 1 : P.MINSPAN - 1) : (P.MINSPAN - 1);
+    for (int d = L - 1; d >= d_out0; d--) {
+      if (warp < a.nXw) outside_X<CONTRA>(v, T, lut, P, Z, d, tid, nXl);
+      else outside_Y<CONTRA>(v, T, lut, d, tid - nXl, nYl + nZl);
+      __syncthreads();
+    }
+
+    // ================================ BPP = expf(P) =====================================================
+    for (int x = tid; x < TRI; x += nt) {
+      const float val = v.E[x];
+      v.E[x] = (val > NEG) ? approx_expf(val) : -1.0f;
+    }
+    __syncthreads();
+    if (a.out_bpp) {
+      float* ob = a.out_bpp + a.bpp_offsets[sidx];
+      for (int i = 0; i < L - 1; i++) {
+        const size_t rowoff = (size_t)i * (size_t)(2 * L - i - 1) / 2;
+        for (int x = tid; x < L - 1 - i; x += nt) ob[rowoff + x] = v.E[doff(x + 1, L) + i];
+      }
+    }
+    // ================================ centroid (src/centroid_fold.rs:25-105) ============================
+    {
+      const float* Pm = v.E;
+      auto getp = [=](int d, int i) -> float { return Pm[doff(d, L) + i]; };
+      centroid_run<MODE>(a, sidx, sbeg, L, v.R, tstack, getp);
+    }
+  }
+}
+
+}  // namespace rna

@@ -3,8 +3,7 @@
 // IEEE f32 operation (__fmul_rn/__fadd_rn never contract to FMA), evaluated in the reference's order,
 // with the reference's f32 coefficient literals.
 #pragma once
-#include <cuda_runtime.h>
-#include <stdint.h>
+#include "portable.h"
 
 namespace rna {
 
@@ -14,7 +13,7 @@ namespace rna {
 // Coefficient table of ln_exp_1p: 8 segments x {a, b, c, d}, poly = ((a*x + b)*x + c)*x + d.
 // Staged into shared memory once per CTA (per-lane segment index => LDS.128, conflict-free: each
 // 16-byte row lives in its own 4 banks, equal rows broadcast).
-__device__ __constant__ float4 kLnExp1pCoef[8] = {
+RNA_CONST_TABLE float4 kLnExp1pCoef[8] = {
     {-0.0065591595f, 0.12764427f, 0.49965546f, 0.6931542f},     // x < 0.66153675
     {-0.015515756f, 0.14467756f, 0.48829398f, 0.6958093f},      // x < 1.6320158
     {-0.012890925f, 0.13010283f, 0.51503986f, 0.6795586f},      // x < 2.4912589
@@ -25,12 +24,14 @@ __device__ __constant__ float4 kLnExp1pCoef[8] = {
     {-0.0000113994f, 0.0003734731f, 0.9959107f, 0.0149855051f}  // else
 };
 
+#ifdef __CUDACC__
 __device__ __forceinline__ void load_lse_lut(float4* lut_smem) {
   if (threadIdx.x < 8) lut_smem[threadIdx.x] = kLnExp1pCoef[threadIdx.x];
 }
+#endif
 
 // Segment index of the reference's comparison tree (src/utils.rs:604-626), branch-free.
-__device__ __forceinline__ int ln_exp_1p_segment(float x) {
+RNA_DEV int ln_exp_1p_segment(float x) {
   const bool p1 = x < 3.37925f;
   const float t2 = p1 ? 1.6320158f : 5.789071f;
   const bool p2 = x < t2;
@@ -39,7 +40,7 @@ __device__ __forceinline__ int ln_exp_1p_segment(float x) {
   return (p1 ? 0 : 4) + (p2 ? 0 : 2) + (p3 ? 0 : 1);
 }
 
-__device__ __forceinline__ float ln_exp_1p(float x, const float4* __restrict__ lut) {
+RNA_DEV float ln_exp_1p(float x, const float4* __restrict__ lut) {
   const float4 c = lut[ln_exp_1p_segment(x)];
   float r = __fadd_rn(__fmul_rn(c.x, x), c.y);
   r = __fadd_rn(__fmul_rn(r, x), c.z);
@@ -47,10 +48,10 @@ __device__ __forceinline__ float ln_exp_1p(float x, const float4* __restrict__ l
   return r;
 }
 
-__device__ __forceinline__ bool is_finite(float x) { return fabsf(x) < __int_as_float(0x7f800000); }
+RNA_DEV bool is_finite(float x) { return fabsf(x) < __int_as_float(0x7f800000); }
 
 // logsumexp(&mut sum, x): src/utils.rs:580-596.  Returns the new sum.
-__device__ __forceinline__ float lse(float sum, float x, const float4* __restrict__ lut) {
+RNA_DEV float lse(float sum, float x, const float4* __restrict__ lut) {
   const float y = fminf(sum, x);
   const float z = __fsub_rn(fmaxf(sum, x), y);
   // z is NaN/inf when either operand is not finite; the LUT index stays in range (all compares false => 7).
@@ -61,14 +62,14 @@ __device__ __forceinline__ float lse(float sum, float x, const float4* __restric
 }
 
 // lse with a per-lane enable predicate (disabled lanes keep `sum`).
-__device__ __forceinline__ float lse_if(bool on, float sum, float x, const float4* __restrict__ lut) {
+RNA_DEV float lse_if(bool on, float sum, float x, const float4* __restrict__ lut) {
   return lse(sum, on ? x : RNA_NEG_INF, lut);
 }
 
 // expf: src/utils.rs:631-655.  For x >= 0 the reference calls libm expf; here exp is evaluated in f64
 // and rounded once to f32, which equals the correctly rounded f32 result (and glibc's <1-ULP expf)
 // except for ~1e-8 of inputs (DESIGN.md "numerics").
-__device__ __forceinline__ float approx_expf(float x) {
+RNA_DEV float approx_expf(float x) {
   if (x < -2.4915035f) {
     if (x < -5.8622823f) {
       if (x < -9.91152f) return 0.f;
@@ -90,11 +91,11 @@ __device__ __forceinline__ float approx_expf(float x) {
   return (float)exp((double)x);
 }
 
-__device__ __forceinline__ bool canonical_pair(int x, int y) {
+RNA_DEV bool canonical_pair(int x, int y) {
   // AU CG GC GU UA UG with A=0 C=1 G=2 U=3: bitmask over x*4+y
   return (0x5a48u >> (x * 4 + y)) & 1u;   // bits 3(AU) 6(CG) 9(GC) 11(GU) 12(UA) 14(UG)
 }
-__device__ __forceinline__ bool augu_pair(int x, int y) {
+RNA_DEV bool augu_pair(int x, int y) {
   return (0x5808u >> (x * 4 + y)) & 1u;   // bits 3(AU) 11(GU) 12(UA) 14(UG)
 }
 

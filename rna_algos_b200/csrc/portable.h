@@ -1,0 +1,36 @@
+// portable.h — lets the DP "phase" functions (scorers, numerics, per-diagonal phases) compile both as
+// CUDA device code (the product) and as plain host C++ (tests/emu: a barrier-by-barrier emulator of the
+// kernel used to check the parallel decomposition against the oracle without a GPU).  The host build
+// defines the handful of CUDA intrinsics the phases use with identical IEEE-754 semantics; it must be
+// compiled with -ffp-contract=off so that no a*b+c is fused (the device code uses __fmul_rn/__fadd_rn,
+// which never contract).
+#pragma once
+#include <stdint.h>
+
+#ifdef __CUDACC__
+#include <cuda_runtime.h>
+#define RNA_DEV __device__ __forceinline__
+#define RNA_CONST_TABLE __device__ __constant__
+#else
+#include <math.h>
+#include <string.h>
+#define RNA_DEV static inline
+#define RNA_CONST_TABLE static const
+#define __restrict__ __restrict
+struct float4 { float x, y, z, w; };
+static inline float __fadd_rn(float a, float b) { volatile float r = a + b; return r; }
+static inline float __fsub_rn(float a, float b) { volatile float r = a - b; return r; }
+static inline float __fmul_rn(float a, float b) { volatile float r = a * b; return r; }
+static inline float __int_as_float(int x) { float f; memcpy(&f, &x, 4); return f; }
+static inline int __float_as_int(float f) { int x; memcpy(&x, &f, 4); return x; }
+template <class T> static inline T __ldg(const T* p) { return *p; }
+static inline int __clz(unsigned x) { return x ? __builtin_clz(x) : 32; }
+static inline int __ffs(unsigned x) { return __builtin_ffs((int)x); }
+static inline int __popc(unsigned x) { return __builtin_popcount(x); }
+static inline unsigned __funnelshift_r(unsigned lo, unsigned hi, unsigned sh) {
+  const unsigned long long v = ((unsigned long long)hi << 32) | lo;
+  return (unsigned)(v >> (sh & 31));
+}
+template <class T> static inline T min(T a, T b) { return a < b ? a : b; }
+template <class T> static inline T max(T a, T b) { return a > b ? a : b; }
+#endif

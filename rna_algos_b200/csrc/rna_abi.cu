@@ -14,7 +14,8 @@
 #include "../../include/rna_algos_b200.h"
 #include "dev_tables.h"
 #include "durbin_kernel.cuh"
-#include "fold_kernel.cuh"
+#include "fold_kernel2.cuh"
+#include "table_pack.h"
 
 using namespace rna;
 
@@ -150,72 +151,10 @@ extern "C" void rna_align_tables_contralign_v201(RnaAlignTables* t) {
 
 extern "C" int rna_set_turner_tables(rna_handle* h, const RnaTurnerTables* t) {
   if (!h || !t) return RNA_ERR_BAD_ARG;
-  if (t->max_2loop_len < 0 || t->max_2loop_len > 30 || t->min_span_hairpin_close < 2 ||
-      t->min_hairpin_len < 0 || t->min_hairpin_len > 30 || t->max_hairpin_len_extrapolation > 30 ||
-      t->max_hairpin_len_extrapolation < t->min_hairpin_len || t->min_hairpin_len_extrapolation < 2 ||
-      t->min_hairpin_len_extrapolation > 31 || t->num_special_hairpins < 0 ||
-      t->num_special_hairpins > RNA_MAX_SPECIAL_HAIRPINS) {
-    h->err = "Turner blob: caps out of range";
-    return RNA_ERR_BAD_TABLES;
-  }
-  CU(h, cudaSetDevice(h->device));
   DevTurner d;
-  memset(&d, 0, sizeof d);
-  d.max_2loop_len = t->max_2loop_len;
-  d.min_span = t->min_span_hairpin_close;
-  d.min_hairpin_len = t->min_hairpin_len;
-  d.num_special = t->num_special_hairpins;
-  d.augu_pen = t->helix_augu_end_penalty;
-  d.init_mb_base = t->init_multibranch_base;
-  d.coeff_num_branches = t->coeff_num_branches;
-  memcpy(d.bulge_init, t->bulge_scores_init, sizeof d.bulge_init);
-  for (int a = 0; a < 31; a++)
-    for (int b = 0; b < 31; b++) {
-      float v = 0.f;
-      if (a + b <= 30) {
-        const int diff = a > b ? a - b : b - a;
-        volatile float nin = t->ninio_coeff * (float)diff;          // NINIO_COEFF * diff as Score
-        float nn = fmaxf(nin, t->ninio_max);                        // .max(NINIO_MAX), src/utils.rs:307
-        volatile float s = t->interior_scores_init[a + b] + nn;
-        v = s;
-      }
-      d.interior_init_ninio[a * 31 + b] = v;
-    }
-  for (int x = 0; x < t->num_special_hairpins; x++) {
-    const RnaSpecialHairpin& e = t->hairpin_scores_special[x];
-    if (e.len < 2 || e.len > RNA_MAX_SPECIAL_HAIRPIN_LEN) { h->err = "Turner blob: special hairpin length"; return RNA_ERR_BAD_TABLES; }
-    unsigned key = 0;
-    for (int p = 0; p < e.len; p++) {
-      if (e.seq[p] > 3) { h->err = "Turner blob: special hairpin base"; return RNA_ERR_BAD_TABLES; }
-      key |= (unsigned)e.seq[p] << (2 * p);
-    }
-    d.special_key[x] = key;
-    d.special_len[x] = e.len;
-    d.special_score[x] = e.score;
-    d.special_len_mask |= 1u << e.len;
-  }
-  memcpy(d.small.tm_hairpin, t->terminal_mismatch_scores_hairpin, 1024);
-  memcpy(d.small.stack, t->stack_scores, 1024);
-  memcpy(d.small.tm_1xmany, t->terminal_mismatch_scores_1xmany, 1024);
-  memcpy(d.small.tm_2x3, t->terminal_mismatch_scores_2x3, 1024);
-  memcpy(d.small.tm_interior, t->terminal_mismatch_scores_interior, 1024);
-  memcpy(d.small.tm_multi, t->terminal_mismatch_scores_multibranch, 1024);
-  memcpy(d.small.d5, t->dangling_scores_5prime, 256);
-  memcpy(d.small.d3, t->dangling_scores_3prime, 256);
-  // hairpin initiation for every loop length: table, or the f32 ln-extrapolation of src/utils.rs:178-184
-  std::vector<float> hp(RNA_HAIRPIN_EXT_LEN);
-  const int mex = t->min_hairpin_len_extrapolation - 1;
-  for (int len = 0; len < RNA_HAIRPIN_EXT_LEN; len++) {
-    if (len <= t->max_hairpin_len_extrapolation) {
-      hp[len] = t->hairpin_scores_init[len];
-    } else {
-      volatile float ratio = (float)len / (float)mex;
-      volatile float lg = logf(ratio);
-      volatile float pr = t->coeff_hairpin_len_extrapolation * lg;
-      volatile float s = t->hairpin_scores_init[mex] + pr;
-      hp[len] = s;
-    }
-  }
+  std::vector<float> hp;
+  TRY(pack_turner(t, &d, &hp, &h->err));
+  CU(h, cudaSetDevice(h->device));
   if (!h->d_turner) {
     CU(h, cudaMalloc(&h->d_turner, sizeof(DevTurner)));
     CU(h, cudaMalloc(&h->d_hp_ext, sizeof(float) * RNA_HAIRPIN_EXT_LEN));
@@ -238,37 +177,9 @@ extern "C" int rna_set_turner_tables(rna_handle* h, const RnaTurnerTables* t) {
 
 extern "C" int rna_set_contra_tables(rna_handle* h, const RnaContraTables* t) {
   if (!h || !t) return RNA_ERR_BAD_ARG;
-  if (t->max_loop_len != RNA_CONTRA_MAX_LOOP_LEN || t->min_span_hairpin_close < 2 ||
-      t->max_interior_explicit < 0 || t->max_interior_explicit > RNA_CONTRA_MAX_INTERIOR_EXPLICIT) {
-    h->err = "CONTRAfold blob: caps out of range";
-    return RNA_ERR_BAD_TABLES;
-  }
-  CU(h, cudaSetDevice(h->device));
   DevContra d;
-  memset(&d, 0, sizeof d);
-  d.max_loop_len = t->max_loop_len;
-  d.min_span = t->min_span_hairpin_close;
-  d.max_explicit = t->max_interior_explicit;
-  d.mb_base = t->multibranch_score_base;
-  d.mb_bp = t->multibranch_score_basepair;
-  d.mb_unpair = t->multibranch_score_unpair;
-  d.ext_bp = t->external_score_basepair;
-  d.ext_unpair = t->external_score_unpair;
-  { volatile float s = t->multibranch_score_base + t->multibranch_score_basepair; d.mb_base_plus_bp = s; }
-  memcpy(d.hairpin_cum, t->hairpin_scores_len_cumulative, sizeof d.hairpin_cum);
-  memcpy(d.bulge_cum, t->bulge_scores_len_cumulative, sizeof d.bulge_cum);
-  memcpy(d.interior_cum, t->interior_scores_len_cumulative, sizeof d.interior_cum);
-  memcpy(d.sym_cum, t->interior_scores_symmetric_cumulative, sizeof d.sym_cum);
-  memcpy(d.asym_cum, t->interior_scores_asymmetric_cumulative, sizeof d.asym_cum);
-  memcpy(d.explicit_, t->interior_scores_explicit, sizeof d.explicit_);
-  memcpy(d.small.stack, t->stack_scores, 1024);
-  memcpy(d.small.tm, t->terminal_mismatch_scores, 1024);
-  memcpy(d.small.dl, t->dangling_scores_left, 256);
-  memcpy(d.small.dr, t->dangling_scores_right, 256);
-  memcpy(d.small.hc, t->helix_close_scores, 64);
-  memcpy(d.small.bp, t->basepair_scores, 64);
-  memcpy(d.small.bulge0x1, t->bulge_scores_0x1, 16);
-  memcpy(d.small.int1x1, t->interior_scores_1x1, 64);
+  TRY(pack_contra(t, &d, &h->err));
+  CU(h, cudaSetDevice(h->device));
   if (!h->d_contra) CU(h, cudaMalloc(&h->d_contra, sizeof(DevContra)));
   CU(h, cudaMemcpy(h->d_contra, &d, sizeof d, cudaMemcpyHostToDevice));
   h->has_contra = true;
@@ -279,13 +190,7 @@ extern "C" int rna_set_align_tables(rna_handle* h, const RnaAlignTables* t) {
   if (!h || !t) return RNA_ERR_BAD_ARG;
   CU(h, cudaSetDevice(h->device));
   DevAlign d;
-  d.m2m = t->match2match_score;
-  d.m2i = t->match2insert_score;
-  d.iex = t->insert_extend_score;
-  d.inm = t->init_match_score;
-  d.ini = t->init_insert_score;
-  memcpy(d.insert, t->insert_scores, 16);
-  memcpy(d.match, t->match_scores, 64);
+  pack_align(t, &d);
   if (!h->d_align) CU(h, cudaMalloc(&h->d_align, sizeof(DevAlign)));
   CU(h, cudaMemcpy(h->d_align, &d, sizeof d, cudaMemcpyHostToDevice));
   h->has_align = true;
@@ -353,12 +258,17 @@ static int launch_fold_model(rna_handle* h, const RnaFoldBatchDev* b, cudaStream
                    [&](uint32_t x, uint32_t y) { return ho[x + 1] - ho[x] > ho[y + 1] - ho[y]; });
   auto len_of = [&](uint32_t pos) { return (int)(ho[order[pos] + 1] - ho[order[pos]]); };
   const size_t smem_cap = h->smem_optin;
+  static const bool use_v1 = getenv("RNA_FOLD_V1") != nullptr;   // A/B switch: the thread-per-cell kernel
+  const bool v2 = !centroid_only && !use_v1;
+  const int gran = v2 ? 4 : 8;                                     // bucket width in nt
   auto smem_need = [&](int Lcap) -> size_t {
-    return centroid_only ? centroid_ws_floats(Lcap) * 4 : fold_smem_bytes<CONTRA>(Lcap, true);
+    if (centroid_only) return centroid_ws_floats(Lcap) * 4;
+    if (v2) return fold2_fixed_bytes<CONTRA>(Lcap) + fold2_seq_bytes(Lcap, 1);
+    return fold_smem_bytes<CONTRA>(Lcap, true);
   };
-  // largest L whose matrices fit in shared memory
+  // largest L whose matrices fit in shared memory (v2 keeps u8 cell lists there: L <= 252)
   int Lsmem = 0;
-  for (int L = 16; L <= 1024; L += 8) { if (smem_need(L) + 1024 <= smem_cap) Lsmem = L; else break; }
+  for (int L = 16; L <= (v2 ? 252 : 1024); L += gran) { if (smem_need(L) + 1024 <= smem_cap) Lsmem = L; else break; }
   const int Lcoop_min = 1025;   // longer sequences get the whole grid (one at a time)
   std::vector<Bucket> buckets;
   uint32_t pos = 0;
@@ -375,8 +285,8 @@ static int launch_fold_model(rna_handle* h, const RnaFoldBatchDev* b, cudaStream
       bk.end = e;
     } else {
       bk.mode = MODE_SMEM;
-      bk.Lcap = std::max(16, (L + 7) / 8 * 8);
-      const int lo = bk.Lcap > 16 ? bk.Lcap - 8 : 0;   // bucket = lengths in (Lcap-8, Lcap]; the smallest takes 1..16
+      bk.Lcap = std::max(16, (L + gran - 1) / gran * gran);
+      const int lo = bk.Lcap > 16 ? bk.Lcap - gran : 0;   // bucket = lengths in (Lcap-gran, Lcap]; the smallest takes 1..16
       uint32_t e = pos;
       while (e < n && len_of(e) > lo) e++;
       bk.end = e;
@@ -397,7 +307,9 @@ static int launch_fold_model(rna_handle* h, const RnaFoldBatchDev* b, cudaStream
   for (size_t k = 0; k < buckets.size(); k++) {
     const Bucket& bk = buckets[k];
     if (bk.mode == MODE_SMEM) continue;
-    const size_t per = (centroid_only ? centroid_ws_floats(bk.Lcap) : fold_ws_floats<CONTRA>(bk.Lcap)) + 32;
+    const size_t per = (centroid_only ? centroid_ws_floats(bk.Lcap)
+                        : (v2 && bk.mode == MODE_GLOBAL) ? fold2_seq_bytes(bk.Lcap, 2) / 4
+                                                         : fold_ws_floats<CONTRA>(bk.Lcap)) + 32;
     stride_of[k] = per;
     if (bk.mode == MODE_COOP) {
       ws_floats = std::max(ws_floats, per);
@@ -440,7 +352,23 @@ static int launch_fold_model(rna_handle* h, const RnaFoldBatchDev* b, cudaStream
     a.work_counter = (int*)h->counters.p + k;
     a.Lcap = bk.Lcap;
     a.ws_stride = stride_of[k];
-    if (bk.mode == MODE_SMEM) {
+    if (v2 && bk.mode != MODE_COOP) {
+      const Roles ro = fold2_roles(bk.Lcap, CONTRA, 16);
+      a.nXw = ro.nX; a.nYw = ro.nY; a.nZw = ro.nZ;
+      const int nt = 32 * (ro.nX + ro.nY + ro.nZ);
+      if (bk.mode == MODE_SMEM) {
+        const size_t smem = smem_need(bk.Lcap);
+        int occ = 1;
+        TRY(set_smem_attr(h, fold_kernel2<CONTRA, MODE_SMEM>, smem));
+        CU(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fold_kernel2<CONTRA, MODE_SMEM>, nt, smem));
+        const int grid = (int)std::min<size_t>(a.n_launch, (size_t)std::max(1, occ) * h->sm_count);
+        fold_kernel2<CONTRA, MODE_SMEM><<<grid, nt, smem, st>>>(a);
+      } else {
+        const size_t smem = fold2_fixed_bytes<CONTRA>(bk.Lcap);
+        TRY(set_smem_attr(h, fold_kernel2<CONTRA, MODE_GLOBAL>, smem));
+        fold_kernel2<CONTRA, MODE_GLOBAL><<<grid_of[k], nt, smem, st>>>(a);
+      }
+    } else if (bk.mode == MODE_SMEM) {
       const int nt = std::min(256, std::max(32, (bk.Lcap + 31) / 32 * 32));
       const size_t smem = smem_need(bk.Lcap);
       int occ = 1;

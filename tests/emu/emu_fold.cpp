@@ -1,0 +1,99 @@
+// emu_fold.cpp — HOST emulator of the v2 fold kernel (rna_algos_b200/csrc/fold_kernel2.cuh).
+// TEST INFRASTRUCTURE ONLY: it compiles the product's phase functions (fold_phases.cuh) with g++ and runs
+// them role by role, barrier by barrier, exactly as the CUDA kernel schedules them — with a configurable
+// lane / role order — so that the parallel decomposition (who computes what, in which step, from which
+// inputs) can be checked bit-for-bit against the oracle on a machine without a GPU.  It is never loaded by
+// the product package.
+//   g++ -O1 -std=c++17 -ffp-contract=off -fno-fast-math -shared -fPIC -o _emu.so emu_fold.cpp
+#include <stdlib.h>
+
+#include <vector>
+
+#include "../../rna_algos_b200/csrc/fold_phases.cuh"
+#include "../../rna_algos_b200/csrc/table_pack.h"
+
+using namespace rna;
+
+namespace {
+template <bool CONTRA>
+int run(const uint8_t* seq, int L, int allows_short, const typename Model2<CONTRA>::Dev* dev, int nX, int nY, int nZ,
+        int order, float* out_bpp, float* out_logz) {
+  typedef typename Model2<CONTRA>::View View;
+  View T;
+  T.g = dev;
+  T.sm = dev_small<CONTRA>(dev);
+  const float4* lut = kLnExp1pCoef;
+  ModelParams P;
+  P.MINSPAN = dev->min_span;
+  if constexpr (CONTRA) P.MAX2 = dev->max_loop_len; else P.MAX2 = dev->max_2loop_len;
+  P.allows_short = allows_short;
+  const float NEG = RNA_NEG_INF;
+  const int TRI = L * (L + 1) / 2;
+  std::vector<uint8_t> sbuf(L + 8, 0);
+  for (int x = 0; x < L; x++) sbuf[4 + x] = seq[x];
+  SeqViewT<uint16_t> v;
+  v.L = L;
+  v.W2 = (L + 31) / 32 + 2;
+  v.s = sbuf.data() + 4;
+  std::vector<uint32_t> mask((size_t)L * v.W2);
+  std::vector<uint16_t> plist(TRI), pcnt(L);
+  std::vector<float> C(TRI, NEG), R(TRI, NEG), X(TRI, NEG), E(TRI, 0.f), M1(TRI, NEG), Mroll(3 * L, NEG), E0(L), EL(L);
+  v.mask = mask.data(); v.plist = plist.data(); v.pcnt = pcnt.data();
+  v.C = C.data(); v.R = R.data(); v.X = X.data(); v.E = E.data(); v.M1 = M1.data(); v.Mroll = Mroll.data();
+  v.E0 = E0.data(); v.EL = EL.data();
+  // setup (two barriers in the kernel: masks, then lists)
+  for (int x = 0; x < L * v.W2; x++) setup_mask_word<CONTRA>(v, P, x);
+  for (int d = 0; d < L; d++) setup_list_diag(v, d);
+  auto lanes = [&](int n, auto&& fn) {
+    if (order == 0) for (int l = 0; l < n; l++) fn(l);
+    else for (int l = n - 1; l >= 0; l--) fn(l);
+  };
+  // inside: step t runs X(t) | Y(t) | Z(t-1)
+  const int d_in0 = CONTRA ? 0 : (P.MINSPAN - 1);
+  for (int t = d_in0; t <= L; t++) {
+    auto rX = [&] { if (t < L) lanes(nX, [&](int l) { inside_X<CONTRA>(v, T, lut, P, t, l, nX); }); };
+    auto rY = [&] { if constexpr (CONTRA) { if (t < L) lanes(nY, [&](int l) { inside_Y_contra(v, T, lut, t, l, nY); }); } };
+    auto rZ = [&] { if (t - 1 >= d_in0) lanes(nZ, [&](int l) { inside_Z<CONTRA>(v, T, lut, t - 1, l, nZ); }); };
+    if (order == 0) { rX(); rY(); rZ(); } else { rZ(); rY(); rX(); }
+  }
+  for (int x = 0; x < L; x++) { E0[x] = E[doff(x, L)]; EL[x] = E[doff(L - 1 - x, L) + x]; }
+  const float Z = E0[L - 1];
+  for (int x = 0; x < TRI; x++) { E[x] = NEG; R[x] = NEG; X[x] = NEG; }
+  if (out_logz) *out_logz = Z;
+  const int d_out0 = CONTRA ? (allows_short ? 1 : P.MINSPAN - 1) : (P.MINSPAN - 1);
+  for (int d = L - 1; d >= d_out0; d--) {
+    auto rX = [&] { lanes(nX, [&](int l) { outside_X<CONTRA>(v, T, lut, P, Z, d, l, nX); }); };
+    auto rY = [&] { lanes(nY + nZ, [&](int l) { outside_Y<CONTRA>(v, T, lut, d, l, nY + nZ); }); };
+    if (order == 0) { rX(); rY(); } else { rY(); rX(); }
+  }
+  if (out_bpp) {
+    for (int i = 0; i < L - 1; i++) {
+      const size_t rowoff = (size_t)i * (size_t)(2 * L - i - 1) / 2;
+      for (int x = 0; x < L - 1 - i; x++) {
+        const float val = E[doff(x + 1, L) + i];
+        out_bpp[rowoff + x] = (val > NEG) ? approx_expf(val) : -1.0f;
+      }
+    }
+  }
+  return 0;
+}
+}  // namespace
+
+extern "C" int emu_fold(const uint8_t* seq, int L, int contra, int allows_short, const RnaTurnerTables* tt,
+                        const RnaContraTables* ct, int nX, int nY, int nZ, int order, float* out_bpp,
+                        float* out_logz) {
+  std::string err;
+  if (contra) {
+    static DevContra d;   // big struct: keep off the stack
+    if (pack_contra(ct, &d, &err)) return 1;
+    return run<true>(seq, L, allows_short, &d, nX, nY, nZ, order, out_bpp, out_logz);
+  }
+  static DevTurner d;
+  std::vector<float> hp;
+  if (pack_turner(tt, &d, &hp, &err)) return 1;
+  d.hairpin_init_ext = hp.data();
+  d.int11 = &tt->interior_scores_1x1[0][0][0][0][0][0];
+  d.int12 = &tt->interior_scores_1x2[0][0][0][0][0][0][0];
+  d.int22 = &tt->interior_scores_2x2[0][0][0][0][0][0][0][0];
+  return run<false>(seq, L, allows_short, &d, nX, nY, nZ, order, out_bpp, out_logz);
+}

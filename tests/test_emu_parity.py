@@ -1,0 +1,62 @@
+"""The v2 kernel's parallel decomposition (roles X/Y/Z pipelined over anti-diagonals, fold_phases.cuh),
+compiled for the HOST and run barrier by barrier (tests/emu), must be bit-identical to the oracle for any
+lane count and any execution order of lanes and roles between two barriers.  No GPU needed."""
+import numpy as np
+import pytest
+
+from common import default_tables, load_trnas, random_seqs
+from emu_lib import Emu
+from oracle_lib import Oracle
+from rna_algos_b200 import tables as T
+
+
+@pytest.fixture(scope="module")
+def emu():
+    return Emu()
+
+
+@pytest.fixture(scope="module")
+def oracle():
+    return Oracle()
+
+
+def check(emu, oracle, seqs, contra, short, tt, ct, **kw):
+    for s in seqs:
+        wb, wz = oracle.mccaskill(s, contra, short, tt, ct)
+        gb, gz = emu.fold(s, contra, short, tt, ct, **kw)
+        assert (gb.view(np.uint32) == wb.view(np.uint32)).all(), (len(s), contra, kw)
+        assert np.float32(gz).view(np.uint32) == np.float32(wz).view(np.uint32), (len(s), contra, kw)
+
+
+@pytest.mark.parametrize("contra", [False, True])
+def test_trnas(emu, oracle, contra):
+    tt, ct, _ = default_tables()
+    check(emu, oracle, load_trnas(), contra, False, tt, ct)
+    check(emu, oracle, load_trnas()[:3], contra, False, tt, ct, order=1, nX=7, nY=5, nZ=3)
+
+
+@pytest.mark.parametrize("contra", [False, True])
+def test_edge_lengths(emu, oracle, contra):
+    tt, ct, _ = default_tables()
+    check(emu, oracle, random_seqs(11, list(range(1, 41))), contra, False, tt, ct, order=1)
+
+
+def test_allows_short(emu, oracle):
+    tt, ct, _ = default_tables()
+    check(emu, oracle, random_seqs(12, [2, 3, 4, 5, 9, 17, 33, 60]), True, True, tt, ct)
+
+
+@pytest.mark.parametrize("seed", [1, 2])
+@pytest.mark.parametrize("contra", [False, True])
+def test_random_tables(emu, oracle, seed, contra):
+    rt, rc = T.random_turner_tables(100 + seed), T.random_contra_tables(200 + seed)
+    seqs = random_seqs(20 + seed, [5, 8, 13, 21, 34, 55, 76, 100])
+    rng = np.random.default_rng(seed)
+    seqs += [rng.choice(4, size=64, p=[0.15, 0.35, 0.35, 0.15]).astype(np.uint8) for _ in range(3)]
+    check(emu, oracle, seqs, contra, False, rt, rc, order=seed % 2)
+
+
+def test_mid_length(emu, oracle):
+    tt, ct, _ = default_tables()
+    check(emu, oracle, random_seqs(31, [150, 260]), True, False, tt, ct, nX=64, nY=128, nZ=128)
+    check(emu, oracle, random_seqs(32, [201]), False, False, tt, ct, order=1)
