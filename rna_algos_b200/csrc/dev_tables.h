@@ -18,6 +18,20 @@ struct TurnerSmall {
   float d3[64];            // DANGLING_SCORES_3PRIME[i][j][j+1]
 };
 
+// v2 kernels: the three interior-mismatch tables re-indexed by the per-position base codes
+//   RR[p] = s[p]*4 + s[p+1],  LL[p] = s[p]*4 + s[p-1]:   tm2[X][RR*16 + LL] = TERMINAL_MISMATCH_X[x][y][x1][y1]
+// (X = 0: 1xMANY, 1: 2x3, 2: INTERIOR), so one byte per partner position addresses them.
+struct TurnerSmall2 {
+  float stack[256];
+  float tm2[3][256];
+  float tm_hairpin[256];
+  float tm_multi[256];
+  float d5[64];
+  float d3[64];
+  float ninio[31 * 31];     // [a][b] = INTERIOR_SCORES_INIT[a+b] + max(NINIO_COEFF*|a-b|, NINIO_MAX)
+  float bulge_init[32];
+};
+
 #define RNA_HAIRPIN_EXT_LEN 65536
 
 struct DevTurner {
@@ -35,6 +49,7 @@ struct DevTurner {
   unsigned char special_len[128];
   float special_score[128];
   TurnerSmall small;
+  TurnerSmall2 small2;
   // device-global arrays
   const float* hairpin_init_ext;    // [RNA_HAIRPIN_EXT_LEN]: INIT[len] or the ln-extrapolation (src/utils.rs:178-184)
   const float* int11;               // [4^6]
@@ -57,15 +72,22 @@ struct ContraSmall {
 // every entry is produced by the same f32 operations, in the same order, as the reference's scorer
 // (src/utils.rs:456-520, 545-548), so using them is bit-identical to evaluating the scorer in-line.
 struct ContraSmall2 {
-  float stack[256];
-  float js[256];          // helix_close[x][y] + terminal_mismatch[x][y][p][q]   (get_junction_score_single)
+  float js2[256];         // [RR*16 + LL] = helix_close[x][y] + terminal_mismatch[x][y][x1][y1]  (get_junction_score_single)
   float dl[64];
   float dr[64];
   float hc[16];
   float bp[16];
-  float b1[4];            // bulge_scores_0x1[x] + bulge_cum[0]                    (bulge of length 1)
-  float i11[16];          // ((interior_1x1[x][y] + sym_cum[0]) + explicit[0][0]) + interior_cum[0]   (1x1 interior)
+  float U[276 + 31 * 31];   // unified two-loop table, see below
 };
+// Unified two-loop table U: one gather per term.
+//   [0,256)    stack_scores[i][j][k][l]
+//   [256,260)  bulge_scores_0x1[x] + bulge_cum[0]                                              (bulge of length 1)
+//   [260,276)  ((interior_1x1[x][y] + sym_cum[0]) + explicit[0][0]) + interior_cum[0]          (1x1 interior)
+//   [276+a*31+b]  a+b>=2: bulge: 0 + bulge_cum[len-1]; interior: ((sym|asym) + explicit|0) + interior_cum[len-2]
+#define RNA_CU_B1 256
+#define RNA_CU_I11 260
+#define RNA_CU_PTAB 276
+#define RNA_CU_LEN (276 + 31 * 31)
 
 struct DevContra {
   int max_loop_len;
@@ -81,8 +103,6 @@ struct DevContra {
   float explicit_[16];
   ContraSmall small;
   ContraSmall2 small2;
-  // [a*31+b], a+b>=2: bulge (a==0 or b==0): 0 + bulge_cum[len-1]; interior (not 1x1): ((sym|asym) + explicit|0) + interior_cum[len-2]
-  float ptab[31 * 31];
 };
 
 struct DevAlign {

@@ -52,6 +52,10 @@ struct FoldArgs {
   int* work_counter;         // MODE_SMEM / MODE_GLOBAL: dynamic work queue
   int Lcap;                  // capacity the shared-memory carve-up was sized for
   int nXw, nYw, nZw;         // fold_kernel2: warps per role
+  unsigned char* stream_ws;  // fold_kernel2: per-CTA slots for the two-loop term streams (null: score on the fly)
+  unsigned long long stream_stride;   // bytes per slot
+  uint32_t tcap;             // terms per stream a slot can hold
+  long long* dbg;            // optional per-step per-warp cycle counts of CTA 0's first sequence (RNA_FOLD_DBG)
 };
 
 template <int MODE>

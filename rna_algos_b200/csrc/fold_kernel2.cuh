@@ -19,6 +19,12 @@ template <bool CONTRA>
 __host__ __device__ inline size_t fold2_fixed_bytes(int Lcap) {
   return 128 + align16(sizeof(typename Model2<CONTRA>::Small)) + align16((size_t)Lcap + 8);
 }
+// upper bound of the number of lane groups of a sequence of length <= Lcap: sum over diagonals of ceil(cells/32)
+__host__ __device__ inline size_t fold2_ngcap(int Lcap) {
+  size_t n = 0;
+  for (int c = 1; c <= Lcap; c++) n += (size_t)(c + 31) / 32;
+  return n;
+}
 // bytes of one sequence's working set (SeqViewT) for capacity Lcap
 __host__ __device__ inline size_t fold2_seq_bytes(int Lcap, size_t pidx_size) {
   const size_t T = (size_t)Lcap * ((size_t)Lcap + 1) / 2;
@@ -27,9 +33,18 @@ __host__ __device__ inline size_t fold2_seq_bytes(int Lcap, size_t pidx_size) {
   b += (3 + 2) * (size_t)Lcap * 4;              // Mroll, E0, EL
   b += align16(2 * ((size_t)Lcap + 2) * 4);     // traceback stack
   b += align16((size_t)Lcap * W2 * 4);          // closable bit matrix
-  b += align16((size_t)Lcap * 2);               // pcnt
+  b += align16((size_t)Lcap * 4 + 4);           // pcnt, RR, LL
+  b += align16(((size_t)Lcap + 1) * 4);         // gcum
+  b += align16(2 * (fold2_ngcap(Lcap) + 1) * 4);   // gbin, gbout
   b += align16(T * pidx_size);                  // closable-cell lists
   return align16(b);
+}
+
+// bytes of one CTA's term-stream slot
+__host__ __device__ inline size_t fold2_stream_bytes(int Lcap, uint32_t tcap) {
+  const size_t Tc = (size_t)Lcap * ((size_t)Lcap + 1) / 2;
+  (void)Tc;
+  return align16(2 * (size_t)tcap * 8);
 }
 
 struct Roles { int nX, nY, nZ; };   // warps per role
@@ -91,6 +106,7 @@ __global__ void __launch_bounds__(512) fold_kernel2(const FoldArgs a) {
     const uint32_t sbeg = a.offsets[sidx];
     const int L = (int)(a.offsets[sidx + 1] - sbeg);
     const int TRI = L * (L + 1) / 2;
+    const int ngcap = (int)fold2_ngcap(a.Lcap);
 
     // ---- carve the working set (sizes by L: every pointer stays inside the Lcap-sized region) -----------
     unsigned char* base = (MODE == MODE_SMEM) ? sregion
@@ -111,22 +127,56 @@ __global__ void __launch_bounds__(512) fold_kernel2(const FoldArgs a) {
     v.EL = f; f += L;
     int* tstack = reinterpret_cast<int*>(f);
     v.mask = reinterpret_cast<uint32_t*>(tstack + 2 * (L + 2));
-    v.pcnt = reinterpret_cast<uint16_t*>(v.mask + L * v.W2);
-    v.plist = reinterpret_cast<PIdx*>(v.pcnt + ((L + 1) & ~1));
+    v.gcum = v.mask + L * v.W2;                                  // 4-byte items first, then 2-byte, then bytes
+    v.gbin = v.gcum + L + 1;
+    v.gbout = v.gbin + ngcap + 1;
+    v.pcnt = reinterpret_cast<uint16_t*>(v.gbout + ngcap + 1);
+    v.plist = reinterpret_cast<PIdx*>(v.pcnt + ((L + 1) & ~1));   // (u8 or u16: 2-byte aligned)
+    v.RR = reinterpret_cast<uint8_t*>(v.plist + TRI);
+    v.LL = v.RR + L;
+    v.tin = nullptr; v.tout = nullptr; v.ccnt = nullptr; v.tcap = a.tcap;
 
     for (int x = tid; x < L; x += nt) s[x] = a.bases[sbeg + x];
     if (tid < 4) { sseq[tid] = 0; s[L + tid] = 0; }
-    for (int x = tid; x < TRI; x += nt) { v.C[x] = NEG; v.R[x] = NEG; v.X[x] = NEG; v.E[x] = 0.f; v.M1[x] = NEG; }
-    for (int x = tid; x < 3 * L; x += nt) v.Mroll[x] = NEG;
+    const bool dbg_on = a.dbg && w == 0;
+    long long tc0 = dbg_on ? clock64() : 0;
     __syncthreads();
     for (int x = tid; x < L * v.W2; x += nt) setup_mask_word<CONTRA>(v, P, x);
+    for (int x = tid; x < L; x += nt) setup_codes(v, x);
     __syncthreads();
     for (int d = tid; d < L; d += nt) setup_list_diag(v, d);
+    __syncthreads();
+    if (dbg_on && tid == 0) { a.dbg[2040 * 16 + 0] = clock64() - tc0; tc0 = clock64(); }
+    // ---- two-loop term streams: count, group maxima, scan, fill (all threads; fold_phases.cuh "term streams")
+    if (a.stream_ws) {
+      if (tid == 0) setup_gcum(v);
+      v.ccnt = reinterpret_cast<uint16_t*>(v.C);   // scratch: 2 x TRI u16 = the not-yet-initialised C matrix
+      __syncthreads();
+      stream_count(v, P, tid, nt);
+      __syncthreads();
+      stream_groupmax(v, tid, nt);
+      __syncthreads();
+      if (tid == 0) stream_scan(v);
+      __syncthreads();
+      if (dbg_on && tid == 0) { a.dbg[2040 * 16 + 1] = clock64() - tc0; tc0 = clock64(); }
+      const uint32_t NG = v.gcum[L];
+      if (v.gbin[NG] <= a.tcap && v.gbout[NG] <= a.tcap) {   // else: does not fit its slot, score on the fly
+        unsigned char* sw = a.stream_ws + (size_t)blockIdx.x * a.stream_stride;
+        v.tin = reinterpret_cast<uint2*>(sw);
+        v.tout = v.tin + a.tcap;
+        stream_fill<CONTRA>(v, T, P, tid, nt);
+      }
+      __syncthreads();
+      if (dbg_on && tid == 0) { a.dbg[2040 * 16 + 3] = clock64() - tc0; a.dbg[2040 * 16 + 4] = v.gbin[NG]; }
+    }
+    for (int x = tid; x < TRI; x += nt) { v.C[x] = NEG; v.R[x] = NEG; v.X[x] = NEG; v.E[x] = 0.f; v.M1[x] = NEG; }
+    for (int x = tid; x < 3 * L; x += nt) v.Mroll[x] = NEG;
     __syncthreads();
 
     // ================================ inside: step t = X(t) | Y(t) | Z(t-1) ==============================
     const int d_in0 = CONTRA ? 0 : (P.MINSPAN - 1);
     for (int t = d_in0; t <= L; t++) {
+      const long long c0 = dbg_on ? clock64() : 0;
       if (warp < a.nXw) {
         if (t < L) inside_X<CONTRA>(v, T, lut, P, t, tid, nXl);
       } else if (warp < a.nXw + a.nYw) {
@@ -134,6 +184,7 @@ __global__ void __launch_bounds__(512) fold_kernel2(const FoldArgs a) {
       } else {
         if (t - 1 >= d_in0) inside_Z<CONTRA>(v, T, lut, t - 1, tid - nXl - nYl, nZl);
       }
+      if (dbg_on && (tid & 31) == 0) a.dbg[(size_t)t * 16 + warp] = clock64() - c0;
       __syncthreads();
     }
 
@@ -149,8 +200,10 @@ __global__ void __launch_bounds__(512) fold_kernel2(const FoldArgs a) {
     __syncthreads();
     const int d_out0 = CONTRA ? (a.allows_short ? 1 : P.MINSPAN - 1) : (P.MINSPAN - 1);
     for (int d = L - 1; d >= d_out0; d--) {
+      const long long c0 = dbg_on ? clock64() : 0;
       if (warp < a.nXw) outside_X<CONTRA>(v, T, lut, P, Z, d, tid, nXl);
       else outside_Y<CONTRA>(v, T, lut, d, tid - nXl, nYl + nZl);
+      if (dbg_on && (tid & 31) == 0) a.dbg[(size_t)(1024 + d) * 16 + warp] = clock64() - c0;
       __syncthreads();
     }
 

@@ -40,6 +40,16 @@ struct SeqViewT {
   uint32_t* mask;         // [L][W2]: bit l of row k (data words start at index 1) <=> (k,l) statically closable
   PIdx* plist;            // diagonal-major: plist[doff(d) + r] = i of the r-th closable cell of diagonal d
   uint16_t* pcnt;         // [L] closable cells per diagonal
+  uint8_t* RR;            // [L] base codes s[p]*4 + s[p+1]   (s[L] = 0)
+  uint8_t* LL;            // [L] base codes s[p]*4 + s[p-1]   (s[-1] = 0)
+  // static two-loop term streams (global memory, see "term streams" below); tin == null => scored on the fly
+  uint32_t* gcum;         // [L+1] lane groups (32 consecutive closable cells of a diagonal) on diagonals < d
+  uint32_t* gbin;         // [NG+1] first element of each group's block in tin
+  uint32_t* gbout;        // [NG+1] ... in tout
+  uint2* tin;             // closing-pair-major: terms of the inside chains, lane-interleaved per group
+  uint2* tout;            // enclosed-pair-major: terms of the outside chains
+  uint16_t* ccnt;         // scratch [2][L(L+1)/2]: terms per closable cell (indexed like plist)
+  uint32_t tcap;          // capacity of tin / tout in elements
   float* C;               // sums_close
   float* R;               // sums_rightmost_basepairs_external   -> outside: probs_multibranch
   float* X;               // CONTRAfold: sums_rightmost_basepairs_multibranch -> outside: probs_multibranch2
@@ -80,6 +90,21 @@ RNA_DEV void setup_mask_word(const SV& v, const ModelParams& P, int x) {
   v.mask[x] = bits;
 }
 
+// group base of every diagonal (serial over L entries: one thread)
+template <class SV>
+RNA_DEV void setup_gcum(const SV& v) {
+  uint32_t run = 0;
+  for (int d = 0; d < v.L; d++) { v.gcum[d] = run; run += (v.pcnt[d] + 31u) >> 5; }
+  v.gcum[v.L] = run;
+}
+
+template <class SV>
+RNA_DEV void setup_codes(const SV& v, int p) {
+  const uint8_t* s = v.s;   // s[-1] and s[L] are zero pads
+  v.RR[p] = (uint8_t)(s[p] * 4 + s[p + 1]);
+  v.LL[p] = (uint8_t)(s[p] * 4 + s[p - 1]);
+}
+
 template <class PIdx>
 RNA_DEV void setup_list_diag(const SeqViewT<PIdx>& v, int d) {
   const int L = v.L, od = doff(d, L);
@@ -91,13 +116,17 @@ RNA_DEV void setup_list_diag(const SeqViewT<PIdx>& v, int d) {
   v.pcnt[d] = (uint16_t)cnt;
 }
 
-// ---- CONTRAfold scorers over ContraSmall2 (bit-identical to c_* in scorers.cuh, fewer loads) ------------------
+// ---- v2 views -----------------------------------------------------------------------------------------------
 struct ContraView2 {
   const DevContra* g;
   const ContraSmall2* sm;
 };
+struct TurnerView2 {
+  const DevTurner* g;
+  const TurnerSmall2* sm;
+};
 RNA_DEV float c2_js(const ContraView2& T, const uint8_t* s, int p0, int p1) {
-  return T.sm->js[idx4(s[p0], s[p1], s[p0 + 1], s[p1 - 1])];
+  return T.sm->js2[(s[p0] * 4 + s[p0 + 1]) * 16 + s[p1] * 4 + s[p1 - 1]];
 }
 RNA_DEV float c2_junction(const ContraView2& T, const uint8_t* s, int L, int p0, int p1) {
   const int x = s[p0], y = s[p1];
@@ -107,51 +136,17 @@ RNA_DEV float c2_junction(const ContraView2& T, const uint8_t* s, int L, int p0,
 RNA_DEV float c2_hairpin(const ContraView2& T, const uint8_t* s, int i, int j) {
   return __fadd_rn(T.g->hairpin_cum[min(j - i - 1, T.g->max_loop_len)], c2_js(T, s, i, j));
 }
-struct C2Outer { float js; int pq, p1, q1; };   // js(i,j); s[i]*4+s[j]; s[i+1]; s[j-1]
-struct C2Inner { float js, bp; int kl; };       // js(j,i); basepair_scores[s[i]][s[j]]; s[i]*4+s[j]
-
-// get_2loop_score_contra (src/utils.rs:423-520) with the closing pair fixed: (k,l) enclosed, a = k-i-1, b = j-l-1
-RNA_DEV float c2_twoloop_outer(const ContraView2& T, const uint8_t* s, const C2Outer& o, int k, int l, int a, int b) {
-  const int sk = s[k], sl = s[l];
-  float sc;
-  if ((a | b) == 0) {
-    sc = T.sm->stack[o.pq * 16 + sk * 4 + sl];
-  } else {
-    float pv;
-    if (a + b == 1) pv = T.sm->b1[a == 1 ? o.p1 : o.q1];
-    else if (a == 1 && b == 1) pv = T.sm->i11[o.p1 * 4 + o.q1];
-    else pv = __ldg(&T.g->ptab[a * 31 + b]);
-    sc = __fadd_rn(__fadd_rn(pv, o.js), T.sm->js[idx4(sl, sk, s[l + 1], s[k - 1])]);
-  }
-  return __fadd_rn(sc, T.sm->bp[sk * 4 + sl]);
-}
-// the same with the ENCLOSED pair fixed: (p,q) closes, a = i-p-1, b = q-j-1
-RNA_DEV float c2_twoloop_inner(const ContraView2& T, const uint8_t* s, const C2Inner& in, int p, int q, int a, int b) {
-  const int sp = s[p], sq = s[q];
-  float sc;
-  if ((a | b) == 0) {
-    sc = T.sm->stack[(sp * 4 + sq) * 16 + in.kl];
-  } else {
-    const int p1 = s[p + 1], q1 = s[q - 1];
-    float pv;
-    if (a + b == 1) pv = T.sm->b1[a == 1 ? p1 : q1];
-    else if (a == 1 && b == 1) pv = T.sm->i11[p1 * 4 + q1];
-    else pv = __ldg(&T.g->ptab[a * 31 + b]);
-    sc = __fadd_rn(__fadd_rn(pv, T.sm->js[idx4(sp, sq, p1, q1)]), in.js);
-  }
-  return __fadd_rn(sc, in.bp);
-}
 
 template <bool CONTRA> struct Model2;
 template <> struct Model2<false> {
-  typedef DevTurner Dev; typedef TurnerSmall Small; typedef TurnerView View;
+  typedef DevTurner Dev; typedef TurnerSmall2 Small; typedef TurnerView2 View;
 };
 template <> struct Model2<true> {
   typedef DevContra Dev; typedef ContraSmall2 Small; typedef ContraView2 View;
 };
 template <bool CONTRA>
 RNA_DEV const typename Model2<CONTRA>::Small* dev_small(const typename Model2<CONTRA>::Dev* d) {
-  if constexpr (CONTRA) return &d->small2; else return &d->small;
+  return &d->small2;
 }
 
 template <bool CONTRA>
@@ -163,6 +158,372 @@ template <bool CONTRA>
 RNA_DEV float v2_acc(const typename Model2<CONTRA>::View& T, const uint8_t* s, int L, int i, int j) {
   if constexpr (CONTRA) return __fadd_rn(c2_junction(T, s, L, j, i), T.sm->bp[s[i] * 4 + s[j]]);
   else return t_acc(T, s, L, i, j);
+}
+
+// =========================================================================================================
+// Two-loop chains (src/mccaskill_algo.rs:305-323, 574-593 / 410-434, 681-700): one lane folds, in the
+// reference's order, over the partner pairs (k,l) of its cell (i,j).  The chain of logsumexp's is strictly
+// sequential, so its latency IS the critical path of a diagonal; everything that does not depend on the
+// running sum is taken off it by a 3-stage software pipeline over the lane's partner list:
+//     stage 1 (term n+2)  advance the bit-window iterator; first-level loads: C[q] (and log P[q]), base code
+//     stage 2 (term n+1)  second-level gathers: the score-table entries addressed by the base code
+//     stage 3 (term n)    combine the loaded values into the operand y; sum = logsumexp(sum, y)
+// An exhausted iterator keeps feeding c = -inf, which makes y = -inf and the fold a no-op (utils.rs:580-583).
+//
+// Base codes: RR[p] = s[p]*4+s[p+1], LL[p] = s[p]*4+s[p-1].  A partner's code is RR[5' base]*16 + LL[3' base]
+// of the side that VARIES: INSIDE the enclosed pair seen from outside in, (l,k): RR[l]*16+LL[k];
+// OUTSIDE the closing pair (k,l): RR[k]*16+LL[l].  code = [x:2][x1:2][y:2][y1:2].
+// =========================================================================================================
+struct Term1 { float c, pv; int code, a, b, q; };     // q = matrix index of the partner, -1 = none
+struct Term2 { float c, pv, u, v; int cls, aux, q; };
+
+// ---- CONTRAfold: get_2loop_score_contra, src/utils.rs:423-520 -------------------------------------------------
+template <bool INSIDE>
+struct ContraLoop {
+  const ContraView2& T;
+  float js_fixed, bp_fixed;   // INSIDE: js(i,j), unused.  OUTSIDE: js(j,i), basepair_scores[s[i]][s[j]]
+  int pq, p1, q1;             // s[i]*4+s[j]; INSIDE: s[i+1], s[j-1]
+  RNA_DEVM ContraLoop(const ContraView2& T_, const uint8_t* RR, const uint8_t* LL, int i, int j) : T(T_) {
+    const int ri = RR[i], lj = LL[j];
+    pq = (ri >> 2) * 4 + (lj >> 2);
+    p1 = ri & 3;
+    q1 = lj & 3;
+    if (INSIDE) { js_fixed = T.sm->js2[ri * 16 + lj]; bp_fixed = 0.f; }
+    else { js_fixed = T.sm->js2[RR[j] * 16 + LL[i]]; bp_fixed = T.sm->bp[pq]; }
+  }
+  RNA_DEVM Term2 stage2(const Term1& t) const {
+    Term2 r;
+    r.c = t.c; r.pv = t.pv; r.q = t.q;
+    const int a = t.a, b = t.b, code = t.code;
+    const int x = code >> 6, x1 = (code >> 4) & 3, y = (code >> 2) & 3, y1 = code & 3;
+    const bool st = (a | b) == 0;
+    int ui;
+    if (INSIDE) {   // code = (l,k): x = s[l], y = s[k]
+      ui = st ? pq * 16 + y * 4 + x
+              : (a + b == 1) ? RNA_CU_B1 + (a == 1 ? p1 : q1)
+              : (a == 1 && b == 1) ? RNA_CU_I11 + p1 * 4 + q1 : RNA_CU_PTAB + a * 31 + b;
+      r.aux = y * 4 + x;   // s[k]*4+s[l]
+    } else {        // code = (k,l) closing: x = s[k], x1 = s[k+1], y = s[l], y1 = s[l-1]
+      ui = st ? (x * 4 + y) * 16 + pq
+              : (a + b == 1) ? RNA_CU_B1 + (a == 1 ? x1 : y1)
+              : (a == 1 && b == 1) ? RNA_CU_I11 + x1 * 4 + y1 : RNA_CU_PTAB + a * 31 + b;
+      r.aux = 0;
+    }
+    r.u = T.sm->U[ui];
+    r.v = T.sm->js2[code];
+    r.cls = st ? 1 : 0;
+    return r;
+  }
+  // the two-loop score: a pure function of the sequence (the reference memoises it: mccaskill_algo.rs:431,696)
+  RNA_DEVM float score(const Term2& t) const {
+    if (INSIDE) {
+      const float sc = t.cls ? t.u : __fadd_rn(__fadd_rn(t.u, js_fixed), t.v);
+      return __fadd_rn(sc, T.sm->bp[t.aux]);
+    } else {
+      const float sc = t.cls ? t.u : __fadd_rn(__fadd_rn(t.u, t.v), js_fixed);
+      return __fadd_rn(sc, bp_fixed);
+    }
+  }
+};
+
+// ---- Turner: get_2loop_score, src/utils.rs:207-366 ------------------------------------------------------------
+template <bool INSIDE>
+struct TurnerLoop {
+  const TurnerView2& T;
+  const uint8_t* s;
+  int i, j;
+  float tm_f0, tm_f1, tm_f2;   // interior-mismatch term of the fixed pair for the three table classes
+  float pen_fixed;     // AU/GU end penalty of the fixed pair
+  int pq;              // s[i]*4+s[j]
+  RNA_DEVM TurnerLoop(const TurnerView2& T_, const uint8_t* s_, const uint8_t* RR, const uint8_t* LL, int i_, int j_)
+      : T(T_), s(s_), i(i_), j(j_) {
+    const int si = s[i], sj = s[j];
+    pq = si * 4 + sj;
+    pen_fixed = t_pen(T, si, sj);
+    const int code = INSIDE ? RR[i] * 16 + LL[j] : RR[j] * 16 + LL[i];
+    tm_f0 = T.sm->tm2[0][code];
+    tm_f1 = T.sm->tm2[1][code];
+    tm_f2 = T.sm->tm2[2][code];
+  }
+  // cls: 0 stack, 1 bulge of 1, 2 longer bulge, 3 explicit 1x1/1x2/2x1/2x2 table, 4.. generic interior (4 + table class)
+  RNA_DEVM Term2 stage2(const Term1& t) const {
+    Term2 r;
+    r.c = t.c; r.pv = t.pv; r.q = t.q; r.u = 0.f; r.v = 0.f;
+    const int a = t.a, b = t.b, code = t.code;
+    const int x = code >> 6, x1 = (code >> 4) & 3, y = (code >> 2) & 3, y1 = code & 3;
+    // INSIDE: closing (i,j) fixed, enclosed (k,l): x = s[l], x1 = s[l+1], y = s[k], y1 = s[k-1]
+    // OUTSIDE: enclosed (i,j) fixed, closing (k,l): x = s[k], x1 = s[k+1], y = s[l], y1 = s[l-1]
+    const int si = INSIDE ? (pq >> 2) : x, sj = INSIDE ? (pq & 3) : y;   // closing pair
+    const int sk = INSIDE ? y : (pq >> 2), sl = INSIDE ? x : (pq & 3);   // enclosed pair
+    r.aux = augu_pair(INSIDE ? sk : si, INSIDE ? sl : sj) ? 1 : 0;       // AU/GU penalty of the varying pair
+    const int st = (si * 4 + sj) * 16 + sk * 4 + sl;
+    if ((a | b) == 0) {
+      r.cls = 0;
+      r.u = T.sm->stack[st];
+    } else if (a == 0 || b == 0) {
+      const int len = a + b;
+      r.v = T.sm->bulge_init[len];
+      if (len == 1) { r.cls = 1; r.u = T.sm->stack[st]; } else { r.cls = 2; }
+    } else if (a <= 2 && b <= 2) {
+      r.cls = 3;
+      // closing pair (ci,cj) and its inner neighbours i1 = s[ci+1], j1 = s[cj-1], i2 = s[ci+2], j2 = s[cj-2]
+      int i1, j1, i2, j2;
+      if (INSIDE) { i1 = s[i + 1]; j1 = s[j - 1]; i2 = s[i + 2]; j2 = s[j - 2]; }
+      else {
+        const int k = i - 1 - a, l = j + 1 + b;
+        i1 = x1; j1 = y1; i2 = s[k + 2]; j2 = s[l - 2];
+      }
+      const int kl = sk * 4 + sl, ij11 = ((si * 4 + sj) * 4 + i1) * 4 + j1;
+      if (a == 1 && b == 1) r.u = __ldg(&T.g->int11[ij11 * 16 + kl]);
+      else if (a == 1 && b == 2) r.u = __ldg(&T.g->int12[(ij11 * 4 + j2) * 16 + kl]);
+      else if (a == 2 && b == 1) r.u = __ldg(&T.g->int12[((((sl * 4 + sk) * 4 + j1) * 4 + i2) * 4 + i1) * 16 + sj * 4 + si]);
+      else r.u = __ldg(&T.g->int22[(ij11 * 16 + i2 * 4 + j2) * 16 + kl]);
+    } else {
+      const int X = (a == 1 || b == 1) ? 0 : ((a == 2 && b == 3) || (a == 3 && b == 2)) ? 1 : 2;
+      r.cls = 4 + X;
+      r.v = T.sm->ninio[a * 31 + b];
+      r.u = T.sm->tm2[X][code];
+    }
+    return r;
+  }
+  RNA_DEVM float score(const Term2& t) const {
+    const float pen_var = t.aux ? T.g->augu_pen : 0.f;
+    const float pen_close = INSIDE ? pen_fixed : pen_var, pen_encl = INSIDE ? pen_var : pen_fixed;
+    float sc;
+    if (t.cls == 0 || t.cls == 3) sc = t.u;
+    else if (t.cls == 1) sc = __fadd_rn(t.v, t.u);
+    else if (t.cls == 2) sc = __fadd_rn(__fadd_rn(t.v, pen_close), pen_encl);
+    else {
+      const float tf = (t.cls == 4) ? tm_f0 : (t.cls == 5) ? tm_f1 : tm_f2;
+      const float mm = INSIDE ? __fadd_rn(tf, t.u) : __fadd_rn(t.u, tf);   // closing-side term first
+      sc = __fadd_rn(__fadd_rn(__fadd_rn(t.v, mm), pen_close), pen_encl);
+    }
+    return sc;
+  }
+};
+
+template <bool CONTRA, bool INSIDE> struct LoopOf;
+template <bool INSIDE> struct LoopOf<true, INSIDE> { typedef ContraLoop<INSIDE> type; };
+template <bool INSIDE> struct LoopOf<false, INSIDE> { typedef TurnerLoop<INSIDE> type; };
+
+template <bool CONTRA, bool INSIDE, class SV>
+RNA_DEV typename LoopOf<CONTRA, INSIDE>::type make_loop(const SV& v, const typename Model2<CONTRA>::View& T, int i, int j) {
+  if constexpr (CONTRA) return ContraLoop<INSIDE>(T, v.RR, v.LL, i, j);
+  else return TurnerLoop<INSIDE>(T, v.s, v.RR, v.LL, i, j);
+}
+
+// operand of the fold from a term's dynamic values and its static score:
+// INSIDE: y = C(k,l) + score.   OUTSIDE: y = ((P(k,l) + C(i,j)) - C(k,l)) + score
+template <bool INSIDE>
+RNA_DEV float term_operand(float c, float pv, float Cij, float score) {
+  if (INSIDE) return __fadd_rn(c, score);
+  return __fadd_rn(__fsub_rn(__fadd_rn(pv, Cij), c), score);
+}
+
+// windows of the closable bit matrix that hold the partners of cell (i,j) in row a of its two-loop enumeration.
+// INSIDE: partners k = i+1+a ascending, l descending from j-1 (a+b <= MAX2, k <= j-2).
+// OUTSIDE: k = i-1-a descending, l ascending from j+1 (k >= 0, l <= L-1).
+template <bool INSIDE, class SV>
+struct Windows {
+  const SV& v;
+  int i, j, MAX2, amax, wpos, bcap;
+  RNA_DEVM Windows(const SV& v_, int MAX2_, int i_, int j_) : v(v_), i(i_), j(j_), MAX2(MAX2_) {
+    bcap = v.L - 2 - j;
+    amax = INSIDE ? min(MAX2, j - i - 3) : ((bcap >= 0) ? min(MAX2, i - 1) : -1);
+    wpos = INSIDE ? j - 32 : j + 1;
+  }
+  RNA_DEVM uint32_t operator()(int aa) const {
+    if (aa > amax) return 0u;
+    const int kk = INSIDE ? i + 1 + aa : i - 1 - aa;
+    const uint32_t raw = get32(v.mask + kk * v.W2, wpos);
+    if (INSIDE) return raw & (0xffffffffu << (31 - (MAX2 - aa)));
+    return raw & (0xffffffffu >> (31 - min(MAX2 - aa, bcap)));
+  }
+};
+
+// The pipelined enumeration: sink(t2) is called once per term in the reference's order (and a few times with
+// the neutral term q = -1, c = -inf while the pipeline fills and drains).  LOADS: fetch C (and log P).
+template <bool INSIDE, bool LOADS, class SV, class LOOP, class SINK>
+RNA_DEV void twoloop_foreach(const SV& v, const LOOP& lp, int MAX2, int i, int j, SINK& sink) {
+  const int L = v.L;
+  const float NEG = RNA_NEG_INF;
+  const Windows<INSIDE, SV> window(v, MAX2, i, j);
+  const int amax = window.amax;
+  int a = -1, k = i, kcode = 0;
+  uint32_t w = 0;
+  uint32_t wnext = window(0);   // the window of the NEXT row is loaded one row ahead
+  Term1 t1;  t1.c = NEG; t1.pv = NEG; t1.code = 0; t1.a = 0; t1.b = 0; t1.q = -1;
+  Term2 t2 = lp.stage2(t1);
+  int idle = 0;
+  for (;;) {
+    // ---- stage 2: term n+1 -------------------------------------------------------------------------------
+    const Term2 t2n = lp.stage2(t1);
+    // ---- stage 1: term n+2 -------------------------------------------------------------------------------
+    while (w == 0 && a < amax) {
+      a++;
+      w = wnext;
+      wnext = window(a + 1);
+      k = INSIDE ? i + 1 + a : i - 1 - a;
+      kcode = INSIDE ? v.LL[k] : v.RR[k] * 16;
+    }
+    t1.c = NEG; t1.pv = NEG; t1.code = 0; t1.a = 0; t1.b = 0; t1.q = -1;
+    if (w != 0) {
+      int l, b;
+      if (INSIDE) { const int t = 31 - __clz(w); w &= ~(1u << t); l = j - 32 + t; b = 31 - t; }
+      else { const int t = __ffs(w) - 1; w &= w - 1; l = j + 1 + t; b = t; }
+      const int q = doff(l - k, L) + k;
+      if (LOADS) {
+        t1.c = v.C[q];
+        if (!INSIDE) t1.pv = v.E[q];
+      }
+      t1.code = INSIDE ? v.RR[l] * 16 + kcode : kcode + v.LL[l];
+      t1.a = a; t1.b = b; t1.q = q;
+      idle = 0;
+    } else {
+      idle++;
+    }
+    // ---- stage 3: term n ---------------------------------------------------------------------------------
+    sink(t2);
+    t2 = t2n;
+    if (idle >= 2) break;
+  }
+}
+
+// the fold with scores computed on the fly (sequences whose term streams do not fit their workspace slot,
+// and the HBM-resident mode for long sequences)
+template <bool INSIDE, class SV, class LOOP>
+RNA_DEV float twoloop_chain(const SV& v, const LOOP& lp, const float4* lut, int MAX2, int i, int j, float Cij,
+                            float sum) {
+  auto sink = [&](const Term2& t) { sum = lse(sum, term_operand<INSIDE>(t.c, t.pv, Cij, lp.score(t)), lut); };
+  twoloop_foreach<INSIDE, true>(v, lp, MAX2, i, j, sink);
+  return sum;
+}
+
+// =========================================================================================================
+// Term streams.  The two-loop scores and the partner lists are pure functions of the sequence, and both
+// passes walk them (the reference caches them in a 4-D hash map, mccaskill_algo.rs:320,431,589,696).  They
+// are materialised ONCE per sequence, by all threads of the CTA, as two streams of (score, partner index)
+// in the CTA's HBM workspace slot: closing-pair-major for the inside chains, enclosed-pair-major for the
+// outside chains, every cell's terms in the reference's fold order.
+//
+// Layout: the closable cells of a diagonal are cut into GROUPS of 32 consecutive cells = the 32 lanes of the
+// warp that will fold them.  A group's block is lane-interleaved, element (lane, n) at base + wd n + lane
+// (wd = cells in the group), and padded to the longest chain of the group with the neutral element (score 0, partner cell (0,0), whose
+// sums_close is -inf: the operand becomes -inf and logsumexp skips it, utils.rs:580-583).  So a warp reads
+// 256 contiguous bytes per step, all its lanes run the same trip count, and the latency-critical chain is:
+// one coalesced stream load (prefetched a block ahead), one gather of C (and log P), logsumexp.
+// =========================================================================================================
+template <bool INSIDE, class SV>
+RNA_DEV uint32_t count_terms(const SV& v, int MAX2, int i, int j) {
+  const Windows<INSIDE, SV> window(v, MAX2, i, j);
+  uint32_t n = 0;
+  for (int a = 0; a <= window.amax; a++) n += (uint32_t)__popc(window(a));
+  return n;
+}
+
+// phase 1: per closable cell, the number of terms of its inside and outside chains
+template <class SV>
+RNA_DEV void stream_count(const SV& v, const ModelParams& P, int lane, int nl) {
+  const int L = v.L, TRI = L * (L + 1) / 2;
+  for (int d = 0; d < L; d++) {
+    const int cnt = v.pcnt[d], od = doff(d, L);
+    for (int r = (lane - od % nl + nl) % nl; r < cnt; r += nl) {   // round-robin over all cells
+      const int i = v.plist[od + r], j = i + d;
+      v.ccnt[od + r] = (uint16_t)count_terms<true>(v, P.MAX2, i, j);
+      v.ccnt[TRI + od + r] = (uint16_t)count_terms<false>(v, P.MAX2, i, j);
+    }
+  }
+}
+// phase 2: per group, the longest chain -> gbin[G+1], gbout[G+1]
+template <class SV>
+RNA_DEV void stream_groupmax(const SV& v, int tid, int nt) {
+  const int L = v.L, TRI = L * (L + 1) / 2;
+  for (int d = 0; d < L; d++) {
+    const int cnt = v.pcnt[d], od = doff(d, L), g0 = (int)v.gcum[d], ng = (cnt + 31) >> 5;
+    for (int c = (tid - g0 % nt + nt) % nt; c < ng; c += nt) {
+      uint32_t mi = 0, mo = 0;
+      for (int r = 32 * c; r < min(cnt, 32 * c + 32); r++) {
+        mi = max(mi, (uint32_t)v.ccnt[od + r]);
+        mo = max(mo, (uint32_t)v.ccnt[TRI + od + r]);
+      }
+      v.gbin[g0 + c + 1] = mi;
+      v.gbout[g0 + c + 1] = mo;
+    }
+  }
+}
+// cells in group c of a diagonal with cnt closable cells
+RNA_DEV uint32_t group_width(int cnt, int c) { return (uint32_t)min(32, cnt - 32 * c); }
+// phase 3 (one thread): block offsets
+template <class SV>
+RNA_DEV void stream_scan(const SV& v) {
+  uint32_t ri = 0, ro = 0;
+  v.gbin[0] = 0;
+  v.gbout[0] = 0;
+  for (int d = 0; d < v.L; d++) {
+    const int cnt = v.pcnt[d], ng = (cnt + 31) >> 5;
+    for (int c = 0; c < ng; c++) {
+      const uint32_t g = v.gcum[d] + c, wd = group_width(cnt, c);
+      ri += wd * v.gbin[g + 1]; v.gbin[g + 1] = ri;
+      ro += wd * v.gbout[g + 1]; v.gbout[g + 1] = ro;
+    }
+  }
+}
+// phase 4: score every term once and write both streams; warp w takes the groups G = w (mod number of warps),
+// lane = cell of the group, so the stores of a warp are contiguous
+template <bool CONTRA, bool INSIDE, class SV>
+RNA_DEV void stream_fill_cell(const SV& v, const typename Model2<CONTRA>::View& T, const ModelParams& P, int i, int j,
+                              uint2* out, uint32_t wd, uint32_t nmax) {
+  uint32_t n = 0;
+  typename LoopOf<CONTRA, INSIDE>::type lp = make_loop<CONTRA, INSIDE>(v, T, i, j);
+  auto sink = [&](const Term2& t) {
+    if (t.q >= 0) { out[wd * n] = make_uint2((unsigned)__float_as_int(lp.score(t)), (unsigned)t.q); n++; }
+  };
+  twoloop_foreach<INSIDE, false>(v, lp, P.MAX2, i, j, sink);
+  for (; n < nmax; n++) out[wd * n] = make_uint2(0u, 0u);   // neutral padding
+}
+template <bool CONTRA, class SV>
+RNA_DEV void stream_fill(const SV& v, const typename Model2<CONTRA>::View& T, const ModelParams& P, int lane, int nl) {
+  const int L = v.L;
+  const int wv = lane >> 5, nw = max(nl >> 5, 1), ln = lane & 31;
+  for (int d = 0; d < L; d++) {
+    const int cnt = v.pcnt[d], od = doff(d, L), g0 = (int)v.gcum[d], ng = (cnt + 31) >> 5;
+    for (int c = (wv - g0 % nw + nw) % nw; c < ng; c += nw) {
+      const int r = 32 * c + ln;
+      if (r >= cnt) continue;
+      const int i = v.plist[od + r], j = i + d;
+      const uint32_t G = g0 + c, wd = group_width(cnt, c);
+      stream_fill_cell<CONTRA, true>(v, T, P, i, j, v.tin + v.gbin[G] + ln, wd, (v.gbin[G + 1] - v.gbin[G]) / wd);
+      stream_fill_cell<CONTRA, false>(v, T, P, i, j, v.tout + v.gbout[G] + ln, wd, (v.gbout[G + 1] - v.gbout[G]) / wd);
+    }
+  }
+}
+// the latency-critical fold over a lane's column of its group's block.  Every step of the warp touches a new
+// 256-byte line pair, so the stream is read a block of 8 steps ahead (>= 800 cycles of logsumexp), and the
+// gathers of a block are issued before its chain starts.
+template <bool INSIDE, class SV>
+RNA_DEV float stream_chain(const SV& v, const uint2* __restrict__ st, uint32_t wd, uint32_t n, const float4* lut,
+                           float Cij, float sum) {
+  if (n == 0) return sum;
+  uint2 nx[8];
+#pragma unroll
+  for (int k = 0; k < 8; k++) nx[k] = ((uint32_t)k < n) ? st[wd * k] : make_uint2(0u, 0u);
+  for (uint32_t pos = 0; pos < n; pos += 8) {
+    uint2 cur[8];
+    float c[8], p[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) cur[k] = nx[k];
+#pragma unroll
+    for (int k = 0; k < 8; k++) nx[k] = (pos + 8 + k < n) ? st[wd * (pos + 8 + k)] : make_uint2(0u, 0u);
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+      c[k] = v.C[cur[k].y];                    // neutral element: C[0] = -inf => operand -inf => no-op
+      p[k] = INSIDE ? 0.f : v.E[cur[k].y];
+    }
+#pragma unroll
+    for (int k = 0; k < 8; k++)
+      sum = lse(sum, term_operand<INSIDE>(c[k], p[k], Cij, __int_as_float((int)cur[k].x)), lut);
+  }
+  return sum;
 }
 
 // =========================================================================================================
@@ -185,28 +546,12 @@ RNA_DEV void inside_X(const SV& v, const typename Model2<CONTRA>::View& T, const
     } else {
       sum = lse(sum, t_hairpin(T, s, i, j), lut);
     }
-    C2Outer o;
-    if constexpr (CONTRA) { o.js = c2_js(T, s, i, j); o.pq = s[i] * 4 + s[j]; o.p1 = s[i + 1]; o.q1 = s[j - 1]; }
-    // enclosed pairs: k ascending from i+1, l descending from j-1, a + b <= MAX2
-    const int amax = min(P.MAX2, d - 3);
-    int a = -1, k = i;
-    uint32_t w = 0;
-    for (;;) {
-      while (w == 0 && a < amax) {
-        a++;
-        k = i + 1 + a;
-        // window = positions [j-32, j-1] of row k; keep l >= j-1-(MAX2-a)
-        w = get32(v.mask + k * v.W2, j - 32) & (0xffffffffu << (31 - (P.MAX2 - a)));
-      }
-      if (w == 0) break;
-      const int t = 31 - __clz(w);
-      w &= ~(1u << t);
-      const int l = j - 32 + t, b = 31 - t;
-      const float c = v.C[doff(l - k, L) + k];
-      float sc;
-      if constexpr (CONTRA) sc = c2_twoloop_outer(T, s, o, k, l, a, b);
-      else sc = t_twoloop(T, s, i, j, k, l, a, b);
-      sum = lse(sum, __fadd_rn(c, sc), lut);
+    if (v.tin) {
+      const uint32_t G = v.gcum[d] + (r >> 5), gb = v.gbin[G], wd = group_width(cnt, r >> 5);
+      sum = stream_chain<true>(v, v.tin + gb + (r & 31), wd, (v.gbin[G + 1] - gb) / wd, lut, 0.f, sum);
+    } else {
+      typename LoopOf<CONTRA, true>::type lp = make_loop<CONTRA, true>(v, T, i, j);
+      sum = twoloop_chain<true>(v, lp, lut, P.MAX2, i, j, 0.f, sum);
     }
     const float mb = (d >= 2) ? Mm2[i + 1] : NEG;
     sum = lse(sum, __fadd_rn(mb, v2_mbclose<CONTRA>(T, s, L, i, j)), lut);
@@ -367,29 +712,12 @@ RNA_DEV void outside_X(const SV& v, const typename Model2<CONTRA>::View& T, cons
     if constexpr (CONTRA) sm = __fsub_rn(__fadd_rn(__fadd_rn(__fadd_rn(El, Er), Aij), dev->ext_bp), Z);
     else sm = __fsub_rn(__fadd_rn(__fadd_rn(El, Aij), Er), Z);
     // enclosing two-loops: k descending from i-1, l ascending from j+1
-    C2Inner in;
-    if constexpr (CONTRA) { in.js = c2_js(T, s, j, i); in.bp = T.sm->bp[s[i] * 4 + s[j]]; in.kl = s[i] * 4 + s[j]; }
-    const int bcap = L - 2 - j;
-    const int amax = (bcap >= 0) ? min(P.MAX2, i - 1) : -1;
-    int a = -1, k = i;
-    uint32_t w = 0;
-    for (;;) {
-      while (w == 0 && a < amax) {
-        a++;
-        k = i - 1 - a;
-        const int n = min(P.MAX2 - a, bcap) + 1;   // 1..31 positions j+1 .. j+n
-        w = get32(v.mask + k * v.W2, j + 1) & (0xffffffffu >> (32 - n));
-      }
-      if (w == 0) break;
-      const int t = __ffs(w) - 1;
-      w &= w - 1;
-      const int l = j + 1 + t, b = t;
-      const int q = doff(l - k, L) + k;
-      const float c = v.C[q], pv = v.E[q];
-      float tl;
-      if constexpr (CONTRA) tl = c2_twoloop_inner(T, s, in, k, l, a, b);
-      else tl = t_twoloop(T, s, k, l, i, j, a, b);
-      sm = lse(sm, __fadd_rn(__fsub_rn(__fadd_rn(pv, Cij), c), tl), lut);
+    if (v.tin) {
+      const uint32_t G = v.gcum[d] + (r >> 5), gb = v.gbout[G], wd = group_width(cnt, r >> 5);
+      sm = stream_chain<false>(v, v.tout + gb + (r & 31), wd, (v.gbout[G + 1] - gb) / wd, lut, Cij, sm);
+    } else {
+      typename LoopOf<CONTRA, false>::type lp = make_loop<CONTRA, false>(v, T, i, j);
+      sm = twoloop_chain<false>(v, lp, lut, P.MAX2, i, j, Cij, sm);
     }
     // enclosing multiloops: k ascending 0..i-1
     float sa;

@@ -10,14 +10,18 @@
 #ifdef __CUDACC__
 #include <cuda_runtime.h>
 #define RNA_DEV __device__ __forceinline__
+#define RNA_DEVM __device__ __forceinline__   // member functions
 #define RNA_CONST_TABLE __device__ __constant__
 #else
 #include <math.h>
 #include <string.h>
 #define RNA_DEV static inline
+#define RNA_DEVM inline
 #define RNA_CONST_TABLE static const
 #define __restrict__ __restrict
 struct float4 { float x, y, z, w; };
+struct uint2 { unsigned x, y; };
+static inline uint2 make_uint2(unsigned x, unsigned y) { uint2 r; r.x = x; r.y = y; return r; }
 static inline float __fadd_rn(float a, float b) { volatile float r = a + b; return r; }
 static inline float __fsub_rn(float a, float b) { volatile float r = a - b; return r; }
 static inline float __fmul_rn(float a, float b) { volatile float r = a * b; return r; }

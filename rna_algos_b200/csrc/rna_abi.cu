@@ -38,7 +38,7 @@ struct rna_handle {
   DevContra* d_contra = nullptr;
   DevAlign* d_align = nullptr;
   float *d_hp_ext = nullptr, *d_int11 = nullptr, *d_int12 = nullptr, *d_int22 = nullptr;
-  DevBuf ws, counters, order;                                      // kernel scratch
+  DevBuf ws, counters, order, stream_ws;                           // kernel scratch
   DevBuf b_bases, b_offsets, b_bppoff, b_gammas, b_logz, b_bpp, b_structs, b_ea, b_pairs, b_probs, b_proboff;
   RnaCallStats stats{};
   bool attrs_set = false;
@@ -97,7 +97,7 @@ extern "C" int rna_destroy(rna_handle* h) {
   if (!h) return RNA_OK;
   cudaSetDevice(h->device);
   cudaStreamSynchronize(h->stream);
-  DevBuf* bufs[] = {&h->ws, &h->counters, &h->order, &h->b_bases, &h->b_offsets, &h->b_bppoff, &h->b_gammas,
+  DevBuf* bufs[] = {&h->ws, &h->counters, &h->order, &h->stream_ws, &h->b_bases, &h->b_offsets, &h->b_bppoff, &h->b_gammas,
                     &h->b_logz, &h->b_bpp, &h->b_structs, &h->b_ea, &h->b_pairs, &h->b_probs, &h->b_proboff};
   for (DevBuf* b : bufs) free_buf(*b);
   cudaFree(h->d_turner); cudaFree(h->d_contra); cudaFree(h->d_align);
@@ -325,6 +325,32 @@ static int launch_fold_model(rna_handle* h, const RnaFoldBatchDev* b, cudaStream
     }
   }
   if (ws_floats) TRY(ensure(h, h->ws, ws_floats * 4));
+  // v2 shared-memory buckets: grid size and the per-CTA slots of the two-loop term streams
+  std::vector<size_t> stream_stride_of(buckets.size(), 0);
+  std::vector<uint32_t> tcap_of(buckets.size(), 0);
+  static const bool no_streams = getenv("RNA_FOLD_NOSTREAMS") != nullptr;   // A/B switch
+  size_t stream_bytes = 0;
+  if (v2) {
+    for (size_t k = 0; k < buckets.size(); k++) {
+      const Bucket& bk = buckets[k];
+      if (bk.mode != MODE_SMEM) continue;
+      const Roles ro = fold2_roles(bk.Lcap, CONTRA, 16);
+      const int nt = 32 * (ro.nX + ro.nY + ro.nZ);
+      const size_t smem = smem_need(bk.Lcap);
+      int occ = 1;
+      TRY(set_smem_attr(h, fold_kernel2<CONTRA, MODE_SMEM>, smem));
+      CU(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fold_kernel2<CONTRA, MODE_SMEM>, nt, smem));
+      grid_of[k] = (int)std::min<size_t>(bk.end - bk.begin, (size_t)std::max(1, occ) * h->sm_count);
+      if (!no_streams) {
+        // room for 128 stream elements per cell (random sequences need ~50 incl. padding); sequences with longer
+        // lists score on the fly
+        tcap_of[k] = (uint32_t)(128 * ((size_t)bk.Lcap * (bk.Lcap + 1) / 2));
+        stream_stride_of[k] = fold2_stream_bytes(bk.Lcap, tcap_of[k]);
+        stream_bytes = std::max(stream_bytes, (size_t)grid_of[k] * stream_stride_of[k]);
+      }
+    }
+    if (stream_bytes) TRY(ensure(h, h->stream_ws, stream_bytes));
+  }
 
   FoldArgs a;
   memset(&a, 0, sizeof a);
@@ -345,6 +371,9 @@ static int launch_fold_model(rna_handle* h, const RnaFoldBatchDev* b, cudaStream
   a.out_npairs = b->d_out_num_pairs;
   a.workspace = (float*)h->ws.p;
 
+  static const bool dbg_roles = getenv("RNA_FOLD_DBG") != nullptr;
+  long long* d_dbg = nullptr;
+  if (dbg_roles) { cudaMalloc(&d_dbg, 2048 * 16 * 8); cudaMemset(d_dbg, 0, 2048 * 16 * 8); a.dbg = d_dbg; }
   for (size_t k = 0; k < buckets.size(); k++) {
     const Bucket& bk = buckets[k];
     a.order = (const uint32_t*)h->order.p + bk.begin;
@@ -356,13 +385,16 @@ static int launch_fold_model(rna_handle* h, const RnaFoldBatchDev* b, cudaStream
       const Roles ro = fold2_roles(bk.Lcap, CONTRA, 16);
       a.nXw = ro.nX; a.nYw = ro.nY; a.nZw = ro.nZ;
       const int nt = 32 * (ro.nX + ro.nY + ro.nZ);
+      a.stream_ws = nullptr;
       if (bk.mode == MODE_SMEM) {
         const size_t smem = smem_need(bk.Lcap);
-        int occ = 1;
         TRY(set_smem_attr(h, fold_kernel2<CONTRA, MODE_SMEM>, smem));
-        CU(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fold_kernel2<CONTRA, MODE_SMEM>, nt, smem));
-        const int grid = (int)std::min<size_t>(a.n_launch, (size_t)std::max(1, occ) * h->sm_count);
-        fold_kernel2<CONTRA, MODE_SMEM><<<grid, nt, smem, st>>>(a);
+        if (stream_stride_of[k]) {
+          a.tcap = tcap_of[k];
+          a.stream_stride = stream_stride_of[k];
+          a.stream_ws = (unsigned char*)h->stream_ws.p;
+        }
+        fold_kernel2<CONTRA, MODE_SMEM><<<grid_of[k], nt, smem, st>>>(a);
       } else {
         const size_t smem = fold2_fixed_bytes<CONTRA>(bk.Lcap);
         TRY(set_smem_attr(h, fold_kernel2<CONTRA, MODE_GLOBAL>, smem));
@@ -412,7 +444,38 @@ static int launch_fold_model(rna_handle* h, const RnaFoldBatchDev* b, cudaStream
     }
     CU(h, cudaGetLastError());
     h->stats.kernel_launches++;
+    if (dbg_roles && k == 0) {   // debug aid: where do the cycles of one sequence go, per role and pass
+      cudaStreamSynchronize(st);
+      std::vector<long long> hd(2048 * 16);
+      cudaMemcpy(hd.data(), d_dbg, hd.size() * 8, cudaMemcpyDeviceToHost);
+      for (int pass = 0; pass < 2; pass++) {
+        long long role[3] = {0, 0, 0}, crit = 0, critrole[3] = {0, 0, 0};
+        for (int t = 0; t < 1024; t++) {
+          long long m[3] = {0, 0, 0};
+          for (int wv = 0; wv < 16; wv++) {
+            const int r = wv < a.nXw ? 0 : wv < a.nXw + a.nYw ? 1 : 2;
+            m[r] = std::max(m[r], hd[(size_t)(pass * 1024 + t) * 16 + wv]);
+          }
+          const long long mx = std::max(m[0], std::max(m[1], m[2]));
+          crit += mx;
+          for (int r = 0; r < 3; r++) { role[r] += m[r]; if (m[r] == mx && mx) critrole[r] += mx; }
+        }
+        fprintf(stderr, "[RNA_FOLD_DBG] bucket Lcap=%d pass=%s roles X/Y/Z warps %d/%d/%d: sum of per-step max cycles X=%lld Y=%lld Z=%lld, "
+                "critical path=%lld (X %lld, Y %lld, Z %lld)\n", bk.Lcap, pass ? "outside" : "inside", a.nXw, a.nYw, a.nZw,
+                role[0], role[1], role[2], crit, critrole[0], critrole[1], critrole[2]);
+      }
+      for (int t = 1024; t < 2040; t++) {
+        long long my = 0, mx = 0;
+        for (int wv = 0; wv < 16; wv++) { (wv < a.nXw ? mx : my) = std::max(wv < a.nXw ? mx : my, hd[(size_t)t * 16 + wv]); }
+        if (my > 200000) fprintf(stderr, "[RNA_FOLD_DBG]   outside d=%d: X=%lld Y=%lld\n", t - 1024, mx, my);
+      }
+      fprintf(stderr, "[RNA_FOLD_DBG]   setup=%lld count=%lld scan=%lld fill=%lld cycles, terms=%lld\n", hd[2040 * 16], hd[2040 * 16 + 1],
+              hd[2040 * 16 + 2], hd[2040 * 16 + 3], hd[2040 * 16 + 4]);
+      if (!hd[2040 * 16 + 3]) fprintf(stderr, "[RNA_FOLD_DBG]   (streams did not fit: scored on the fly)\n");
+      cudaMemset(d_dbg, 0, 2048 * 16 * 8);
+    }
   }
+  if (d_dbg) cudaFree(d_dbg);
   return RNA_OK;
 }
 

@@ -18,12 +18,14 @@ struct TurnerView {
   const TurnerSmall* sm;     // shared copy (per-lane gathers)
 };
 
-RNA_DEV float t_pen(const TurnerView& T, int x, int y) {
+template <class TV>
+RNA_DEV float t_pen(const TV& T, int x, int y) {
   return augu_pair(x, y) ? T.g->augu_pen : 0.f;
 }
 
 // get_hairpin_score, src/utils.rs:166-196 (special-loop scan :198-205 via packed keys)
-RNA_DEV float t_hairpin(const TurnerView& T, const uint8_t* s, int i, int j) {
+template <class TV>
+RNA_DEV float t_hairpin(const TV& T, const uint8_t* s, int i, int j) {
   const int span = j - i + 1;
   if (span < 32 && ((T.g->special_len_mask >> span) & 1u)) {
     unsigned key = 0;
@@ -72,14 +74,16 @@ RNA_DEV float t_twoloop(const TurnerView& T, const uint8_t* s, int i, int j, int
 }
 
 // get_multibranch_close_score, src/utils.rs:368-382
-RNA_DEV float t_mbclose(const TurnerView& T, const uint8_t* s, int i, int j) {
+template <class TV>
+RNA_DEV float t_mbclose(const TV& T, const uint8_t* s, int i, int j) {
   const int si = s[i], sj = s[j];
   const float tm = T.sm->tm_multi[idx4(sj, si, s[j - 1], s[i + 1])];
   return __fadd_rn(__fadd_rn(T.g->init_mb_base, tm), t_pen(T, si, sj));
 }
 
 // get_accessible_score (uses_sentinel_bases = false), src/utils.rs:384-411
-RNA_DEV float t_acc(const TurnerView& T, const uint8_t* s, int L, int i, int j) {
+template <class TV>
+RNA_DEV float t_acc(const TV& T, const uint8_t* s, int L, int i, int j) {
   const int si = s[i], sj = s[j];
   float sc;
   if (i > 0 && j < L - 1) sc = T.sm->tm_multi[idx4(si, sj, s[i - 1], s[j + 1])];

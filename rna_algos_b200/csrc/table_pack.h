@@ -70,6 +70,22 @@ static inline int pack_turner(const RnaTurnerTables* t, DevTurner* d, std::vecto
   memcpy(d->small.tm_multi, t->terminal_mismatch_scores_multibranch, 1024);
   memcpy(d->small.d5, t->dangling_scores_5prime, 256);
   memcpy(d->small.d3, t->dangling_scores_3prime, 256);
+  memcpy(d->small2.stack, t->stack_scores, 1024);
+  memcpy(d->small2.tm_hairpin, t->terminal_mismatch_scores_hairpin, 1024);
+  memcpy(d->small2.tm_multi, t->terminal_mismatch_scores_multibranch, 1024);
+  memcpy(d->small2.d5, t->dangling_scores_5prime, 256);
+  memcpy(d->small2.d3, t->dangling_scores_3prime, 256);
+  for (int x = 0; x < 4; x++)
+    for (int y = 0; y < 4; y++)
+      for (int x1 = 0; x1 < 4; x1++)
+        for (int y1 = 0; y1 < 4; y1++) {
+          const int code = (x * 4 + x1) * 16 + (y * 4 + y1);
+          d->small2.tm2[0][code] = t->terminal_mismatch_scores_1xmany[x][y][x1][y1];
+          d->small2.tm2[1][code] = t->terminal_mismatch_scores_2x3[x][y][x1][y1];
+          d->small2.tm2[2][code] = t->terminal_mismatch_scores_interior[x][y][x1][y1];
+        }
+  memcpy(d->small2.ninio, d->interior_init_ninio, sizeof d->small2.ninio);
+  memcpy(d->small2.bulge_init, t->bulge_scores_init, sizeof(float) * 31);
   hp_ext->assign(RNA_HAIRPIN_EXT_LEN, 0.f);
   const int mex = t->min_hairpin_len_extrapolation - 1;
   for (int len = 0; len < RNA_HAIRPIN_EXT_LEN; len++) {
@@ -117,25 +133,25 @@ static inline int pack_contra(const RnaContraTables* t, DevContra* d, std::strin
   memcpy(d->small.int1x1, t->interior_scores_1x1, 64);
   // ---- v2 combinations --------------------------------------------------------------------------
   ContraSmall2& s2 = d->small2;
-  memcpy(s2.stack, t->stack_scores, 1024);
   memcpy(s2.dl, t->dangling_scores_left, 256);
   memcpy(s2.dr, t->dangling_scores_right, 256);
   memcpy(s2.hc, t->helix_close_scores, 64);
   memcpy(s2.bp, t->basepair_scores, 64);
   for (int x = 0; x < 4; x++)
     for (int y = 0; y < 4; y++)
-      for (int p = 0; p < 4; p++)
-        for (int q = 0; q < 4; q++)   // get_junction_score_single, src/utils.rs:545-548
-          s2.js[((x * 4 + y) * 4 + p) * 4 + q] = f32_add(t->helix_close_scores[x][y], t->terminal_mismatch_scores[x][y][p][q]);
+      for (int x1 = 0; x1 < 4; x1++)
+        for (int y1 = 0; y1 < 4; y1++)   // get_junction_score_single, src/utils.rs:545-548
+          s2.js2[(x * 4 + x1) * 16 + (y * 4 + y1)] = f32_add(t->helix_close_scores[x][y], t->terminal_mismatch_scores[x][y][x1][y1]);
   const int me = t->max_interior_explicit;
+  memcpy(s2.U, t->stack_scores, 1024);
   for (int x = 0; x < 4; x++)       // src/utils.rs:464-474: score(0x1) + bulge_cum[len-1], len == 1
-    s2.b1[x] = f32_add(t->bulge_scores_0x1[x], t->bulge_scores_len_cumulative[0]);
+    s2.U[RNA_CU_B1 + x] = f32_add(t->bulge_scores_0x1[x], t->bulge_scores_len_cumulative[0]);
   for (int x = 0; x < 4; x++)
     for (int y = 0; y < 4; y++) {   // src/utils.rs:495-514 with loop_len_pair == (1,1)
       float v = f32_add(t->interior_scores_1x1[x][y], t->interior_scores_symmetric_cumulative[0]);
       v = f32_add(v, me >= 1 ? t->interior_scores_explicit[0][0] : 0.f);
       v = f32_add(v, t->interior_scores_len_cumulative[0]);
-      s2.i11[x * 4 + y] = v;
+      s2.U[RNA_CU_I11 + x * 4 + y] = v;
     }
   for (int a = 0; a < 31; a++)
     for (int b = 0; b < 31; b++) {
@@ -151,7 +167,7 @@ static inline int pack_contra(const RnaContraTables* t, DevContra* d, std::strin
           v = f32_add(v, t->interior_scores_len_cumulative[len - 2]);
         }
       }
-      d->ptab[a * 31 + b] = v;
+      s2.U[RNA_CU_PTAB + a * 31 + b] = v;
     }
   return RNA_OK;
 }

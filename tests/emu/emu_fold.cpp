@@ -17,7 +17,7 @@ using namespace rna;
 namespace {
 template <bool CONTRA>
 int run(const uint8_t* seq, int L, int allows_short, const typename Model2<CONTRA>::Dev* dev, int nX, int nY, int nZ,
-        int order, float* out_bpp, float* out_logz) {
+        int order, int tcap, float* out_bpp, float* out_logz) {
   typedef typename Model2<CONTRA>::View View;
   View T;
   T.g = dev;
@@ -37,13 +37,36 @@ int run(const uint8_t* seq, int L, int allows_short, const typename Model2<CONTR
   v.s = sbuf.data() + 4;
   std::vector<uint32_t> mask((size_t)L * v.W2);
   std::vector<uint16_t> plist(TRI), pcnt(L);
+  std::vector<uint8_t> RR(L), LL(L);
   std::vector<float> C(TRI, NEG), R(TRI, NEG), X(TRI, NEG), E(TRI, 0.f), M1(TRI, NEG), Mroll(3 * L, NEG), E0(L), EL(L);
-  v.mask = mask.data(); v.plist = plist.data(); v.pcnt = pcnt.data();
+  v.mask = mask.data(); v.plist = plist.data(); v.pcnt = pcnt.data(); v.RR = RR.data(); v.LL = LL.data();
   v.C = C.data(); v.R = R.data(); v.X = X.data(); v.E = E.data(); v.M1 = M1.data(); v.Mroll = Mroll.data();
   v.E0 = E0.data(); v.EL = EL.data();
   // setup (two barriers in the kernel: masks, then lists)
   for (int x = 0; x < L * v.W2; x++) setup_mask_word<CONTRA>(v, P, x);
+  for (int p = 0; p < L; p++) setup_codes(v, p);
   for (int d = 0; d < L; d++) setup_list_diag(v, d);
+  // term streams (tcap: -1 unbounded, 0 = score on the fly (the kernel's fallback), n = streams if they fit)
+  const int nt = nX + nY + nZ, ntr = (nt + 31) / 32 * 32;
+  std::vector<uint32_t> gcum(L + 1);
+  v.gcum = gcum.data();
+  setup_gcum(v);
+  const uint32_t NG = gcum[L];
+  std::vector<uint32_t> gbin(NG + 1, 0), gbout(NG + 1, 0);
+  std::vector<uint16_t> ccnt(2 * (size_t)TRI + 2, 0);
+  std::vector<uint2> tin, tout;
+  v.tin = nullptr; v.tout = nullptr; v.gbin = gbin.data(); v.gbout = gbout.data(); v.ccnt = ccnt.data(); v.tcap = 0;
+  if (tcap != 0) {
+    for (int l = 0; l < nt; l++) stream_count(v, P, l, nt);
+    for (int l = nt - 1; l >= 0; l--) stream_groupmax(v, l, nt);
+    stream_scan(v);
+    if (tcap < 0 || (gbin[NG] <= (uint32_t)tcap && gbout[NG] <= (uint32_t)tcap)) {
+      tin.assign(gbin[NG] + 1, make_uint2(0xdeadbeefu, 0x7fffffffu));    // poison: every element must be written
+      tout.assign(gbout[NG] + 1, make_uint2(0xdeadbeefu, 0x7fffffffu));
+      v.tin = tin.data(); v.tout = tout.data();
+      for (int l = ntr - 1; l >= 0; l--) stream_fill<CONTRA>(v, T, P, l, ntr);
+    }
+  }
   auto lanes = [&](int n, auto&& fn) {
     if (order == 0) for (int l = 0; l < n; l++) fn(l);
     else for (int l = n - 1; l >= 0; l--) fn(l);
@@ -80,13 +103,13 @@ int run(const uint8_t* seq, int L, int allows_short, const typename Model2<CONTR
 }  // namespace
 
 extern "C" int emu_fold(const uint8_t* seq, int L, int contra, int allows_short, const RnaTurnerTables* tt,
-                        const RnaContraTables* ct, int nX, int nY, int nZ, int order, float* out_bpp,
+                        const RnaContraTables* ct, int nX, int nY, int nZ, int order, int tcap, float* out_bpp,
                         float* out_logz) {
   std::string err;
   if (contra) {
     static DevContra d;   // big struct: keep off the stack
     if (pack_contra(ct, &d, &err)) return 1;
-    return run<true>(seq, L, allows_short, &d, nX, nY, nZ, order, out_bpp, out_logz);
+    return run<true>(seq, L, allows_short, &d, nX, nY, nZ, order, tcap, out_bpp, out_logz);
   }
   static DevTurner d;
   std::vector<float> hp;
@@ -95,5 +118,5 @@ extern "C" int emu_fold(const uint8_t* seq, int L, int contra, int allows_short,
   d.int11 = &tt->interior_scores_1x1[0][0][0][0][0][0];
   d.int12 = &tt->interior_scores_1x2[0][0][0][0][0][0][0];
   d.int22 = &tt->interior_scores_2x2[0][0][0][0][0][0][0][0];
-  return run<false>(seq, L, allows_short, &d, nX, nY, nZ, order, out_bpp, out_logz);
+  return run<false>(seq, L, allows_short, &d, nX, nY, nZ, order, tcap, out_bpp, out_logz);
 }

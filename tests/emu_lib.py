@@ -29,15 +29,16 @@ class Emu:
         self.lib = C.CDLL(LIB)
         self.lib.emu_fold.restype = C.c_int
         self.lib.emu_fold.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(TurnerTables),
-                                      C.POINTER(ContraTables), C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p,
+                                      C.POINTER(ContraTables), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p,
                                       C.POINTER(C.c_float)]
 
-    def fold(self, seq, contra, allows_short, tt, ct, nX=32, nY=64, nZ=64, order=0):
+    def fold(self, seq, contra, allows_short, tt, ct, nX=32, nY=64, nZ=64, order=0, tcap=-1):
+        """tcap: -1 = term streams (unbounded), 0 = scores on the fly, n = streams if they fit n terms."""
         seq = np.ascontiguousarray(seq, dtype=np.uint8)
         L = seq.shape[0]
         bpp = np.empty(L * (L - 1) // 2, dtype=np.float32)
         logz = C.c_float()
         rc = self.lib.emu_fold(seq.ctypes.data, L, int(contra), int(allows_short), C.byref(tt), C.byref(ct), nX, nY, nZ,
-                               order, bpp.ctypes.data, C.byref(logz))
+                               order, tcap, bpp.ctypes.data, C.byref(logz))
         assert rc == 0
         return bpp, np.float32(logz.value)

@@ -56,6 +56,15 @@ def test_random_tables(emu, oracle, seed, contra):
     check(emu, oracle, seqs, contra, False, rt, rc, order=seed % 2)
 
 
+@pytest.mark.parametrize("contra", [False, True])
+def test_on_the_fly_fallback(emu, oracle, contra):
+    """tcap = 0: no term streams (two-loop scores computed inside the chains); tcap = 1000: some sequences
+    fit their stream slot, some fall back."""
+    tt, ct, _ = default_tables()
+    check(emu, oracle, load_trnas()[:2] + random_seqs(5, [12, 40]), contra, False, tt, ct, tcap=0)
+    check(emu, oracle, random_seqs(6, [20, 30, 60, 90]), contra, False, tt, ct, tcap=1000, order=1)
+
+
 def test_mid_length(emu, oracle):
     tt, ct, _ = default_tables()
     check(emu, oracle, random_seqs(31, [150, 260]), True, False, tt, ct, nX=64, nY=128, nZ=128)
