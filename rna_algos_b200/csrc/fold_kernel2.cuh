@@ -50,7 +50,7 @@ __host__ __device__ inline size_t fold2_stream_bytes(int Lcap, uint32_t tcap) {
 struct Roles { int nX, nY, nZ; };   // warps per role
 __host__ __device__ inline Roles fold2_roles(int Lcap, bool contra, int max_warps) {
   Roles r;
-  r.nX = (Lcap + 63) / 64;
+  r.nX = (Lcap + 39) / 40;   // two diagonals of closable cells (~0.37 L each) per step
   r.nZ = (Lcap + 31) / 32;
   r.nY = contra ? r.nZ : 0;
   while (r.nX + r.nY + r.nZ > max_warps) {       // long sequences: strided roles
@@ -146,7 +146,7 @@ __global__ void __launch_bounds__(512) fold_kernel2(const FoldArgs a) {
     __syncthreads();
     for (int d = tid; d < L; d += nt) setup_list_diag(v, d);
     __syncthreads();
-    if (dbg_on && tid == 0) { a.dbg[2040 * 16 + 0] = clock64() - tc0; tc0 = clock64(); }
+    if (dbg_on && tid == 0) { a.dbg[2047 * 16 + 0] = clock64() - tc0; tc0 = clock64(); }
     // ---- two-loop term streams: count, group maxima, scan, fill (all threads; fold_phases.cuh "term streams")
     if (a.stream_ws) {
       if (tid == 0) setup_gcum(v);
@@ -158,7 +158,7 @@ __global__ void __launch_bounds__(512) fold_kernel2(const FoldArgs a) {
       __syncthreads();
       if (tid == 0) stream_scan(v);
       __syncthreads();
-      if (dbg_on && tid == 0) { a.dbg[2040 * 16 + 1] = clock64() - tc0; tc0 = clock64(); }
+      if (dbg_on && tid == 0) { a.dbg[2047 * 16 + 1] = clock64() - tc0; tc0 = clock64(); }
       const uint32_t NG = v.gcum[L];
       if (v.gbin[NG] <= a.tcap && v.gbout[NG] <= a.tcap) {   // else: does not fit its slot, score on the fly
         unsigned char* sw = a.stream_ws + (size_t)blockIdx.x * a.stream_stride;
@@ -167,24 +167,32 @@ __global__ void __launch_bounds__(512) fold_kernel2(const FoldArgs a) {
         stream_fill<CONTRA>(v, T, P, tid, nt);
       }
       __syncthreads();
-      if (dbg_on && tid == 0) { a.dbg[2040 * 16 + 3] = clock64() - tc0; a.dbg[2040 * 16 + 4] = v.gbin[NG]; }
+      if (dbg_on && tid == 0) { a.dbg[2047 * 16 + 3] = clock64() - tc0; a.dbg[2047 * 16 + 4] = v.gbin[NG]; }
     }
     for (int x = tid; x < TRI; x += nt) { v.C[x] = NEG; v.R[x] = NEG; v.X[x] = NEG; v.E[x] = 0.f; v.M1[x] = NEG; }
     for (int x = tid; x < 3 * L; x += nt) v.Mroll[x] = NEG;
     __syncthreads();
 
-    // ================================ inside: step t = X(t) | Y(t) | Z(t-1) ==============================
+    // ================================ inside, pair steps ================================================
+    // phase 1: X = two-loop parts of sums_close(t), (t+1)  |  Z(t-2), Y(t-1); bar(Y,Z); Z(t-1), Y(t)
+    // phase 2: X = closing multibranch terms of (t), (t+1)
     const int d_in0 = CONTRA ? 0 : (P.MINSPAN - 1);
-    for (int t = d_in0; t <= L; t++) {
+    const int nYZl = nYl + nZl;
+    for (int t = d_in0; t <= L + 1; t += 2) {
       const long long c0 = dbg_on ? clock64() : 0;
       if (warp < a.nXw) {
-        if (t < L) inside_X<CONTRA>(v, T, lut, P, t, tid, nXl);
-      } else if (warp < a.nXw + a.nYw) {
-        if constexpr (CONTRA) { if (t < L) inside_Y_contra(v, T, lut, t, tid - nXl, nYl); }
+        inside_X<CONTRA>(v, T, lut, P, t, tid, nXl);
       } else {
-        if (t - 1 >= d_in0) inside_Z<CONTRA>(v, T, lut, t - 1, tid - nXl - nYl, nZl);
+        const bool isY = warp < a.nXw + a.nYw;
+        if (isY) { if constexpr (CONTRA) { if (t - 1 >= d_in0 && t - 1 < L) inside_Y_contra(v, T, lut, t - 1, tid - nXl, nYl); } }
+        else if (t - 2 >= d_in0 && t - 2 < L) inside_Z<CONTRA>(v, T, lut, t - 2, tid - nXl - nYl, nZl);
+        asm volatile("bar.sync 1, %0;" ::"r"(nYZl) : "memory");
+        if (isY) { if constexpr (CONTRA) { if (t < L) inside_Y_contra(v, T, lut, t, tid - nXl, nYl); } }
+        else if (t - 1 >= d_in0 && t - 1 < L) inside_Z<CONTRA>(v, T, lut, t - 1, tid - nXl - nYl, nZl);
       }
       if (dbg_on && (tid & 31) == 0) a.dbg[(size_t)t * 16 + warp] = clock64() - c0;
+      __syncthreads();
+      if (warp < a.nXw) inside_X_fin<CONTRA>(v, T, lut, t, tid, nXl);
       __syncthreads();
     }
 
@@ -199,11 +207,21 @@ __global__ void __launch_bounds__(512) fold_kernel2(const FoldArgs a) {
     if (tid == 0 && a.out_logz) a.out_logz[sidx] = Z;
     __syncthreads();
     const int d_out0 = CONTRA ? (a.allows_short ? 1 : P.MINSPAN - 1) : (P.MINSPAN - 1);
-    for (int d = L - 1; d >= d_out0; d--) {
+    // pair steps.  phase 1: X = exterior + two-loop parts of log P(d), (d-1)  |  Y = probs_multibranch(2) of d+1, d
+    //             phase 2: X = multiloop parts
+    for (int d = L - 1; d >= d_out0; d -= 2) {
       const long long c0 = dbg_on ? clock64() : 0;
-      if (warp < a.nXw) outside_X<CONTRA>(v, T, lut, P, Z, d, tid, nXl);
-      else outside_Y<CONTRA>(v, T, lut, d, tid - nXl, nYl + nZl);
+      if (warp < a.nXw) {
+        outside_X<CONTRA>(v, T, lut, P, Z, d, d_out0, tid, nXl);
+      } else {
+        if (d + 1 < L) outside_Y<CONTRA>(v, T, lut, d + 1, tid - nXl, nYZl);
+        outside_Y<CONTRA>(v, T, lut, d, tid - nXl, nYZl);
+      }
       if (dbg_on && (tid & 31) == 0) a.dbg[(size_t)(1024 + d) * 16 + warp] = clock64() - c0;
+      __syncthreads();
+      const long long c1 = dbg_on ? clock64() : 0;
+      if (warp < a.nXw) outside_X_ml<CONTRA>(v, T, lut, d, d_out0, tid, nXl);
+      if (dbg_on && (tid & 31) == 0 && warp < a.nXw) a.dbg[(size_t)(1024 + d) * 16 + 8 + warp] = clock64() - c1;
       __syncthreads();
     }
 

@@ -531,31 +531,50 @@ RNA_DEV float stream_chain(const SV& v, const uint2* __restrict__ st, uint32_t w
 // Needs: sums_close of diagonals <= d-2, sums_multibranch of diagonal d-2.
 // =========================================================================================================
 template <bool CONTRA, class SV>
-RNA_DEV void inside_X(const SV& v, const typename Model2<CONTRA>::View& T, const float4* lut,
-                      const ModelParams& P, int d, int lane, int nl) {
+RNA_DEV void inside_X_cell(const SV& v, const typename Model2<CONTRA>::View& T, const float4* lut,
+                           const ModelParams& P, int d, int r) {
   const int L = v.L;
   const uint8_t* s = v.s;
   const float NEG = RNA_NEG_INF;
   const int cnt = v.pcnt[d], od = doff(d, L);
-  const float* Mm2 = v.Mroll + ((d + 1) % 3) * L;   // diagonal d-2
-  for (int r = lane; r < cnt; r += nl) {
-    const int i = v.plist[od + r], j = i + d;
-    float sum = NEG;
-    if constexpr (CONTRA) {
-      if (d - 1 <= P.MAX2) sum = lse(sum, c2_hairpin(T, s, i, j), lut);
-    } else {
-      sum = lse(sum, t_hairpin(T, s, i, j), lut);
-    }
-    if (v.tin) {
-      const uint32_t G = v.gcum[d] + (r >> 5), gb = v.gbin[G], wd = group_width(cnt, r >> 5);
-      sum = stream_chain<true>(v, v.tin + gb + (r & 31), wd, (v.gbin[G + 1] - gb) / wd, lut, 0.f, sum);
-    } else {
-      typename LoopOf<CONTRA, true>::type lp = make_loop<CONTRA, true>(v, T, i, j);
-      sum = twoloop_chain<true>(v, lp, lut, P.MAX2, i, j, 0.f, sum);
-    }
-    const float mb = (d >= 2) ? Mm2[i + 1] : NEG;
-    sum = lse(sum, __fadd_rn(mb, v2_mbclose<CONTRA>(T, s, L, i, j)), lut);
-    if (sum > NEG) v.C[od + i] = sum;
+  const int i = v.plist[od + r], j = i + d;
+  float sum = NEG;
+  if constexpr (CONTRA) {
+    if (d - 1 <= P.MAX2) sum = lse(sum, c2_hairpin(T, s, i, j), lut);
+  } else {
+    sum = lse(sum, t_hairpin(T, s, i, j), lut);
+  }
+  if (v.tin) {
+    const uint32_t G = v.gcum[d] + (r >> 5), gb = v.gbin[G], wd = group_width(cnt, r >> 5);
+    sum = stream_chain<true>(v, v.tin + gb + (r & 31), wd, (v.gbin[G + 1] - gb) / wd, lut, 0.f, sum);
+  } else {
+    typename LoopOf<CONTRA, true>::type lp = make_loop<CONTRA, true>(v, T, i, j);
+    sum = twoloop_chain<true>(v, lp, lut, P.MAX2, i, j, 0.f, sum);
+  }
+  v.C[od + i] = sum;   // still without the multibranch term: no one reads diagonal d before inside_X_fin
+}
+// X, phase 1 of a pair step: hairpin + two-loop part of sums_close for diagonals d and d+1.  Both only need
+// sums_close of diagonals <= d-1, so the two longest chains of the inside pass run side by side.
+template <bool CONTRA, class SV>
+RNA_DEV void inside_X(const SV& v, const typename Model2<CONTRA>::View& T, const float4* lut,
+                      const ModelParams& P, int d, int lane, int nl) {
+  const int c0 = (d < v.L) ? v.pcnt[d] : 0, c1 = (d + 1 < v.L) ? v.pcnt[d + 1] : 0;
+  for (int x = lane; x < c0 + c1; x += nl)   // ONE call site: lanes of both diagonals run the chain together
+    inside_X_cell<CONTRA>(v, T, lut, P, (x < c0) ? d : d + 1, (x < c0) ? x : x - c0);
+}
+// X, phase 2: the closing multibranch term (needs sums_multibranch of d-2 resp. d-1, computed by Z in phase 1)
+template <bool CONTRA, class SV>
+RNA_DEV void inside_X_fin(const SV& v, const typename Model2<CONTRA>::View& T, const float4* lut, int d, int lane,
+                          int nl) {
+  const int L = v.L;
+  const float NEG = RNA_NEG_INF;
+  const int c0 = (d < L) ? v.pcnt[d] : 0, c1 = (d + 1 < L) ? v.pcnt[d + 1] : 0;
+  for (int x = lane; x < c0 + c1; x += nl) {
+    const int dd = (x < c0) ? d : d + 1, r = (x < c0) ? x : x - c0;
+    const int od = doff(dd, L), i = v.plist[od + r], j = i + dd;
+    const float* Mm2 = v.Mroll + ((dd + 1) % 3) * L;   // diagonal dd-2
+    const float mb = (dd >= 2) ? Mm2[i + 1] : NEG;
+    v.C[od + i] = lse(v.C[od + i], __fadd_rn(mb, v2_mbclose<CONTRA>(T, v.s, L, i, j)), lut);
   }
 }
 
@@ -694,45 +713,71 @@ RNA_DEV void outside_Y(const SV& v, const typename Model2<CONTRA>::View& T, cons
 // Needs: log P, probs_multibranch, probs_multibranch2 of diagonals > d.
 // =========================================================================================================
 template <bool CONTRA, class SV>
-RNA_DEV void outside_X(const SV& v, const typename Model2<CONTRA>::View& T, const float4* lut,
-                       const ModelParams& P, float Z, int d, int lane, int nl) {
+RNA_DEV void outside_X_cell(const SV& v, const typename Model2<CONTRA>::View& T, const float4* lut,
+                            const ModelParams& P, float Z, int d, int r) {
   const int L = v.L;
   const uint8_t* s = v.s;
   const float NEG = RNA_NEG_INF;
   const int cnt = v.pcnt[d], od = doff(d, L);
   const typename Model2<CONTRA>::Dev* dev = T.g;
-  for (int r = lane; r < cnt; r += nl) {
-    const int i = v.plist[od + r], j = i + d;
+  const int i = v.plist[od + r], j = i + d;
+  const float Cij = v.C[od + i];
+  if (!(Cij > NEG)) return;
+  const float Aij = __fadd_rn(Cij, v2_acc<CONTRA>(T, s, L, i, j));
+  const float El = (i < 1) ? 0.f : v.E0[i - 1];
+  const float Er = (j > L - 2) ? 0.f : v.EL[j + 1];
+  float sm;
+  if constexpr (CONTRA) sm = __fsub_rn(__fadd_rn(__fadd_rn(__fadd_rn(El, Er), Aij), dev->ext_bp), Z);
+  else sm = __fsub_rn(__fadd_rn(__fadd_rn(El, Aij), Er), Z);
+  // enclosing two-loops: k descending from i-1, l ascending from j+1
+  if (v.tin) {
+    const uint32_t G = v.gcum[d] + (r >> 5), gb = v.gbout[G], wd = group_width(cnt, r >> 5);
+    sm = stream_chain<false>(v, v.tout + gb + (r & 31), wd, (v.gbout[G + 1] - gb) / wd, lut, Cij, sm);
+  } else {
+    typename LoopOf<CONTRA, false>::type lp = make_loop<CONTRA, false>(v, T, i, j);
+    sm = twoloop_chain<false>(v, lp, lut, P.MAX2, i, j, Cij, sm);
+  }
+  v.E[od + i] = sm;   // exterior + two-loop part; outside_X_ml continues the fold
+}
+// X, phase 1 of a pair step: exterior term + enclosing two-loops of log P for diagonals d and d-1: both only
+// need log P of diagonals >= d+1.
+template <bool CONTRA, class SV>
+RNA_DEV void outside_X(const SV& v, const typename Model2<CONTRA>::View& T, const float4* lut,
+                       const ModelParams& P, float Z, int d, int dmin, int lane, int nl) {
+  const int c0 = v.pcnt[d], c1 = (d - 1 >= dmin) ? v.pcnt[d - 1] : 0;
+  for (int x = lane; x < c0 + c1; x += nl)   // ONE call site: lanes of both diagonals run the chain together
+    outside_X_cell<CONTRA>(v, T, lut, P, Z, (x < c0) ? d : d - 1, (x < c0) ? x : x - c0);
+}
+// X, phase 2: enclosing multiloops, k ascending 0..i-1 (needs probs_multibranch(2) of diagonals >= d resp. d+1)
+template <bool CONTRA, class SV>
+RNA_DEV void outside_X_ml(const SV& v, const typename Model2<CONTRA>::View& T, const float4* lut, int d, int dmin,
+                          int lane, int nl) {
+  const int L = v.L;
+  const uint8_t* s = v.s;
+  const float NEG = RNA_NEG_INF;
+  const typename Model2<CONTRA>::Dev* dev = T.g;
+  const int c0 = v.pcnt[d], c1 = (d - 1 >= dmin) ? v.pcnt[d - 1] : 0;
+  for (int x = lane; x < c0 + c1; x += nl) {
+    const int dd = (x < c0) ? d : d - 1, r = (x < c0) ? x : x - c0;
+    const int od = doff(dd, L), i = v.plist[od + r], j = i + dd;
     const float Cij = v.C[od + i];
     if (!(Cij > NEG)) continue;
+    float sm = v.E[od + i];
     const float Aij = __fadd_rn(Cij, v2_acc<CONTRA>(T, s, L, i, j));
-    const float El = (i < 1) ? 0.f : v.E0[i - 1];
-    const float Er = (j > L - 2) ? 0.f : v.EL[j + 1];
-    float sm;
-    if constexpr (CONTRA) sm = __fsub_rn(__fadd_rn(__fadd_rn(__fadd_rn(El, Er), Aij), dev->ext_bp), Z);
-    else sm = __fsub_rn(__fadd_rn(__fadd_rn(El, Aij), Er), Z);
-    // enclosing two-loops: k descending from i-1, l ascending from j+1
-    if (v.tin) {
-      const uint32_t G = v.gcum[d] + (r >> 5), gb = v.gbout[G], wd = group_width(cnt, r >> 5);
-      sm = stream_chain<false>(v, v.tout + gb + (r & 31), wd, (v.gbout[G + 1] - gb) / wd, lut, Cij, sm);
-    } else {
-      typename LoopOf<CONTRA, false>::type lp = make_loop<CONTRA, false>(v, T, i, j);
-      sm = twoloop_chain<false>(v, lp, lut, P.MAX2, i, j, Cij, sm);
-    }
-    // enclosing multiloops: k ascending 0..i-1
     float sa;
     if constexpr (CONTRA) sa = __fadd_rn(Aij, dev->mb_bp); else sa = __fadd_rn(Aij, dev->coeff_num_branches);
     for (int kk = 0; kk < i; kk++) {
       const int m = i - 1 - kk;
       const int q = doff(j - kk, L) + kk;
-      const float x = (m >= 1) ? v.M1[doff(m - 1, L) + kk + 1] : NEG;
+      const float x1 = (m >= 1) ? v.M1[doff(m - 1, L) + kk + 1] : NEG;
       const float p2 = v.X[q], y = v.R[q];
-      sm = lse(sm, __fadd_rn(__fadd_rn(sa, p2), x), lut);
+      sm = lse(sm, __fadd_rn(__fadd_rn(sa, p2), x1), lut);
       if constexpr (CONTRA) sm = lse(sm, __fadd_rn(__fadd_rn(sa, y), __fmul_rn(dev->mb_unpair, (float)m)), lut);
       else sm = lse(sm, __fadd_rn(sa, y), lut);
-      sm = lse(sm, __fadd_rn(__fadd_rn(sa, x), y), lut);
+      sm = lse(sm, __fadd_rn(__fadd_rn(sa, x1), y), lut);
     }
-    if (sm > NEG) v.E[od + i] = sm;
+    if (!(sm > NEG)) sm = NEG;
+    v.E[od + i] = sm;
   }
 }
 

@@ -450,7 +450,7 @@ static int launch_fold_model(rna_handle* h, const RnaFoldBatchDev* b, cudaStream
       cudaMemcpy(hd.data(), d_dbg, hd.size() * 8, cudaMemcpyDeviceToHost);
       for (int pass = 0; pass < 2; pass++) {
         long long role[3] = {0, 0, 0}, crit = 0, critrole[3] = {0, 0, 0};
-        for (int t = 0; t < 1024; t++) {
+        for (int t = 0; t < 1000; t++) {
           long long m[3] = {0, 0, 0};
           for (int wv = 0; wv < 16; wv++) {
             const int r = wv < a.nXw ? 0 : wv < a.nXw + a.nYw ? 1 : 2;
@@ -464,14 +464,14 @@ static int launch_fold_model(rna_handle* h, const RnaFoldBatchDev* b, cudaStream
                 "critical path=%lld (X %lld, Y %lld, Z %lld)\n", bk.Lcap, pass ? "outside" : "inside", a.nXw, a.nYw, a.nZw,
                 role[0], role[1], role[2], crit, critrole[0], critrole[1], critrole[2]);
       }
-      for (int t = 1024; t < 2040; t++) {
+      for (int t = 1024; t < 1024; t++) {
         long long my = 0, mx = 0;
         for (int wv = 0; wv < 16; wv++) { (wv < a.nXw ? mx : my) = std::max(wv < a.nXw ? mx : my, hd[(size_t)t * 16 + wv]); }
         if (my > 200000) fprintf(stderr, "[RNA_FOLD_DBG]   outside d=%d: X=%lld Y=%lld\n", t - 1024, mx, my);
       }
-      fprintf(stderr, "[RNA_FOLD_DBG]   setup=%lld count=%lld scan=%lld fill=%lld cycles, terms=%lld\n", hd[2040 * 16], hd[2040 * 16 + 1],
-              hd[2040 * 16 + 2], hd[2040 * 16 + 3], hd[2040 * 16 + 4]);
-      if (!hd[2040 * 16 + 3]) fprintf(stderr, "[RNA_FOLD_DBG]   (streams did not fit: scored on the fly)\n");
+      fprintf(stderr, "[RNA_FOLD_DBG]   setup=%lld count=%lld scan=%lld fill=%lld cycles, terms=%lld\n", hd[2047 * 16], hd[2047 * 16 + 1],
+              hd[2047 * 16 + 2], hd[2047 * 16 + 3], hd[2047 * 16 + 4]);
+      if (!hd[2047 * 16 + 3]) fprintf(stderr, "[RNA_FOLD_DBG]   (streams did not fit: scored on the fly)\n");
       cudaMemset(d_dbg, 0, 2048 * 16 * 8);
     }
   }

@@ -71,23 +71,34 @@ int run(const uint8_t* seq, int L, int allows_short, const typename Model2<CONTR
     if (order == 0) for (int l = 0; l < n; l++) fn(l);
     else for (int l = n - 1; l >= 0; l--) fn(l);
   };
-  // inside: step t runs X(t) | Y(t) | Z(t-1)
+  // inside, pair step t: phase 1 = X(t, t+1) two-loop parts | [Z(t-2), Y(t-1)] bar [Z(t-1), Y(t)]; phase 2 = X fin
   const int d_in0 = CONTRA ? 0 : (P.MINSPAN - 1);
-  for (int t = d_in0; t <= L; t++) {
-    auto rX = [&] { if (t < L) lanes(nX, [&](int l) { inside_X<CONTRA>(v, T, lut, P, t, l, nX); }); };
-    auto rY = [&] { if constexpr (CONTRA) { if (t < L) lanes(nY, [&](int l) { inside_Y_contra(v, T, lut, t, l, nY); }); } };
-    auto rZ = [&] { if (t - 1 >= d_in0) lanes(nZ, [&](int l) { inside_Z<CONTRA>(v, T, lut, t - 1, l, nZ); }); };
-    if (order == 0) { rX(); rY(); rZ(); } else { rZ(); rY(); rX(); }
+  auto validZ = [&](int d) { return d >= d_in0 && d < L; };
+  for (int t = d_in0; t <= L + 1; t += 2) {
+    auto rX = [&] { lanes(nX, [&](int l) { inside_X<CONTRA>(v, T, lut, P, t, l, nX); }); };
+    auto rZ = [&](int d) { if (validZ(d)) lanes(nZ, [&](int l) { inside_Z<CONTRA>(v, T, lut, d, l, nZ); }); };
+    auto rY = [&](int d) { if constexpr (CONTRA) { if (validZ(d)) lanes(nY, [&](int l) { inside_Y_contra(v, T, lut, d, l, nY); }); } };
+    auto rYZ = [&] {
+      if (order == 0) { rZ(t - 2); rY(t - 1); } else { rY(t - 1); rZ(t - 2); }
+      if (order == 0) { rY(t); rZ(t - 1); } else { rZ(t - 1); rY(t); }
+    };
+    if (order == 0) { rX(); rYZ(); } else { rYZ(); rX(); }
+    lanes(nX, [&](int l) { inside_X_fin<CONTRA>(v, T, lut, t, l, nX); });
   }
   for (int x = 0; x < L; x++) { E0[x] = E[doff(x, L)]; EL[x] = E[doff(L - 1 - x, L) + x]; }
   const float Z = E0[L - 1];
   for (int x = 0; x < TRI; x++) { E[x] = NEG; R[x] = NEG; X[x] = NEG; }
   if (out_logz) *out_logz = Z;
   const int d_out0 = CONTRA ? (allows_short ? 1 : P.MINSPAN - 1) : (P.MINSPAN - 1);
-  for (int d = L - 1; d >= d_out0; d--) {
-    auto rX = [&] { lanes(nX, [&](int l) { outside_X<CONTRA>(v, T, lut, P, Z, d, l, nX); }); };
-    auto rY = [&] { lanes(nY + nZ, [&](int l) { outside_Y<CONTRA>(v, T, lut, d, l, nY + nZ); }); };
+  for (int d = L - 1; d >= d_out0; d -= 2) {
+    auto rX = [&] { lanes(nX, [&](int l) { outside_X<CONTRA>(v, T, lut, P, Z, d, d_out0, l, nX); }); };
+    auto rY = [&] {
+      const int nl = nY + nZ;
+      if (d + 1 < L) lanes(nl, [&](int l) { outside_Y<CONTRA>(v, T, lut, d + 1, l, nl); });
+      lanes(nl, [&](int l) { outside_Y<CONTRA>(v, T, lut, d, l, nl); });
+    };
     if (order == 0) { rX(); rY(); } else { rY(); rX(); }
+    lanes(nX, [&](int l) { outside_X_ml<CONTRA>(v, T, lut, d, d_out0, l, nX); });
   }
   if (out_bpp) {
     for (int i = 0; i < L - 1; i++) {
