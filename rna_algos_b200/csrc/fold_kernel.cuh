@@ -51,7 +51,7 @@ struct FoldArgs {
   unsigned long long ws_stride;   // floats per workspace slot
   int* work_counter;         // MODE_SMEM / MODE_GLOBAL: dynamic work queue
   int Lcap;                  // capacity the shared-memory carve-up was sized for
-  int nXw, nYw, nZw;         // fold_kernel2: warps per role
+  int nXw, nYw, nZw;         // fold_kernel2: warps per role (threads beyond them only help in the all-thread phases)
   unsigned char* stream_ws;  // fold_kernel2: per-CTA slots for the two-loop term streams (null: score on the fly)
   unsigned long long stream_stride;   // bytes per slot
   uint32_t tcap;             // terms per stream a slot can hold

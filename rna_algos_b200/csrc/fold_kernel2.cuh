@@ -34,8 +34,9 @@ __host__ __device__ inline size_t fold2_seq_bytes(int Lcap, size_t pidx_size) {
   b += align16(2 * ((size_t)Lcap + 2) * 4);     // traceback stack
   b += align16((size_t)Lcap * W2 * 4);          // closable bit matrix
   b += align16((size_t)Lcap * 4 + 4);           // pcnt, RR, LL
-  b += align16(((size_t)Lcap + 1) * 4);         // gcum
-  b += align16(2 * (fold2_ngcap(Lcap) + 1) * 4);   // gbin, gbout
+  b += align16(2 * ((size_t)Lcap / 2 + 3) * 4);    // gcumI, gcumO
+  b += align16(2 * (fold2_ngcap(Lcap) + 2) * 4);   // gbin, gbout
+  b += align16(2 * (fold2_ngcap(Lcap) + 2) * 2);   // gstepI, gstepO
   b += align16(T * pidx_size);                  // closable-cell lists
   return align16(b);
 }
@@ -62,7 +63,7 @@ __host__ __device__ inline Roles fold2_roles(int Lcap, bool contra, int max_warp
 }
 
 template <bool CONTRA, int MODE>
-__global__ void __launch_bounds__(512) fold_kernel2(const FoldArgs a) {
+__global__ void __launch_bounds__(512, 2) fold_kernel2(const FoldArgs a) {
   typedef typename Model2<CONTRA>::Dev Dev;
   typedef typename Model2<CONTRA>::Small Small;
   typedef typename Model2<CONTRA>::View View;
@@ -74,7 +75,7 @@ __global__ void __launch_bounds__(512) fold_kernel2(const FoldArgs a) {
   Small* small = reinterpret_cast<Small*>(smem_raw + 128);
   uint8_t* sseq = smem_raw + 128 + align16(sizeof(Small));
   unsigned char* sregion = smem_raw + fold2_fixed_bytes<CONTRA>(a.Lcap);
-  __shared__ int s_work;
+  __shared__ int s_work, s_fill_next;
 
   const Dev* dev = reinterpret_cast<const Dev*>(a.tables);
   const int tid = threadIdx.x, nt = blockDim.x;
@@ -127,10 +128,15 @@ __global__ void __launch_bounds__(512) fold_kernel2(const FoldArgs a) {
     v.EL = f; f += L;
     int* tstack = reinterpret_cast<int*>(f);
     v.mask = reinterpret_cast<uint32_t*>(tstack + 2 * (L + 2));
-    v.gcum = v.mask + L * v.W2;                                  // 4-byte items first, then 2-byte, then bytes
-    v.gbin = v.gcum + L + 1;
-    v.gbout = v.gbin + ngcap + 1;
-    v.pcnt = reinterpret_cast<uint16_t*>(v.gbout + ngcap + 1);
+    v.gcumI = v.mask + L * v.W2;                                 // 4-byte items first, then 2-byte, then bytes
+    v.gcumO = v.gcumI + L / 2 + 3;
+    v.gbin = v.gcumO + L / 2 + 3;
+    v.gbout = v.gbin + ngcap + 2;
+    v.gstepI = reinterpret_cast<uint16_t*>(v.gbout + ngcap + 2);
+    v.gstepO = v.gstepI + ngcap + 2;
+    v.pcnt = v.gstepO + ngcap + 2;
+    v.din0 = CONTRA ? 0 : (P.MINSPAN - 1);
+    v.dout0 = CONTRA ? (a.allows_short ? 1 : P.MINSPAN - 1) : (P.MINSPAN - 1);
     v.plist = reinterpret_cast<PIdx*>(v.pcnt + ((L + 1) & ~1));   // (u8 or u16: 2-byte aligned)
     v.RR = reinterpret_cast<uint8_t*>(v.plist + TRI);
     v.LL = v.RR + L;
@@ -140,6 +146,7 @@ __global__ void __launch_bounds__(512) fold_kernel2(const FoldArgs a) {
     if (tid < 4) { sseq[tid] = 0; s[L + tid] = 0; }
     const bool dbg_on = a.dbg && w == 0;
     long long tc0 = dbg_on ? clock64() : 0;
+    const long long tseq0 = tc0;
     __syncthreads();
     for (int x = tid; x < L * v.W2; x += nt) setup_mask_word<CONTRA>(v, P, x);
     for (int x = tid; x < L; x += nt) setup_codes(v, x);
@@ -149,7 +156,7 @@ __global__ void __launch_bounds__(512) fold_kernel2(const FoldArgs a) {
     if (dbg_on && tid == 0) { a.dbg[2047 * 16 + 0] = clock64() - tc0; tc0 = clock64(); }
     // ---- two-loop term streams: count, group maxima, scan, fill (all threads; fold_phases.cuh "term streams")
     if (a.stream_ws) {
-      if (tid == 0) setup_gcum(v);
+      if (tid == 0) { setup_groups(v); s_fill_next = 0; }
       v.ccnt = reinterpret_cast<uint16_t*>(v.C);   // scratch: 2 x TRI u16 = the not-yet-initialised C matrix
       __syncthreads();
       stream_count(v, P, tid, nt);
@@ -159,15 +166,24 @@ __global__ void __launch_bounds__(512) fold_kernel2(const FoldArgs a) {
       if (tid == 0) stream_scan(v);
       __syncthreads();
       if (dbg_on && tid == 0) { a.dbg[2047 * 16 + 1] = clock64() - tc0; tc0 = clock64(); }
-      const uint32_t NG = v.gcum[L];
-      if (v.gbin[NG] <= a.tcap && v.gbout[NG] <= a.tcap) {   // else: does not fit its slot, score on the fly
+      const uint32_t NGI = v.gcumI[max(num_steps_inside(v), 0)], NGO = v.gcumO[max(num_steps_outside(v), 0)];
+      if (v.gbin[NGI] <= a.tcap && v.gbout[NGO] <= a.tcap) {   // else: does not fit its slot, score on the fly
         unsigned char* sw = a.stream_ws + (size_t)blockIdx.x * a.stream_stride;
         v.tin = reinterpret_cast<uint2*>(sw);
         v.tout = v.tin + a.tcap;
-        stream_fill<CONTRA>(v, T, P, tid, nt);
+        // one group per warp at a time, handed out dynamically, longest partner lists first
+        const uint32_t ntask = NGI + NGO;
+        for (;;) {
+          uint32_t tau = 0;
+          if ((tid & 31) == 0) tau = (uint32_t)atomicAdd(&s_fill_next, 1);
+          tau = __shfl_sync(0xffffffffu, tau, 0);
+          if (tau >= ntask) break;
+          stream_fill_task<CONTRA>(v, T, P, tau, tid & 31);
+          __syncwarp();
+        }
       }
       __syncthreads();
-      if (dbg_on && tid == 0) { a.dbg[2047 * 16 + 3] = clock64() - tc0; a.dbg[2047 * 16 + 4] = v.gbin[NG]; }
+      if (dbg_on && tid == 0) { a.dbg[2047 * 16 + 3] = clock64() - tc0; a.dbg[2047 * 16 + 4] = v.gbin[NGI]; }
     }
     for (int x = tid; x < TRI; x += nt) { v.C[x] = NEG; v.R[x] = NEG; v.X[x] = NEG; v.E[x] = 0.f; v.M1[x] = NEG; }
     for (int x = tid; x < 3 * L; x += nt) v.Mroll[x] = NEG;
@@ -176,13 +192,15 @@ __global__ void __launch_bounds__(512) fold_kernel2(const FoldArgs a) {
     // ================================ inside, pair steps ================================================
     // phase 1: X = two-loop parts of sums_close(t), (t+1)  |  Z(t-2), Y(t-1); bar(Y,Z); Z(t-1), Y(t)
     // phase 2: X = closing multibranch terms of (t), (t+1)
-    const int d_in0 = CONTRA ? 0 : (P.MINSPAN - 1);
+    const int d_in0 = v.din0;
     const int nYZl = nYl + nZl;
-    for (int t = d_in0; t <= L + 1; t += 2) {
+    const bool helper = warp >= a.nXw + a.nYw + a.nZw;   // extra warps: only the all-thread phases (setup, fill, output)
+    for (int st = 0; d_in0 + 2 * st <= L + 1; st++) {
+      const int t = d_in0 + 2 * st;
       const long long c0 = dbg_on ? clock64() : 0;
       if (warp < a.nXw) {
-        inside_X<CONTRA>(v, T, lut, P, t, tid, nXl);
-      } else {
+        inside_X<CONTRA>(v, T, lut, P, st, tid, nXl);
+      } else if (!helper) {
         const bool isY = warp < a.nXw + a.nYw;
         if (isY) { if constexpr (CONTRA) { if (t - 1 >= d_in0 && t - 1 < L) inside_Y_contra(v, T, lut, t - 1, tid - nXl, nYl); } }
         else if (t - 2 >= d_in0 && t - 2 < L) inside_Z<CONTRA>(v, T, lut, t - 2, tid - nXl - nYl, nZl);
@@ -190,9 +208,9 @@ __global__ void __launch_bounds__(512) fold_kernel2(const FoldArgs a) {
         if (isY) { if constexpr (CONTRA) { if (t < L) inside_Y_contra(v, T, lut, t, tid - nXl, nYl); } }
         else if (t - 1 >= d_in0 && t - 1 < L) inside_Z<CONTRA>(v, T, lut, t - 1, tid - nXl - nYl, nZl);
       }
-      if (dbg_on && (tid & 31) == 0) a.dbg[(size_t)t * 16 + warp] = clock64() - c0;
+      if (dbg_on && (tid & 31) == 0 && !helper) a.dbg[(size_t)t * 16 + warp] = clock64() - c0;
       __syncthreads();
-      if (warp < a.nXw) inside_X_fin<CONTRA>(v, T, lut, t, tid, nXl);
+      if (warp < a.nXw) inside_X_fin<CONTRA>(v, T, lut, st, tid, nXl);
       __syncthreads();
     }
 
@@ -206,25 +224,27 @@ __global__ void __launch_bounds__(512) fold_kernel2(const FoldArgs a) {
     for (int x = tid; x < TRI; x += nt) { v.E[x] = NEG; v.R[x] = NEG; v.X[x] = NEG; }
     if (tid == 0 && a.out_logz) a.out_logz[sidx] = Z;
     __syncthreads();
-    const int d_out0 = CONTRA ? (a.allows_short ? 1 : P.MINSPAN - 1) : (P.MINSPAN - 1);
+    const int d_out0 = v.dout0;
     // pair steps.  phase 1: X = exterior + two-loop parts of log P(d), (d-1)  |  Y = probs_multibranch(2) of d+1, d
     //             phase 2: X = multiloop parts
-    for (int d = L - 1; d >= d_out0; d -= 2) {
+    for (int st = 0; L - 1 - 2 * st >= d_out0; st++) {
+      const int d = L - 1 - 2 * st;
       const long long c0 = dbg_on ? clock64() : 0;
       if (warp < a.nXw) {
-        outside_X<CONTRA>(v, T, lut, P, Z, d, d_out0, tid, nXl);
-      } else {
+        outside_X<CONTRA>(v, T, lut, P, Z, st, tid, nXl);
+      } else if (!helper) {
         if (d + 1 < L) outside_Y<CONTRA>(v, T, lut, d + 1, tid - nXl, nYZl);
         outside_Y<CONTRA>(v, T, lut, d, tid - nXl, nYZl);
       }
-      if (dbg_on && (tid & 31) == 0) a.dbg[(size_t)(1024 + d) * 16 + warp] = clock64() - c0;
+      if (dbg_on && (tid & 31) == 0 && !helper) a.dbg[(size_t)(1024 + d) * 16 + warp] = clock64() - c0;
       __syncthreads();
       const long long c1 = dbg_on ? clock64() : 0;
-      if (warp < a.nXw) outside_X_ml<CONTRA>(v, T, lut, d, d_out0, tid, nXl);
+      if (warp < a.nXw) outside_X_ml<CONTRA>(v, T, lut, st, tid, nXl);
       if (dbg_on && (tid & 31) == 0 && warp < a.nXw) a.dbg[(size_t)(1024 + d) * 16 + 8 + warp] = clock64() - c1;
       __syncthreads();
     }
 
+    const long long tpost0 = dbg_on ? clock64() : 0;
     // ================================ BPP = expf(P) =====================================================
     for (int x = tid; x < TRI; x += nt) {
       const float val = v.E[x];
@@ -244,6 +264,7 @@ __global__ void __launch_bounds__(512) fold_kernel2(const FoldArgs a) {
       auto getp = [=](int d, int i) -> float { return Pm[doff(d, L) + i]; };
       centroid_run<MODE>(a, sidx, sbeg, L, v.R, tstack, getp);
     }
+    if (dbg_on && tid == 0) { a.dbg[2047 * 16 + 5] = clock64() - tpost0; a.dbg[2047 * 16 + 6] = clock64() - tseq0; a.dbg[2047 * 16 + 7] = L; }
   }
 }
 

@@ -43,9 +43,15 @@ struct SeqViewT {
   uint8_t* RR;            // [L] base codes s[p]*4 + s[p+1]   (s[L] = 0)
   uint8_t* LL;            // [L] base codes s[p]*4 + s[p-1]   (s[-1] = 0)
   // static two-loop term streams (global memory, see "term streams" below); tin == null => scored on the fly
-  uint32_t* gcum;         // [L+1] lane groups (32 consecutive closable cells of a diagonal) on diagonals < d
-  uint32_t* gbin;         // [NG+1] first element of each group's block in tin
-  uint32_t* gbout;        // [NG+1] ... in tout
+  int din0, dout0;        // first diagonal of the inside pass / last diagonal of the outside pass
+  // A STEP of a pass handles two diagonals: inside step s = (din0+2s, din0+2s+1), outside step s = (L-1-2s, L-2-2s).
+  // The closable cells of a step, diagonal A first, are cut into lane GROUPS of 32 (the lanes of one warp).
+  uint32_t* gcumI;        // [NS+1] groups before inside step s
+  uint32_t* gcumO;        // [NS+1] groups before outside step s
+  uint16_t* gstepI;       // [NG] step of an inside group
+  uint16_t* gstepO;       // [NG] step of an outside group
+  uint32_t* gbin;         // [NG+1] first element of each inside group's block in tin
+  uint32_t* gbout;        // [NG+1] ... of each outside group's block in tout
   uint2* tin;             // closing-pair-major: terms of the inside chains, lane-interleaved per group
   uint2* tout;            // enclosed-pair-major: terms of the outside chains
   uint16_t* ccnt;         // scratch [2][L(L+1)/2]: terms per closable cell (indexed like plist)
@@ -90,12 +96,54 @@ RNA_DEV void setup_mask_word(const SV& v, const ModelParams& P, int x) {
   v.mask[x] = bits;
 }
 
-// group base of every diagonal (serial over L entries: one thread)
+// the two diagonals of a step and their closable-cell counts
+struct StepCells { int dA, dB, cA, cB; };
+template <bool INSIDE, class SV>
+RNA_DEV StepCells step_cells(const SV& v, int st) {
+  StepCells c;
+  if (INSIDE) {
+    c.dA = v.din0 + 2 * st; c.dB = c.dA + 1;
+    c.cA = (c.dA < v.L) ? v.pcnt[c.dA] : 0;
+    c.cB = (c.dB < v.L) ? v.pcnt[c.dB] : 0;
+  } else {
+    c.dA = v.L - 1 - 2 * st; c.dB = c.dA - 1;
+    c.cA = (c.dA >= v.dout0) ? v.pcnt[c.dA] : 0;
+    c.cB = (c.dB >= v.dout0) ? v.pcnt[c.dB] : 0;
+  }
+  return c;
+}
+template <class SV> RNA_DEV int num_steps_inside(const SV& v) { return (v.L - v.din0 + 1) / 2; }
+template <class SV> RNA_DEV int num_steps_outside(const SV& v) { return (v.L - v.dout0 + 1) / 2; }
+// x-th cell of a step -> (diagonal, rank on the diagonal)
+RNA_DEV void step_cell(const StepCells& c, int x, int& dd, int& r) {
+  const bool first = x < c.cA;
+  dd = first ? c.dA : c.dB;
+  r = first ? x : x - c.cA;
+}
+RNA_DEV uint32_t group_width(int tot, int c) { return (uint32_t)min(32, tot - 32 * c); }
+
+// group bases of every step (serial over <= L entries: one thread)
 template <class SV>
-RNA_DEV void setup_gcum(const SV& v) {
+RNA_DEV void setup_groups(const SV& v) {
   uint32_t run = 0;
-  for (int d = 0; d < v.L; d++) { v.gcum[d] = run; run += (v.pcnt[d] + 31u) >> 5; }
-  v.gcum[v.L] = run;
+  const int nsi = max(num_steps_inside(v), 0), nso = max(num_steps_outside(v), 0);
+  for (int st = 0; st < nsi; st++) {
+    const StepCells c = step_cells<true>(v, st);
+    v.gcumI[st] = run;
+    const uint32_t ng = (uint32_t)(c.cA + c.cB + 31) >> 5;
+    for (uint32_t g = 0; g < ng; g++) v.gstepI[run + g] = (uint16_t)st;
+    run += ng;
+  }
+  v.gcumI[nsi] = run;
+  run = 0;
+  for (int st = 0; st < nso; st++) {
+    const StepCells c = step_cells<false>(v, st);
+    v.gcumO[st] = run;
+    const uint32_t ng = (uint32_t)(c.cA + c.cB + 31) >> 5;
+    for (uint32_t g = 0; g < ng; g++) v.gstepO[run + g] = (uint16_t)st;
+    run += ng;
+  }
+  v.gcumO[nso] = run;
 }
 
 template <class SV>
@@ -435,92 +483,159 @@ RNA_DEV void stream_count(const SV& v, const ModelParams& P, int lane, int nl) {
   }
 }
 // phase 2: per group, the longest chain -> gbin[G+1], gbout[G+1]
+template <bool INSIDE, class SV>
+RNA_DEV void stream_groupmax_pass(const SV& v, int tid, int nt) {
+  const int L = v.L, TRI = L * (L + 1) / 2;
+  const uint32_t* gcum = INSIDE ? v.gcumI : v.gcumO;
+  const uint16_t* gstep = INSIDE ? v.gstepI : v.gstepO;
+  uint32_t* gb = INSIDE ? v.gbin : v.gbout;
+  const int ns = INSIDE ? num_steps_inside(v) : num_steps_outside(v);
+  const uint32_t NG = gcum[max(ns, 0)];
+  for (uint32_t G = tid; G < NG; G += nt) {
+    const int st = gstep[G], c = (int)(G - gcum[st]);
+    const StepCells sc = step_cells<INSIDE>(v, st);
+    uint32_t mx = 0;
+    for (int x = 32 * c; x < min(sc.cA + sc.cB, 32 * c + 32); x++) {
+      int dd, r;
+      step_cell(sc, x, dd, r);
+      mx = max(mx, (uint32_t)v.ccnt[(INSIDE ? 0 : TRI) + doff(dd, L) + r]);
+    }
+    gb[G + 1] = mx;
+  }
+}
 template <class SV>
 RNA_DEV void stream_groupmax(const SV& v, int tid, int nt) {
-  const int L = v.L, TRI = L * (L + 1) / 2;
-  for (int d = 0; d < L; d++) {
-    const int cnt = v.pcnt[d], od = doff(d, L), g0 = (int)v.gcum[d], ng = (cnt + 31) >> 5;
-    for (int c = (tid - g0 % nt + nt) % nt; c < ng; c += nt) {
-      uint32_t mi = 0, mo = 0;
-      for (int r = 32 * c; r < min(cnt, 32 * c + 32); r++) {
-        mi = max(mi, (uint32_t)v.ccnt[od + r]);
-        mo = max(mo, (uint32_t)v.ccnt[TRI + od + r]);
-      }
-      v.gbin[g0 + c + 1] = mi;
-      v.gbout[g0 + c + 1] = mo;
+  stream_groupmax_pass<true>(v, tid, nt);
+  stream_groupmax_pass<false>(v, tid, nt);
+}
+// phase 3 (one thread): block offsets
+template <bool INSIDE, class SV>
+RNA_DEV void stream_scan_pass(const SV& v) {
+  const uint32_t* gcum = INSIDE ? v.gcumI : v.gcumO;
+  uint32_t* gb = INSIDE ? v.gbin : v.gbout;
+  const int ns = INSIDE ? num_steps_inside(v) : num_steps_outside(v);
+  uint32_t run = 0;
+  gb[0] = 0;
+  for (int st = 0; st < ns; st++) {
+    const StepCells sc = step_cells<INSIDE>(v, st);
+    const int tot = sc.cA + sc.cB, ng = (tot + 31) >> 5;
+    for (int c = 0; c < ng; c++) {
+      const uint32_t g = gcum[st] + c;
+      run += group_width(tot, c) * gb[g + 1];
+      gb[g + 1] = run;
     }
   }
 }
-// cells in group c of a diagonal with cnt closable cells
-RNA_DEV uint32_t group_width(int cnt, int c) { return (uint32_t)min(32, cnt - 32 * c); }
-// phase 3 (one thread): block offsets
 template <class SV>
 RNA_DEV void stream_scan(const SV& v) {
-  uint32_t ri = 0, ro = 0;
-  v.gbin[0] = 0;
-  v.gbout[0] = 0;
-  for (int d = 0; d < v.L; d++) {
-    const int cnt = v.pcnt[d], ng = (cnt + 31) >> 5;
-    for (int c = 0; c < ng; c++) {
-      const uint32_t g = v.gcum[d] + c, wd = group_width(cnt, c);
-      ri += wd * v.gbin[g + 1]; v.gbin[g + 1] = ri;
-      ro += wd * v.gbout[g + 1]; v.gbout[g + 1] = ro;
-    }
-  }
+  stream_scan_pass<true>(v);
+  stream_scan_pass<false>(v);
 }
-// phase 4: score every term once and write both streams; warp w takes the groups G = w (mod number of warps),
-// lane = cell of the group, so the stores of a warp are contiguous
+// phase 4: score every term once and write both streams.  One warp fills one group at a time (lane = cell, so
+// the stores of a warp are contiguous); each lane walks its own partner list (a, bits of the row window).
 template <bool CONTRA, bool INSIDE, class SV>
 RNA_DEV void stream_fill_cell(const SV& v, const typename Model2<CONTRA>::View& T, const ModelParams& P, int i, int j,
                               uint2* out, uint32_t wd, uint32_t nmax) {
+  const int L = v.L;
   uint32_t n = 0;
-  typename LoopOf<CONTRA, INSIDE>::type lp = make_loop<CONTRA, INSIDE>(v, T, i, j);
-  auto sink = [&](const Term2& t) {
-    if (t.q >= 0) { out[wd * n] = make_uint2((unsigned)__float_as_int(lp.score(t)), (unsigned)t.q); n++; }
-  };
-  twoloop_foreach<INSIDE, false>(v, lp, P.MAX2, i, j, sink);
+  const typename LoopOf<CONTRA, INSIDE>::type lp = make_loop<CONTRA, INSIDE>(v, T, i, j);
+  const Windows<INSIDE, SV> window(v, P.MAX2, i, j);
+  const int amax = window.amax;
+  int a = -1, k = i, kcode = 0;
+  uint32_t w = 0, wnext = window(0);
+  for (;;) {
+    if (w == 0) {           // next row (its window was loaded one row ahead)
+      if (a >= amax) break;
+      a++;
+      w = wnext;
+      wnext = window(a + 1);
+      k = INSIDE ? i + 1 + a : i - 1 - a;
+      kcode = INSIDE ? v.LL[k] : v.RR[k] * 16;
+    }
+    if (w != 0) {
+      int l, b;
+      if (INSIDE) { const int t = 31 - __clz(w); w &= ~(1u << t); l = j - 32 + t; b = 31 - t; }
+      else { const int t = __ffs(w) - 1; w &= w - 1; l = j + 1 + t; b = t; }
+      Term1 t1;
+      t1.c = 0.f; t1.pv = 0.f;
+      t1.q = doff(l - k, L) + k;
+      t1.code = INSIDE ? v.RR[l] * 16 + kcode : kcode + v.LL[l];
+      t1.a = a; t1.b = b;
+      out[wd * n] = make_uint2((unsigned)__float_as_int(lp.score(lp.stage2(t1))), (unsigned)t1.q);
+      n++;
+    }
+  }
   for (; n < nmax; n++) out[wd * n] = make_uint2(0u, 0u);   // neutral padding
 }
+// number of fill tasks (= groups of both passes); task tau -> (pass, group), longest chains first
+template <class SV>
+RNA_DEV uint32_t stream_num_tasks(const SV& v) {
+  return v.gcumI[max(num_steps_inside(v), 0)] + v.gcumO[max(num_steps_outside(v), 0)];
+}
 template <bool CONTRA, class SV>
-RNA_DEV void stream_fill(const SV& v, const typename Model2<CONTRA>::View& T, const ModelParams& P, int lane, int nl) {
+RNA_DEV void stream_fill_task(const SV& v, const typename Model2<CONTRA>::View& T, const ModelParams& P, uint32_t tau,
+                              int ln) {
   const int L = v.L;
-  const int wv = lane >> 5, nw = max(nl >> 5, 1), ln = lane & 31;
-  for (int d = 0; d < L; d++) {
-    const int cnt = v.pcnt[d], od = doff(d, L), g0 = (int)v.gcum[d], ng = (cnt + 31) >> 5;
-    for (int c = (wv - g0 % nw + nw) % nw; c < ng; c += nw) {
-      const int r = 32 * c + ln;
-      if (r >= cnt) continue;
-      const int i = v.plist[od + r], j = i + d;
-      const uint32_t G = g0 + c, wd = group_width(cnt, c);
-      stream_fill_cell<CONTRA, true>(v, T, P, i, j, v.tin + v.gbin[G] + ln, wd, (v.gbin[G + 1] - v.gbin[G]) / wd);
-      stream_fill_cell<CONTRA, false>(v, T, P, i, j, v.tout + v.gbout[G] + ln, wd, (v.gbout[G + 1] - v.gbout[G]) / wd);
-    }
+  const uint32_t NGI = v.gcumI[max(num_steps_inside(v), 0)], NGO = v.gcumO[max(num_steps_outside(v), 0)];
+  // interleave the two passes, last groups (longest partner lists) first
+  const uint32_t both = 2 * min(NGI, NGO);
+  bool inside;
+  uint32_t G;
+  if (tau < both) { inside = (tau & 1u) == 0; G = (inside ? NGI : NGO) - 1 - (tau >> 1); }
+  else { inside = NGI > NGO; G = (inside ? NGI : NGO) - 1 - (tau - both) - (both >> 1); }
+  if (inside) {
+    const int st = v.gstepI[G], c = (int)(G - v.gcumI[st]);
+    const StepCells sc = step_cells<true>(v, st);
+    const int x = 32 * c + ln, tot = sc.cA + sc.cB;
+    if (x >= tot) return;
+    int dd, r;
+    step_cell(sc, x, dd, r);
+    const int i = v.plist[doff(dd, L) + r];
+    const uint32_t wd = group_width(tot, c), gb = v.gbin[G];
+    stream_fill_cell<CONTRA, true>(v, T, P, i, i + dd, v.tin + gb + ln, wd, (v.gbin[G + 1] - gb) / wd);
+  } else {
+    const int st = v.gstepO[G], c = (int)(G - v.gcumO[st]);
+    const StepCells sc = step_cells<false>(v, st);
+    const int x = 32 * c + ln, tot = sc.cA + sc.cB;
+    if (x >= tot) return;
+    int dd, r;
+    step_cell(sc, x, dd, r);
+    const int i = v.plist[doff(dd, L) + r];
+    const uint32_t wd = group_width(tot, c), gb = v.gbout[G];
+    stream_fill_cell<CONTRA, false>(v, T, P, i, i + dd, v.tout + gb + ln, wd, (v.gbout[G + 1] - gb) / wd);
   }
 }
 // the latency-critical fold over a lane's column of its group's block.  Every step of the warp touches a new
 // 256-byte line pair, so the stream is read a block of 8 steps ahead (>= 800 cycles of logsumexp), and the
 // gathers of a block are issued before its chain starts.
+#define RNA_STREAM_BLOCK 4
 template <bool INSIDE, class SV>
 RNA_DEV float stream_chain(const SV& v, const uint2* __restrict__ st, uint32_t wd, uint32_t n, const float4* lut,
                            float Cij, float sum) {
+  constexpr int B = RNA_STREAM_BLOCK;
   if (n == 0) return sum;
-  uint2 nx[8];
+  uint2 nx[B];
 #pragma unroll
-  for (int k = 0; k < 8; k++) nx[k] = ((uint32_t)k < n) ? st[wd * k] : make_uint2(0u, 0u);
-  for (uint32_t pos = 0; pos < n; pos += 8) {
-    uint2 cur[8];
-    float c[8], p[8];
+  for (int k = 0; k < B; k++) nx[k] = ((uint32_t)k < n) ? st[wd * k] : make_uint2(0u, 0u);
+  for (uint32_t pos = 0; pos < n; pos += B) {
+    uint2 cur[B];
+    float c[B], p[B];
 #pragma unroll
-    for (int k = 0; k < 8; k++) cur[k] = nx[k];
+    for (int k = 0; k < B; k++) cur[k] = nx[k];
 #pragma unroll
-    for (int k = 0; k < 8; k++) nx[k] = (pos + 8 + k < n) ? st[wd * (pos + 8 + k)] : make_uint2(0u, 0u);
+    for (int k = 0; k < B; k++) nx[k] = (pos + B + k < n) ? st[wd * (pos + B + k)] : make_uint2(0u, 0u);
+    // HBM latency exceeds a block of logsumexp's: pull the lines into L2 well ahead (one 8-byte element per
+    // lane and step => a warp's step covers at most 256 bytes; every other step touches all lines)
 #pragma unroll
-    for (int k = 0; k < 8; k++) {
+    for (int k = 0; k < B; k += 2)
+      if (pos + 32 + k < n) RNA_PREFETCH_L2(st + wd * (pos + 32 + k));
+#pragma unroll
+    for (int k = 0; k < B; k++) {
       c[k] = v.C[cur[k].y];                    // neutral element: C[0] = -inf => operand -inf => no-op
       p[k] = INSIDE ? 0.f : v.E[cur[k].y];
     }
 #pragma unroll
-    for (int k = 0; k < 8; k++)
+    for (int k = 0; k < B; k++)
       sum = lse(sum, term_operand<INSIDE>(c[k], p[k], Cij, __int_as_float((int)cur[k].x)), lut);
   }
   return sum;
@@ -530,47 +645,46 @@ RNA_DEV float stream_chain(const SV& v, const uint2* __restrict__ st, uint32_t w
 // inside, role X: sums_close of the closable cells of diagonal d (src/mccaskill_algo.rs:290-343, 395-467).
 // Needs: sums_close of diagonals <= d-2, sums_multibranch of diagonal d-2.
 // =========================================================================================================
+// X, phase 1 of inside step st: hairpin + two-loop part of sums_close for the diagonals d and d+1 of the step.
+// Both only need sums_close of diagonals <= d-1, so the two longest chains of the pass run side by side.
 template <bool CONTRA, class SV>
-RNA_DEV void inside_X_cell(const SV& v, const typename Model2<CONTRA>::View& T, const float4* lut,
-                           const ModelParams& P, int d, int r) {
+RNA_DEV void inside_X(const SV& v, const typename Model2<CONTRA>::View& T, const float4* lut,
+                      const ModelParams& P, int st, int lane, int nl) {
   const int L = v.L;
   const uint8_t* s = v.s;
   const float NEG = RNA_NEG_INF;
-  const int cnt = v.pcnt[d], od = doff(d, L);
-  const int i = v.plist[od + r], j = i + d;
-  float sum = NEG;
-  if constexpr (CONTRA) {
-    if (d - 1 <= P.MAX2) sum = lse(sum, c2_hairpin(T, s, i, j), lut);
-  } else {
-    sum = lse(sum, t_hairpin(T, s, i, j), lut);
+  const StepCells sc = step_cells<true>(v, st);
+  const int tot = sc.cA + sc.cB;
+  for (int x = lane; x < tot; x += nl) {   // ONE loop body: lanes of both diagonals run their chains together
+    int d, r;
+    step_cell(sc, x, d, r);
+    const int od = doff(d, L), i = v.plist[od + r], j = i + d;
+    float sum = NEG;
+    if constexpr (CONTRA) {
+      if (d - 1 <= P.MAX2) sum = lse(sum, c2_hairpin(T, s, i, j), lut);
+    } else {
+      sum = lse(sum, t_hairpin(T, s, i, j), lut);
+    }
+    if (v.tin) {
+      const uint32_t G = v.gcumI[st] + (x >> 5), gb = v.gbin[G], wd = group_width(tot, x >> 5);
+      sum = stream_chain<true>(v, v.tin + gb + (x & 31), wd, (v.gbin[G + 1] - gb) / wd, lut, 0.f, sum);
+    } else {
+      typename LoopOf<CONTRA, true>::type lp = make_loop<CONTRA, true>(v, T, i, j);
+      sum = twoloop_chain<true>(v, lp, lut, P.MAX2, i, j, 0.f, sum);
+    }
+    v.C[od + i] = sum;   // still without the multibranch term: no one reads these diagonals before inside_X_fin
   }
-  if (v.tin) {
-    const uint32_t G = v.gcum[d] + (r >> 5), gb = v.gbin[G], wd = group_width(cnt, r >> 5);
-    sum = stream_chain<true>(v, v.tin + gb + (r & 31), wd, (v.gbin[G + 1] - gb) / wd, lut, 0.f, sum);
-  } else {
-    typename LoopOf<CONTRA, true>::type lp = make_loop<CONTRA, true>(v, T, i, j);
-    sum = twoloop_chain<true>(v, lp, lut, P.MAX2, i, j, 0.f, sum);
-  }
-  v.C[od + i] = sum;   // still without the multibranch term: no one reads diagonal d before inside_X_fin
-}
-// X, phase 1 of a pair step: hairpin + two-loop part of sums_close for diagonals d and d+1.  Both only need
-// sums_close of diagonals <= d-1, so the two longest chains of the inside pass run side by side.
-template <bool CONTRA, class SV>
-RNA_DEV void inside_X(const SV& v, const typename Model2<CONTRA>::View& T, const float4* lut,
-                      const ModelParams& P, int d, int lane, int nl) {
-  const int c0 = (d < v.L) ? v.pcnt[d] : 0, c1 = (d + 1 < v.L) ? v.pcnt[d + 1] : 0;
-  for (int x = lane; x < c0 + c1; x += nl)   // ONE call site: lanes of both diagonals run the chain together
-    inside_X_cell<CONTRA>(v, T, lut, P, (x < c0) ? d : d + 1, (x < c0) ? x : x - c0);
 }
 // X, phase 2: the closing multibranch term (needs sums_multibranch of d-2 resp. d-1, computed by Z in phase 1)
 template <bool CONTRA, class SV>
-RNA_DEV void inside_X_fin(const SV& v, const typename Model2<CONTRA>::View& T, const float4* lut, int d, int lane,
+RNA_DEV void inside_X_fin(const SV& v, const typename Model2<CONTRA>::View& T, const float4* lut, int st, int lane,
                           int nl) {
   const int L = v.L;
   const float NEG = RNA_NEG_INF;
-  const int c0 = (d < L) ? v.pcnt[d] : 0, c1 = (d + 1 < L) ? v.pcnt[d + 1] : 0;
-  for (int x = lane; x < c0 + c1; x += nl) {
-    const int dd = (x < c0) ? d : d + 1, r = (x < c0) ? x : x - c0;
+  const StepCells sc = step_cells<true>(v, st);
+  for (int x = lane; x < sc.cA + sc.cB; x += nl) {
+    int dd, r;
+    step_cell(sc, x, dd, r);
     const int od = doff(dd, L), i = v.plist[od + r], j = i + dd;
     const float* Mm2 = v.Mroll + ((dd + 1) % 3) * L;   // diagonal dd-2
     const float mb = (dd >= 2) ? Mm2[i + 1] : NEG;
@@ -712,53 +826,54 @@ RNA_DEV void outside_Y(const SV& v, const typename Model2<CONTRA>::View& T, cons
 // outside, role X: log P(i,j) of the closable cells of diagonal d (src/mccaskill_algo.rs:558-604, 662-719).
 // Needs: log P, probs_multibranch, probs_multibranch2 of diagonals > d.
 // =========================================================================================================
+// X, phase 1 of outside step st: exterior term + enclosing two-loops of log P for the diagonals d and d-1 of the
+// step: both only need log P of diagonals >= d+1.
 template <bool CONTRA, class SV>
-RNA_DEV void outside_X_cell(const SV& v, const typename Model2<CONTRA>::View& T, const float4* lut,
-                            const ModelParams& P, float Z, int d, int r) {
+RNA_DEV void outside_X(const SV& v, const typename Model2<CONTRA>::View& T, const float4* lut,
+                       const ModelParams& P, float Z, int st, int lane, int nl) {
   const int L = v.L;
   const uint8_t* s = v.s;
   const float NEG = RNA_NEG_INF;
-  const int cnt = v.pcnt[d], od = doff(d, L);
   const typename Model2<CONTRA>::Dev* dev = T.g;
-  const int i = v.plist[od + r], j = i + d;
-  const float Cij = v.C[od + i];
-  if (!(Cij > NEG)) return;
-  const float Aij = __fadd_rn(Cij, v2_acc<CONTRA>(T, s, L, i, j));
-  const float El = (i < 1) ? 0.f : v.E0[i - 1];
-  const float Er = (j > L - 2) ? 0.f : v.EL[j + 1];
-  float sm;
-  if constexpr (CONTRA) sm = __fsub_rn(__fadd_rn(__fadd_rn(__fadd_rn(El, Er), Aij), dev->ext_bp), Z);
-  else sm = __fsub_rn(__fadd_rn(__fadd_rn(El, Aij), Er), Z);
-  // enclosing two-loops: k descending from i-1, l ascending from j+1
-  if (v.tin) {
-    const uint32_t G = v.gcum[d] + (r >> 5), gb = v.gbout[G], wd = group_width(cnt, r >> 5);
-    sm = stream_chain<false>(v, v.tout + gb + (r & 31), wd, (v.gbout[G + 1] - gb) / wd, lut, Cij, sm);
-  } else {
-    typename LoopOf<CONTRA, false>::type lp = make_loop<CONTRA, false>(v, T, i, j);
-    sm = twoloop_chain<false>(v, lp, lut, P.MAX2, i, j, Cij, sm);
+  const StepCells sc = step_cells<false>(v, st);
+  const int tot = sc.cA + sc.cB;
+  for (int x = lane; x < tot; x += nl) {
+    int d, r;
+    step_cell(sc, x, d, r);
+    const int od = doff(d, L), i = v.plist[od + r], j = i + d;
+    const float Cij = v.C[od + i];
+    // a statically closable cell without a structure (CONTRAfold, rare): its lane still walks the (padded) block
+    const bool has = Cij > NEG;
+    const float Aij = __fadd_rn(Cij, v2_acc<CONTRA>(T, s, L, i, j));
+    const float El = (i < 1) ? 0.f : v.E0[i - 1];
+    const float Er = (j > L - 2) ? 0.f : v.EL[j + 1];
+    float sm;
+    if constexpr (CONTRA) sm = __fsub_rn(__fadd_rn(__fadd_rn(__fadd_rn(El, Er), Aij), dev->ext_bp), Z);
+    else sm = __fsub_rn(__fadd_rn(__fadd_rn(El, Aij), Er), Z);
+    if (!has) continue;
+    // enclosing two-loops: k descending from i-1, l ascending from j+1
+    if (v.tin) {
+      const uint32_t G = v.gcumO[st] + (x >> 5), gb = v.gbout[G], wd = group_width(tot, x >> 5);
+      sm = stream_chain<false>(v, v.tout + gb + (x & 31), wd, (v.gbout[G + 1] - gb) / wd, lut, Cij, sm);
+    } else {
+      typename LoopOf<CONTRA, false>::type lp = make_loop<CONTRA, false>(v, T, i, j);
+      sm = twoloop_chain<false>(v, lp, lut, P.MAX2, i, j, Cij, sm);
+    }
+    v.E[od + i] = sm;   // exterior + two-loop part; outside_X_ml continues the fold
   }
-  v.E[od + i] = sm;   // exterior + two-loop part; outside_X_ml continues the fold
-}
-// X, phase 1 of a pair step: exterior term + enclosing two-loops of log P for diagonals d and d-1: both only
-// need log P of diagonals >= d+1.
-template <bool CONTRA, class SV>
-RNA_DEV void outside_X(const SV& v, const typename Model2<CONTRA>::View& T, const float4* lut,
-                       const ModelParams& P, float Z, int d, int dmin, int lane, int nl) {
-  const int c0 = v.pcnt[d], c1 = (d - 1 >= dmin) ? v.pcnt[d - 1] : 0;
-  for (int x = lane; x < c0 + c1; x += nl)   // ONE call site: lanes of both diagonals run the chain together
-    outside_X_cell<CONTRA>(v, T, lut, P, Z, (x < c0) ? d : d - 1, (x < c0) ? x : x - c0);
 }
 // X, phase 2: enclosing multiloops, k ascending 0..i-1 (needs probs_multibranch(2) of diagonals >= d resp. d+1)
 template <bool CONTRA, class SV>
-RNA_DEV void outside_X_ml(const SV& v, const typename Model2<CONTRA>::View& T, const float4* lut, int d, int dmin,
-                          int lane, int nl) {
+RNA_DEV void outside_X_ml(const SV& v, const typename Model2<CONTRA>::View& T, const float4* lut, int st, int lane,
+                          int nl) {
   const int L = v.L;
   const uint8_t* s = v.s;
   const float NEG = RNA_NEG_INF;
   const typename Model2<CONTRA>::Dev* dev = T.g;
-  const int c0 = v.pcnt[d], c1 = (d - 1 >= dmin) ? v.pcnt[d - 1] : 0;
-  for (int x = lane; x < c0 + c1; x += nl) {
-    const int dd = (x < c0) ? d : d - 1, r = (x < c0) ? x : x - c0;
+  const StepCells sc = step_cells<false>(v, st);
+  for (int x = lane; x < sc.cA + sc.cB; x += nl) {
+    int dd, r;
+    step_cell(sc, x, dd, r);
     const int od = doff(dd, L), i = v.plist[od + r], j = i + dd;
     const float Cij = v.C[od + i];
     if (!(Cij > NEG)) continue;
@@ -766,17 +881,26 @@ RNA_DEV void outside_X_ml(const SV& v, const typename Model2<CONTRA>::View& T, c
     const float Aij = __fadd_rn(Cij, v2_acc<CONTRA>(T, s, L, i, j));
     float sa;
     if constexpr (CONTRA) sa = __fadd_rn(Aij, dev->mb_bp); else sa = __fadd_rn(Aij, dev->coeff_num_branches);
+    // operands of step kk+1 are loaded before the three dependent logsumexp's of step kk
+    float nx1 = NEG, np2 = NEG, ny = NEG;
+    if (i > 0) {
+      const int q = doff(j, L);
+      nx1 = (i - 1 >= 1) ? v.M1[doff(i - 2, L) + 1] : NEG;
+      np2 = v.X[q]; ny = v.R[q];
+    }
     for (int kk = 0; kk < i; kk++) {
       const int m = i - 1 - kk;
-      const int q = doff(j - kk, L) + kk;
-      const float x1 = (m >= 1) ? v.M1[doff(m - 1, L) + kk + 1] : NEG;
-      const float p2 = v.X[q], y = v.R[q];
+      const float x1 = nx1, p2 = np2, y = ny;
+      if (kk + 1 < i) {
+        const int q = doff(j - kk - 1, L) + kk + 1;
+        nx1 = (m - 1 >= 1) ? v.M1[doff(m - 2, L) + kk + 2] : NEG;
+        np2 = v.X[q]; ny = v.R[q];
+      }
       sm = lse(sm, __fadd_rn(__fadd_rn(sa, p2), x1), lut);
       if constexpr (CONTRA) sm = lse(sm, __fadd_rn(__fadd_rn(sa, y), __fmul_rn(dev->mb_unpair, (float)m)), lut);
       else sm = lse(sm, __fadd_rn(sa, y), lut);
       sm = lse(sm, __fadd_rn(__fadd_rn(sa, x1), y), lut);
     }
-    if (!(sm > NEG)) sm = NEG;
     v.E[od + i] = sm;
   }
 }

@@ -12,12 +12,14 @@
 #define RNA_DEV __device__ __forceinline__
 #define RNA_DEVM __device__ __forceinline__   // member functions
 #define RNA_CONST_TABLE __device__ __constant__
+#define RNA_PREFETCH_L2(p) asm volatile("prefetch.global.L2 [%0];" ::"l"(p))
 #else
 #include <math.h>
 #include <string.h>
 #define RNA_DEV static inline
 #define RNA_DEVM inline
 #define RNA_CONST_TABLE static const
+#define RNA_PREFETCH_L2(p) ((void)(p))
 #define __restrict__ __restrict
 struct float4 { float x, y, z, w; };
 struct uint2 { unsigned x, y; };

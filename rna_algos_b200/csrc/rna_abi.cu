@@ -328,18 +328,32 @@ static int launch_fold_model(rna_handle* h, const RnaFoldBatchDev* b, cudaStream
   // v2 shared-memory buckets: grid size and the per-CTA slots of the two-loop term streams
   std::vector<size_t> stream_stride_of(buckets.size(), 0);
   std::vector<uint32_t> tcap_of(buckets.size(), 0);
-  static const bool no_streams = getenv("RNA_FOLD_NOSTREAMS") != nullptr;   // A/B switch
+  static const bool no_streams = getenv("RNA_FOLD_NOSTREAMS") != nullptr;   // A/B switches
+  static const bool no_helpers = getenv("RNA_FOLD_NOHELPERS") != nullptr;
+  std::vector<int> nt_of(buckets.size(), 0);
   size_t stream_bytes = 0;
   if (v2) {
     for (size_t k = 0; k < buckets.size(); k++) {
       const Bucket& bk = buckets[k];
       if (bk.mode != MODE_SMEM) continue;
       const Roles ro = fold2_roles(bk.Lcap, CONTRA, 16);
-      const int nt = 32 * (ro.nX + ro.nY + ro.nZ);
+      int nt = 32 * (ro.nX + ro.nY + ro.nZ);
       const size_t smem = smem_need(bk.Lcap);
       int occ = 1;
       TRY(set_smem_attr(h, fold_kernel2<CONTRA, MODE_SMEM>, smem));
       CU(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fold_kernel2<CONTRA, MODE_SMEM>, nt, smem));
+      // helper warps for the throughput phases (term-stream fill, setup, output): as many as fit without
+      // lowering the number of resident CTAs (shared memory bounds it) -- 1024 threads per SM at 64 registers
+      if (!no_helpers) {
+        int want = std::min(512, (1024 / std::max(1, occ)) / 32 * 32);
+        while (want > nt) {
+          int o2 = 0;
+          CU(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o2, fold_kernel2<CONTRA, MODE_SMEM>, want, smem));
+          if (o2 >= occ) { nt = want; break; }
+          want -= 32;
+        }
+      }
+      nt_of[k] = nt;
       grid_of[k] = (int)std::min<size_t>(bk.end - bk.begin, (size_t)std::max(1, occ) * h->sm_count);
       if (!no_streams) {
         // room for 128 stream elements per cell (random sequences need ~50 incl. padding); sequences with longer
@@ -384,7 +398,7 @@ static int launch_fold_model(rna_handle* h, const RnaFoldBatchDev* b, cudaStream
     if (v2 && bk.mode != MODE_COOP) {
       const Roles ro = fold2_roles(bk.Lcap, CONTRA, 16);
       a.nXw = ro.nX; a.nYw = ro.nY; a.nZw = ro.nZ;
-      const int nt = 32 * (ro.nX + ro.nY + ro.nZ);
+      const int nt = (bk.mode == MODE_SMEM) ? nt_of[k] : 32 * (ro.nX + ro.nY + ro.nZ);
       a.stream_ws = nullptr;
       if (bk.mode == MODE_SMEM) {
         const size_t smem = smem_need(bk.Lcap);
@@ -444,7 +458,7 @@ static int launch_fold_model(rna_handle* h, const RnaFoldBatchDev* b, cudaStream
     }
     CU(h, cudaGetLastError());
     h->stats.kernel_launches++;
-    if (dbg_roles && k == 0) {   // debug aid: where do the cycles of one sequence go, per role and pass
+    if (dbg_roles) {   // debug aid: where do the cycles of one sequence go, per role and pass
       cudaStreamSynchronize(st);
       std::vector<long long> hd(2048 * 16);
       cudaMemcpy(hd.data(), d_dbg, hd.size() * 8, cudaMemcpyDeviceToHost);
@@ -471,6 +485,8 @@ static int launch_fold_model(rna_handle* h, const RnaFoldBatchDev* b, cudaStream
       }
       fprintf(stderr, "[RNA_FOLD_DBG]   setup=%lld count=%lld scan=%lld fill=%lld cycles, terms=%lld\n", hd[2047 * 16], hd[2047 * 16 + 1],
               hd[2047 * 16 + 2], hd[2047 * 16 + 3], hd[2047 * 16 + 4]);
+      fprintf(stderr, "[RNA_FOLD_DBG]   L=%lld: output+centroid=%lld cycles, whole sequence=%lld cycles; launch: %d threads, grid %d, smem %zu\n",
+              hd[2047 * 16 + 7], hd[2047 * 16 + 5], hd[2047 * 16 + 6], nt_of[k], grid_of[k], smem_need(bk.Lcap));
       if (!hd[2047 * 16 + 3]) fprintf(stderr, "[RNA_FOLD_DBG]   (streams did not fit: scored on the fly)\n");
       cudaMemset(d_dbg, 0, 2048 * 16 * 8);
     }

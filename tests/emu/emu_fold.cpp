@@ -47,35 +47,49 @@ int run(const uint8_t* seq, int L, int allows_short, const typename Model2<CONTR
   for (int p = 0; p < L; p++) setup_codes(v, p);
   for (int d = 0; d < L; d++) setup_list_diag(v, d);
   // term streams (tcap: -1 unbounded, 0 = score on the fly (the kernel's fallback), n = streams if they fit)
-  const int nt = nX + nY + nZ, ntr = (nt + 31) / 32 * 32;
-  std::vector<uint32_t> gcum(L + 1);
-  v.gcum = gcum.data();
-  setup_gcum(v);
-  const uint32_t NG = gcum[L];
-  std::vector<uint32_t> gbin(NG + 1, 0), gbout(NG + 1, 0);
+  const int nt = nX + nY + nZ, nwarps = (nt + 31) / 32;
+  const int d_in0 = CONTRA ? 0 : (P.MINSPAN - 1);
+  const int d_out0 = CONTRA ? (allows_short ? 1 : P.MINSPAN - 1) : (P.MINSPAN - 1);
+  v.din0 = d_in0; v.dout0 = d_out0;
+  const int nsmax = L / 2 + 2;
+  size_t ngcap = 0;
+  for (int c = 1; c <= L; c += 1) ngcap += (size_t)(c + 31) / 32;
+  std::vector<uint32_t> gcumI(nsmax + 1, 0), gcumO(nsmax + 1, 0), gbin(ngcap + 2, 0), gbout(ngcap + 2, 0);
+  std::vector<uint16_t> gstepI(ngcap + 1, 0), gstepO(ngcap + 1, 0);
+  v.gcumI = gcumI.data(); v.gcumO = gcumO.data(); v.gstepI = gstepI.data(); v.gstepO = gstepO.data();
+  v.gbin = gbin.data(); v.gbout = gbout.data();
+  setup_groups(v);
+  const uint32_t NGI = gcumI[std::max(num_steps_inside(v), 0)], NGO = gcumO[std::max(num_steps_outside(v), 0)];
+  if (NGI > ngcap || NGO > ngcap) return 3;
   std::vector<uint16_t> ccnt(2 * (size_t)TRI + 2, 0);
   std::vector<uint2> tin, tout;
-  v.tin = nullptr; v.tout = nullptr; v.gbin = gbin.data(); v.gbout = gbout.data(); v.ccnt = ccnt.data(); v.tcap = 0;
+  v.tin = nullptr; v.tout = nullptr; v.ccnt = ccnt.data(); v.tcap = 0;
   if (tcap != 0) {
     for (int l = 0; l < nt; l++) stream_count(v, P, l, nt);
     for (int l = nt - 1; l >= 0; l--) stream_groupmax(v, l, nt);
     stream_scan(v);
-    if (tcap < 0 || (gbin[NG] <= (uint32_t)tcap && gbout[NG] <= (uint32_t)tcap)) {
-      tin.assign(gbin[NG] + 1, make_uint2(0xdeadbeefu, 0x7fffffffu));    // poison: every element must be written
-      tout.assign(gbout[NG] + 1, make_uint2(0xdeadbeefu, 0x7fffffffu));
+    if (tcap < 0 || (gbin[NGI] <= (uint32_t)tcap && gbout[NGO] <= (uint32_t)tcap)) {
+      tin.assign(gbin[NGI] + 1, make_uint2(0xdeadbeefu, 0x7fffffffu));    // poison: every element must be written
+      tout.assign(gbout[NGO] + 1, make_uint2(0xdeadbeefu, 0x7fffffffu));
       v.tin = tin.data(); v.tout = tout.data();
-      for (int l = ntr - 1; l >= 0; l--) stream_fill<CONTRA>(v, T, P, l, ntr);
+      const uint32_t ntask = stream_num_tasks(v);
+      for (uint32_t tau = 0; tau < ntask; tau++) {     // (the kernel hands tasks to warps dynamically)
+        const uint32_t tk = (order == 0) ? tau : ntask - 1 - tau;
+        for (int ln = 31; ln >= 0; ln--) stream_fill_task<CONTRA>(v, T, P, tk, ln);
+      }
+      (void)nwarps;
     }
   }
   auto lanes = [&](int n, auto&& fn) {
     if (order == 0) for (int l = 0; l < n; l++) fn(l);
     else for (int l = n - 1; l >= 0; l--) fn(l);
   };
-  // inside, pair step t: phase 1 = X(t, t+1) two-loop parts | [Z(t-2), Y(t-1)] bar [Z(t-1), Y(t)]; phase 2 = X fin
-  const int d_in0 = CONTRA ? 0 : (P.MINSPAN - 1);
+  // inside step st (diagonals t = d_in0 + 2 st, t+1): phase 1 = X two-loop parts | [Z(t-2), Y(t-1)] bar [Z(t-1), Y(t)];
+  // phase 2 = X closing multibranch terms
   auto validZ = [&](int d) { return d >= d_in0 && d < L; };
-  for (int t = d_in0; t <= L + 1; t += 2) {
-    auto rX = [&] { lanes(nX, [&](int l) { inside_X<CONTRA>(v, T, lut, P, t, l, nX); }); };
+  for (int st = 0; d_in0 + 2 * st <= L + 1; st++) {
+    const int t = d_in0 + 2 * st;
+    auto rX = [&] { lanes(nX, [&](int l) { inside_X<CONTRA>(v, T, lut, P, st, l, nX); }); };
     auto rZ = [&](int d) { if (validZ(d)) lanes(nZ, [&](int l) { inside_Z<CONTRA>(v, T, lut, d, l, nZ); }); };
     auto rY = [&](int d) { if constexpr (CONTRA) { if (validZ(d)) lanes(nY, [&](int l) { inside_Y_contra(v, T, lut, d, l, nY); }); } };
     auto rYZ = [&] {
@@ -83,22 +97,22 @@ int run(const uint8_t* seq, int L, int allows_short, const typename Model2<CONTR
       if (order == 0) { rY(t); rZ(t - 1); } else { rZ(t - 1); rY(t); }
     };
     if (order == 0) { rX(); rYZ(); } else { rYZ(); rX(); }
-    lanes(nX, [&](int l) { inside_X_fin<CONTRA>(v, T, lut, t, l, nX); });
+    lanes(nX, [&](int l) { inside_X_fin<CONTRA>(v, T, lut, st, l, nX); });
   }
   for (int x = 0; x < L; x++) { E0[x] = E[doff(x, L)]; EL[x] = E[doff(L - 1 - x, L) + x]; }
   const float Z = E0[L - 1];
   for (int x = 0; x < TRI; x++) { E[x] = NEG; R[x] = NEG; X[x] = NEG; }
   if (out_logz) *out_logz = Z;
-  const int d_out0 = CONTRA ? (allows_short ? 1 : P.MINSPAN - 1) : (P.MINSPAN - 1);
-  for (int d = L - 1; d >= d_out0; d -= 2) {
-    auto rX = [&] { lanes(nX, [&](int l) { outside_X<CONTRA>(v, T, lut, P, Z, d, d_out0, l, nX); }); };
+  for (int st = 0; L - 1 - 2 * st >= d_out0; st++) {
+    const int d = L - 1 - 2 * st;
+    auto rX = [&] { lanes(nX, [&](int l) { outside_X<CONTRA>(v, T, lut, P, Z, st, l, nX); }); };
     auto rY = [&] {
       const int nl = nY + nZ;
       if (d + 1 < L) lanes(nl, [&](int l) { outside_Y<CONTRA>(v, T, lut, d + 1, l, nl); });
       lanes(nl, [&](int l) { outside_Y<CONTRA>(v, T, lut, d, l, nl); });
     };
     if (order == 0) { rX(); rY(); } else { rY(); rX(); }
-    lanes(nX, [&](int l) { outside_X_ml<CONTRA>(v, T, lut, d, d_out0, l, nX); });
+    lanes(nX, [&](int l) { outside_X_ml<CONTRA>(v, T, lut, st, l, nX); });
   }
   if (out_bpp) {
     for (int i = 0; i < L - 1; i++) {
