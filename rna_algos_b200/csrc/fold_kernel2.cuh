@@ -26,10 +26,12 @@ __host__ __device__ inline size_t fold2_ngcap(int Lcap) {
   return n;
 }
 // bytes of one sequence's working set (SeqViewT) for capacity Lcap
-__host__ __device__ inline size_t fold2_seq_bytes(int Lcap, size_t pidx_size) {
+// nmat = matrices inside this region: 2 (C, log P: shared-memory mode, the dense matrices live in the CTA's
+// HBM/L2 slot) or 5 (everything in one space, log P aliasing E)
+__host__ __device__ inline size_t fold2_seq_bytes(int Lcap, size_t pidx_size, int nmat) {
   const size_t T = (size_t)Lcap * ((size_t)Lcap + 1) / 2;
   const size_t W2 = ((size_t)Lcap + 31) / 32 + 2;
-  size_t b = 5 * T * 4;                         // C R X E M1
+  size_t b = (size_t)nmat * T * 4;
   b += (3 + 2) * (size_t)Lcap * 4;              // Mroll, E0, EL
   b += align16(2 * ((size_t)Lcap + 2) * 4);     // traceback stack
   b += align16((size_t)Lcap * W2 * 4);          // closable bit matrix
@@ -49,15 +51,25 @@ __host__ __device__ inline size_t fold2_stream_bytes(int Lcap, uint32_t tcap) {
 }
 
 struct Roles { int nX, nY, nZ; };   // warps per role
+// X (the latency-critical two-loop chains) gets a lane for every closable cell of a step (two diagonals, ~0.37 of
+// the cells each); the dense chains (Z) and the sparse rightmost-pair chains (Y, CONTRAfold) share the rest and
+// stride over their cells when they have fewer lanes than cells.
+__host__ __device__ inline int fold2_x_warps(int Lcap) { return (3 * Lcap / 4 + 31) / 32; }
+__host__ __device__ inline int fold2_min_warps(int Lcap, bool contra) { return fold2_x_warps(Lcap) + (contra ? 4 : 2); }
 __host__ __device__ inline Roles fold2_roles(int Lcap, bool contra, int max_warps) {
   Roles r;
-  r.nX = (Lcap + 39) / 40;   // two diagonals of closable cells (~0.37 L each) per step
-  r.nZ = (Lcap + 31) / 32;
-  r.nY = contra ? r.nZ : 0;
-  while (r.nX + r.nY + r.nZ > max_warps) {       // long sequences: strided roles
-    if (r.nZ > 1) r.nZ--;
-    if (r.nY > 1 && r.nX + r.nY + r.nZ > max_warps) r.nY--;
-    if (r.nX > 1 && r.nX + r.nY + r.nZ > max_warps) r.nX--;
+  const int full = (Lcap + 31) / 32;
+  r.nX = fold2_x_warps(Lcap);
+  if (r.nX > max_warps - (contra ? 2 : 1)) r.nX = max_warps - (contra ? 2 : 1) > 1 ? max_warps - (contra ? 2 : 1) : 1;
+  int rest = max_warps - r.nX;
+  if (rest < (contra ? 2 : 1)) rest = contra ? 2 : 1;
+  if (contra) {
+    r.nZ = (rest + 1) / 2 < full ? (rest + 1) / 2 : full;
+    r.nY = rest - r.nZ < full ? rest - r.nZ : full;
+    if (r.nY < 1) r.nY = 1;
+  } else {
+    r.nZ = rest < full ? rest : full;
+    r.nY = 0;
   }
   return r;
 }
@@ -119,10 +131,19 @@ __global__ void __launch_bounds__(512, 2) fold_kernel2(const FoldArgs a) {
     v.s = s;
     float* f = reinterpret_cast<float*>(base);
     v.C = f; f += TRI;
-    v.R = f; f += TRI;
-    v.X = f; f += TRI;
-    v.E = f; f += TRI;
-    v.M1 = f; f += TRI;
+    if (MODE == MODE_SMEM) {
+      // on chip: sums_close and log P (gathered by the latency-critical chains); in the CTA's HBM/L2 slot: the
+      // dense matrices, read with affine addresses that the phases prefetch
+      v.Pm = f; f += TRI;
+      float* g = a.workspace + (size_t)blockIdx.x * a.ws_stride;
+      v.R = g; v.X = g + TRI; v.E = g + 2 * (size_t)TRI; v.M1 = g + 3 * (size_t)TRI;
+    } else {
+      v.R = f; f += TRI;
+      v.X = f; f += TRI;
+      v.E = f; f += TRI;
+      v.M1 = f; f += TRI;
+      v.Pm = v.E;
+    }
     v.Mroll = f; f += 3 * L;
     v.E0 = f; f += L;
     v.EL = f; f += L;
@@ -221,7 +242,7 @@ __global__ void __launch_bounds__(512, 2) fold_kernel2(const FoldArgs a) {
     }
     __syncthreads();
     const float Z = v.E0[L - 1];
-    for (int x = tid; x < TRI; x += nt) { v.E[x] = NEG; v.R[x] = NEG; v.X[x] = NEG; }
+    for (int x = tid; x < TRI; x += nt) { v.Pm[x] = NEG; v.R[x] = NEG; v.X[x] = NEG; }
     if (tid == 0 && a.out_logz) a.out_logz[sidx] = Z;
     __syncthreads();
     const int d_out0 = v.dout0;
@@ -247,22 +268,22 @@ __global__ void __launch_bounds__(512, 2) fold_kernel2(const FoldArgs a) {
     const long long tpost0 = dbg_on ? clock64() : 0;
     // ================================ BPP = expf(P) =====================================================
     for (int x = tid; x < TRI; x += nt) {
-      const float val = v.E[x];
-      v.E[x] = (val > NEG) ? approx_expf(val) : -1.0f;
+      const float val = v.Pm[x];
+      v.Pm[x] = (val > NEG) ? approx_expf(val) : -1.0f;
     }
     __syncthreads();
     if (a.out_bpp) {
       float* ob = a.out_bpp + a.bpp_offsets[sidx];
       for (int i = 0; i < L - 1; i++) {
         const size_t rowoff = (size_t)i * (size_t)(2 * L - i - 1) / 2;
-        for (int x = tid; x < L - 1 - i; x += nt) ob[rowoff + x] = v.E[doff(x + 1, L) + i];
+        for (int x = tid; x < L - 1 - i; x += nt) ob[rowoff + x] = v.Pm[doff(x + 1, L) + i];
       }
     }
     // ================================ centroid (src/centroid_fold.rs:25-105) ============================
     {
-      const float* Pm = v.E;
+      const float* Pm = v.Pm;
       auto getp = [=](int d, int i) -> float { return Pm[doff(d, L) + i]; };
-      centroid_run<MODE>(a, sidx, sbeg, L, v.R, tstack, getp);
+      centroid_run<MODE>(a, sidx, sbeg, L, v.C, tstack, getp);   // W reuses sums_close (dead after the outside pass)
     }
     if (dbg_on && tid == 0) { a.dbg[2047 * 16 + 5] = clock64() - tpost0; a.dbg[2047 * 16 + 6] = clock64() - tseq0; a.dbg[2047 * 16 + 7] = L; }
   }

@@ -59,7 +59,8 @@ struct SeqViewT {
   float* C;               // sums_close
   float* R;               // sums_rightmost_basepairs_external   -> outside: probs_multibranch
   float* X;               // CONTRAfold: sums_rightmost_basepairs_multibranch -> outside: probs_multibranch2
-  float* E;               // sums_external                        -> outside: log P(i,j) -> BPP
+  float* E;               // sums_external
+  float* Pm;              // outside: log P(i,j) -> BPP  (may alias E: sums_external is dead after the inside pass)
   float* M1;              // sums_1ormore_basepairs
   float* Mroll;           // sums_multibranch, 3 rolling diagonals of L
   float* E0;              // sums_external[0][x]
@@ -422,7 +423,7 @@ RNA_DEV void twoloop_foreach(const SV& v, const LOOP& lp, int MAX2, int i, int j
       const int q = doff(l - k, L) + k;
       if (LOADS) {
         t1.c = v.C[q];
-        if (!INSIDE) t1.pv = v.E[q];
+        if (!INSIDE) t1.pv = v.Pm[q];
       }
       t1.code = INSIDE ? v.RR[l] * 16 + kcode : kcode + v.LL[l];
       t1.a = a; t1.b = b; t1.q = q;
@@ -632,7 +633,7 @@ RNA_DEV float stream_chain(const SV& v, const uint2* __restrict__ st, uint32_t w
 #pragma unroll
     for (int k = 0; k < B; k++) {
       c[k] = v.C[cur[k].y];                    // neutral element: C[0] = -inf => operand -inf => no-op
-      p[k] = INSIDE ? 0.f : v.E[cur[k].y];
+      p[k] = INSIDE ? 0.f : v.Pm[cur[k].y];
     }
 #pragma unroll
     for (int k = 0; k < B; k++)
@@ -765,13 +766,26 @@ RNA_DEV void inside_Z(const SV& v, const typename Model2<CONTRA>::View& T, const
       sM1 = __fadd_rn(Rij, dev->coeff_num_branches);
     }
     sE = lse(sE, __fadd_rn(Rij, 0.f), lut);   // k = i: E[i][i-1] = 0 (lower triangle / literal 0)
+    // operands two split points ahead are in flight while the three folds of the current one execute
+    // (R, Rm, E, M1 may live in HBM/L2: their addresses do not depend on the running sums)
+    float r1 = NEG, e1 = NEG, q1 = NEG, x1 = NEG, r2 = NEG, e2 = NEG, q2 = NEG, x2 = NEG;
+    if (1 < d) {
+      r1 = v.R[doff(d - 1, L) + i + 1]; e1 = v.E[doff(0, L) + i]; q1 = v.M1[doff(0, L) + i];
+      if (CONTRA) x1 = v.X[doff(d - 1, L) + i + 1];
+    }
+    if (2 < d) {
+      r2 = v.R[doff(d - 2, L) + i + 2]; e2 = v.E[doff(1, L) + i]; q2 = v.M1[doff(1, L) + i];
+      if (CONTRA) x2 = v.X[doff(d - 2, L) + i + 2];
+    }
     for (int m = 1; m < d; m++) {
-      const float r = v.R[doff(d - m, L) + i + m];
-      const float e = v.E[doff(m - 1, L) + i];
-      const float m1 = v.M1[doff(m - 1, L) + i];
+      const float r = r1, e = e1, m1 = q1, rm = x1;
+      r1 = r2; e1 = e2; q1 = q2; x1 = x2;
+      if (m + 2 < d) {
+        r2 = v.R[doff(d - m - 2, L) + i + m + 2]; e2 = v.E[doff(m + 1, L) + i]; q2 = v.M1[doff(m + 1, L) + i];
+        if (CONTRA) x2 = v.X[doff(d - m - 2, L) + i + m + 2];
+      }
       sE = lse(sE, __fadd_rn(r, e), lut);
       if constexpr (CONTRA) {
-        const float rm = v.X[doff(d - m, L) + i + m];
         sM1 = lse(sM1, __fadd_rn(rm, __fmul_rn(dev->mb_unpair, (float)m)), lut);
         sM = lse(sM, __fadd_rn(m1, rm), lut);
       } else {
@@ -802,20 +816,40 @@ RNA_DEV void outside_Y(const SV& v, const typename Model2<CONTRA>::View& T, cons
     const int j = i + d;
     float pm = NEG, pm2 = NEG;
     const uint32_t* row = v.mask + i * v.W2;
-    for (int p = j + 1; p < L; p += 32) {
-      uint32_t w = get32(row, p);
-      while (w) {
-        const int t = __ffs(w) - 1;
-        w &= w - 1;
-        const int k = p + t, m = k - j;
-        const int q = doff(k - i, L) + i;
-        const float c = v.C[q], pv = v.E[q];
-        const float x = __fsub_rn(__fadd_rn(pv, v2_mbclose<CONTRA>(T, s, L, i, k)), c);
-        const float m1 = (m >= 2) ? v.M1[doff(m - 2, L) + j + 1] : NEG;
-        pm = lse(pm, __fadd_rn(x, m1), lut);
-        if constexpr (CONTRA) pm2 = lse(pm2, __fadd_rn(x, __fmul_rn(T.g->mb_unpair, (float)(m - 1))), lut);
-        else pm2 = lse(pm2, x, lut);
+    // closable (i,k), k > j ascending; the operands of the next term are fetched before the two folds of the
+    // current one (sums_1ormore_basepairs may live in HBM/L2)
+    int p = j + 1;
+    uint32_t w = (p < L) ? get32(row, p) : 0u;
+    auto next_k = [&]() -> int {
+      while (w == 0) {
+        p += 32;
+        if (p >= L) return -1;
+        w = get32(row, p);
       }
+      const int t = __ffs(w) - 1;
+      w &= w - 1;
+      return p + t;
+    };
+    int k1 = (p < L) ? next_k() : -1;
+    float c1 = NEG, pv1 = NEG, m11 = NEG;
+    if (k1 >= 0) {
+      const int q = doff(k1 - i, L) + i;
+      c1 = v.C[q]; pv1 = v.Pm[q];
+      m11 = (k1 - j >= 2) ? v.M1[doff(k1 - j - 2, L) + j + 1] : NEG;
+    }
+    while (k1 >= 0) {
+      const int k = k1, m = k - j;
+      const float c = c1, pv = pv1, m1 = m11;
+      k1 = next_k();
+      if (k1 >= 0) {
+        const int q = doff(k1 - i, L) + i;
+        c1 = v.C[q]; pv1 = v.Pm[q];
+        m11 = (k1 - j >= 2) ? v.M1[doff(k1 - j - 2, L) + j + 1] : NEG;
+      }
+      const float x = __fsub_rn(__fadd_rn(pv, v2_mbclose<CONTRA>(T, s, L, i, k)), c);
+      pm = lse(pm, __fadd_rn(x, m1), lut);
+      if constexpr (CONTRA) pm2 = lse(pm2, __fadd_rn(x, __fmul_rn(T.g->mb_unpair, (float)(m - 1))), lut);
+      else pm2 = lse(pm2, x, lut);
     }
     v.R[od + i] = pm;
     v.X[od + i] = pm2;
@@ -859,7 +893,7 @@ RNA_DEV void outside_X(const SV& v, const typename Model2<CONTRA>::View& T, cons
       typename LoopOf<CONTRA, false>::type lp = make_loop<CONTRA, false>(v, T, i, j);
       sm = twoloop_chain<false>(v, lp, lut, P.MAX2, i, j, Cij, sm);
     }
-    v.E[od + i] = sm;   // exterior + two-loop part; outside_X_ml continues the fold
+    v.Pm[od + i] = sm;   // exterior + two-loop part; outside_X_ml continues the fold
   }
 }
 // X, phase 2: enclosing multiloops, k ascending 0..i-1 (needs probs_multibranch(2) of diagonals >= d resp. d+1)
@@ -877,7 +911,7 @@ RNA_DEV void outside_X_ml(const SV& v, const typename Model2<CONTRA>::View& T, c
     const int od = doff(dd, L), i = v.plist[od + r], j = i + dd;
     const float Cij = v.C[od + i];
     if (!(Cij > NEG)) continue;
-    float sm = v.E[od + i];
+    float sm = v.Pm[od + i];
     const float Aij = __fadd_rn(Cij, v2_acc<CONTRA>(T, s, L, i, j));
     float sa;
     if constexpr (CONTRA) sa = __fadd_rn(Aij, dev->mb_bp); else sa = __fadd_rn(Aij, dev->coeff_num_branches);
@@ -901,7 +935,7 @@ RNA_DEV void outside_X_ml(const SV& v, const typename Model2<CONTRA>::View& T, c
       else sm = lse(sm, __fadd_rn(sa, y), lut);
       sm = lse(sm, __fadd_rn(__fadd_rn(sa, x1), y), lut);
     }
-    v.E[od + i] = sm;
+    v.Pm[od + i] = sm;
   }
 }
 

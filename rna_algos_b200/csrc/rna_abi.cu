@@ -263,7 +263,7 @@ static int launch_fold_model(rna_handle* h, const RnaFoldBatchDev* b, cudaStream
   const int gran = v2 ? 4 : 8;                                     // bucket width in nt
   auto smem_need = [&](int Lcap) -> size_t {
     if (centroid_only) return centroid_ws_floats(Lcap) * 4;
-    if (v2) return fold2_fixed_bytes<CONTRA>(Lcap) + fold2_seq_bytes(Lcap, 1);
+    if (v2) return fold2_fixed_bytes<CONTRA>(Lcap) + fold2_seq_bytes(Lcap, 1, 2);
     return fold_smem_bytes<CONTRA>(Lcap, true);
   };
   // largest L whose matrices fit in shared memory (v2 keeps u8 cell lists there: L <= 252)
@@ -306,9 +306,9 @@ static int launch_fold_model(rna_handle* h, const RnaFoldBatchDev* b, cudaStream
   std::vector<size_t> stride_of(buckets.size(), 0);
   for (size_t k = 0; k < buckets.size(); k++) {
     const Bucket& bk = buckets[k];
-    if (bk.mode == MODE_SMEM) continue;
+    if (bk.mode == MODE_SMEM) continue;   // (v2: sized below, once the grid is known)
     const size_t per = (centroid_only ? centroid_ws_floats(bk.Lcap)
-                        : (v2 && bk.mode == MODE_GLOBAL) ? fold2_seq_bytes(bk.Lcap, 2) / 4
+                        : (v2 && bk.mode == MODE_GLOBAL) ? fold2_seq_bytes(bk.Lcap, 2, 5) / 4
                                                          : fold_ws_floats<CONTRA>(bk.Lcap)) + 32;
     stride_of[k] = per;
     if (bk.mode == MODE_COOP) {
@@ -324,37 +324,39 @@ static int launch_fold_model(rna_handle* h, const RnaFoldBatchDev* b, cudaStream
       ws_floats = std::max(ws_floats, (size_t)g * per);
     }
   }
-  if (ws_floats) TRY(ensure(h, h->ws, ws_floats * 4));
   // v2 shared-memory buckets: grid size and the per-CTA slots of the two-loop term streams
   std::vector<size_t> stream_stride_of(buckets.size(), 0);
   std::vector<uint32_t> tcap_of(buckets.size(), 0);
   static const bool no_streams = getenv("RNA_FOLD_NOSTREAMS") != nullptr;   // A/B switches
   static const bool no_helpers = getenv("RNA_FOLD_NOHELPERS") != nullptr;
   std::vector<int> nt_of(buckets.size(), 0);
+  std::vector<Roles> ro_of(buckets.size());
   size_t stream_bytes = 0;
   if (v2) {
     for (size_t k = 0; k < buckets.size(); k++) {
       const Bucket& bk = buckets[k];
       if (bk.mode != MODE_SMEM) continue;
-      const Roles ro = fold2_roles(bk.Lcap, CONTRA, 16);
-      int nt = 32 * (ro.nX + ro.nY + ro.nZ);
+      // CTAs per SM: bounded by shared memory (C, log P and the small per-sequence tables) and by 1024 threads per SM
+      // at 64 registers.  The chains are latency-bound, so residency is what fills the SM: take all the CTAs that
+      // fit (<= 6) and give each 1024 / CTAs threads: roles first, the rest help in the all-thread phases.
       const size_t smem = smem_need(bk.Lcap);
+      static const int occ_cap = getenv("RNA_FOLD_OCC") ? atoi(getenv("RNA_FOLD_OCC")) : 6;
+      int occ_s = (int)std::min<size_t>((size_t)std::max(1, occ_cap), (size_t)233472 / (smem + 1024 + 64));
+      occ_s = std::max(1, occ_s);
+      occ_s = std::min(occ_s, std::max(1, 32 / fold2_min_warps(bk.Lcap, CONTRA)));
+      int warps = std::min(16, 32 / occ_s);
+      if (no_helpers) { const Roles fr = fold2_roles(bk.Lcap, CONTRA, 16); warps = std::min(warps, fr.nX + fr.nY + fr.nZ); }
+      const Roles ro = fold2_roles(bk.Lcap, CONTRA, warps);
+      ro_of[k] = ro;
+      int nt = 32 * warps;
       int occ = 1;
       TRY(set_smem_attr(h, fold_kernel2<CONTRA, MODE_SMEM>, smem));
       CU(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fold_kernel2<CONTRA, MODE_SMEM>, nt, smem));
-      // helper warps for the throughput phases (term-stream fill, setup, output): as many as fit without
-      // lowering the number of resident CTAs (shared memory bounds it) -- 1024 threads per SM at 64 registers
-      if (!no_helpers) {
-        int want = std::min(512, (1024 / std::max(1, occ)) / 32 * 32);
-        while (want > nt) {
-          int o2 = 0;
-          CU(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o2, fold_kernel2<CONTRA, MODE_SMEM>, want, smem));
-          if (o2 >= occ) { nt = want; break; }
-          want -= 32;
-        }
-      }
+      occ = std::max(1, std::min(occ, occ_cap));
       nt_of[k] = nt;
       grid_of[k] = (int)std::min<size_t>(bk.end - bk.begin, (size_t)std::max(1, occ) * h->sm_count);
+      stride_of[k] = 4 * ((size_t)bk.Lcap * (bk.Lcap + 1) / 2) + 32;   // R X E M1 of one CTA
+      ws_floats = std::max(ws_floats, (size_t)grid_of[k] * stride_of[k]);
       if (!no_streams) {
         // room for 128 stream elements per cell (random sequences need ~50 incl. padding); sequences with longer
         // lists score on the fly
@@ -365,6 +367,7 @@ static int launch_fold_model(rna_handle* h, const RnaFoldBatchDev* b, cudaStream
     }
     if (stream_bytes) TRY(ensure(h, h->stream_ws, stream_bytes));
   }
+  if (ws_floats) TRY(ensure(h, h->ws, ws_floats * 4));
 
   FoldArgs a;
   memset(&a, 0, sizeof a);
@@ -396,7 +399,7 @@ static int launch_fold_model(rna_handle* h, const RnaFoldBatchDev* b, cudaStream
     a.Lcap = bk.Lcap;
     a.ws_stride = stride_of[k];
     if (v2 && bk.mode != MODE_COOP) {
-      const Roles ro = fold2_roles(bk.Lcap, CONTRA, 16);
+      const Roles ro = (bk.mode == MODE_SMEM) ? ro_of[k] : fold2_roles(bk.Lcap, CONTRA, 16);
       a.nXw = ro.nX; a.nYw = ro.nY; a.nZw = ro.nZ;
       const int nt = (bk.mode == MODE_SMEM) ? nt_of[k] : 32 * (ro.nX + ro.nY + ro.nZ);
       a.stream_ws = nullptr;

@@ -42,6 +42,11 @@ int run(const uint8_t* seq, int L, int allows_short, const typename Model2<CONTR
   v.mask = mask.data(); v.plist = plist.data(); v.pcnt = pcnt.data(); v.RR = RR.data(); v.LL = LL.data();
   v.C = C.data(); v.R = R.data(); v.X = X.data(); v.E = E.data(); v.M1 = M1.data(); v.Mroll = Mroll.data();
   v.E0 = E0.data(); v.EL = EL.data();
+  // log P either aliases sums_external (all-in-one-space modes) or is a matrix of its own (the shared-memory mode
+  // keeps C and log P on chip and the dense matrices in its HBM/L2 slot)
+  std::vector<float> Pown(TRI, NEG);
+  const bool separateP = (order == 1);
+  v.Pm = separateP ? Pown.data() : E.data();
   // setup (two barriers in the kernel: masks, then lists)
   for (int x = 0; x < L * v.W2; x++) setup_mask_word<CONTRA>(v, P, x);
   for (int p = 0; p < L; p++) setup_codes(v, p);
@@ -101,7 +106,7 @@ int run(const uint8_t* seq, int L, int allows_short, const typename Model2<CONTR
   }
   for (int x = 0; x < L; x++) { E0[x] = E[doff(x, L)]; EL[x] = E[doff(L - 1 - x, L) + x]; }
   const float Z = E0[L - 1];
-  for (int x = 0; x < TRI; x++) { E[x] = NEG; R[x] = NEG; X[x] = NEG; }
+  for (int x = 0; x < TRI; x++) { v.Pm[x] = NEG; R[x] = NEG; X[x] = NEG; }
   if (out_logz) *out_logz = Z;
   for (int st = 0; L - 1 - 2 * st >= d_out0; st++) {
     const int d = L - 1 - 2 * st;
@@ -118,7 +123,7 @@ int run(const uint8_t* seq, int L, int allows_short, const typename Model2<CONTR
     for (int i = 0; i < L - 1; i++) {
       const size_t rowoff = (size_t)i * (size_t)(2 * L - i - 1) / 2;
       for (int x = 0; x < L - 1 - i; x++) {
-        const float val = E[doff(x + 1, L) + i];
+        const float val = v.Pm[doff(x + 1, L) + i];
         out_bpp[rowoff + x] = (val > NEG) ? approx_expf(val) : -1.0f;
       }
     }
