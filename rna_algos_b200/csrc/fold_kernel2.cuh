@@ -36,7 +36,7 @@ __host__ __device__ inline size_t fold2_seq_bytes(int Lcap, size_t pidx_size, in
   b += align16(2 * ((size_t)Lcap + 2) * 4);     // traceback stack
   b += align16((size_t)Lcap * W2 * 4);          // closable bit matrix
   b += align16((size_t)Lcap * 4 + 4);           // pcnt, RR, LL
-  b += align16(2 * ((size_t)Lcap / 2 + 3) * 4);    // gcumI, gcumO
+  b += align16(4 * ((size_t)Lcap / 2 + 3) * 4);    // gcumI, gcumO, ccumI, ccumO
   b += align16(2 * (fold2_ngcap(Lcap) + 2) * 4);   // gbin, gbout
   b += align16(2 * (fold2_ngcap(Lcap) + 2) * 2);   // gstepI, gstepO
   b += align16(T * pidx_size);                  // closable-cell lists
@@ -151,7 +151,9 @@ __global__ void __launch_bounds__(512, 2) fold_kernel2(const FoldArgs a) {
     v.mask = reinterpret_cast<uint32_t*>(tstack + 2 * (L + 2));
     v.gcumI = v.mask + L * v.W2;                                 // 4-byte items first, then 2-byte, then bytes
     v.gcumO = v.gcumI + L / 2 + 3;
-    v.gbin = v.gcumO + L / 2 + 3;
+    v.ccumI = v.gcumO + L / 2 + 3;
+    v.ccumO = v.ccumI + L / 2 + 3;
+    v.gbin = v.ccumO + L / 2 + 3;
     v.gbout = v.gbin + ngcap + 2;
     v.gstepI = reinterpret_cast<uint16_t*>(v.gbout + ngcap + 2);
     v.gstepO = v.gstepI + ngcap + 2;
@@ -193,7 +195,7 @@ __global__ void __launch_bounds__(512, 2) fold_kernel2(const FoldArgs a) {
         v.tin = reinterpret_cast<uint2*>(sw);
         v.tout = v.tin + a.tcap;
         // one group per warp at a time, handed out dynamically, longest partner lists first
-        const uint32_t ntask = NGI + NGO;
+        const uint32_t ntask = stream_num_tasks(v);
         for (;;) {
           uint32_t tau = 0;
           if ((tid & 31) == 0) tau = (uint32_t)atomicAdd(&s_fill_next, 1);

@@ -48,6 +48,8 @@ struct SeqViewT {
   // The closable cells of a step, diagonal A first, are cut into lane GROUPS of 32 (the lanes of one warp).
   uint32_t* gcumI;        // [NS+1] groups before inside step s
   uint32_t* gcumO;        // [NS+1] groups before outside step s
+  uint32_t* ccumI;        // [NS+1] closable cells before inside step s
+  uint32_t* ccumO;        // [NS+1] closable cells before outside step s
   uint16_t* gstepI;       // [NG] step of an inside group
   uint16_t* gstepO;       // [NG] step of an outside group
   uint32_t* gbin;         // [NG+1] first element of each inside group's block in tin
@@ -126,25 +128,31 @@ RNA_DEV uint32_t group_width(int tot, int c) { return (uint32_t)min(32, tot - 32
 // group bases of every step (serial over <= L entries: one thread)
 template <class SV>
 RNA_DEV void setup_groups(const SV& v) {
-  uint32_t run = 0;
+  uint32_t run = 0, cells = 0;
   const int nsi = max(num_steps_inside(v), 0), nso = max(num_steps_outside(v), 0);
   for (int st = 0; st < nsi; st++) {
     const StepCells c = step_cells<true>(v, st);
     v.gcumI[st] = run;
+    v.ccumI[st] = cells;
     const uint32_t ng = (uint32_t)(c.cA + c.cB + 31) >> 5;
     for (uint32_t g = 0; g < ng; g++) v.gstepI[run + g] = (uint16_t)st;
     run += ng;
+    cells += (uint32_t)(c.cA + c.cB);
   }
   v.gcumI[nsi] = run;
-  run = 0;
+  v.ccumI[nsi] = cells;
+  run = 0; cells = 0;
   for (int st = 0; st < nso; st++) {
     const StepCells c = step_cells<false>(v, st);
     v.gcumO[st] = run;
+    v.ccumO[st] = cells;
     const uint32_t ng = (uint32_t)(c.cA + c.cB + 31) >> 5;
     for (uint32_t g = 0; g < ng; g++) v.gstepO[run + g] = (uint16_t)st;
     run += ng;
+    cells += (uint32_t)(c.cA + c.cB);
   }
   v.gcumO[nso] = run;
+  v.ccumO[nso] = cells;
 }
 
 template <class SV>
@@ -263,6 +271,16 @@ struct ContraLoop {
     r.cls = st ? 1 : 0;
     return r;
   }
+  // rows a >= 2 hold no stack / bulge-of-1 / 1x1 term: one gather of the length table, same additions
+  static constexpr int kFastFrom = 2;
+  RNA_DEVM float fast(int a, int b, int code) const {
+    const float u = T.sm->U[RNA_CU_PTAB + a * 31 + b], vv = T.sm->js2[code];
+    if (INSIDE) {
+      const float sc = __fadd_rn(__fadd_rn(u, js_fixed), vv);
+      return __fadd_rn(sc, T.sm->bp[((code >> 2) & 3) * 4 + (code >> 6)]);
+    }
+    return __fadd_rn(__fadd_rn(__fadd_rn(u, vv), js_fixed), bp_fixed);
+  }
   // the two-loop score: a pure function of the sequence (the reference memoises it: mccaskill_algo.rs:431,696)
   RNA_DEVM float score(const Term2& t) const {
     if (INSIDE) {
@@ -334,6 +352,20 @@ struct TurnerLoop {
       r.u = T.sm->tm2[X][code];
     }
     return r;
+  }
+  // rows a >= 3 hold only long bulges (b == 0) and generic interior loops.  x + (-0.0f) == x bit for bit, which
+  // lets the bulge skip the mismatch term without a branch.
+  static constexpr int kFastFrom = 3;
+  RNA_DEVM float fast(int a, int b, int code) const {
+    const int X = (b == 1) ? 0 : (a == 3 && b == 2) ? 1 : 2;
+    const float tf = (X == 0) ? tm_f0 : (X == 1) ? tm_f1 : tm_f2;
+    const float u = T.sm->tm2[X][code];
+    const float vv = (b == 0) ? T.sm->bulge_init[a] : T.sm->ninio[a * 31 + b];
+    float mm = INSIDE ? __fadd_rn(tf, u) : __fadd_rn(u, tf);   // closing-side term first
+    if (b == 0) mm = __int_as_float((int)0x80000000u);
+    const float pen_var = augu_pair(INSIDE ? (code >> 2) & 3 : code >> 6, INSIDE ? code >> 6 : (code >> 2) & 3) ? T.g->augu_pen : 0.f;
+    const float pen_close = INSIDE ? pen_fixed : pen_var, pen_encl = INSIDE ? pen_var : pen_fixed;
+    return __fadd_rn(__fadd_rn(__fadd_rn(vv, mm), pen_close), pen_encl);
   }
   RNA_DEVM float score(const Term2& t) const {
     const float pen_var = t.aux ? T.g->augu_pen : 0.f;
@@ -532,24 +564,21 @@ RNA_DEV void stream_scan(const SV& v) {
   stream_scan_pass<true>(v);
   stream_scan_pass<false>(v);
 }
-// phase 4: score every term once and write both streams.  One warp fills one group at a time (lane = cell, so
-// the stores of a warp are contiguous); each lane walks its own partner list (a, bits of the row window).
-template <bool CONTRA, bool INSIDE, class SV>
-RNA_DEV void stream_fill_cell(const SV& v, const typename Model2<CONTRA>::View& T, const ModelParams& P, int i, int j,
-                              uint2* out, uint32_t wd, uint32_t nmax) {
+// phase 4: score every term once and write both streams.  Each lane walks the partner list of one cell (row a,
+// bits of the row window); a warp takes 32 consecutive cells of the pass at a time.
+template <bool CONTRA, bool INSIDE, bool FAST, class SV, class LOOP>
+RNA_DEV uint32_t stream_fill_rows(const SV& v, const LOOP& lp, const Windows<INSIDE, SV>& window, int i, int j, int a0,
+                                  int a1, uint2* out, uint32_t wd, uint32_t n) {
   const int L = v.L;
-  uint32_t n = 0;
-  const typename LoopOf<CONTRA, INSIDE>::type lp = make_loop<CONTRA, INSIDE>(v, T, i, j);
-  const Windows<INSIDE, SV> window(v, P.MAX2, i, j);
-  const int amax = window.amax;
-  int a = -1, k = i, kcode = 0;
-  uint32_t w = 0, wnext = window(0);
+  if (a0 > a1) return n;
+  int a = a0 - 1, k = i, kcode = 0;
+  uint32_t w = 0, wnext = window(a0);
   for (;;) {
     if (w == 0) {           // next row (its window was loaded one row ahead)
-      if (a >= amax) break;
+      if (a >= a1) break;
       a++;
       w = wnext;
-      wnext = window(a + 1);
+      wnext = (a + 1 <= a1) ? window(a + 1) : 0u;
       k = INSIDE ? i + 1 + a : i - 1 - a;
       kcode = INSIDE ? v.LL[k] : v.RR[k] * 16;
     }
@@ -557,54 +586,73 @@ RNA_DEV void stream_fill_cell(const SV& v, const typename Model2<CONTRA>::View& 
       int l, b;
       if (INSIDE) { const int t = 31 - __clz(w); w &= ~(1u << t); l = j - 32 + t; b = 31 - t; }
       else { const int t = __ffs(w) - 1; w &= w - 1; l = j + 1 + t; b = t; }
-      Term1 t1;
-      t1.c = 0.f; t1.pv = 0.f;
-      t1.q = doff(l - k, L) + k;
-      t1.code = INSIDE ? v.RR[l] * 16 + kcode : kcode + v.LL[l];
-      t1.a = a; t1.b = b;
-      out[wd * n] = make_uint2((unsigned)__float_as_int(lp.score(lp.stage2(t1))), (unsigned)t1.q);
+      const int q = doff(l - k, L) + k;
+      const int code = INSIDE ? v.RR[l] * 16 + kcode : kcode + v.LL[l];
+      float sc;
+      if (FAST) {
+        sc = lp.fast(a, b, code);
+      } else {
+        Term1 t1;
+        t1.c = 0.f; t1.pv = 0.f; t1.q = q; t1.code = code; t1.a = a; t1.b = b;
+        sc = lp.score(lp.stage2(t1));
+      }
+      out[wd * n] = make_uint2((unsigned)__float_as_int(sc), (unsigned)q);
       n++;
     }
   }
+  return n;
+}
+template <bool CONTRA, bool INSIDE, class SV>
+RNA_DEV void stream_fill_cell(const SV& v, const typename Model2<CONTRA>::View& T, const ModelParams& P, int i, int j,
+                              uint2* out, uint32_t wd, uint32_t nmax) {
+  typedef typename LoopOf<CONTRA, INSIDE>::type LOOP;
+  const LOOP lp = make_loop<CONTRA, INSIDE>(v, T, i, j);
+  const Windows<INSIDE, SV> window(v, P.MAX2, i, j);
+  uint32_t n = 0;
+  n = stream_fill_rows<CONTRA, INSIDE, false>(v, lp, window, i, j, 0, min(LOOP::kFastFrom - 1, window.amax), out, wd, n);
+  n = stream_fill_rows<CONTRA, INSIDE, true>(v, lp, window, i, j, LOOP::kFastFrom, window.amax, out, wd, n);
   for (; n < nmax; n++) out[wd * n] = make_uint2(0u, 0u);   // neutral padding
 }
-// number of fill tasks (= groups of both passes); task tau -> (pass, group), longest chains first
+// fill tasks: chunks of 32 consecutive cells of a pass; task tau -> (pass, chunk), longest partner lists first
 template <class SV>
 RNA_DEV uint32_t stream_num_tasks(const SV& v) {
-  return v.gcumI[max(num_steps_inside(v), 0)] + v.gcumO[max(num_steps_outside(v), 0)];
+  const uint32_t nci = v.ccumI[max(num_steps_inside(v), 0)], nco = v.ccumO[max(num_steps_outside(v), 0)];
+  return ((nci + 31) >> 5) + ((nco + 31) >> 5);
+}
+template <bool CONTRA, bool INSIDE, class SV>
+RNA_DEV void stream_fill_chunk(const SV& v, const typename Model2<CONTRA>::View& T, const ModelParams& P, uint32_t cell) {
+  const int L = v.L;
+  const uint32_t* ccum = INSIDE ? v.ccumI : v.ccumO;
+  const uint32_t* gcum = INSIDE ? v.gcumI : v.gcumO;
+  const uint32_t* gb = INSIDE ? v.gbin : v.gbout;
+  const int ns = INSIDE ? num_steps_inside(v) : num_steps_outside(v);
+  if (cell >= ccum[max(ns, 0)]) return;
+  int lo = 0, hi = ns - 1;            // last step with ccum[st] <= cell
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (ccum[mid] <= cell) lo = mid; else hi = mid - 1;
+  }
+  const int st = lo, x = (int)(cell - ccum[st]);
+  const StepCells sc = step_cells<INSIDE>(v, st);
+  int dd, r;
+  step_cell(sc, x, dd, r);
+  const int i = v.plist[doff(dd, L) + r];
+  const uint32_t G = gcum[st] + (uint32_t)(x >> 5), wd = group_width(sc.cA + sc.cB, x >> 5), g0 = gb[G];
+  stream_fill_cell<CONTRA, INSIDE>(v, T, P, i, i + dd, (INSIDE ? v.tin : v.tout) + g0 + (x & 31), wd, (gb[G + 1] - g0) / wd);
 }
 template <bool CONTRA, class SV>
 RNA_DEV void stream_fill_task(const SV& v, const typename Model2<CONTRA>::View& T, const ModelParams& P, uint32_t tau,
                               int ln) {
-  const int L = v.L;
-  const uint32_t NGI = v.gcumI[max(num_steps_inside(v), 0)], NGO = v.gcumO[max(num_steps_outside(v), 0)];
-  // interleave the two passes, last groups (longest partner lists) first
-  const uint32_t both = 2 * min(NGI, NGO);
+  const uint32_t nci = v.ccumI[max(num_steps_inside(v), 0)], nco = v.ccumO[max(num_steps_outside(v), 0)];
+  const uint32_t NKI = (nci + 31) >> 5, NKO = (nco + 31) >> 5;
+  // interleave the two passes, last chunks (longest partner lists) first
+  const uint32_t both = 2 * min(NKI, NKO);
   bool inside;
-  uint32_t G;
-  if (tau < both) { inside = (tau & 1u) == 0; G = (inside ? NGI : NGO) - 1 - (tau >> 1); }
-  else { inside = NGI > NGO; G = (inside ? NGI : NGO) - 1 - (tau - both) - (both >> 1); }
-  if (inside) {
-    const int st = v.gstepI[G], c = (int)(G - v.gcumI[st]);
-    const StepCells sc = step_cells<true>(v, st);
-    const int x = 32 * c + ln, tot = sc.cA + sc.cB;
-    if (x >= tot) return;
-    int dd, r;
-    step_cell(sc, x, dd, r);
-    const int i = v.plist[doff(dd, L) + r];
-    const uint32_t wd = group_width(tot, c), gb = v.gbin[G];
-    stream_fill_cell<CONTRA, true>(v, T, P, i, i + dd, v.tin + gb + ln, wd, (v.gbin[G + 1] - gb) / wd);
-  } else {
-    const int st = v.gstepO[G], c = (int)(G - v.gcumO[st]);
-    const StepCells sc = step_cells<false>(v, st);
-    const int x = 32 * c + ln, tot = sc.cA + sc.cB;
-    if (x >= tot) return;
-    int dd, r;
-    step_cell(sc, x, dd, r);
-    const int i = v.plist[doff(dd, L) + r];
-    const uint32_t wd = group_width(tot, c), gb = v.gbout[G];
-    stream_fill_cell<CONTRA, false>(v, T, P, i, i + dd, v.tout + gb + ln, wd, (v.gbout[G + 1] - gb) / wd);
-  }
+  uint32_t K;
+  if (tau < both) { inside = (tau & 1u) == 0; K = (inside ? NKI : NKO) - 1 - (tau >> 1); }
+  else { inside = NKI > NKO; K = (inside ? NKI : NKO) - 1 - (tau - both) - (both >> 1); }
+  if (inside) stream_fill_chunk<CONTRA, true>(v, T, P, 32 * K + (uint32_t)ln);
+  else stream_fill_chunk<CONTRA, false>(v, T, P, 32 * K + (uint32_t)ln);
 }
 // the latency-critical fold over a lane's column of its group's block.  Every step of the warp touches a new
 // 256-byte line pair, so the stream is read a block of 8 steps ahead (>= 800 cycles of logsumexp), and the

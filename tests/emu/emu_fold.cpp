@@ -59,9 +59,9 @@ int run(const uint8_t* seq, int L, int allows_short, const typename Model2<CONTR
   const int nsmax = L / 2 + 2;
   size_t ngcap = 0;
   for (int c = 1; c <= L; c += 1) ngcap += (size_t)(c + 31) / 32;
-  std::vector<uint32_t> gcumI(nsmax + 1, 0), gcumO(nsmax + 1, 0), gbin(ngcap + 2, 0), gbout(ngcap + 2, 0);
+  std::vector<uint32_t> gcumI(nsmax + 1, 0), gcumO(nsmax + 1, 0), ccumI(nsmax + 1, 0), ccumO(nsmax + 1, 0), gbin(ngcap + 2, 0), gbout(ngcap + 2, 0);
   std::vector<uint16_t> gstepI(ngcap + 1, 0), gstepO(ngcap + 1, 0);
-  v.gcumI = gcumI.data(); v.gcumO = gcumO.data(); v.gstepI = gstepI.data(); v.gstepO = gstepO.data();
+  v.gcumI = gcumI.data(); v.gcumO = gcumO.data(); v.ccumI = ccumI.data(); v.ccumO = ccumO.data(); v.gstepI = gstepI.data(); v.gstepO = gstepO.data();
   v.gbin = gbin.data(); v.gbout = gbout.data();
   setup_groups(v);
   const uint32_t NGI = gcumI[std::max(num_steps_inside(v), 0)], NGO = gcumO[std::max(num_steps_outside(v), 0)];
