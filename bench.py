@@ -349,10 +349,21 @@ def gpu_arm(args):
                              f"reference algorithm, one sequence per task on {cores} threads)"}
         per_gpu_bytes = abytes_all / world
         achieved = per_gpu_bytes / sec_per_step / 1e9
+        # DRAM bytes per step of the same command, from the committed ncu capture (profiles/), if it matches
+        traffic = None
+        try:
+            tj = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))
+            if tj.get("workload") == args.workload and tj.get("nseq_per_gpu") == args.nseq and tj.get("gammas") == gammas:
+                traffic = tj["dram_bytes_per_step"]
+        except Exception:
+            pass
         roof = {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                "traffic": None, "peak_source": peak_src, "kernel": f"fold_kernel<{'CONTRA' if contra else 'TURNER'}>",
-                "note": "algorithmic bytes per step / CUDA-event time of the step's fold_kernel launches; the path is "
-                        "FP32-issue bound, see 'compute'"}
+                "traffic": traffic, "peak_source": peak_src, "kernel": f"fold_kernel2<{'CONTRA' if contra else 'TURNER'}, SMEM>",
+                "algorithmic_bytes_per_step": per_gpu_bytes,
+                "note": "achieved = algorithmic bytes per step (bases+offsets in, packed BPP+logZ+structures out) / CUDA-event "
+                        "time of the step's fold_kernel2 launches; traffic = DRAM bytes per step from the ncu capture in "
+                        "profiles/ (two-loop term streams dominate it); the path is bound by the latency of the "
+                        "reference-exact logsumexp chains and FP32/ALU issue, see 'compute' and DESIGN.md 3.3"}
         comp = None
         if lse_per_seq is not None:
             sm_mhz = (clocks or {}).get("sm_mhz") or 1965.0

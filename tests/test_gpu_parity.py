@@ -169,3 +169,66 @@ def test_errors_do_not_abort(handle):
         handle.fold_batch(np.array([0, 1, 7], dtype=np.uint8), np.array([0, 3], dtype=np.uint32), False)
     with pytest.raises(RnaError):
         handle.fold_batch(np.zeros(0, dtype=np.uint8), np.array([0, 0], dtype=np.uint32), False)
+
+
+@pytest.mark.parametrize("contra", [False, True])
+def test_golden_vectors(handle, contra):
+    """The committed golden vectors (tests/golden/trna_oracle.npz, made by tests/golden/make_golden.py)."""
+    import os
+    from common import ROOT
+    g = np.load(os.path.join(ROOT, "tests", "golden", "trna_oracle.npz"))
+    bases, offsets = pack(load_trnas())
+    got = handle.fold_batch(bases, offsets, contra, False, g["gammas"].tolist())
+    k = "contra" if contra else "turner"
+    assert_bits_equal(got["logz"], g[k + "_logz"], "logZ")
+    assert_bits_equal(got["bpp"], g[k + "_bpp"], "BPP")
+    assert_bits_equal(got["expect_acc"], g[k + "_expect_acc"], "expect_accuracy")
+    assert (got["structs"] == g[k + "_structs"]).all()
+
+
+@pytest.mark.parametrize("contra", [False, True])
+def test_full_bench_size_properties(handle, oracle, contra):
+    """BASELINE configs[0]/[1] at bench size (24 576 tiled tRNAs): every copy of a sequence must reproduce the
+    oracle's result for that sequence bit for bit (determinism across CTAs, work-queue order and stream slots)."""
+    tt, ct, _ = default_tables()
+    base = load_trnas()
+    n = 24576
+    seqs = [base[i % 6] for i in range(n)]
+    bases, offsets = pack(seqs)
+    got = handle.fold_batch(bases, offsets, contra, False, [1.0, 2.0])
+    b6, o6 = pack(base)
+    want = oracle.fold_batch(b6, o6, contra, False, tt, ct, [1.0, 2.0], n_threads=6)
+    lz = got["logz"].view(np.uint32).reshape(-1, 6)
+    assert (lz == want["logz"].view(np.uint32)[None, :]).all(), "logZ differs between copies"
+    ea = got["expect_acc"].view(np.uint32).reshape(2, -1, 6)
+    assert (ea == want["expect_acc"].view(np.uint32)[:, None, :]).all()
+    bo, wo = got["bpp_offsets"].astype(np.int64), want["bpp_offsets"].astype(np.int64)
+    for s in range(6):
+        ref = want["bpp"][wo[s]:wo[s + 1]].view(np.uint32)
+        L = len(base[s])
+        idx = np.arange(s, n, 6)
+        blk = np.stack([got["bpp"][bo[k]:bo[k + 1]] for k in idx[:: max(1, len(idx) // 64)]]).view(np.uint32)
+        assert (blk == ref[None, :]).all(), f"BPP of tRNA {s} differs between copies"
+        st = got["structs"][:, offsets[idx[-1]]:offsets[idx[-1]] + L]
+        assert (st == want["structs"][:, o6[s]:o6[s] + L]).all()
+    p = got["bpp"][got["bpp"] != T.BPP_ABSENT]
+    assert (p >= -0.001).all() and (p < 1.001).all()            # the reference's range assertion at full size
+
+
+def test_rfam_like_lengths(handle, oracle):
+    """BASELINE configs[2] stand-in: ragged 50..500-nt batch across shared-memory and HBM-resident buckets."""
+    tt, ct, _ = default_tables()
+    rng = np.random.default_rng(77)
+    lens = np.exp(rng.uniform(np.log(50), np.log(500), size=24)).astype(int)
+    check_fold(handle, oracle, random_seqs(78, lens), True, False, [1.0, 4.0], tt, ct)
+    check_fold(handle, oracle, random_seqs(79, lens[:10]), False, False, [2.0], tt, ct)
+
+
+def test_skewed_composition_falls_back(handle, oracle):
+    """GU-only sequences make ~half of all cells closable: their term streams overflow the slot and the kernel
+    must fall back to scoring on the fly, with identical results."""
+    tt, ct, _ = default_tables()
+    rng = np.random.default_rng(3)
+    seqs = [rng.choice(np.array([2, 3], dtype=np.uint8), size=L) for L in (60, 90, 120)]
+    check_fold(handle, oracle, seqs, True, False, [2.0], tt, ct)
+    check_fold(handle, oracle, seqs, False, False, [2.0], tt, ct)
