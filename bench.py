@@ -397,6 +397,107 @@ def gpu_arm(args):
         dist.destroy_process_group()
 
 
+# ----------------------------------------------------------------------------------------------------
+# Durbin pair-HMM arm (BASELINE configs[4]; secondary metric, same JSON shape): --workload durbin
+# ----------------------------------------------------------------------------------------------------
+def durbin_arm(args):
+    """All 15 pairs of the 6 bundled tRNAs (the reference's own Durbin benchmark set, benches/benches.rs:58-93)
+    tiled to --nseq pairs per GPU, CONTRAlign v2.01 scores.  value = pairs/s device-resident; e2e = host buffers."""
+    import torch
+    from common import default_tables, load_trnas, pack
+    from oracle_lib import Oracle
+    from rna_algos_b200 import _lib
+    from rna_algos_b200.api import Handle
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device")
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(dev)
+    tt, ct, at = default_tables()
+    h = Handle(0, None, None, at)
+    lib = h.lib
+    seqs = load_trnas()
+    bases, offsets = pack(seqs)
+    base_pairs = [(a, b) for a in range(6) for b in range(a + 1, 6)]
+    npairs = args.nseq
+    pairs = np.array([base_pairs[i % 15] for i in range(npairs)], dtype=np.uint32)
+    lens = np.diff(offsets.astype(np.int64))
+    sizes = (lens[pairs[:, 0]] + 2) * (lens[pairs[:, 1]] + 2)
+    po = np.zeros(npairs + 1, dtype=np.uint64)
+    po[1:] = np.cumsum(sizes)
+    d_bases = torch.from_numpy(bases).to(dev)
+    d_off = torch.from_numpy(offsets.view(np.int32)).to(dev)
+    d_pairs = torch.from_numpy(pairs.view(np.int32).reshape(-1)).to(dev)
+    d_po = torch.from_numpy(po.view(np.int64)).to(dev)
+    d_out = torch.empty(int(po[-1]), dtype=torch.float32, device=dev)
+    db = _lib.DurbinBatchDev()
+    db.h_offsets = offsets.ctypes.data; db.h_pairs = pairs.ctypes.data
+    db.d_bases = d_bases.data_ptr(); db.d_offsets = d_off.data_ptr(); db.d_pairs = d_pairs.data_ptr()
+    db.d_prob_offsets = d_po.data_ptr(); db.n_seqs = 6; db.n_pairs = npairs; db.max_len = int(lens.max())
+    db.d_out_probs = d_out.data_ptr()
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
+    sptr = C.c_void_p(stream.cuda_stream)
+
+    def step():
+        rc = lib.rna_durbin_batch_dev(h.h, C.byref(db), sptr)
+        if rc:
+            raise RuntimeError(f"rna_durbin_batch_dev rc={rc}: {lib.rna_last_error(h.h)}")
+    for _ in range(max(args.warmup, 3)):
+        step()
+    torch.cuda.synchronize()
+    sampler = ClockSampler(0)
+    sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record(stream)
+    for _ in range(args.steps):
+        step()
+    ev1.record(stream)
+    torch.cuda.synchronize()
+    ms = ev0.elapsed_time(ev1)
+    clocks = sampler.stop()
+    host_out = torch.empty(int(po[-1]), dtype=torch.float32).pin_memory().numpy()
+    for _ in range(2):
+        h.durbin_batch(bases, offsets, pairs, out=host_out)
+    st = h.stats()
+    t0 = time.perf_counter()
+    e2e_steps = max(1, min(args.steps, args.e2e_steps))
+    for _ in range(e2e_steps):
+        h.durbin_batch(bases, offsets, pairs, out=host_out)
+    e2e_dt = time.perf_counter() - t0
+    # parity spot check + cpu baseline on a bounded sample (oracle port, all cores)
+    cores = os.cpu_count() or 1
+    orc = Oracle()
+    ncpu = min(npairs, 15 * 64)
+    t0 = time.perf_counter()
+    want = orc.durbin_batch(bases, offsets, pairs[:ncpu], at, n_threads=cores)
+    cdt = time.perf_counter() - t0
+    assert (host_out[: int(po[ncpu])].view(np.uint32) == want["probs"].view(np.uint32)).all(), "Durbin parity"
+    cells = int(sizes.sum())
+    abytes = 4 * cells + 8 * npairs + 8 * npairs
+    sec = ms / 1e3 / args.steps
+    try:
+        hbm_peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
+    except Exception:
+        hbm_peak = 6650.0
+    line = {
+        "metric": "durbin_match_prob_pairs_per_s", "value": npairs / sec, "unit": "pairs/s", "n_gpus": 1, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": 1e3 * sec, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic (bundled tRNA pairs tiled)",
+        "config": {"workload": f"15 tRNA pairs of assets/sampled_trnas.fa tiled to {npairs} pairs, CONTRAlign v2.01, sentinel-padded"},
+        "cells_per_s": cells / sec,
+        "e2e": {"value": npairs * e2e_steps / e2e_dt, "unit": "pairs/s", "h2d_bytes_per_step": st["h2d_bytes"],
+                "d2h_bytes_per_step": st["d2h_bytes"], "steps": e2e_steps, "path": "rna_durbin_batch (host buffers)"},
+        "gpu_launches": args.steps, "clocks": clocks,
+        "roofline": {"bound": "hbm", "achieved": abytes / sec / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                     "frac": abytes / sec / 1e9 / hbm_peak, "traffic": None, "kernel": "durbin_kernel",
+                     "note": "algorithmic bytes = match-probability matrices out (4 B per cell) + pair list"},
+        "cpu_baseline": {"value": ncpu / cdt, "unit": "pairs/s", "cores": cores, "kind": "port",
+                         "sample": f"first {ncpu} pairs, {cdt:.2f} s wall (oracle port, bit-identical to the GPU result)"},
+    }
+    print(json.dumps(line), flush=True)
+    h.close()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -414,6 +515,8 @@ def main():
     args = ap.parse_args()
     if args.impl == "reference":
         reference_arm(args)
+    elif args.workload == "durbin":
+        durbin_arm(args)
     else:
         gpu_arm(args)
 
