@@ -233,6 +233,7 @@ def gpu_arm(args):
     gammas = [float(g) for g in args.gammas.split(",")]
     # global batch = world x nseq, length-balanced LPT partition over ranks (no collective on the data path)
     seqs_all, contra, desc = make_workload(args.workload, args.nseq * world, length=args.length)
+    desc = desc.replace(f"{args.nseq * world} seqs/GPU", f"{args.nseq} seqs/GPU")
     if world > 1:
         part = partition_lpt(fold_cost([len(s) for s in seqs_all]), world)
         seqs = [s for s, p in zip(seqs_all, part) if p == rank]

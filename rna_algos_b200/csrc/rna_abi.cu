@@ -32,6 +32,9 @@ struct rna_handle {
   int sm_count = 0;
   size_t smem_optin = 0;
   cudaStream_t stream = nullptr;
+  static const int kLanes = 4;                  // length buckets of one call run on up to 4 concurrent streams
+  cudaStream_t aux[kLanes] = {nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t ev_fork = nullptr, ev_join[kLanes] = {nullptr, nullptr, nullptr, nullptr};
   std::string err;
   bool has_turner = false, has_contra = false, has_align = false;
   DevTurner* d_turner = nullptr;
@@ -87,6 +90,12 @@ extern "C" int rna_create(int device, rna_handle** out) {
   h->sm_count = prop.multiProcessorCount;
   h->smem_optin = prop.sharedMemPerBlockOptin;
   if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) { delete h; return RNA_ERR_CUDA; }
+  bool ok = cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming) == cudaSuccess;
+  for (int x = 0; x < rna_handle::kLanes; x++) {
+    ok = ok && cudaStreamCreateWithFlags(&h->aux[x], cudaStreamNonBlocking) == cudaSuccess;
+    ok = ok && cudaEventCreateWithFlags(&h->ev_join[x], cudaEventDisableTiming) == cudaSuccess;
+  }
+  if (!ok) { delete h; return RNA_ERR_CUDA; }
   *out = h;
   return RNA_OK;
 }
@@ -102,6 +111,8 @@ extern "C" int rna_destroy(rna_handle* h) {
   for (DevBuf* b : bufs) free_buf(*b);
   cudaFree(h->d_turner); cudaFree(h->d_contra); cudaFree(h->d_align);
   cudaFree(h->d_hp_ext); cudaFree(h->d_int11); cudaFree(h->d_int12); cudaFree(h->d_int22);
+  for (int x = 0; x < rna_handle::kLanes; x++) { cudaStreamSynchronize(h->aux[x]); cudaStreamDestroy(h->aux[x]); cudaEventDestroy(h->ev_join[x]); }
+  cudaEventDestroy(h->ev_fork);
   cudaStreamDestroy(h->stream);
   delete h;
   return RNA_OK;
@@ -365,9 +376,20 @@ static int launch_fold_model(rna_handle* h, const RnaFoldBatchDev* b, cudaStream
         stream_bytes = std::max(stream_bytes, (size_t)grid_of[k] * stream_stride_of[k]);
       }
     }
-    if (stream_bytes) TRY(ensure(h, h->stream_ws, stream_bytes));
   }
-  if (ws_floats) TRY(ensure(h, h->ws, ws_floats * 4));
+  // Buckets run concurrently on up to kLanes streams (bucket k on lane k % kLanes; small buckets would otherwise
+  // leave most SMs idle, and the tails of big ones overlap).  Kernels of one lane are stream-ordered, so the
+  // scratch is one region per lane, each sized for the largest bucket.
+  static const bool serial = getenv("RNA_FOLD_SERIAL") != nullptr || getenv("RNA_FOLD_DBG") != nullptr;
+  // (only when some buckets cannot fill the GPU by themselves: full-size launches run best one after the other)
+  size_t small_buckets = 0;
+  for (size_t k = 0; k < buckets.size(); k++)
+    if (buckets[k].mode != MODE_COOP && (size_t)(buckets[k].end - buckets[k].begin) < (size_t)2 * h->sm_count) small_buckets++;
+  const int nlanes = (serial || small_buckets < 2) ? 1 : (int)std::min<size_t>(rna_handle::kLanes, buckets.size());
+  ws_floats = (ws_floats + 63) / 64 * 64;
+  stream_bytes = (stream_bytes + 255) / 256 * 256;
+  if (stream_bytes) TRY(ensure(h, h->stream_ws, stream_bytes * nlanes));
+  if (ws_floats) TRY(ensure(h, h->ws, ws_floats * 4 * nlanes));
 
   FoldArgs a;
   memset(&a, 0, sizeof a);
@@ -387,12 +409,25 @@ static int launch_fold_model(rna_handle* h, const RnaFoldBatchDev* b, cudaStream
   a.out_pairs = b->d_out_pairs;
   a.out_npairs = b->d_out_num_pairs;
   a.workspace = (float*)h->ws.p;
+  if (nlanes > 1) {
+    CU(h, cudaEventRecord(h->ev_fork, st));
+    for (int x = 0; x < nlanes; x++) CU(h, cudaStreamWaitEvent(h->aux[x], h->ev_fork, 0));
+  }
+  cudaStream_t st_main = st;
 
   static const bool dbg_roles = getenv("RNA_FOLD_DBG") != nullptr;
   long long* d_dbg = nullptr;
   if (dbg_roles) { cudaMalloc(&d_dbg, 2048 * 16 * 8); cudaMemset(d_dbg, 0, 2048 * 16 * 8); a.dbg = d_dbg; }
   for (size_t k = 0; k < buckets.size(); k++) {
     const Bucket& bk = buckets[k];
+    const int lane = (nlanes > 1 && bk.mode != MODE_COOP) ? (int)(k % nlanes) : 0;
+    if (nlanes > 1 && bk.mode == MODE_COOP) {   // a cooperative grid wants the whole GPU: join, run it on the main stream
+      for (int x = 0; x < nlanes; x++) { CU(h, cudaEventRecord(h->ev_join[x], h->aux[x])); CU(h, cudaStreamWaitEvent(st_main, h->ev_join[x], 0)); }
+      CU(h, cudaEventRecord(h->ev_fork, st_main));
+      for (int x = 0; x < nlanes; x++) CU(h, cudaStreamWaitEvent(h->aux[x], h->ev_fork, 0));
+    }
+    st = (nlanes > 1 && bk.mode != MODE_COOP) ? h->aux[lane] : st_main;
+    a.workspace = (float*)h->ws.p + (size_t)lane * ws_floats;
     a.order = (const uint32_t*)h->order.p + bk.begin;
     a.n_launch = bk.end - bk.begin;
     a.work_counter = (int*)h->counters.p + k;
@@ -409,7 +444,7 @@ static int launch_fold_model(rna_handle* h, const RnaFoldBatchDev* b, cudaStream
         if (stream_stride_of[k]) {
           a.tcap = tcap_of[k];
           a.stream_stride = stream_stride_of[k];
-          a.stream_ws = (unsigned char*)h->stream_ws.p;
+          a.stream_ws = (unsigned char*)h->stream_ws.p + (size_t)lane * stream_bytes;
         }
         fold_kernel2<CONTRA, MODE_SMEM><<<grid_of[k], nt, smem, st>>>(a);
       } else {
@@ -493,6 +528,9 @@ static int launch_fold_model(rna_handle* h, const RnaFoldBatchDev* b, cudaStream
       if (!hd[2047 * 16 + 3]) fprintf(stderr, "[RNA_FOLD_DBG]   (streams did not fit: scored on the fly)\n");
       cudaMemset(d_dbg, 0, 2048 * 16 * 8);
     }
+  }
+  if (nlanes > 1) {
+    for (int x = 0; x < nlanes; x++) { CU(h, cudaEventRecord(h->ev_join[x], h->aux[x])); CU(h, cudaStreamWaitEvent(st_main, h->ev_join[x], 0)); }
   }
   if (d_dbg) cudaFree(d_dbg);
   return RNA_OK;
