@@ -131,7 +131,8 @@ __device__ __forceinline__ void centroid_run(const FoldArgs& a, uint32_t sidx, u
           e = __fsub_rn(__fadd_rn(inner, __fmul_rn(gamma, p)), 1.0f);
           if (e > wv) wv = e;
         }
-        for (int m = 1; m < d; m++) {
+#pragma unroll 8
+        for (int m = 1; m < d; m++) {   // (loads are independent of the running maximum: unrolled, they overlap)
           e = __fadd_rn(X::ld(&W[X::off(m, L) + i]), X::ld(&W[X::off(d - m - 1, L) + i + m + 1]));
           if (e > wv) wv = e;
         }

@@ -225,11 +225,11 @@ __global__ void __launch_bounds__(512, 2) fold_kernel2(const FoldArgs a) {
         inside_X<CONTRA>(v, T, lut, P, st, tid, nXl);
       } else if (!helper) {
         const bool isY = warp < a.nXw + a.nYw;
-        if (isY) { if constexpr (CONTRA) { if (t - 1 >= d_in0 && t - 1 < L) inside_Y_contra(v, T, lut, t - 1, tid - nXl, nYl); } }
-        else if (t - 2 >= d_in0 && t - 2 < L) inside_Z<CONTRA>(v, T, lut, t - 2, tid - nXl - nYl, nZl);
+        if (isY) { if constexpr (CONTRA) { if (t - 1 >= d_in0 && t - 1 < L) inside_Y_contra<(MODE == MODE_SMEM ? 1 : 4)>(v, T, lut, t - 1, tid - nXl, nYl); } }
+        else if (t - 2 >= d_in0 && t - 2 < L) inside_Z<CONTRA, (MODE == MODE_SMEM ? 2 : 4)>(v, T, lut, t - 2, tid - nXl - nYl, nZl);
         asm volatile("bar.sync 1, %0;" ::"r"(nYZl) : "memory");
-        if (isY) { if constexpr (CONTRA) { if (t < L) inside_Y_contra(v, T, lut, t, tid - nXl, nYl); } }
-        else if (t - 1 >= d_in0 && t - 1 < L) inside_Z<CONTRA>(v, T, lut, t - 1, tid - nXl - nYl, nZl);
+        if (isY) { if constexpr (CONTRA) { if (t < L) inside_Y_contra<(MODE == MODE_SMEM ? 1 : 4)>(v, T, lut, t, tid - nXl, nYl); } }
+        else if (t - 1 >= d_in0 && t - 1 < L) inside_Z<CONTRA, (MODE == MODE_SMEM ? 2 : 4)>(v, T, lut, t - 1, tid - nXl - nYl, nZl);
       }
       if (dbg_on && (tid & 31) == 0 && !helper) a.dbg[(size_t)t * 16 + warp] = clock64() - c0;
       __syncthreads();
@@ -256,13 +256,13 @@ __global__ void __launch_bounds__(512, 2) fold_kernel2(const FoldArgs a) {
       if (warp < a.nXw) {
         outside_X<CONTRA>(v, T, lut, P, Z, st, tid, nXl);
       } else if (!helper) {
-        if (d + 1 < L) outside_Y<CONTRA>(v, T, lut, d + 1, tid - nXl, nYZl);
-        outside_Y<CONTRA>(v, T, lut, d, tid - nXl, nYZl);
+        if (d + 1 < L) outside_Y<CONTRA, (MODE == MODE_SMEM ? 1 : 4)>(v, T, lut, d + 1, tid - nXl, nYZl);
+        outside_Y<CONTRA, (MODE == MODE_SMEM ? 1 : 4)>(v, T, lut, d, tid - nXl, nYZl);
       }
       if (dbg_on && (tid & 31) == 0 && !helper) a.dbg[(size_t)(1024 + d) * 16 + warp] = clock64() - c0;
       __syncthreads();
       const long long c1 = dbg_on ? clock64() : 0;
-      if (warp < a.nXw) outside_X_ml<CONTRA>(v, T, lut, st, tid, nXl);
+      if (warp < a.nXw) outside_X_ml<CONTRA, (MODE == MODE_SMEM ? 1 : 3)>(v, T, lut, st, tid, nXl);
       if (dbg_on && (tid & 31) == 0 && warp < a.nXw) a.dbg[(size_t)(1024 + d) * 16 + 8 + warp] = clock64() - c1;
       __syncthreads();
     }
@@ -288,6 +288,185 @@ __global__ void __launch_bounds__(512, 2) fold_kernel2(const FoldArgs a) {
       centroid_run<MODE>(a, sidx, sbeg, L, v.C, tstack, getp);   // W reuses sums_close (dead after the outside pass)
     }
     if (dbg_on && tid == 0) { a.dbg[2047 * 16 + 5] = clock64() - tpost0; a.dbg[2047 * 16 + 6] = clock64() - tseq0; a.dbg[2047 * 16 + 7] = L; }
+  }
+}
+
+}  // namespace rna
+
+namespace rna {
+
+// =========================================================================================================
+// fold_kernel2_coop — one LONG sequence at a time on the whole GPU (cooperative launch, HBM-resident working set).
+// Same phases and roles as fold_kernel2; a role's lanes are spread over the grid (consecutive warps of a role sit
+// on different SMs: the chains are latency-bound, so an SM per warp is the fastest placement), a step is ONE
+// diagonal (whole folds, no partial sums across steps) and the barrier is grid-wide.  grid.sync() orders memory
+// for every thread of the grid, so plain loads see what other CTAs wrote in earlier steps.
+// =========================================================================================================
+template <bool CONTRA>
+__global__ void __launch_bounds__(256, 2) fold_kernel2_coop(const FoldArgs a) {
+  typedef typename Model2<CONTRA>::Dev Dev;
+  typedef typename Model2<CONTRA>::Small Small;
+  typedef typename Model2<CONTRA>::View View;
+  typedef SeqViewT<uint16_t> SV;
+  cg::grid_group grid = cg::this_grid();
+
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float4* lut = reinterpret_cast<float4*>(smem_raw);
+  Small* small = reinterpret_cast<Small*>(smem_raw + 128);
+  uint8_t* sseq = smem_raw + 128 + align16(sizeof(Small));
+
+  const Dev* dev = reinterpret_cast<const Dev*>(a.tables);
+  const int tid = threadIdx.x;
+  load_lse_lut(lut);
+  {
+    const Small* gs = dev_small<CONTRA>(dev);
+    for (int x = tid; x < (int)(sizeof(Small) / 4); x += blockDim.x)
+      reinterpret_cast<float*>(small)[x] = reinterpret_cast<const float*>(gs)[x];
+  }
+  View T;
+  T.g = dev;
+  T.sm = small;
+  ModelParams P;
+  P.MINSPAN = dev->min_span;
+  if constexpr (CONTRA) P.MAX2 = dev->max_loop_len; else P.MAX2 = dev->max_2loop_len;
+  P.allows_short = a.allows_short;
+  const float NEG = RNA_NEG_INF;
+  const int gtid = (int)(blockIdx.x * blockDim.x + threadIdx.x), gnt = (int)(gridDim.x * blockDim.x);
+  // global warp id with consecutive ids on different SMs; role lanes are counted from the role's first warp
+  const int gw = (tid >> 5) * (int)gridDim.x + (int)blockIdx.x;
+  const int nXl = a.nXw * 32, nYl = a.nYw * 32, nZl = a.nZw * 32;
+  const int lnX = gw * 32 + (tid & 31), lnY = (gw - a.nXw) * 32 + (tid & 31), lnZ = (gw - a.nXw - a.nYw) * 32 + (tid & 31);
+  const bool isX = gw < a.nXw, isY = !isX && gw < a.nXw + a.nYw, isZ = !isX && !isY && gw < a.nXw + a.nYw + a.nZw;
+  __syncthreads();
+
+  for (uint32_t w = 0; w < a.n_launch; w++) {
+    const uint32_t sidx = a.order ? a.order[w] : w;
+    const uint32_t sbeg = a.offsets[sidx];
+    const int L = (int)(a.offsets[sidx + 1] - sbeg);
+    const size_t TRI = (size_t)L * (L + 1) / 2;
+    size_t ngcap = 0;
+    for (int c = 1; c <= L; c += 32) ngcap += (size_t)min(32, L - c + 1) * ((c + 31) / 32);   // = fold2_ngcap(L)
+
+    SV v;
+    v.L = L;
+    v.W2 = (L + 31) / 32 + 2;
+    uint8_t* s = sseq + 4;
+    v.s = s;
+    float* f = a.workspace;
+    v.C = f; f += TRI;
+    v.R = f; f += TRI;
+    v.X = f; f += TRI;
+    v.E = f; f += TRI;
+    v.M1 = f; f += TRI;
+    v.Pm = v.E;
+    v.Mroll = f; f += 3 * L;
+    v.E0 = f; f += L;
+    v.EL = f; f += L;
+    int* tstack = reinterpret_cast<int*>(f);
+    int* fill_ctr = tstack + 2 * (L + 2);
+    v.mask = reinterpret_cast<uint32_t*>(fill_ctr + 2);
+    v.gcumI = v.mask + (size_t)L * v.W2;
+    v.gcumO = v.gcumI + L / 2 + 3;
+    v.ccumI = v.gcumO + L / 2 + 3;
+    v.ccumO = v.ccumI + L / 2 + 3;
+    v.gbin = v.ccumO + L / 2 + 3;
+    v.gbout = v.gbin + ngcap + 2;
+    v.gstepI = reinterpret_cast<uint16_t*>(v.gbout + ngcap + 2);
+    v.gstepO = v.gstepI + ngcap + 2;
+    v.pcnt = v.gstepO + ngcap + 2;
+    v.din0 = CONTRA ? 0 : (P.MINSPAN - 1);
+    v.dout0 = CONTRA ? (a.allows_short ? 1 : P.MINSPAN - 1) : (P.MINSPAN - 1);
+    v.plist = v.pcnt + ((L + 1) & ~1);
+    v.RR = reinterpret_cast<uint8_t*>(v.plist + TRI);
+    v.LL = v.RR + L;
+    v.tin = nullptr; v.tout = nullptr; v.ccnt = nullptr; v.tcap = a.tcap;
+
+    long long tk = (a.dbg && gtid == 0) ? clock64() : 0;
+    auto mark = [&](int slot) { if (a.dbg && gtid == 0) { const long long now = clock64(); a.dbg[slot] = now - tk; tk = now; } };
+    __syncthreads();
+    for (int x = tid; x < L; x += blockDim.x) s[x] = a.bases[sbeg + x];   // every CTA keeps its own copy of the bases
+    if (tid < 4) { sseq[tid] = 0; s[L + tid] = 0; }
+    __syncthreads();
+    for (int x = gtid; x < L * v.W2; x += gnt) setup_mask_word<CONTRA>(v, P, x);
+    for (int x = gtid; x < L; x += gnt) setup_codes(v, x);
+    grid.sync();
+    for (int d = gtid; d < L; d += gnt) setup_list_diag(v, d);
+    grid.sync();
+    if (a.stream_ws) {
+      if (gtid == 0) { setup_groups(v); *fill_ctr = 0; }
+      v.ccnt = reinterpret_cast<uint16_t*>(v.C);
+      grid.sync();
+      stream_count(v, P, gtid, gnt);
+      grid.sync();
+      stream_groupmax(v, gtid, gnt);
+      grid.sync();
+      if (gtid == 0) stream_scan(v);
+      grid.sync();
+      const uint32_t NGI = v.gcumI[max(num_steps_inside(v), 0)], NGO = v.gcumO[max(num_steps_outside(v), 0)];
+      if (v.gbin[NGI] <= a.tcap && v.gbout[NGO] <= a.tcap) {
+        v.tin = reinterpret_cast<uint2*>(a.stream_ws);
+        v.tout = v.tin + a.tcap;
+        const uint32_t ntask = stream_num_tasks(v);
+        for (;;) {
+          uint32_t tau = 0;
+          if ((tid & 31) == 0) tau = (uint32_t)atomicAdd(fill_ctr, 1);
+          tau = __shfl_sync(0xffffffffu, tau, 0);
+          if (tau >= ntask) break;
+          stream_fill_task<CONTRA>(v, T, P, tau, tid & 31);
+          __syncwarp();
+        }
+      }
+      grid.sync();
+    }
+    for (size_t x = gtid; x < TRI; x += gnt) { v.C[x] = NEG; v.R[x] = NEG; v.X[x] = NEG; v.E[x] = 0.f; v.M1[x] = NEG; }
+    for (int x = gtid; x < 3 * L; x += gnt) v.Mroll[x] = NEG;
+    grid.sync();
+    mark(0);   // setup + term streams
+
+    // ---- inside, one diagonal per step: X(t) | Y(t) | Z(t-1) -------------------------------------------------
+    const int d_in0 = v.din0;
+    for (int t = d_in0; t <= L; t++) {
+      if (isX) { if (t < L) inside_X_diag<CONTRA>(v, T, lut, P, t, lnX, nXl); }
+      else if (isY) { if constexpr (CONTRA) { if (t < L) inside_Y_contra<4>(v, T, lut, t, lnY, nYl); } }
+      else if (isZ) { if (t - 1 >= d_in0) inside_Z<CONTRA, 6>(v, T, lut, t - 1, lnZ, nZl); }
+      grid.sync();
+    }
+    for (int x = gtid; x < L; x += gnt) {
+      v.E0[x] = v.E[doff(x, L)];
+      v.EL[x] = v.E[doff(L - 1 - x, L) + x];
+    }
+    grid.sync();
+    mark(1);   // inside
+    const float Z = v.E0[L - 1];
+    for (size_t x = gtid; x < TRI; x += gnt) { v.Pm[x] = NEG; v.R[x] = NEG; v.X[x] = NEG; }
+    if (gtid == 0 && a.out_logz) a.out_logz[sidx] = Z;
+    grid.sync();
+    // ---- outside, one diagonal per step: X(d) | Y(d) --------------------------------------------------------------
+    const int d_out0 = v.dout0;
+    for (int d = L - 1; d >= d_out0; d--) {
+      if (isX) outside_X_diag<CONTRA, 4>(v, T, lut, P, Z, d, lnX, nXl);
+      else if (isY || isZ) outside_Y<CONTRA, 4>(v, T, lut, d, lnY, nYl + nZl);
+      grid.sync();
+    }
+    mark(2);   // outside
+    for (size_t x = gtid; x < TRI; x += gnt) {
+      const float val = v.Pm[x];
+      v.Pm[x] = (val > NEG) ? approx_expf(val) : -1.0f;
+    }
+    grid.sync();
+    if (a.out_bpp) {
+      float* ob = a.out_bpp + a.bpp_offsets[sidx];
+      for (int i = (int)blockIdx.x; i < L - 1; i += (int)gridDim.x) {
+        const size_t rowoff = (size_t)i * (size_t)(2 * L - i - 1) / 2;
+        for (int x = tid; x < L - 1 - i; x += blockDim.x) ob[rowoff + x] = v.Pm[doff(x + 1, L) + i];
+      }
+    }
+    {
+      const float* Pm = v.Pm;
+      auto getp = [=](int d, int i) -> float { return __ldcg(&Pm[doff(d, L) + i]); };
+      centroid_run<MODE_COOP>(a, sidx, sbeg, L, v.C, tstack, getp);
+    }
+    mark(3);   // BPP + centroid
   }
 }
 

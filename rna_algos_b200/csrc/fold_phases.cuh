@@ -694,34 +694,48 @@ RNA_DEV float stream_chain(const SV& v, const uint2* __restrict__ st, uint32_t w
 // inside, role X: sums_close of the closable cells of diagonal d (src/mccaskill_algo.rs:290-343, 395-467).
 // Needs: sums_close of diagonals <= d-2, sums_multibranch of diagonal d-2.
 // =========================================================================================================
+// hairpin + two-loop part of sums_close of the x-th closable cell of inside step st (no multibranch term yet)
+template <bool CONTRA, class SV>
+RNA_DEV float inside_cell_partial(const SV& v, const typename Model2<CONTRA>::View& T, const float4* lut,
+                                  const ModelParams& P, int st, int tot, int x, int d, int i, int j) {
+  const uint8_t* s = v.s;
+  float sum = RNA_NEG_INF;
+  if constexpr (CONTRA) {
+    if (d - 1 <= P.MAX2) sum = lse(sum, c2_hairpin(T, s, i, j), lut);
+  } else {
+    sum = lse(sum, t_hairpin(T, s, i, j), lut);
+  }
+  if (v.tin) {
+    const uint32_t G = v.gcumI[st] + (x >> 5), gb = v.gbin[G], wd = group_width(tot, x >> 5);
+    sum = stream_chain<true>(v, v.tin + gb + (x & 31), wd, (v.gbin[G + 1] - gb) / wd, lut, 0.f, sum);
+  } else {
+    typename LoopOf<CONTRA, true>::type lp = make_loop<CONTRA, true>(v, T, i, j);
+    sum = twoloop_chain<true>(v, lp, lut, P.MAX2, i, j, 0.f, sum);
+  }
+  return sum;
+}
+// the closing multibranch term (needs sums_multibranch of diagonal d-2)
+template <bool CONTRA, class SV>
+RNA_DEV float inside_cell_fin(const SV& v, const typename Model2<CONTRA>::View& T, const float4* lut, int d, int i, int j,
+                              float sum) {
+  const float* Mm2 = v.Mroll + ((d + 1) % 3) * v.L;   // diagonal d-2
+  const float mb = (d >= 2) ? Mm2[i + 1] : RNA_NEG_INF;
+  return lse(sum, __fadd_rn(mb, v2_mbclose<CONTRA>(T, v.s, v.L, i, j)), lut);
+}
 // X, phase 1 of inside step st: hairpin + two-loop part of sums_close for the diagonals d and d+1 of the step.
 // Both only need sums_close of diagonals <= d-1, so the two longest chains of the pass run side by side.
 template <bool CONTRA, class SV>
 RNA_DEV void inside_X(const SV& v, const typename Model2<CONTRA>::View& T, const float4* lut,
                       const ModelParams& P, int st, int lane, int nl) {
   const int L = v.L;
-  const uint8_t* s = v.s;
-  const float NEG = RNA_NEG_INF;
   const StepCells sc = step_cells<true>(v, st);
   const int tot = sc.cA + sc.cB;
   for (int x = lane; x < tot; x += nl) {   // ONE loop body: lanes of both diagonals run their chains together
     int d, r;
     step_cell(sc, x, d, r);
-    const int od = doff(d, L), i = v.plist[od + r], j = i + d;
-    float sum = NEG;
-    if constexpr (CONTRA) {
-      if (d - 1 <= P.MAX2) sum = lse(sum, c2_hairpin(T, s, i, j), lut);
-    } else {
-      sum = lse(sum, t_hairpin(T, s, i, j), lut);
-    }
-    if (v.tin) {
-      const uint32_t G = v.gcumI[st] + (x >> 5), gb = v.gbin[G], wd = group_width(tot, x >> 5);
-      sum = stream_chain<true>(v, v.tin + gb + (x & 31), wd, (v.gbin[G + 1] - gb) / wd, lut, 0.f, sum);
-    } else {
-      typename LoopOf<CONTRA, true>::type lp = make_loop<CONTRA, true>(v, T, i, j);
-      sum = twoloop_chain<true>(v, lp, lut, P.MAX2, i, j, 0.f, sum);
-    }
-    v.C[od + i] = sum;   // still without the multibranch term: no one reads these diagonals before inside_X_fin
+    const int od = doff(d, L), i = v.plist[od + r];
+    // still without the multibranch term: no one reads these diagonals before inside_X_fin
+    v.C[od + i] = inside_cell_partial<CONTRA>(v, T, lut, P, st, tot, x, d, i, i + d);
   }
 }
 // X, phase 2: the closing multibranch term (needs sums_multibranch of d-2 resp. d-1, computed by Z in phase 1)
@@ -729,24 +743,64 @@ template <bool CONTRA, class SV>
 RNA_DEV void inside_X_fin(const SV& v, const typename Model2<CONTRA>::View& T, const float4* lut, int st, int lane,
                           int nl) {
   const int L = v.L;
-  const float NEG = RNA_NEG_INF;
   const StepCells sc = step_cells<true>(v, st);
   for (int x = lane; x < sc.cA + sc.cB; x += nl) {
     int dd, r;
     step_cell(sc, x, dd, r);
-    const int od = doff(dd, L), i = v.plist[od + r], j = i + dd;
-    const float* Mm2 = v.Mroll + ((dd + 1) % 3) * L;   // diagonal dd-2
-    const float mb = (dd >= 2) ? Mm2[i + 1] : NEG;
-    v.C[od + i] = lse(v.C[od + i], __fadd_rn(mb, v2_mbclose<CONTRA>(T, v.s, L, i, j)), lut);
+    const int od = doff(dd, L), i = v.plist[od + r];
+    v.C[od + i] = inside_cell_fin<CONTRA>(v, T, lut, dd, i, i + dd, v.C[od + i]);
   }
 }
+// X of a ONE-diagonal step (the grid-wide wavefront for long sequences: a barrier costs microseconds there, so a
+// step is one diagonal and the whole fold of a cell runs in it; needs sums_close <= d-2 and sums_multibranch(d-2))
+template <bool CONTRA, class SV>
+RNA_DEV void inside_X_diag(const SV& v, const typename Model2<CONTRA>::View& T, const float4* lut,
+                           const ModelParams& P, int d, int lane, int nl) {
+  const int L = v.L;
+  if (d < v.din0) return;
+  const int st = (d - v.din0) >> 1;
+  const StepCells sc = step_cells<true>(v, st);
+  const int tot = sc.cA + sc.cB, x0 = (d == sc.dA) ? 0 : sc.cA, cnt = v.pcnt[d], od = doff(d, L);
+  for (int r = lane; r < cnt; r += nl) {
+    const int i = v.plist[od + r], j = i + d;
+    const float sum = inside_cell_partial<CONTRA>(v, T, lut, P, st, tot, x0 + r, d, i, j);
+    v.C[od + i] = inside_cell_fin<CONTRA>(v, T, lut, d, i, j, sum);
+  }
+}
+
+// ascending iterator over the set bits of a bit-matrix row within [lo, hi]
+struct RowBits {
+  const uint32_t* row;
+  int p, hi;
+  uint32_t w;
+  RNA_DEVM RowBits(const uint32_t* row_, int lo, int hi_) : row(row_), p(lo), hi(hi_), w(0u) {
+    if (p <= hi) w = window();
+  }
+  RNA_DEVM uint32_t window() const {
+    uint32_t x = get32(row, p);
+    const int n = hi - p + 1;
+    if (n < 32) x &= (1u << n) - 1u;
+    return x;
+  }
+  RNA_DEVM int next() {   // -1 when exhausted
+    if (p > hi) return -1;
+    while (w == 0) {
+      p += 32;
+      if (p > hi) return -1;
+      w = window();
+    }
+    const int t = __ffs(w) - 1;
+    w &= w - 1;
+    return p + t;
+  }
+};
 
 // =========================================================================================================
 // inside, role Y (CONTRAfold): the k < j part of sums_rightmost_basepairs_{external,multibranch}[i][j]
 // (src/mccaskill_algo.rs:468-486); the k == j term is added by role Z one step later.
 // Needs: sums_close of diagonals < d.
 // =========================================================================================================
-template <class SV>
+template <int CH, class SV>
 RNA_DEV void inside_Y_contra(const SV& v, const ContraView2& T, const float4* lut, int d, int lane, int nl) {
   const int L = v.L;
   const uint8_t* s = v.s;
@@ -756,6 +810,7 @@ RNA_DEV void inside_Y_contra(const SV& v, const ContraView2& T, const float4* lu
   for (int i = lane; i < ncell; i += nl) {
     const int j = i + d;
     float r = NEG, rm = NEG;
+    if constexpr (CH <= 1) {
     const uint32_t* row = v.mask + i * v.W2;
     for (int p = i + 1; p <= j - 1; p += 32) {
       uint32_t w = get32(row, p);
@@ -771,6 +826,33 @@ RNA_DEV void inside_Y_contra(const SV& v, const ContraView2& T, const float4* lu
         rm = lse(rm, __fadd_rn(__fadd_rn(av, dev->mb_bp), __fmul_rn(dev->mb_unpair, nn)), lut);
       }
     }
+    } else {
+    // closable (i,k), i < k < j ascending, CH terms at a time: the sums_close gathers of the next chunk are in
+    // flight while the folds of the current one execute
+    RowBits it(v.mask + i * v.W2, i + 1, j - 1);
+    int kb[CH];
+    float cb[CH];
+#pragma unroll
+    for (int u = 0; u < CH; u++) { kb[u] = it.next(); cb[u] = (kb[u] >= 0) ? v.C[doff(kb[u] - i, L) + i] : NEG; }
+    while (kb[0] >= 0) {
+      int ka[CH];
+      float ca[CH];
+#pragma unroll
+      for (int u = 0; u < CH; u++) { ka[u] = kb[u]; ca[u] = cb[u]; }
+#pragma unroll
+      for (int u = 0; u < CH; u++) { kb[u] = it.next(); cb[u] = (kb[u] >= 0) ? v.C[doff(kb[u] - i, L) + i] : NEG; }
+#pragma unroll
+      for (int u = 0; u < CH; u++) {
+        if (ka[u] >= 0) {
+          const int k = ka[u];
+          const float av = __fadd_rn(ca[u], v2_acc<true>(T, s, L, i, k));
+          const float nn = (float)(j - k);
+          r = lse(r, __fadd_rn(__fadd_rn(av, dev->ext_bp), __fmul_rn(dev->ext_unpair, nn)), lut);
+          rm = lse(rm, __fadd_rn(__fadd_rn(av, dev->mb_bp), __fmul_rn(dev->mb_unpair, nn)), lut);
+        }
+      }
+    }
+    }
     v.R[od + i] = r;
     v.X[od + i] = rm;
   }
@@ -781,7 +863,7 @@ RNA_DEV void inside_Y_contra(const SV& v, const ContraView2& T, const float4* lu
 // sums_external, sums_multibranch, sums_1ormore_basepairs (src/mccaskill_algo.rs:344-374, 468-512).
 // Needs: sums_close(d) (role X, previous step), partial R/Rm(d) (role Y, previous step), R/Rm/E/M1 of < d.
 // =========================================================================================================
-template <bool CONTRA, class SV>
+template <bool CONTRA, int PF, class SV>
 RNA_DEV void inside_Z(const SV& v, const typename Model2<CONTRA>::View& T, const float4* lut, int d,
                       int lane, int nl) {
   const int L = v.L;
@@ -814,6 +896,7 @@ RNA_DEV void inside_Z(const SV& v, const typename Model2<CONTRA>::View& T, const
       sM1 = __fadd_rn(Rij, dev->coeff_num_branches);
     }
     sE = lse(sE, __fadd_rn(Rij, 0.f), lut);   // k = i: E[i][i-1] = 0 (lower triangle / literal 0)
+    if constexpr (PF <= 2) {
     // operands two split points ahead are in flight while the three folds of the current one execute
     // (R, Rm, E, M1 may live in HBM/L2: their addresses do not depend on the running sums)
     float r1 = NEG, e1 = NEG, q1 = NEG, x1 = NEG, r2 = NEG, e2 = NEG, q2 = NEG, x2 = NEG;
@@ -842,6 +925,43 @@ RNA_DEV void inside_Z(const SV& v, const typename Model2<CONTRA>::View& T, const
         sM = lse(sM, __fadd_rn(m1, xx), lut);
       }
     }
+    } else {
+    // operands PF split points ahead are in flight while the three folds of the current one execute (R, Rm, E, M1
+    // may live in HBM/L2: their addresses do not depend on the running sums); PF ~ memory latency / fold latency
+    float pr[PF], pe[PF], pq[PF], px[PF];
+#pragma unroll
+    for (int u = 0; u < PF; u++) {
+      pr[u] = NEG; pe[u] = NEG; pq[u] = NEG; px[u] = NEG;
+      const int m = 1 + u;
+      if (m < d) {
+        pr[u] = v.R[doff(d - m, L) + i + m]; pe[u] = v.E[doff(m - 1, L) + i]; pq[u] = v.M1[doff(m - 1, L) + i];
+        if (CONTRA) px[u] = v.X[doff(d - m, L) + i + m];
+      }
+    }
+    for (int m0 = 1; m0 < d; m0 += PF) {
+#pragma unroll
+      for (int u = 0; u < PF; u++) {
+        const int m = m0 + u;
+        if (m < d) {
+          const float r = pr[u], e = pe[u], m1 = pq[u], rm = px[u];
+          const int mn = m + PF;
+          if (mn < d) {
+            pr[u] = v.R[doff(d - mn, L) + i + mn]; pe[u] = v.E[doff(mn - 1, L) + i]; pq[u] = v.M1[doff(mn - 1, L) + i];
+            if (CONTRA) px[u] = v.X[doff(d - mn, L) + i + mn];
+          }
+          sE = lse(sE, __fadd_rn(r, e), lut);
+          if constexpr (CONTRA) {
+            sM1 = lse(sM1, __fadd_rn(rm, __fmul_rn(dev->mb_unpair, (float)m)), lut);
+            sM = lse(sM, __fadd_rn(m1, rm), lut);
+          } else {
+            const float xx = __fadd_rn(r, dev->coeff_num_branches);
+            sM1 = lse(sM1, xx, lut);
+            sM = lse(sM, __fadd_rn(m1, xx), lut);
+          }
+        }
+      }
+    }
+    }
     v.E[od + i] = sE;
     Mcur[i] = sM;
     sM1 = lse(sM1, sM, lut);
@@ -853,7 +973,7 @@ RNA_DEV void inside_Z(const SV& v, const typename Model2<CONTRA>::View& T, const
 // outside, role Y: probs_multibranch / probs_multibranch2 of every cell of diagonal d
 // (src/mccaskill_algo.rs:540-557, 641-661).  Needs: log P of diagonals > d.
 // =========================================================================================================
-template <bool CONTRA, class SV>
+template <bool CONTRA, int CH, class SV>
 RNA_DEV void outside_Y(const SV& v, const typename Model2<CONTRA>::View& T, const float4* lut, int d,
                        int lane, int nl) {
   const int L = v.L;
@@ -863,6 +983,7 @@ RNA_DEV void outside_Y(const SV& v, const typename Model2<CONTRA>::View& T, cons
   for (int i = lane; i < ncell; i += nl) {
     const int j = i + d;
     float pm = NEG, pm2 = NEG;
+    if constexpr (CH <= 1) {
     const uint32_t* row = v.mask + i * v.W2;
     // closable (i,k), k > j ascending; the operands of the next term are fetched before the two folds of the
     // current one (sums_1ormore_basepairs may live in HBM/L2)
@@ -899,6 +1020,42 @@ RNA_DEV void outside_Y(const SV& v, const typename Model2<CONTRA>::View& T, cons
       if constexpr (CONTRA) pm2 = lse(pm2, __fadd_rn(x, __fmul_rn(T.g->mb_unpair, (float)(m - 1))), lut);
       else pm2 = lse(pm2, x, lut);
     }
+    } else {
+    // closable (i,k), k > j ascending, CH terms at a time; the operands of the next chunk are in flight while
+    // the folds of the current one execute (sums_1ormore_basepairs, and in the HBM modes everything, is far away)
+    RowBits it(v.mask + i * v.W2, j + 1, L - 1);
+    int kb[CH];
+    float cb[CH], pb[CH], mb[CH];
+    auto fetch = [&](int u) {
+      kb[u] = it.next();
+      cb[u] = NEG; pb[u] = NEG; mb[u] = NEG;
+      if (kb[u] >= 0) {
+        const int q = doff(kb[u] - i, L) + i;
+        cb[u] = v.C[q]; pb[u] = v.Pm[q];
+        if (kb[u] - j >= 2) mb[u] = v.M1[doff(kb[u] - j - 2, L) + j + 1];
+      }
+    };
+#pragma unroll
+    for (int u = 0; u < CH; u++) fetch(u);
+    while (kb[0] >= 0) {
+      int ka[CH];
+      float ca[CH], pa[CH], ma[CH];
+#pragma unroll
+      for (int u = 0; u < CH; u++) { ka[u] = kb[u]; ca[u] = cb[u]; pa[u] = pb[u]; ma[u] = mb[u]; }
+#pragma unroll
+      for (int u = 0; u < CH; u++) fetch(u);
+#pragma unroll
+      for (int u = 0; u < CH; u++) {
+        if (ka[u] >= 0) {
+          const int k = ka[u], m = k - j;
+          const float x = __fsub_rn(__fadd_rn(pa[u], v2_mbclose<CONTRA>(T, s, L, i, k)), ca[u]);
+          pm = lse(pm, __fadd_rn(x, ma[u]), lut);
+          if constexpr (CONTRA) pm2 = lse(pm2, __fadd_rn(x, __fmul_rn(T.g->mb_unpair, (float)(m - 1))), lut);
+          else pm2 = lse(pm2, x, lut);
+        }
+      }
+    }
+    }
     v.R[od + i] = pm;
     v.X[od + i] = pm2;
   }
@@ -908,61 +1065,40 @@ RNA_DEV void outside_Y(const SV& v, const typename Model2<CONTRA>::View& T, cons
 // outside, role X: log P(i,j) of the closable cells of diagonal d (src/mccaskill_algo.rs:558-604, 662-719).
 // Needs: log P, probs_multibranch, probs_multibranch2 of diagonals > d.
 // =========================================================================================================
-// X, phase 1 of outside step st: exterior term + enclosing two-loops of log P for the diagonals d and d-1 of the
-// step: both only need log P of diagonals >= d+1.
+// exterior term + enclosing two-loops of log P of the x-th closable cell of outside step st
 template <bool CONTRA, class SV>
-RNA_DEV void outside_X(const SV& v, const typename Model2<CONTRA>::View& T, const float4* lut,
-                       const ModelParams& P, float Z, int st, int lane, int nl) {
+RNA_DEV float outside_cell_partial(const SV& v, const typename Model2<CONTRA>::View& T, const float4* lut,
+                                   const ModelParams& P, float Z, int st, int tot, int x, int i, int j, float Cij) {
   const int L = v.L;
   const uint8_t* s = v.s;
-  const float NEG = RNA_NEG_INF;
   const typename Model2<CONTRA>::Dev* dev = T.g;
-  const StepCells sc = step_cells<false>(v, st);
-  const int tot = sc.cA + sc.cB;
-  for (int x = lane; x < tot; x += nl) {
-    int d, r;
-    step_cell(sc, x, d, r);
-    const int od = doff(d, L), i = v.plist[od + r], j = i + d;
-    const float Cij = v.C[od + i];
-    // a statically closable cell without a structure (CONTRAfold, rare): its lane still walks the (padded) block
-    const bool has = Cij > NEG;
-    const float Aij = __fadd_rn(Cij, v2_acc<CONTRA>(T, s, L, i, j));
-    const float El = (i < 1) ? 0.f : v.E0[i - 1];
-    const float Er = (j > L - 2) ? 0.f : v.EL[j + 1];
-    float sm;
-    if constexpr (CONTRA) sm = __fsub_rn(__fadd_rn(__fadd_rn(__fadd_rn(El, Er), Aij), dev->ext_bp), Z);
-    else sm = __fsub_rn(__fadd_rn(__fadd_rn(El, Aij), Er), Z);
-    if (!has) continue;
-    // enclosing two-loops: k descending from i-1, l ascending from j+1
-    if (v.tin) {
-      const uint32_t G = v.gcumO[st] + (x >> 5), gb = v.gbout[G], wd = group_width(tot, x >> 5);
-      sm = stream_chain<false>(v, v.tout + gb + (x & 31), wd, (v.gbout[G + 1] - gb) / wd, lut, Cij, sm);
-    } else {
-      typename LoopOf<CONTRA, false>::type lp = make_loop<CONTRA, false>(v, T, i, j);
-      sm = twoloop_chain<false>(v, lp, lut, P.MAX2, i, j, Cij, sm);
-    }
-    v.Pm[od + i] = sm;   // exterior + two-loop part; outside_X_ml continues the fold
+  const float Aij = __fadd_rn(Cij, v2_acc<CONTRA>(T, s, L, i, j));
+  const float El = (i < 1) ? 0.f : v.E0[i - 1];
+  const float Er = (j > L - 2) ? 0.f : v.EL[j + 1];
+  float sm;
+  if constexpr (CONTRA) sm = __fsub_rn(__fadd_rn(__fadd_rn(__fadd_rn(El, Er), Aij), dev->ext_bp), Z);
+  else sm = __fsub_rn(__fadd_rn(__fadd_rn(El, Aij), Er), Z);
+  // enclosing two-loops: k descending from i-1, l ascending from j+1
+  if (v.tin) {
+    const uint32_t G = v.gcumO[st] + (x >> 5), gb = v.gbout[G], wd = group_width(tot, x >> 5);
+    sm = stream_chain<false>(v, v.tout + gb + (x & 31), wd, (v.gbout[G + 1] - gb) / wd, lut, Cij, sm);
+  } else {
+    typename LoopOf<CONTRA, false>::type lp = make_loop<CONTRA, false>(v, T, i, j);
+    sm = twoloop_chain<false>(v, lp, lut, P.MAX2, i, j, Cij, sm);
   }
+  return sm;
 }
-// X, phase 2: enclosing multiloops, k ascending 0..i-1 (needs probs_multibranch(2) of diagonals >= d resp. d+1)
-template <bool CONTRA, class SV>
-RNA_DEV void outside_X_ml(const SV& v, const typename Model2<CONTRA>::View& T, const float4* lut, int st, int lane,
-                          int nl) {
+// enclosing multiloops, k ascending 0..i-1 (needs probs_multibranch(2) of diagonals > j - i)
+template <bool CONTRA, int PF, class SV>
+RNA_DEV float outside_cell_ml(const SV& v, const typename Model2<CONTRA>::View& T, const float4* lut, int i, int j,
+                              float Cij, float sm) {
   const int L = v.L;
-  const uint8_t* s = v.s;
   const float NEG = RNA_NEG_INF;
   const typename Model2<CONTRA>::Dev* dev = T.g;
-  const StepCells sc = step_cells<false>(v, st);
-  for (int x = lane; x < sc.cA + sc.cB; x += nl) {
-    int dd, r;
-    step_cell(sc, x, dd, r);
-    const int od = doff(dd, L), i = v.plist[od + r], j = i + dd;
-    const float Cij = v.C[od + i];
-    if (!(Cij > NEG)) continue;
-    float sm = v.Pm[od + i];
-    const float Aij = __fadd_rn(Cij, v2_acc<CONTRA>(T, s, L, i, j));
-    float sa;
-    if constexpr (CONTRA) sa = __fadd_rn(Aij, dev->mb_bp); else sa = __fadd_rn(Aij, dev->coeff_num_branches);
+  const float Aij = __fadd_rn(Cij, v2_acc<CONTRA>(T, v.s, L, i, j));
+  float sa;
+  if constexpr (CONTRA) sa = __fadd_rn(Aij, dev->mb_bp); else sa = __fadd_rn(Aij, dev->coeff_num_branches);
+  if constexpr (PF <= 1) {
     // operands of step kk+1 are loaded before the three dependent logsumexp's of step kk
     float nx1 = NEG, np2 = NEG, ny = NEG;
     if (i > 0) {
@@ -983,7 +1119,91 @@ RNA_DEV void outside_X_ml(const SV& v, const typename Model2<CONTRA>::View& T, c
       else sm = lse(sm, __fadd_rn(sa, y), lut);
       sm = lse(sm, __fadd_rn(__fadd_rn(sa, x1), y), lut);
     }
-    v.Pm[od + i] = sm;
+  } else {
+  // operands PF steps ahead are in flight while the three dependent logsumexp's of a step execute
+  float bx[PF], bp[PF], by[PF];
+#pragma unroll
+  for (int u = 0; u < PF; u++) {
+    bx[u] = NEG; bp[u] = NEG; by[u] = NEG;
+    const int kk = u;
+    if (kk < i) {
+      const int m = i - 1 - kk, q = doff(j - kk, L) + kk;
+      bx[u] = (m >= 1) ? v.M1[doff(m - 1, L) + kk + 1] : NEG;
+      bp[u] = v.X[q]; by[u] = v.R[q];
+    }
+  }
+  for (int k0 = 0; k0 < i; k0 += PF) {
+#pragma unroll
+    for (int u = 0; u < PF; u++) {
+      const int kk = k0 + u;
+      if (kk < i) {
+        const int m = i - 1 - kk;
+        const float x1 = bx[u], p2 = bp[u], y = by[u];
+        const int kn = kk + PF;
+        if (kn < i) {
+          const int mn = i - 1 - kn, q = doff(j - kn, L) + kn;
+          bx[u] = (mn >= 1) ? v.M1[doff(mn - 1, L) + kn + 1] : NEG;
+          bp[u] = v.X[q]; by[u] = v.R[q];
+        }
+        sm = lse(sm, __fadd_rn(__fadd_rn(sa, p2), x1), lut);
+        if constexpr (CONTRA) sm = lse(sm, __fadd_rn(__fadd_rn(sa, y), __fmul_rn(dev->mb_unpair, (float)m)), lut);
+        else sm = lse(sm, __fadd_rn(sa, y), lut);
+        sm = lse(sm, __fadd_rn(__fadd_rn(sa, x1), y), lut);
+      }
+    }
+  }
+  }
+  return sm;
+}
+// X, phase 1 of outside step st: exterior term + enclosing two-loops of log P for the diagonals d and d-1 of the
+// step: both only need log P of diagonals >= d+1.
+template <bool CONTRA, class SV>
+RNA_DEV void outside_X(const SV& v, const typename Model2<CONTRA>::View& T, const float4* lut,
+                       const ModelParams& P, float Z, int st, int lane, int nl) {
+  const int L = v.L;
+  const StepCells sc = step_cells<false>(v, st);
+  const int tot = sc.cA + sc.cB;
+  for (int x = lane; x < tot; x += nl) {
+    int d, r;
+    step_cell(sc, x, d, r);
+    const int od = doff(d, L), i = v.plist[od + r];
+    const float Cij = v.C[od + i];
+    if (!(Cij > RNA_NEG_INF)) continue;   // statically closable, but no structure closes it (CONTRAfold, rare)
+    // exterior + two-loop part; outside_X_ml continues the fold
+    v.Pm[od + i] = outside_cell_partial<CONTRA>(v, T, lut, P, Z, st, tot, x, i, i + d, Cij);
+  }
+}
+// X, phase 2: enclosing multiloops (needs probs_multibranch(2) of diagonals >= d resp. d+1)
+template <bool CONTRA, int PF, class SV>
+RNA_DEV void outside_X_ml(const SV& v, const typename Model2<CONTRA>::View& T, const float4* lut, int st, int lane,
+                          int nl) {
+  const int L = v.L;
+  const StepCells sc = step_cells<false>(v, st);
+  for (int x = lane; x < sc.cA + sc.cB; x += nl) {
+    int dd, r;
+    step_cell(sc, x, dd, r);
+    const int od = doff(dd, L), i = v.plist[od + r];
+    const float Cij = v.C[od + i];
+    if (!(Cij > RNA_NEG_INF)) continue;
+    v.Pm[od + i] = outside_cell_ml<CONTRA, PF>(v, T, lut, i, i + dd, Cij, v.Pm[od + i]);
+  }
+}
+// X of a ONE-diagonal step (grid-wide wavefront): the whole fold of log P(i,j); needs log P, probs_multibranch(2)
+// of diagonals > d
+template <bool CONTRA, int PF, class SV>
+RNA_DEV void outside_X_diag(const SV& v, const typename Model2<CONTRA>::View& T, const float4* lut,
+                            const ModelParams& P, float Z, int d, int lane, int nl) {
+  const int L = v.L;
+  if (d < v.dout0) return;
+  const int st = (L - 1 - d) >> 1;
+  const StepCells sc = step_cells<false>(v, st);
+  const int tot = sc.cA + sc.cB, x0 = (d == sc.dA) ? 0 : sc.cA, cnt = v.pcnt[d], od = doff(d, L);
+  for (int r = lane; r < cnt; r += nl) {
+    const int i = v.plist[od + r], j = i + d;
+    const float Cij = v.C[od + i];
+    if (!(Cij > RNA_NEG_INF)) continue;
+    const float sm = outside_cell_partial<CONTRA>(v, T, lut, P, Z, st, tot, x0 + r, i, j, Cij);
+    v.Pm[od + i] = outside_cell_ml<CONTRA, PF>(v, T, lut, i, j, Cij, sm);
   }
 }
 

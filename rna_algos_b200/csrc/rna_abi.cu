@@ -319,8 +319,8 @@ static int launch_fold_model(rna_handle* h, const RnaFoldBatchDev* b, cudaStream
     const Bucket& bk = buckets[k];
     if (bk.mode == MODE_SMEM) continue;   // (v2: sized below, once the grid is known)
     const size_t per = (centroid_only ? centroid_ws_floats(bk.Lcap)
-                        : (v2 && bk.mode == MODE_GLOBAL) ? fold2_seq_bytes(bk.Lcap, 2, 5) / 4
-                                                         : fold_ws_floats<CONTRA>(bk.Lcap)) + 32;
+                        : v2 ? fold2_seq_bytes(bk.Lcap, 2, 5) / 4 + 64
+                             : fold_ws_floats<CONTRA>(bk.Lcap)) + 32;
     stride_of[k] = per;
     if (bk.mode == MODE_COOP) {
       ws_floats = std::max(ws_floats, per);
@@ -346,6 +346,19 @@ static int launch_fold_model(rna_handle* h, const RnaFoldBatchDev* b, cudaStream
   if (v2) {
     for (size_t k = 0; k < buckets.size(); k++) {
       const Bucket& bk = buckets[k];
+      if (bk.mode == MODE_COOP && !no_streams) {
+        // one sequence on the whole GPU: a single stream slot, as large as memory comfortably allows (else the kernel
+        // scores on the fly)
+        const size_t Tc = (size_t)bk.Lcap * (bk.Lcap + 1) / 2;
+        size_t freeb = 0, totb = 0;
+        cudaMemGetInfo(&freeb, &totb);
+        size_t cap = std::min<size_t>(96 * Tc, (size_t)0xfffffff0u);
+        const size_t budget = (freeb + h->stream_ws.cap) / 3;
+        if (cap * 16 > budget) cap = budget / 16;
+        tcap_of[k] = (uint32_t)cap;
+        stream_stride_of[k] = fold2_stream_bytes(bk.Lcap, tcap_of[k]);
+        stream_bytes = std::max(stream_bytes, stream_stride_of[k]);
+      }
       if (bk.mode != MODE_SMEM) continue;
       // CTAs per SM: bounded by shared memory (C, log P and the small per-sequence tables) and by 1024 threads per SM
       // at 64 registers.  The chains are latency-bound, so residency is what fills the SM: take all the CTAs that
@@ -475,6 +488,26 @@ static int launch_fold_model(rna_handle* h, const RnaFoldBatchDev* b, cudaStream
         TRY(set_smem_attr(h, fold_kernel<CONTRA, MODE_GLOBAL>, smem));
         fold_kernel<CONTRA, MODE_GLOBAL><<<grid_of[k], nt, smem, st>>>(a);
       }
+    } else if (v2) {
+      // long sequence: cooperative grid, roles spread over the SMs
+      const int nt = 256;
+      const size_t smem = fold2_fixed_bytes<CONTRA>(bk.Lcap);
+      int occ = 1;
+      TRY(set_smem_attr(h, fold_kernel2_coop<CONTRA>, smem));
+      CU(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fold_kernel2_coop<CONTRA>, nt, smem));
+      const int grid = std::max(1, std::min(occ, 2)) * h->sm_count;
+      const int W = grid * (nt / 32);
+      int nX = (3 * bk.Lcap / 4 + 31) / 32, nZ = (bk.Lcap + 31) / 32, nY = CONTRA ? nZ : 0;
+      while (nX + nY + nZ > W) { if (nZ > 1) nZ--; if (nY > 1) nY--; if (nX > 1 && nX + nY + nZ > W) nX--; if (nX + nY + nZ <= 3) break; }
+      a.nXw = nX; a.nYw = nY; a.nZw = nZ;
+      a.stream_ws = nullptr;
+      if (stream_stride_of[k]) {
+        a.tcap = tcap_of[k];
+        a.stream_stride = stream_stride_of[k];
+        a.stream_ws = (unsigned char*)h->stream_ws.p;
+      }
+      void* params[] = {(void*)&a};
+      CU(h, cudaLaunchCooperativeKernel((void*)fold_kernel2_coop<CONTRA>, dim3(grid), dim3(nt), params, smem, st));
     } else {
       const int nt = 128;
       const size_t smem = centroid_only ? 16 : fold_smem_bytes<CONTRA>(bk.Lcap, false);
@@ -496,7 +529,13 @@ static int launch_fold_model(rna_handle* h, const RnaFoldBatchDev* b, cudaStream
     }
     CU(h, cudaGetLastError());
     h->stats.kernel_launches++;
-    if (dbg_roles) {   // debug aid: where do the cycles of one sequence go, per role and pass
+    if (dbg_roles && v2 && bk.mode == MODE_COOP) {
+      cudaStreamSynchronize(st);
+      long long hd[4];
+      cudaMemcpy(hd, d_dbg, sizeof hd, cudaMemcpyDeviceToHost);
+      fprintf(stderr, "[RNA_FOLD_DBG] coop L=%d roles %d/%d/%d: setup+streams=%lld inside=%lld outside=%lld bpp+centroid=%lld cycles\n", bk.Lcap,
+              a.nXw, a.nYw, a.nZw, hd[0], hd[1], hd[2], hd[3]);
+    } else if (dbg_roles) {   // debug aid: where do the cycles of one sequence go, per role and pass
       cudaStreamSynchronize(st);
       std::vector<long long> hd(2048 * 16);
       cudaMemcpy(hd.data(), d_dbg, hd.size() * 8, cudaMemcpyDeviceToHost);

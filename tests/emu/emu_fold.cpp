@@ -89,14 +89,23 @@ int run(const uint8_t* seq, int L, int allows_short, const typename Model2<CONTR
     if (order == 0) for (int l = 0; l < n; l++) fn(l);
     else for (int l = n - 1; l >= 0; l--) fn(l);
   };
+  auto validZ = [&](int d) { return d >= d_in0 && d < L; };
+  const bool single = (order == 2);   // one diagonal per step: the schedule of the cooperative long-sequence kernel
+  if (single) {
+    // step t: X(t) whole fold | Y(t) | Z(t-1)
+    for (int t = d_in0; t <= L; t++) {
+      if (validZ(t - 1)) for (int l = nZ - 1; l >= 0; l--) inside_Z<CONTRA, 3>(v, T, lut, t - 1, l, nZ);
+      if constexpr (CONTRA) { if (t < L) for (int l = 0; l < nY; l++) inside_Y_contra<3>(v, T, lut, t, l, nY); }
+      if (t < L) for (int l = nX - 1; l >= 0; l--) inside_X_diag<CONTRA>(v, T, lut, P, t, l, nX);
+    }
+  } else {
   // inside step st (diagonals t = d_in0 + 2 st, t+1): phase 1 = X two-loop parts | [Z(t-2), Y(t-1)] bar [Z(t-1), Y(t)];
   // phase 2 = X closing multibranch terms
-  auto validZ = [&](int d) { return d >= d_in0 && d < L; };
   for (int st = 0; d_in0 + 2 * st <= L + 1; st++) {
     const int t = d_in0 + 2 * st;
     auto rX = [&] { lanes(nX, [&](int l) { inside_X<CONTRA>(v, T, lut, P, st, l, nX); }); };
-    auto rZ = [&](int d) { if (validZ(d)) lanes(nZ, [&](int l) { inside_Z<CONTRA>(v, T, lut, d, l, nZ); }); };
-    auto rY = [&](int d) { if constexpr (CONTRA) { if (validZ(d)) lanes(nY, [&](int l) { inside_Y_contra(v, T, lut, d, l, nY); }); } };
+    auto rZ = [&](int d) { if (validZ(d)) lanes(nZ, [&](int l) { inside_Z<CONTRA, 2>(v, T, lut, d, l, nZ); }); };
+    auto rY = [&](int d) { if constexpr (CONTRA) { if (validZ(d)) lanes(nY, [&](int l) { inside_Y_contra<1>(v, T, lut, d, l, nY); }); } };
     auto rYZ = [&] {
       if (order == 0) { rZ(t - 2); rY(t - 1); } else { rY(t - 1); rZ(t - 2); }
       if (order == 0) { rY(t); rZ(t - 1); } else { rZ(t - 1); rY(t); }
@@ -104,20 +113,28 @@ int run(const uint8_t* seq, int L, int allows_short, const typename Model2<CONTR
     if (order == 0) { rX(); rYZ(); } else { rYZ(); rX(); }
     lanes(nX, [&](int l) { inside_X_fin<CONTRA>(v, T, lut, st, l, nX); });
   }
+  }
   for (int x = 0; x < L; x++) { E0[x] = E[doff(x, L)]; EL[x] = E[doff(L - 1 - x, L) + x]; }
   const float Z = E0[L - 1];
   for (int x = 0; x < TRI; x++) { v.Pm[x] = NEG; R[x] = NEG; X[x] = NEG; }
   if (out_logz) *out_logz = Z;
-  for (int st = 0; L - 1 - 2 * st >= d_out0; st++) {
+  if (single) {
+    for (int d = L - 1; d >= d_out0; d--) {   // step d: X(d) whole fold | Y(d)
+      const int nl = nY + nZ;
+      for (int l = nX - 1; l >= 0; l--) outside_X_diag<CONTRA, 4>(v, T, lut, P, Z, d, l, nX);
+      for (int l = 0; l < nl; l++) outside_Y<CONTRA, 2>(v, T, lut, d, l, nl);
+    }
+  }
+  for (int st = 0; !single && L - 1 - 2 * st >= d_out0; st++) {
     const int d = L - 1 - 2 * st;
     auto rX = [&] { lanes(nX, [&](int l) { outside_X<CONTRA>(v, T, lut, P, Z, st, l, nX); }); };
     auto rY = [&] {
       const int nl = nY + nZ;
-      if (d + 1 < L) lanes(nl, [&](int l) { outside_Y<CONTRA>(v, T, lut, d + 1, l, nl); });
-      lanes(nl, [&](int l) { outside_Y<CONTRA>(v, T, lut, d, l, nl); });
+      if (d + 1 < L) lanes(nl, [&](int l) { outside_Y<CONTRA, 1>(v, T, lut, d + 1, l, nl); });
+      lanes(nl, [&](int l) { outside_Y<CONTRA, 2>(v, T, lut, d, l, nl); });
     };
     if (order == 0) { rX(); rY(); } else { rY(); rX(); }
-    lanes(nX, [&](int l) { outside_X_ml<CONTRA>(v, T, lut, st, l, nX); });
+    lanes(nX, [&](int l) { outside_X_ml<CONTRA, 1>(v, T, lut, st, l, nX); });
   }
   if (out_bpp) {
     for (int i = 0; i < L - 1; i++) {

@@ -65,6 +65,18 @@ def test_on_the_fly_fallback(emu, oracle, contra):
     check(emu, oracle, random_seqs(6, [20, 30, 60, 90]), contra, False, tt, ct, tcap=1000, order=1)
 
 
+@pytest.mark.parametrize("contra", [False, True])
+def test_one_diagonal_schedule(emu, oracle, contra):
+    """order = 2: one diagonal per step with whole folds (the cooperative long-sequence kernel's schedule), with and
+    without term streams."""
+    tt, ct, _ = default_tables()
+    seqs = load_trnas()[:2] + random_seqs(9, [1, 4, 5, 6, 17, 40, 131])
+    check(emu, oracle, seqs, contra, False, tt, ct, order=2)
+    check(emu, oracle, seqs[:4], contra, False, tt, ct, order=2, tcap=0, nX=5, nY=3, nZ=2)
+    rt, rc = T.random_turner_tables(301), T.random_contra_tables(302)
+    check(emu, oracle, random_seqs(10, [33, 64, 90]), contra, False, rt, rc, order=2)
+
+
 def test_mid_length(emu, oracle):
     tt, ct, _ = default_tables()
     check(emu, oracle, random_seqs(31, [150, 260]), True, False, tt, ct, nX=64, nY=128, nZ=128)

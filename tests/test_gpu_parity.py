@@ -232,3 +232,9 @@ def test_skewed_composition_falls_back(handle, oracle):
     seqs = [rng.choice(np.array([2, 3], dtype=np.uint8), size=L) for L in (60, 90, 120)]
     check_fold(handle, oracle, seqs, True, False, [2.0], tt, ct)
     check_fold(handle, oracle, seqs, False, False, [2.0], tt, ct)
+
+
+def test_long_cooperative_contra(handle, oracle):
+    """> 1024 nt under CONTRAfold: grid-wide one-diagonal wavefront with roles spread over the SMs."""
+    tt, ct, _ = default_tables()
+    check_fold(handle, oracle, random_seqs(33, [1300]), True, False, [2.0, 0.5], tt, ct)
