@@ -362,9 +362,9 @@ static int launch_fold_model(rna_handle* h, const RnaFoldBatchDev* b, cudaStream
       if (bk.mode != MODE_SMEM) continue;
       // CTAs per SM: bounded by shared memory (C, log P and the small per-sequence tables) and by 1024 threads per SM
       // at 64 registers.  The chains are latency-bound, so residency is what fills the SM: take all the CTAs that
-      // fit (<= 6) and give each 1024 / CTAs threads: roles first, the rest help in the all-thread phases.
+      // fit (<= 4, measured best) and give each 1024 / CTAs threads: roles first, the rest help in the all-thread phases.
       const size_t smem = smem_need(bk.Lcap);
-      static const int occ_cap = getenv("RNA_FOLD_OCC") ? atoi(getenv("RNA_FOLD_OCC")) : 6;
+      static const int occ_cap = getenv("RNA_FOLD_OCC") ? atoi(getenv("RNA_FOLD_OCC")) : 4;   // measured best on tRNA-length batches
       int occ_s = (int)std::min<size_t>((size_t)std::max(1, occ_cap), (size_t)233472 / (smem + 1024 + 64));
       occ_s = std::max(1, occ_s);
       occ_s = std::min(occ_s, std::max(1, 32 / fold2_min_warps(bk.Lcap, CONTRA)));
