@@ -51,14 +51,20 @@ RNA_DEV float ln_exp_1p(float x, const float4* __restrict__ lut) {
 RNA_DEV bool is_finite(float x) { return fabsf(x) < __int_as_float(0x7f800000); }
 
 // logsumexp(&mut sum, x): src/utils.rs:580-596.  Returns the new sum.
+// The reference ignores a non-finite x and replaces a non-finite sum by x.  Here x is first normalised off the
+// critical path (NaN -> -inf; +inf never occurs), after which ONE select on the chain covers every case:
+//   both finite        z = max - min is finite            -> y + (z >= T ? z : poly(z))
+//   exactly one -inf   z = +inf                           -> max(sum, x) = the finite one   (bitwise: fmaxf picks it)
+//   both -inf          z = NaN, (z < inf) is false        -> max = -inf
 RNA_DEV float lse(float sum, float x, const float4* __restrict__ lut) {
+  x = (x > RNA_NEG_INF) ? x : RNA_NEG_INF;
   const float y = fminf(sum, x);
-  const float z = __fsub_rn(fmaxf(sum, x), y);
-  // z is NaN/inf when either operand is not finite; the LUT index stays in range (all compares false => 7).
+  const float mx = fmaxf(sum, x);
+  const float z = __fsub_rn(mx, y);
+  // z is NaN/inf when an operand is -inf; the LUT index stays in range (all compares false => 7).
   const float r = ln_exp_1p(z, lut);
   const float v = __fadd_rn(y, (z >= RNA_LSE_THRESHOLD) ? z : r);
-  const float w = is_finite(sum) ? v : x;
-  return is_finite(x) ? w : sum;
+  return (z < __int_as_float(0x7f800000)) ? v : mx;
 }
 
 // lse with a per-lane enable predicate (disabled lanes keep `sum`).
