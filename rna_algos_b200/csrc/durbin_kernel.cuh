@@ -35,7 +35,7 @@ __host__ __device__ inline size_t durbin_smem_bytes(int ncap, int mcap, bool rol
   return b;
 }
 
-__global__ void __launch_bounds__(256) durbin_kernel(const DurbinArgs a) {
+__global__ void __launch_bounds__(256, 6) durbin_kernel(const DurbinArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float4* lut = reinterpret_cast<float4*>(smem_raw);
   DevAlign* T = reinterpret_cast<DevAlign*>(smem_raw + 128);
@@ -83,23 +83,20 @@ __global__ void __launch_bounds__(256) durbin_kernel(const DurbinArgs a) {
         } else {
           if (i > 0 && j > 0) {
             const bool begins = (i == 1 && j == 1);
-            float sum = NEG;
-            sum = lse(sum, __fadd_rn(RM[b2 + i - 1], begins ? inm : m2m), lut);
+            float sum = lse_init(__fadd_rn(RM[b2 + i - 1], begins ? inm : m2m));
             sum = lse(sum, __fadd_rn(RI[b2 + i - 1], m2i), lut);
             sum = lse(sum, __fadd_rn(RD[b2 + i - 1], m2i), lut);
             fm = __fadd_rn(sum, T->match[p0[i] * 4 + p1[j]]);
           }
           if (i > 0) {
             const bool begins = (i == 1 && j == 0);
-            float sum = NEG;
-            sum = lse(sum, __fadd_rn(RM[b1 + i - 1], begins ? ini : m2i), lut);
+            float sum = lse_init(__fadd_rn(RM[b1 + i - 1], begins ? ini : m2i));
             sum = lse(sum, __fadd_rn(RI[b1 + i - 1], iex), lut);
             fi = __fadd_rn(sum, T->insert[p0[i]]);
           }
           if (j > 0) {
             const bool begins = (i == 0 && j == 1);
-            float sum = NEG;
-            sum = lse(sum, __fadd_rn(RM[b1 + i], begins ? ini : m2i), lut);
+            float sum = lse_init(__fadd_rn(RM[b1 + i], begins ? ini : m2i));
             sum = lse(sum, __fadd_rn(RD[b1 + i], iex), lut);
             fd = __fadd_rn(sum, T->insert[p1[j]]);
           }
@@ -134,23 +131,20 @@ __global__ void __launch_bounds__(256) durbin_kernel(const DurbinArgs a) {
         } else {
           if (i < n - 1 && j < m - 1) {
             const bool ends = (i + 1 == n - 1 && j + 1 == m - 1);
-            float sum = NEG;
-            sum = lse(sum, __fadd_rn(RM[b2 + i + 1], ends ? 0.f : m2m), lut);
+            float sum = lse_init(__fadd_rn(RM[b2 + i + 1], ends ? 0.f : m2m));
             sum = lse(sum, __fadd_rn(RI[b2 + i + 1], m2i), lut);
             sum = lse(sum, __fadd_rn(RD[b2 + i + 1], m2i), lut);
             bm = __fadd_rn(sum, T->match[p0[i] * 4 + p1[j]]);
           }
           if (i < n - 1) {
             const bool ends = (i + 1 == n - 1 && j == m - 1);
-            float sum = NEG;
-            sum = lse(sum, __fadd_rn(RM[b1 + i + 1], ends ? 0.f : m2i), lut);
+            float sum = lse_init(__fadd_rn(RM[b1 + i + 1], ends ? 0.f : m2i));
             sum = lse(sum, __fadd_rn(RI[b1 + i + 1], iex), lut);
             bi = __fadd_rn(sum, T->insert[p0[i]]);
           }
           if (j < m - 1) {
             const bool ends = (i == n - 1 && j + 1 == m - 1);
-            float sum = NEG;
-            sum = lse(sum, __fadd_rn(RM[b1 + i], ends ? 0.f : m2i), lut);
+            float sum = lse_init(__fadd_rn(RM[b1 + i], ends ? 0.f : m2i));
             sum = lse(sum, __fadd_rn(RD[b1 + i], iex), lut);
             bd = __fadd_rn(sum, T->insert[p1[j]]);
           }
@@ -158,8 +152,7 @@ __global__ void __launch_bounds__(256) durbin_kernel(const DurbinArgs a) {
         RM[b0 + i] = bm; RI[b0 + i] = bi; RD[b0 + i] = bd;
         if (i >= 2 && j >= 2) {
           // match probability of (i-1, j-1): uses backward sums at (i, j)
-          float t = NEG;
-          t = lse(t, __fadd_rn(corner ? 0.f : m2m, bm), lut);
+          float t = lse_init(__fadd_rn(corner ? 0.f : m2m, bm));
           t = lse(t, __fadd_rn(m2i, bi), lut);
           t = lse(t, __fadd_rn(m2i, bd), lut);
           const size_t q = (size_t)(i - 1) * m + (j - 1);

@@ -699,11 +699,11 @@ template <bool CONTRA, class SV>
 RNA_DEV float inside_cell_partial(const SV& v, const typename Model2<CONTRA>::View& T, const float4* lut,
                                   const ModelParams& P, int st, int tot, int x, int d, int i, int j) {
   const uint8_t* s = v.s;
-  float sum = RNA_NEG_INF;
+  float sum = RNA_NEG_INF;   // (the first fold into the empty sum just takes the finite operand)
   if constexpr (CONTRA) {
-    if (d - 1 <= P.MAX2) sum = lse(sum, c2_hairpin(T, s, i, j), lut);
+    if (d - 1 <= P.MAX2) sum = lse_init(c2_hairpin(T, s, i, j));
   } else {
-    sum = lse(sum, t_hairpin(T, s, i, j), lut);
+    sum = lse_init(t_hairpin(T, s, i, j));
   }
   if (v.tin) {
     const uint32_t G = v.gcumI[st] + (x >> 5), gb = v.gbin[G], wd = group_width(tot, x >> 5);

@@ -67,6 +67,9 @@ RNA_DEV float lse(float sum, float x, const float4* __restrict__ lut) {
   return (z < __int_as_float(0x7f800000)) ? v : mx;
 }
 
+// logsumexp into an EMPTY sum (sum == -inf): the reference takes x if it is finite (src/utils.rs:581-586)
+RNA_DEV float lse_init(float x) { return (x > RNA_NEG_INF) ? x : RNA_NEG_INF; }
+
 // lse with a per-lane enable predicate (disabled lanes keep `sum`).
 RNA_DEV float lse_if(bool on, float sum, float x, const float4* __restrict__ lut) {
   return lse(sum, on ? x : RNA_NEG_INF, lut);
