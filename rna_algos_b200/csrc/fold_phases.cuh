@@ -420,6 +420,16 @@ struct Windows {
     if (INSIDE) return raw & (0xffffffffu << (31 - (MAX2 - aa)));
     return raw & (0xffffffffu >> (31 - min(MAX2 - aa, bcap)));
   }
+  // the same without a branch (rows past amax read a safe row and are masked to 0): for loops whose lanes must not
+  // diverge
+  RNA_DEVM uint32_t flat(int aa) const {
+    const bool valid = aa <= amax;
+    const int ac = valid ? aa : 0;
+    const int kk = valid ? (INSIDE ? i + 1 + ac : i - 1 - ac) : i;
+    const uint32_t raw = get32(v.mask + kk * v.W2, wpos);
+    const uint32_t m = INSIDE ? (0xffffffffu << (31 - (MAX2 - ac))) : (0xffffffffu >> (31 - min(MAX2 - ac, max(bcap, 0))));
+    return valid ? (raw & m) : 0u;
+  }
 };
 
 // The pipelined enumeration: sink(t2) is called once per term in the reference's order (and a few times with
@@ -602,6 +612,40 @@ RNA_DEV uint32_t stream_fill_rows(const SV& v, const LOOP& lp, const Windows<INS
   }
   return n;
 }
+// The fast rows (a >= kFastFrom, the bulk of the terms) without divergence: every lane executes the same
+// instruction stream each iteration -- advance to the next row by selects, score with safe operands, store under
+// a predicate -- so a warp's 32 cells proceed in lock step and only the differences of their term counts idle.
+template <bool CONTRA, bool INSIDE, class SV, class LOOP>
+RNA_DEV uint32_t stream_fill_rows_flat(const SV& v, const LOOP& lp, const Windows<INSIDE, SV>& window, int i, int j,
+                                       int a0, int a1, uint2* out, uint32_t wd, uint32_t n) {
+  const int L = v.L;
+  if (a0 > a1) return n;
+  int a = a0;
+  uint32_t w = window.flat(a0), wnext = window.flat(a0 + 1);
+  while (a <= a1) {
+    const bool has = w != 0;
+    const int k = INSIDE ? i + 1 + a : i - 1 - a;
+    const int kcode = INSIDE ? v.LL[k] : v.RR[k] * 16;
+    const uint32_t ww = has ? w : 1u;
+    int l, b;
+    if (INSIDE) { const int t = 31 - __clz(ww); w = has ? (w & ~(1u << t)) : 0u; l = j - 32 + t; b = 31 - t; }
+    else { const int t = __ffs(ww) - 1; w = has ? (w & (w - 1)) : 0u; l = j + 1 + t; b = t; }
+    l = has ? l : (INSIDE ? k + 1 : min(j + 1, L - 1));   // a safe partner for idle lanes (never stored)
+    b = has ? b : 0;
+    const int q = doff(l - k, L) + k;
+    const int code = INSIDE ? v.RR[l] * 16 + kcode : kcode + v.LL[l];
+    const float sc = lp.fast(a, b, code);
+    if (has) out[wd * n] = make_uint2((unsigned)__float_as_int(sc), (unsigned)q);
+    n += has ? 1u : 0u;
+    // next row when this one is exhausted (its window was loaded one row ahead)
+    const bool adv = w == 0;
+    const uint32_t w2 = window.flat(a + 2);
+    w = adv ? wnext : w;
+    wnext = adv ? w2 : wnext;
+    a += adv ? 1 : 0;
+  }
+  return n;
+}
 template <bool CONTRA, bool INSIDE, class SV>
 RNA_DEV void stream_fill_cell(const SV& v, const typename Model2<CONTRA>::View& T, const ModelParams& P, int i, int j,
                               uint2* out, uint32_t wd, uint32_t nmax) {
@@ -610,7 +654,7 @@ RNA_DEV void stream_fill_cell(const SV& v, const typename Model2<CONTRA>::View& 
   const Windows<INSIDE, SV> window(v, P.MAX2, i, j);
   uint32_t n = 0;
   n = stream_fill_rows<CONTRA, INSIDE, false>(v, lp, window, i, j, 0, min(LOOP::kFastFrom - 1, window.amax), out, wd, n);
-  n = stream_fill_rows<CONTRA, INSIDE, true>(v, lp, window, i, j, LOOP::kFastFrom, window.amax, out, wd, n);
+  n = stream_fill_rows_flat<CONTRA, INSIDE>(v, lp, window, i, j, LOOP::kFastFrom, window.amax, out, wd, n);
   for (; n < nmax; n++) out[wd * n] = make_uint2(0u, 0u);   // neutral padding
 }
 // fill tasks: chunks of 32 consecutive cells of a pass; task tau -> (pass, chunk), longest partner lists first
