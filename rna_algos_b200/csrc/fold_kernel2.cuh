@@ -74,8 +74,10 @@ __host__ __device__ inline Roles fold2_roles(int Lcap, bool contra, int max_warp
   return r;
 }
 
-template <bool CONTRA, int MODE>
-__global__ void __launch_bounds__(512, 2) fold_kernel2(const FoldArgs a) {
+// REGS48: a second build of the same kernel under a 48-register cap (1280 resident threads per SM = 5 CTAs of 8
+// warps), used for the buckets whose shared memory allows a fifth CTA.
+template <bool CONTRA, int MODE, bool REGS48 = false>
+__global__ void __launch_bounds__(REGS48 ? 256 : 512, REGS48 ? 5 : 2) fold_kernel2(const FoldArgs a) {
   typedef typename Model2<CONTRA>::Dev Dev;
   typedef typename Model2<CONTRA>::Small Small;
   typedef typename Model2<CONTRA>::View View;

@@ -342,6 +342,7 @@ static int launch_fold_model(rna_handle* h, const RnaFoldBatchDev* b, cudaStream
   static const bool no_helpers = getenv("RNA_FOLD_NOHELPERS") != nullptr;
   std::vector<int> nt_of(buckets.size(), 0);
   std::vector<Roles> ro_of(buckets.size());
+  std::vector<char> regs48_of(buckets.size(), 0);
   size_t stream_bytes = 0;
   if (v2) {
     for (size_t k = 0; k < buckets.size(); k++) {
@@ -369,14 +370,23 @@ static int launch_fold_model(rna_handle* h, const RnaFoldBatchDev* b, cudaStream
       occ_s = std::max(1, occ_s);
       occ_s = std::min(occ_s, std::max(1, 32 / fold2_min_warps(bk.Lcap, CONTRA)));
       int warps = std::min(16, 32 / occ_s);
+      // a fifth CTA of 8 warps fits when shared memory allows it and the kernel is built under a 48-register cap
+      static const bool allow48 = getenv("RNA_FOLD_REGS48") != nullptr;
+      regs48_of[k] = allow48 && (size_t)233472 / (smem + 1024 + 64) >= 5 && warps == 8 && occ_cap >= 4;
       if (no_helpers) { const Roles fr = fold2_roles(bk.Lcap, CONTRA, 16); warps = std::min(warps, fr.nX + fr.nY + fr.nZ); }
       const Roles ro = fold2_roles(bk.Lcap, CONTRA, warps);
       ro_of[k] = ro;
       int nt = 32 * warps;
       int occ = 1;
-      TRY(set_smem_attr(h, fold_kernel2<CONTRA, MODE_SMEM>, smem));
-      CU(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fold_kernel2<CONTRA, MODE_SMEM>, nt, smem));
-      occ = std::max(1, std::min(occ, occ_cap));
+      if (regs48_of[k]) {
+        TRY(set_smem_attr(h, fold_kernel2<CONTRA, MODE_SMEM, true>, smem));
+        CU(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fold_kernel2<CONTRA, MODE_SMEM, true>, nt, smem));
+        occ = std::max(1, std::min(occ, 5));
+      } else {
+        TRY(set_smem_attr(h, fold_kernel2<CONTRA, MODE_SMEM>, smem));
+        CU(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fold_kernel2<CONTRA, MODE_SMEM>, nt, smem));
+        occ = std::max(1, std::min(occ, occ_cap));
+      }
       nt_of[k] = nt;
       grid_of[k] = (int)std::min<size_t>(bk.end - bk.begin, (size_t)std::max(1, occ) * h->sm_count);
       stride_of[k] = 4 * ((size_t)bk.Lcap * (bk.Lcap + 1) / 2) + 32;   // R X E M1 of one CTA
@@ -453,13 +463,15 @@ static int launch_fold_model(rna_handle* h, const RnaFoldBatchDev* b, cudaStream
       a.stream_ws = nullptr;
       if (bk.mode == MODE_SMEM) {
         const size_t smem = smem_need(bk.Lcap);
-        TRY(set_smem_attr(h, fold_kernel2<CONTRA, MODE_SMEM>, smem));
+        if (regs48_of[k]) TRY(set_smem_attr(h, (fold_kernel2<CONTRA, MODE_SMEM, true>), smem));
+        else TRY(set_smem_attr(h, fold_kernel2<CONTRA, MODE_SMEM>, smem));
         if (stream_stride_of[k]) {
           a.tcap = tcap_of[k];
           a.stream_stride = stream_stride_of[k];
           a.stream_ws = (unsigned char*)h->stream_ws.p + (size_t)lane * stream_bytes;
         }
-        fold_kernel2<CONTRA, MODE_SMEM><<<grid_of[k], nt, smem, st>>>(a);
+        if (regs48_of[k]) fold_kernel2<CONTRA, MODE_SMEM, true><<<grid_of[k], nt, smem, st>>>(a);
+        else fold_kernel2<CONTRA, MODE_SMEM><<<grid_of[k], nt, smem, st>>>(a);
       } else {
         const size_t smem = fold2_fixed_bytes<CONTRA>(bk.Lcap);
         TRY(set_smem_attr(h, fold_kernel2<CONTRA, MODE_GLOBAL>, smem));
