@@ -169,7 +169,7 @@ __global__ void __launch_bounds__(REGS48 ? 256 : 512, REGS48 ? 5 : 2) fold_kerne
 
     for (int x = tid; x < L; x += nt) s[x] = a.bases[sbeg + x];
     if (tid < 4) { sseq[tid] = 0; s[L + tid] = 0; }
-    const bool dbg_on = a.dbg && w == 0;
+    const bool dbg_on = a.dbg && w == 3u * gridDim.x;   // a steady-state sequence (CTAs have desynchronised by then)
     long long tc0 = dbg_on ? clock64() : 0;
     const long long tseq0 = tc0;
     __syncthreads();
@@ -264,7 +264,7 @@ __global__ void __launch_bounds__(REGS48 ? 256 : 512, REGS48 ? 5 : 2) fold_kerne
       if (dbg_on && (tid & 31) == 0 && !helper) a.dbg[(size_t)(1024 + d) * 16 + warp] = clock64() - c0;
       __syncthreads();
       const long long c1 = dbg_on ? clock64() : 0;
-      if (warp < a.nXw) outside_X_ml<CONTRA, (MODE == MODE_SMEM ? 1 : 3)>(v, T, lut, st, tid, nXl);
+      if (warp < a.nXw) outside_X_ml<CONTRA, (MODE == MODE_SMEM ? 2 : 3)>(v, T, lut, st, tid, nXl);
       if (dbg_on && (tid & 31) == 0 && warp < a.nXw) a.dbg[(size_t)(1024 + d) * 16 + 8 + warp] = clock64() - c1;
       __syncthreads();
     }

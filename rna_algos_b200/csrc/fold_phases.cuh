@@ -1142,7 +1142,31 @@ RNA_DEV float outside_cell_ml(const SV& v, const typename Model2<CONTRA>::View& 
   const float Aij = __fadd_rn(Cij, v2_acc<CONTRA>(T, v.s, L, i, j));
   float sa;
   if constexpr (CONTRA) sa = __fadd_rn(Aij, dev->mb_bp); else sa = __fadd_rn(Aij, dev->coeff_num_branches);
-  if constexpr (PF <= 1) {
+  if constexpr (PF == 2) {
+    // operands TWO steps ahead are in flight (explicit registers, no ring): probs_multibranch(2) live in HBM/L2 in
+    // the shared-memory mode and one step of three dependent folds is shorter than that latency
+    auto fetch = [&](int kk, float& fx, float& fp, float& fy) {
+      fx = NEG; fp = NEG; fy = NEG;
+      if (kk < i) {
+        const int m = i - 1 - kk, q = doff(j - kk, L) + kk;
+        fx = (m >= 1) ? v.M1[doff(m - 1, L) + kk + 1] : NEG;
+        fp = v.X[q]; fy = v.R[q];
+      }
+    };
+    float ax, ap, ay, bx, bp, by;
+    fetch(0, ax, ap, ay);
+    fetch(1, bx, bp, by);
+    for (int kk = 0; kk < i; kk++) {
+      const int m = i - 1 - kk;
+      const float x1 = ax, p2 = ap, y = ay;
+      ax = bx; ap = bp; ay = by;
+      fetch(kk + 2, bx, bp, by);
+      sm = lse(sm, __fadd_rn(__fadd_rn(sa, p2), x1), lut);
+      if constexpr (CONTRA) sm = lse(sm, __fadd_rn(__fadd_rn(sa, y), __fmul_rn(dev->mb_unpair, (float)m)), lut);
+      else sm = lse(sm, __fadd_rn(sa, y), lut);
+      sm = lse(sm, __fadd_rn(__fadd_rn(sa, x1), y), lut);
+    }
+  } else if constexpr (PF <= 1) {
     // operands of step kk+1 are loaded before the three dependent logsumexp's of step kk
     float nx1 = NEG, np2 = NEG, ny = NEG;
     if (i > 0) {

@@ -134,7 +134,7 @@ int run(const uint8_t* seq, int L, int allows_short, const typename Model2<CONTR
       lanes(nl, [&](int l) { outside_Y<CONTRA, 2>(v, T, lut, d, l, nl); });
     };
     if (order == 0) { rX(); rY(); } else { rY(); rX(); }
-    lanes(nX, [&](int l) { outside_X_ml<CONTRA, 1>(v, T, lut, st, l, nX); });
+    lanes(nX, [&](int l) { outside_X_ml<CONTRA, 2>(v, T, lut, st, l, nX); });
   }
   if (out_bpp) {
     for (int i = 0; i < L - 1; i++) {
