@@ -280,7 +280,14 @@ static int launch_fold_model(rna_handle* h, const RnaFoldBatchDev* b, cudaStream
   // largest L whose matrices fit in shared memory (v2 keeps u8 cell lists there: L <= 252)
   int Lsmem = 0;
   for (int L = 16; L <= (v2 ? 252 : 1024); L += gran) { if (smem_need(L) + 1024 <= smem_cap) Lsmem = L; else break; }
-  const int Lcoop_min = 1025;   // longer sequences get the whole grid (one at a time)
+  // Sequences beyond 1024 nt get the whole grid, one at a time.  So do the few sequences that are too long for the
+  // shared-memory mode when there are not enough of them to occupy the GPU one CTA each (v2 only).
+  int Lcoop_min = 1025;
+  if (v2) {
+    uint32_t n_long = 0;
+    while (n_long < n && len_of(n_long) > Lsmem) n_long++;
+    if (n_long > 0 && n_long <= 4) Lcoop_min = std::max(Lsmem + 1, 384);
+  }
   std::vector<Bucket> buckets;
   uint32_t pos = 0;
   while (pos < n) {
