@@ -430,7 +430,7 @@ __global__ void __launch_bounds__(256, 2) fold_kernel2_coop(const FoldArgs a) {
     for (int t = d_in0; t <= L; t++) {
       if (isX) { if (t < L) inside_X_diag<CONTRA>(v, T, lut, P, t, lnX, nXl); }
       else if (isY) { if constexpr (CONTRA) { if (t < L) inside_Y_contra<4>(v, T, lut, t, lnY, nYl); } }
-      else if (isZ) { if (t - 1 >= d_in0) inside_Z<CONTRA, 6>(v, T, lut, t - 1, lnZ, nZl); }
+      else if (isZ) { if (t - 1 >= d_in0) inside_Z<CONTRA, 2>(v, T, lut, t - 1, lnZ, nZl); }
       grid.sync();
     }
     for (int x = gtid; x < L; x += gnt) {
@@ -446,7 +446,7 @@ __global__ void __launch_bounds__(256, 2) fold_kernel2_coop(const FoldArgs a) {
     // ---- outside, one diagonal per step: X(d) | Y(d) --------------------------------------------------------------
     const int d_out0 = v.dout0;
     for (int d = L - 1; d >= d_out0; d--) {
-      if (isX) outside_X_diag<CONTRA, 4>(v, T, lut, P, Z, d, lnX, nXl);
+      if (isX) outside_X_diag<CONTRA, 2>(v, T, lut, P, Z, d, lnX, nXl);
       else if (isY || isZ) outside_Y<CONTRA, 4>(v, T, lut, d, lnY, nYl + nZl);
       grid.sync();
     }
