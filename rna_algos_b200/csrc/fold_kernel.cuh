@@ -103,9 +103,12 @@ __host__ __device__ inline size_t fold_smem_bytes(int Lcap, bool smem_mats) {
 // centroid_fold: src/centroid_fold.rs:25-105.  W (max_expect_accuracies) is diagonal-major in `W`;
 // getp(d, i) returns the base-pairing probability of (i, i+d) or -1 when the key is absent.
 // ---------------------------------------------------------------------------------------------------
-template <int MODE, class PF>
+struct NoCentroidFill { __device__ __forceinline__ bool operator()(float) const { return false; } };
+// fill(gamma): optional replacement of the max-plus fill (W is zeroed and a barrier has passed; it must end with a
+// barrier); returns false to get the built-in thread-per-cell fill.
+template <int MODE, class PF, class FILL = NoCentroidFill>
 __device__ __forceinline__ void centroid_run(const FoldArgs& a, uint32_t sidx, uint32_t sbeg, int L, float* W,
-                                             int* tstack, PF getp) {
+                                             int* tstack, PF getp, FILL fill = FILL()) {
   typedef Ctx<MODE> X;
   typedef typename X::ofs_t ofs_t;
   const int tid = threadIdx.x;
@@ -117,6 +120,7 @@ __device__ __forceinline__ void centroid_run(const FoldArgs& a, uint32_t sidx, u
     uint8_t* ostr = a.out_structs ? a.out_structs + (size_t)g * a.total_len + sbeg : nullptr;
     if (ostr) for (int x = c0; x < L; x += cs) ostr[x] = '.';
     X::sync();
+    if (!fill(gamma))
     for (int d = 1; d < L; d++) {
       const int ncell = L - d;
       const ofs_t od = X::off(d, L);

@@ -304,13 +304,79 @@ namespace rna {
 // diagonal (whole folds, no partial sums across steps) and the barrier is grid-wide.  grid.sync() orders memory
 // for every thread of the grid, so plain loads see what other CTAs wrote in earlier steps.
 // =========================================================================================================
+// Grid-wide barrier of the cooperative kernel: one arrival per CTA on a counter that only grows (zeroed by the host
+// before the launch), release/acquire at GPU scope by the CTA's first thread, CTA barriers on both sides.
+__device__ __forceinline__ void coop_barrier(unsigned* ctr, unsigned& target) {
+  target += gridDim.x;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    atomicAdd(ctr, 1u);
+    unsigned seen;
+    do {
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(ctr) : "memory");
+    } while ((int)(seen - target) < 0);
+  }
+  __syncthreads();
+}
+__device__ __forceinline__ unsigned long long global_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+
+// Max-plus fill of centroid_fold (src/centroid_fold.rs:33-64) for ONE long sequence on the whole grid.  A warp task is
+// 32 neighbouring cells of the diagonal (coalesced loads) times a chunk of CENT_CHUNK split points; the partial maxima
+// meet in an integer atomicMax: every W is >= +0 and W starts at 0, so the order of the float bits as signed integers
+// is the float order wherever it matters, and a maximum does not depend on the order of its operands.
+#define RNA_CENT_CHUNK 64
+template <class GETP, class SYNC>
+__device__ __forceinline__ void centroid_fill_coop(float* W, int L, float gamma, GETP getp, SYNC sync, int gw, int nw,
+                                                   int lane32) {
+  for (int d = 1; d < L; d++) {
+    const int ncell = L - d, ng = (ncell + 31) >> 5, nch = max(1, (d - 1 + RNA_CENT_CHUNK - 1) / RNA_CENT_CHUNK);
+    const int od = doff(d, L), od1 = doff(d - 1, L);
+    for (int tau = gw; tau < ng * nch; tau += nw) {
+      const int g = tau % ng, ch = tau / ng, i = g * 32 + lane32;
+      if (i >= ncell) continue;
+      float wv = 0.f;
+      if (ch == 0) {
+        wv = __ldcg(&W[od1 + i + 1]);
+        float e = __ldcg(&W[od1 + i]);
+        if (e > wv) wv = e;
+        const float p = getp(d, i);
+        if (p != -1.0f) {
+          const float inner = (d >= 2) ? __ldcg(&W[doff(d - 2, L) + i + 1]) : 0.f;
+          e = __fsub_rn(__fadd_rn(inner, __fmul_rn(gamma, p)), 1.0f);
+          if (e > wv) wv = e;
+        }
+      }
+      const int m_lo = 1 + ch * RNA_CENT_CHUNK, m_hi = min(d, m_lo + RNA_CENT_CHUNK);
+      const float* pa = W + (doff(m_lo, L) + i);                      // W[i][i+m]
+      const float* pb = W + (doff(d - m_lo - 1, L) + i + m_lo + 1);   // W[i+m+1][j]
+      int sa = L - m_lo, sb = d - m_lo - L - 1;
+#pragma unroll 8
+      for (int m = m_lo; m < m_hi; m++) {
+        const float e = __fadd_rn(__ldcg(pa), __ldcg(pb));
+        if (e > wv) wv = e;
+        pa += sa; sa--;     // doff(m+1) - doff(m) = L - m
+        pb += sb; sb--;     // doff(d-m-2) + i+m+2 - (doff(d-m-1) + i+m+1) = d - m - L - 1
+      }
+      atomicMax(reinterpret_cast<int*>(&W[od + i]), __float_as_int(wv));
+    }
+    sync();
+  }
+}
+
 template <bool CONTRA>
 __global__ void __launch_bounds__(256, 2) fold_kernel2_coop(const FoldArgs a) {
   typedef typename Model2<CONTRA>::Dev Dev;
   typedef typename Model2<CONTRA>::Small Small;
   typedef typename Model2<CONTRA>::View View;
   typedef SeqViewT<uint16_t> SV;
-  cg::grid_group grid = cg::this_grid();
+  unsigned* const bar_ctr = reinterpret_cast<unsigned*>(a.work_counter);
+  unsigned bar_target = 0;
+  auto grid_sync = [&]() { coop_barrier(bar_ctr, bar_target); };
 
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float4* lut = reinterpret_cast<float4*>(smem_raw);
@@ -336,8 +402,8 @@ __global__ void __launch_bounds__(256, 2) fold_kernel2_coop(const FoldArgs a) {
   const int gtid = (int)(blockIdx.x * blockDim.x + threadIdx.x), gnt = (int)(gridDim.x * blockDim.x);
   // global warp id with consecutive ids on different SMs; role lanes are counted from the role's first warp
   const int gw = (tid >> 5) * (int)gridDim.x + (int)blockIdx.x;
-  const int nXl = a.nXw * 32, nYl = a.nYw * 32, nZl = a.nZw * 32;
-  const int lnX = gw * 32 + (tid & 31), lnY = (gw - a.nXw) * 32 + (tid & 31), lnZ = (gw - a.nXw - a.nYw) * 32 + (tid & 31);
+  const int nXl = a.nXw * 32, nYl = a.nYw * 32;
+  const int lnX = gw * 32 + (tid & 31), lnY = (gw - a.nXw) * 32 + (tid & 31);
   const bool isX = gw < a.nXw, isY = !isX && gw < a.nXw + a.nYw, isZ = !isX && !isY && gw < a.nXw + a.nYw + a.nZw;
   __syncthreads();
 
@@ -382,6 +448,8 @@ __global__ void __launch_bounds__(256, 2) fold_kernel2_coop(const FoldArgs a) {
     v.RR = reinterpret_cast<uint8_t*>(v.plist + TRI);
     v.LL = v.RR + L;
     v.tin = nullptr; v.tout = nullptr; v.ccnt = nullptr; v.tcap = a.tcap;
+    v.M1rm = a.workspace + fold2_seq_bytes(L, 2, 5) / 4 + 16;   // two more triangular matrices behind the region
+    v.MB = v.M1rm + TRI;
 
     long long tk = (a.dbg && gtid == 0) ? clock64() : 0;
     auto mark = [&](int slot) { if (a.dbg && gtid == 0) { const long long now = clock64(); a.dbg[slot] = now - tk; tk = now; } };
@@ -391,19 +459,19 @@ __global__ void __launch_bounds__(256, 2) fold_kernel2_coop(const FoldArgs a) {
     __syncthreads();
     for (int x = gtid; x < L * v.W2; x += gnt) setup_mask_word<CONTRA>(v, P, x);
     for (int x = gtid; x < L; x += gnt) setup_codes(v, x);
-    grid.sync();
+    grid_sync();
     for (int d = gtid; d < L; d += gnt) setup_list_diag(v, d);
-    grid.sync();
+    grid_sync();
     if (a.stream_ws) {
       if (gtid == 0) { setup_groups(v); *fill_ctr = 0; }
       v.ccnt = reinterpret_cast<uint16_t*>(v.C);
-      grid.sync();
+      grid_sync();
       stream_count(v, P, gtid, gnt);
-      grid.sync();
+      grid_sync();
       stream_groupmax(v, gtid, gnt);
-      grid.sync();
+      grid_sync();
       if (gtid == 0) stream_scan(v);
-      grid.sync();
+      grid_sync();
       const uint32_t NGI = v.gcumI[max(num_steps_inside(v), 0)], NGO = v.gcumO[max(num_steps_outside(v), 0)];
       if (v.gbin[NGI] <= a.tcap && v.gbout[NGO] <= a.tcap) {
         v.tin = reinterpret_cast<uint2*>(a.stream_ws);
@@ -418,44 +486,85 @@ __global__ void __launch_bounds__(256, 2) fold_kernel2_coop(const FoldArgs a) {
           __syncwarp();
         }
       }
-      grid.sync();
+      grid_sync();
     }
     for (size_t x = gtid; x < TRI; x += gnt) { v.C[x] = NEG; v.R[x] = NEG; v.X[x] = NEG; v.E[x] = 0.f; v.M1[x] = NEG; }
     for (int x = gtid; x < 3 * L; x += gnt) v.Mroll[x] = NEG;
-    grid.sync();
+    grid_sync();
     mark(0);   // setup + term streams
 
-    // ---- inside, one diagonal per step: X(t) | Y(t) | Z(t-1) -------------------------------------------------
+    // ---- inside, pair steps (fold_phases.cuh "PAIR-STEP schedule"): phase A = X two-loop parts of (t, t+1) |
+    //      Y partial rightmost-pair sums of (t, t+1) | Z one dense chain per lane for (t-2, t-1); phase B = finish ----
     const int d_in0 = v.din0;
-    for (int t = d_in0; t <= L; t++) {
-      if (isX) { if (t < L) inside_X_diag<CONTRA>(v, T, lut, P, t, lnX, nXl); }
-      else if (isY) { if constexpr (CONTRA) { if (t < L) inside_Y_contra<4>(v, T, lut, t, lnY, nYl); } }
-      else if (isZ) { if (t - 1 >= d_in0) inside_Z<CONTRA, 2>(v, T, lut, t - 1, lnZ, nZl); }
-      grid.sync();
+    const int wZ = gw - a.nXw - a.nYw, hY = a.nYw / 2;
+    long long cyc[4] = {0, 0, 0, 0};
+    const bool timed = a.dbg && (tid & 31) == 0;
+    for (int t = d_in0; t <= L + 1; t += 2) {
+      const long long c0 = timed ? clock64() : 0;
+      if (isX) inside_X<CONTRA>(v, T, lut, P, (t - d_in0) >> 1, lnX, nXl);
+      else if (isY) {
+        if constexpr (CONTRA) {
+          if (hY == 0) {
+            if (t + 1 < L) inside_Y_contra<4>(v, T, lut, t + 1, lnY, nYl, 1);
+            if (t < L) inside_Y_contra<4>(v, T, lut, t, lnY, nYl, 0);
+          } else if (lnY < hY * 32) {
+            if (t + 1 < L) inside_Y_contra<4>(v, T, lut, t + 1, lnY, hY * 32, 1);
+          } else {
+            if (t < L) inside_Y_contra<4>(v, T, lut, t, lnY - hY * 32, nYl - hY * 32, 0);
+          }
+        }
+      } else if (isZ) inside_chain_pair<CONTRA, 8>(v, T, lut, t, wZ, a.nZw, tid & 31);
+      const long long c1 = timed ? clock64() : 0;
+      unsigned long long* gslot = reinterpret_cast<unsigned long long*>(a.dbg) + 64 + (size_t)((t - d_in0) >> 1) * 8;
+      if (timed) atomicMax(gslot + 5, global_ns());   // last arrival at the phase-A barrier
+      grid_sync();
+      const long long c2 = timed ? clock64() : 0;
+      if (timed) atomicMax(gslot + 6, global_ns());   // last release
+      inside_fin_pair<CONTRA>(v, T, lut, t, gtid, gnt);
+      grid_sync();
+      if (timed) atomicMax(gslot + 7, global_ns());   // end of the step
+      if (timed) {
+        cyc[0] += c1 - c0; cyc[1] += c2 - c1; cyc[2] += clock64() - c2;
+        const int r = isX ? 0 : isY ? 1 : isZ ? 2 + wZ % 3 : -1;   // slowest warp of a role (chain kind) per step
+        if (r >= 0) atomicMax(reinterpret_cast<unsigned long long*>(a.dbg) + 64 + (size_t)((t - d_in0) >> 1) * 8 + r, (unsigned long long)(c1 - c0));
+      }
+    }
+    if (timed) {   // work / wait cycles of the first warp of each role, and of phase B (with its barrier)
+      const int slot = (isX && lnX == 0) ? 8 : (isY && lnY == 0) ? 12 : (isZ && wZ == 0) ? 16 : -1;
+      if (slot >= 0) { a.dbg[slot] = cyc[0]; a.dbg[slot + 1] = cyc[1]; a.dbg[slot + 2] = cyc[2]; }
     }
     for (int x = gtid; x < L; x += gnt) {
       v.E0[x] = v.E[doff(x, L)];
       v.EL[x] = v.E[doff(L - 1 - x, L) + x];
     }
-    grid.sync();
+    grid_sync();
     mark(1);   // inside
     const float Z = v.E0[L - 1];
+    outside_prep<CONTRA>(v, T, gtid, gnt);   // row-major sums_1ormore, table of multibranch closing scores
     for (size_t x = gtid; x < TRI; x += gnt) { v.Pm[x] = NEG; v.R[x] = NEG; v.X[x] = NEG; }
     if (gtid == 0 && a.out_logz) a.out_logz[sidx] = Z;
-    grid.sync();
+    grid_sync();
     // ---- outside, one diagonal per step: X(d) | Y(d) --------------------------------------------------------------
     const int d_out0 = v.dout0;
+    cyc[0] = cyc[1] = 0;
     for (int d = L - 1; d >= d_out0; d--) {
-      if (isX) outside_X_diag<CONTRA, 2>(v, T, lut, P, Z, d, lnX, nXl);
-      else if (isY || isZ) outside_Y<CONTRA, 4>(v, T, lut, d, lnY, nYl + nZl);
-      grid.sync();
+      const long long c0 = timed ? clock64() : 0;
+      if (isX) outside_X_diag_rm<CONTRA, 4>(v, T, lut, P, Z, d, lnX, nXl);
+      else if (isY || isZ) outside_Y_dense<CONTRA, 4>(v, T, lut, d, gw - a.nXw, a.nYw + a.nZw, tid & 31);
+      const long long c1 = timed ? clock64() : 0;
+      grid_sync();
+      if (timed) { cyc[0] += c1 - c0; cyc[1] += clock64() - c1; }
+    }
+    if (timed) {
+      const int slot = (isX && lnX == 0) ? 20 : (!isX && lnY == 0) ? 24 : -1;
+      if (slot >= 0) { a.dbg[slot] = cyc[0]; a.dbg[slot + 1] = cyc[1]; }
     }
     mark(2);   // outside
     for (size_t x = gtid; x < TRI; x += gnt) {
       const float val = v.Pm[x];
       v.Pm[x] = (val > NEG) ? approx_expf(val) : -1.0f;
     }
-    grid.sync();
+    grid_sync();
     if (a.out_bpp) {
       float* ob = a.out_bpp + a.bpp_offsets[sidx];
       for (int i = (int)blockIdx.x; i < L - 1; i += (int)gridDim.x) {
@@ -466,7 +575,12 @@ __global__ void __launch_bounds__(256, 2) fold_kernel2_coop(const FoldArgs a) {
     {
       const float* Pm = v.Pm;
       auto getp = [=](int d, int i) -> float { return __ldcg(&Pm[doff(d, L) + i]); };
-      centroid_run<MODE_COOP>(a, sidx, sbeg, L, v.C, tstack, getp);
+      float* W = v.C;
+      auto fill = [&](float gamma) -> bool {
+        centroid_fill_coop(W, L, gamma, getp, grid_sync, gw, (int)(gridDim.x * (blockDim.x >> 5)), tid & 31);
+        return true;
+      };
+      centroid_run<MODE_COOP>(a, sidx, sbeg, L, W, tstack, getp, fill);
     }
     mark(3);   // BPP + centroid
   }

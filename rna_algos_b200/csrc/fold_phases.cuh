@@ -67,6 +67,9 @@ struct SeqViewT {
   float* Mroll;           // sums_multibranch, 3 rolling diagonals of L
   float* E0;              // sums_external[0][x]
   float* EL;              // sums_external[x][L-1]
+  // cooperative kernel, outside pass only (null elsewhere): ROW-MAJOR triangular copies, index(i,j) = doff(i) + j-i
+  float* M1rm;            // sums_1ormore_basepairs, row-major
+  float* MB;              // multibranch closing score of every closable (i,j) (0 elsewhere), diagonal-major
 };
 
 RNA_DEV int doff(int d, int L) { return d * L - ((d * (d - 1)) >> 1); }
@@ -845,7 +848,8 @@ struct RowBits {
 // Needs: sums_close of diagonals < d.
 // =========================================================================================================
 template <int CH, class SV>
-RNA_DEV void inside_Y_contra(const SV& v, const ContraView2& T, const float4* lut, int d, int lane, int nl) {
+RNA_DEV void inside_Y_contra(const SV& v, const ContraView2& T, const float4* lut, int d, int lane, int nl,
+                                int kskip = 0) {   // kskip: leave the last kskip values of k (j-1, ...) to a later phase
   const int L = v.L;
   const uint8_t* s = v.s;
   const float NEG = RNA_NEG_INF;
@@ -856,9 +860,9 @@ RNA_DEV void inside_Y_contra(const SV& v, const ContraView2& T, const float4* lu
     float r = NEG, rm = NEG;
     if constexpr (CH <= 1) {
     const uint32_t* row = v.mask + i * v.W2;
-    for (int p = i + 1; p <= j - 1; p += 32) {
+    for (int p = i + 1; p <= j - 1 - kskip; p += 32) {
       uint32_t w = get32(row, p);
-      const int n = j - p;
+      const int n = j - kskip - p;
       if (n < 32) w &= (1u << n) - 1u;
       while (w) {
         const int t = __ffs(w) - 1;
@@ -873,7 +877,7 @@ RNA_DEV void inside_Y_contra(const SV& v, const ContraView2& T, const float4* lu
     } else {
     // closable (i,k), i < k < j ascending, CH terms at a time: the sums_close gathers of the next chunk are in
     // flight while the folds of the current one execute
-    RowBits it(v.mask + i * v.W2, i + 1, j - 1);
+    RowBits it(v.mask + i * v.W2, i + 1, j - 1 - kskip);
     int kb[CH];
     float cb[CH];
 #pragma unroll
@@ -1010,6 +1014,156 @@ RNA_DEV void inside_Z(const SV& v, const typename Model2<CONTRA>::View& T, const
     Mcur[i] = sM;
     sM1 = lse(sM1, sM, lut);
     v.M1[od + i] = sM1;
+  }
+}
+
+// =========================================================================================================
+// PAIR-STEP schedule of the cooperative long-sequence kernel (one sequence on the whole GPU).  There a lane is
+// cheap and latency is everything, so the three dense chains of a cell run on three different warps (one
+// logsumexp per split point each instead of three interleaved ones), and the chains of TWO diagonals run side by
+// side.  Inside step s, t = din0 + 2s:
+//   phase A   X: hairpin + two-loop part of sums_close(t), sums_close(t+1)                (inside_X)
+//             Y: CONTRAfold rightmost-pair sums of t over k <= j-1 and of t+1 over k <= j-2 (inside_Y_contra)
+//             Z: chains sums_external | sums_multibranch | sums_1ormore of t-2 and t-1     (inside_chain_pair)
+//   phase B   every thread: finish sums_1ormore(t-2), (t-1) with sums_multibranch; closing multibranch term of
+//             sums_close(t), (t+1); the k = j-1 / k = j terms of the rightmost-pair sums   (inside_fin_pair)
+// Dependencies: the chains of diagonal d read R/Rm of diagonals <= d (R(d) itself only as their first operand),
+// E and M1 of diagonals <= d-2; sums_close(d) needs sums_multibranch(d-2) only in its last term.
+// =========================================================================================================
+// sum = lse(sum, op(m, A[i+m][j], B[i][i+m-1])) for m = 1 .. d-1, operands PF split points ahead in flight
+// (A, B live in HBM/L2; their addresses are affine in m).  A: R or Rm (column j), B: E or M1 (row i) or null.
+template <int PF, bool HASB, class OP>
+RNA_DEV float chain_fold(const float* __restrict__ A, const float* __restrict__ B, int L, int d, int i, float sum,
+                         const float4* lut, OP op) {
+  // Branch-free folds: operands beyond m = d-1 are -inf, which the fold ignores (measured on B200,
+  // tools/chain_microbench.cu: 145 cycles per split point at PF = 4 against 227 with a guarded fold; the bare
+  // logsumexp chain is 115).
+  const float NEG = RNA_NEG_INF;
+  const float* pA = A + (doff(d - 1, L) + i + 1);   // operands of split point mL = 1
+  const float* pB = B + i;
+  int sA = d - 1 - L, sB = L, mL = 1;               // pointer steps to split point mL + 1
+  float pa[PF], pb[PF];
+  auto load = [&](float& a, float& b) {
+    a = NEG; b = NEG;
+    if (mL < d) { a = *pA; if (HASB) b = *pB; }
+    pA += sA; sA--;        // doff(d-m-1) + i+m+1  -  (doff(d-m) + i+m) = d - m - L
+    if (HASB) { pB += sB; sB--; }   // doff(m) - doff(m-1) = L - m + 1
+    mL++;
+  };
+#pragma unroll
+  for (int u = 0; u < PF; u++) load(pa[u], pb[u]);
+  for (int m0 = 1; m0 < d; m0 += PF) {
+#pragma unroll
+    for (int u = 0; u < PF; u++) {
+      const float a = pa[u], b = pb[u];
+      load(pa[u], pb[u]);
+      sum = lse(sum, op(m0 + u, a, b), lut);
+    }
+  }
+  return sum;
+}
+// one dense chain (kind 0: sums_external, 1: sums_1ormore_basepairs without its last term, 2: sums_multibranch) of
+// cell (i, i+d).  Needs the finished R (/Rm) of diagonal d.  src/mccaskill_algo.rs:352-374, 487-512.
+template <bool CONTRA, int PF, class SV>
+RNA_DEV void inside_chain_cell(const SV& v, const typename Model2<CONTRA>::View& T, const float4* lut, int d, int kind,
+                               int i) {
+  const int L = v.L, od = doff(d, L);
+  const typename Model2<CONTRA>::Dev* dev = T.g;
+  if (kind == 0) {
+    float sE;
+    if constexpr (CONTRA) sE = __fmul_rn(dev->ext_unpair, (float)(d + 1)); else sE = 0.f;
+    sE = lse(sE, __fadd_rn(v.R[od + i], 0.f), lut);   // k = i: E[i][i-1] = 0
+    v.E[od + i] = chain_fold<PF, true>(v.R, v.E, L, d, i, sE, lut, [](int, float r, float e) { return __fadd_rn(r, e); });
+  } else if (kind == 1) {
+    if constexpr (CONTRA) {
+      const float u = dev->mb_unpair;
+      v.M1[od + i] = chain_fold<PF, false>(v.X, nullptr, L, d, i, v.X[od + i], lut,
+                                           [u](int m, float rm, float) { return __fadd_rn(rm, __fmul_rn(u, (float)m)); });
+    } else {
+      const float cb = dev->coeff_num_branches;
+      v.M1[od + i] = chain_fold<PF, false>(v.R, nullptr, L, d, i, __fadd_rn(v.R[od + i], cb), lut,
+                                           [cb](int, float r, float) { return __fadd_rn(r, cb); });
+    }
+  } else {
+    float* Mcur = v.Mroll + (d % 3) * L;
+    if constexpr (CONTRA) {
+      Mcur[i] = chain_fold<PF, true>(v.X, v.M1, L, d, i, RNA_NEG_INF, lut,
+                                     [](int, float rm, float m1) { return __fadd_rn(m1, rm); });
+    } else {
+      const float cb = dev->coeff_num_branches;
+      Mcur[i] = chain_fold<PF, true>(v.R, v.M1, L, d, i, RNA_NEG_INF, lut,
+                                     [cb](int, float r, float m1) { return __fadd_rn(m1, __fadd_rn(r, cb)); });
+    }
+  }
+}
+// Z of a pair step: warp-sized tasks (chain kind x 32 cells) of the diagonals t-2 and t-1, the longer diagonal first;
+// warp w of nw takes tasks w, w + nw, ...
+template <bool CONTRA, int PF, class SV>
+RNA_DEV void inside_chain_pair(const SV& v, const typename Model2<CONTRA>::View& T, const float4* lut, int t, int w,
+                               int nw, int lane32) {
+  const int L = v.L;
+  const int dB = t - 1, dA = t - 2;
+  const int gB = (dB >= v.din0 && dB < L) ? (L - dB + 31) >> 5 : 0;
+  const int gA = (dA >= v.din0 && dA < L) ? (L - dA + 31) >> 5 : 0;
+  const int ntask = 3 * (gA + gB);
+  for (int tau = w; tau < ntask; tau += nw) {
+    const int kind = tau % 3;
+    int g = tau / 3, d = dB;
+    if (g >= gB) { g -= gB; d = dA; }
+    const int i = g * 32 + lane32;
+    if (i < L - d) inside_chain_cell<CONTRA, PF>(v, T, lut, d, kind, i);
+  }
+}
+// phase B of a pair step, lane = any thread of the grid
+template <bool CONTRA, class SV>
+RNA_DEV void inside_fin_pair(const SV& v, const typename Model2<CONTRA>::View& T, const float4* lut, int t, int lane,
+                             int nl) {
+  const int L = v.L;
+  const uint8_t* s = v.s;
+  const float NEG = RNA_NEG_INF;
+  const typename Model2<CONTRA>::Dev* dev = T.g;
+  // sums_1ormore_basepairs(d) <- partial (+) sums_multibranch(d), d = t-2, t-1 (first read by the chains of d+2)
+  for (int d = t - 2; d <= t - 1; d++) {
+    if (d < v.din0 || d >= L) continue;
+    const float* Md = v.Mroll + (d % 3) * L;
+    const int od = doff(d, L);
+    for (int i = lane; i < L - d; i += nl) v.M1[od + i] = lse(v.M1[od + i], Md[i], lut);
+  }
+  if (t >= L) return;
+  const int od = doff(t, L), od1 = doff(t + 1, L);
+  for (int i = lane; i < L - t; i += nl) {
+    // diagonal t
+    int j = i + t;
+    float c = v.C[od + i];
+    if (get32(v.mask + i * v.W2, j) & 1u) { c = inside_cell_fin<CONTRA>(v, T, lut, t, i, j, c); v.C[od + i] = c; }
+    const float accv = (c > NEG) ? __fadd_rn(c, v2_acc<CONTRA>(T, s, L, i, j)) : NEG;
+    float Rt, Rmt = NEG;
+    if constexpr (!CONTRA) {
+      // prefix property of the left-to-right fold: R[i][j] = R[i][j-1] (+) A(i,j)
+      Rt = lse((t >= 1) ? v.R[doff(t - 1, L) + i] : NEG, accv, lut);
+    } else {
+      Rt = lse(v.R[od + i], __fadd_rn(__fadd_rn(accv, dev->ext_bp), __fmul_rn(dev->ext_unpair, 0.f)), lut);
+      Rmt = lse(v.X[od + i], __fadd_rn(__fadd_rn(accv, dev->mb_bp), __fmul_rn(dev->mb_unpair, 0.f)), lut);
+      v.X[od + i] = Rmt;
+    }
+    v.R[od + i] = Rt;
+    // diagonal t+1, same row
+    if (t + 1 >= L || i >= L - t - 1) continue;
+    j = i + t + 1;
+    float c1 = v.C[od1 + i];
+    if (get32(v.mask + i * v.W2, j) & 1u) { c1 = inside_cell_fin<CONTRA>(v, T, lut, t + 1, i, j, c1); v.C[od1 + i] = c1; }
+    const float acc1 = (c1 > NEG) ? __fadd_rn(c1, v2_acc<CONTRA>(T, s, L, i, j)) : NEG;
+    if constexpr (!CONTRA) {
+      v.R[od1 + i] = lse(Rt, acc1, lut);
+    } else {
+      // Y left out k = j-1 (sums_close(t) was not finished): A(i,j-1) is accv, one unpaired base to its right
+      float r = lse(v.R[od1 + i], __fadd_rn(__fadd_rn(accv, dev->ext_bp), __fmul_rn(dev->ext_unpair, 1.f)), lut);
+      float rm = lse(v.X[od1 + i], __fadd_rn(__fadd_rn(accv, dev->mb_bp), __fmul_rn(dev->mb_unpair, 1.f)), lut);
+      r = lse(r, __fadd_rn(__fadd_rn(acc1, dev->ext_bp), __fmul_rn(dev->ext_unpair, 0.f)), lut);
+      rm = lse(rm, __fadd_rn(__fadd_rn(acc1, dev->mb_bp), __fmul_rn(dev->mb_unpair, 0.f)), lut);
+      v.R[od1 + i] = r;
+      v.X[od1 + i] = rm;
+    }
   }
 }
 
@@ -1272,6 +1426,140 @@ RNA_DEV void outside_X_diag(const SV& v, const typename Model2<CONTRA>::View& T,
     if (!(Cij > RNA_NEG_INF)) continue;
     const float sm = outside_cell_partial<CONTRA>(v, T, lut, P, Z, st, tot, x0 + r, i, j, Cij);
     v.Pm[od + i] = outside_cell_ml<CONTRA, PF>(v, T, lut, i, j, Cij, sm);
+  }
+}
+
+
+// =========================================================================================================
+// Outside pass of the cooperative long-sequence kernel.  One diagonal per step (log P(d) needs
+// probs_multibranch(d+1), which needs log P(d+2)), but every chain is laid out for latency:
+//   * probs_multibranch / probs_multibranch2 run DENSE over k = j+1 .. L-1 (a non-closable (i,k) has
+//     sums_close = log P = -inf, its operand is NaN -> -inf, the fold ignores it, src/utils.rs:580-583): all
+//     lanes of a warp walk the same offsets, every load is coalesced and affine, the closing scores come from
+//     a table (MB) filled once, and the two sums run on two different lanes;
+//   * both are stored ROW-major, and sums_1ormore_basepairs is copied row-major once, so that the multiloop
+//     part of log P (fixed k, lanes = neighbouring cells of a diagonal) reads neighbouring addresses.
+// =========================================================================================================
+// once, between the passes: lane = any thread of the grid
+template <bool CONTRA, class SV>
+RNA_DEV void outside_prep(const SV& v, const typename Model2<CONTRA>::View& T, int lane, int nl) {
+  const int L = v.L;
+  for (int d = 0; d < L; d++) {
+    const int od = doff(d, L);
+    for (int i = lane; i < L - d; i += nl) {
+      const int j = i + d;
+      v.M1rm[doff(i, L) + d] = v.M1[od + i];
+      v.MB[od + i] = (get32(v.mask + i * v.W2, j) & 1u) ? v2_mbclose<CONTRA>(T, v.s, L, i, j) : 0.f;
+    }
+  }
+}
+// kind 0: probs_multibranch[i][j], kind 1: probs_multibranch2[i][j]   (src/mccaskill_algo.rs:540-557, 641-661)
+template <bool CONTRA, int PF, class SV>
+RNA_DEV void outside_Y_dense_cell(const SV& v, const typename Model2<CONTRA>::View& T, const float4* lut, int d,
+                                  int kind, int i) {
+  const int L = v.L, j = i + d, n = L - 1 - j;   // k = j + m, m = 1 .. n
+  const float NEG = RNA_NEG_INF;
+  const float* pP = v.Pm + (doff(d + 1, L) + i);   // (i, j+1): same offset in Pm, C, MB
+  const float* pC = v.C + (doff(d + 1, L) + i);
+  const float* pS = v.MB + (doff(d + 1, L) + i);
+  const float* pM = v.M1 + (j + 1);                // M1[j+1][k-1] for m = 2: diagonal 0
+  int sP = L - d - 1, sM = L, mL = 1;
+  float rp[PF], rc[PF], rs[PF], rm[PF];
+  auto load = [&](float& a, float& c, float& sc, float& m1) {
+    a = NEG; c = NEG; sc = 0.f; m1 = NEG;
+    if (mL <= n) {
+      a = *pP; c = *pC; sc = *pS;
+      if (kind == 0 && mL >= 2) m1 = *pM;
+    }
+    pP += sP; pC += sP; pS += sP; sP--;          // doff(d+m+1) - doff(d+m) = L - (d+m)
+    if (mL >= 2) { pM += sM; sM--; }             // doff(m-1) - doff(m-2) = L - (m-2)
+    mL++;
+  };
+#pragma unroll
+  for (int u = 0; u < PF; u++) load(rp[u], rc[u], rs[u], rm[u]);
+  float sum = NEG;
+  float unp = 0.f;
+  if constexpr (CONTRA) unp = T.g->mb_unpair;
+  for (int m0 = 1; m0 <= n; m0 += PF) {
+#pragma unroll
+    for (int u = 0; u < PF; u++) {
+      const float a = rp[u], c = rc[u], sc = rs[u], m1 = rm[u];
+      load(rp[u], rc[u], rs[u], rm[u]);
+      const float x = __fsub_rn(__fadd_rn(a, sc), c);
+      float y;
+      if (kind == 0) y = __fadd_rn(x, m1);
+      else if (CONTRA) y = __fadd_rn(x, __fmul_rn(unp, (float)(m0 + u - 1)));
+      else y = x;
+      sum = lse(sum, y, lut);
+    }
+  }
+  (kind == 0 ? v.R : v.X)[doff(i, L) + d] = sum;   // row-major
+}
+template <bool CONTRA, int PF, class SV>
+RNA_DEV void outside_Y_dense(const SV& v, const typename Model2<CONTRA>::View& T, const float4* lut, int d, int w, int nw,
+                             int lane32) {
+  const int L = v.L, ng = (L - d + 31) >> 5;
+  for (int tau = w; tau < 2 * ng; tau += nw) {
+    const int kind = tau & 1, i = (tau >> 1) * 32 + lane32;
+    if (i < L - d) outside_Y_dense_cell<CONTRA, PF>(v, T, lut, d, kind, i);
+  }
+}
+// enclosing multiloops of log P(i,j) from the row-major matrices, k ascending 0 .. i-1
+// (src/mccaskill_algo.rs:594-601, 701-714)
+template <bool CONTRA, int PF, class SV>
+RNA_DEV float outside_cell_ml_rm(const SV& v, const typename Model2<CONTRA>::View& T, const float4* lut, int i, int j,
+                                 float Cij, float sm) {
+  const int L = v.L;
+  const float NEG = RNA_NEG_INF;
+  const typename Model2<CONTRA>::Dev* dev = T.g;
+  const float Aij = __fadd_rn(Cij, v2_acc<CONTRA>(T, v.s, L, i, j));
+  float sa;
+  if constexpr (CONTRA) sa = __fadd_rn(Aij, dev->mb_bp); else sa = __fadd_rn(Aij, dev->coeff_num_branches);
+  const float* pX = v.X + j;                 // probs_multibranch2[k][j], row k = 0
+  const float* pR = v.R + j;                 // probs_multibranch[k][j]
+  const float* pM = v.M1rm + (L + i - 2);    // sums_1ormore[k+1][i-1], row 1: doff(1) + (i-1) - 1
+  int sQ = L - 1, sM = L - 2, kL = 0;
+  float bx[PF], bp[PF], by[PF];
+  auto load = [&](float& fx, float& fp, float& fy) {
+    fx = NEG; fp = NEG; fy = NEG;
+    if (kL < i) {
+      fp = *pX; fy = *pR;
+      if (kL < i - 1) fx = *pM;              // span i-1-k >= 1
+    }
+    pX += sQ; pR += sQ; sQ--;                // doff(k+1) + j-k-1 - (doff(k) + j-k) = L - k - 1
+    pM += sM; sM--;                          // doff(k+2) + i-3-k - (doff(k+1) + i-2-k) = L - k - 2
+    kL++;
+  };
+#pragma unroll
+  for (int u = 0; u < PF; u++) load(bx[u], bp[u], by[u]);
+  for (int k0 = 0; k0 < i; k0 += PF) {
+#pragma unroll
+    for (int u = 0; u < PF; u++) {
+      const float x1 = bx[u], p2 = bp[u], y = by[u];
+      load(bx[u], bp[u], by[u]);
+      const int m = i - 1 - (k0 + u);
+      sm = lse(sm, __fadd_rn(__fadd_rn(sa, p2), x1), lut);
+      if constexpr (CONTRA) sm = lse(sm, __fadd_rn(__fadd_rn(sa, y), __fmul_rn(dev->mb_unpair, (float)m)), lut);
+      else sm = lse(sm, __fadd_rn(sa, y), lut);
+      sm = lse(sm, __fadd_rn(__fadd_rn(sa, x1), y), lut);
+    }
+  }
+  return sm;
+}
+template <bool CONTRA, int PF, class SV>
+RNA_DEV void outside_X_diag_rm(const SV& v, const typename Model2<CONTRA>::View& T, const float4* lut,
+                               const ModelParams& P, float Z, int d, int lane, int nl) {
+  const int L = v.L;
+  if (d < v.dout0) return;
+  const int st = (L - 1 - d) >> 1;
+  const StepCells sc = step_cells<false>(v, st);
+  const int tot = sc.cA + sc.cB, x0 = (d == sc.dA) ? 0 : sc.cA, cnt = v.pcnt[d], od = doff(d, L);
+  for (int r = lane; r < cnt; r += nl) {
+    const int i = v.plist[od + r], j = i + d;
+    const float Cij = v.C[od + i];
+    if (!(Cij > RNA_NEG_INF)) continue;
+    const float sm = outside_cell_partial<CONTRA>(v, T, lut, P, Z, st, tot, x0 + r, i, j, Cij);
+    v.Pm[od + i] = outside_cell_ml_rm<CONTRA, PF>(v, T, lut, i, j, Cij, sm);
   }
 }
 

@@ -330,7 +330,8 @@ static int launch_fold_model(rna_handle* h, const RnaFoldBatchDev* b, cudaStream
                              : fold_ws_floats<CONTRA>(bk.Lcap)) + 32;
     stride_of[k] = per;
     if (bk.mode == MODE_COOP) {
-      ws_floats = std::max(ws_floats, per);
+      // + row-major sums_1ormore and the multibranch closing-score table of the cooperative kernel's outside pass
+      ws_floats = std::max(ws_floats, per + (v2 ? (size_t)bk.Lcap * (bk.Lcap + 1) + 64 : 0));
     } else {
       size_t freeb = 0, totb = 0;
       cudaMemGetInfo(&freeb, &totb);
@@ -516,7 +517,10 @@ static int launch_fold_model(rna_handle* h, const RnaFoldBatchDev* b, cudaStream
       CU(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fold_kernel2_coop<CONTRA>, nt, smem));
       const int grid = std::max(1, std::min(occ, 2)) * h->sm_count;
       const int W = grid * (nt / 32);
-      int nX = (3 * bk.Lcap / 4 + 31) / 32, nZ = (bk.Lcap + 31) / 32, nY = CONTRA ? nZ : 0;
+      // inside pair steps: X = closable cells of two diagonals, Y = all cells of two diagonals, Z = three chains per
+      // cell of two diagonals (one lane each)
+      const int full = (bk.Lcap + 31) / 32;
+      int nX = (3 * bk.Lcap / 4 + 31) / 32, nZ = 6 * full, nY = CONTRA ? 2 * full : 0;
       while (nX + nY + nZ > W) { if (nZ > 1) nZ--; if (nY > 1) nY--; if (nX > 1 && nX + nY + nZ > W) nX--; if (nX + nY + nZ <= 3) break; }
       a.nXw = nX; a.nYw = nY; a.nZw = nZ;
       a.stream_ws = nullptr;
@@ -550,10 +554,29 @@ static int launch_fold_model(rna_handle* h, const RnaFoldBatchDev* b, cudaStream
     h->stats.kernel_launches++;
     if (dbg_roles && v2 && bk.mode == MODE_COOP) {
       cudaStreamSynchronize(st);
-      long long hd[4];
+      long long hd[32];
       cudaMemcpy(hd, d_dbg, sizeof hd, cudaMemcpyDeviceToHost);
       fprintf(stderr, "[RNA_FOLD_DBG] coop L=%d roles %d/%d/%d: setup+streams=%lld inside=%lld outside=%lld bpp+centroid=%lld cycles\n", bk.Lcap,
               a.nXw, a.nYw, a.nZw, hd[0], hd[1], hd[2], hd[3]);
+      fprintf(stderr, "[RNA_FOLD_DBG]   inside, first warp of a role (work, wait A, phase B): X %lld %lld %lld | Y %lld %lld %lld | Z %lld %lld %lld\n",
+              hd[8], hd[9], hd[10], hd[12], hd[13], hd[14], hd[16], hd[17], hd[18]);
+      fprintf(stderr, "[RNA_FOLD_DBG]   outside, first warp of a role (work, wait): X %lld %lld | Y %lld %lld\n", hd[20], hd[21], hd[24], hd[25]);
+      {
+        std::vector<long long> hs((size_t)(bk.Lcap / 2 + 2) * 8);
+        cudaMemcpy(hs.data(), d_dbg + 64, hs.size() * 8, cudaMemcpyDeviceToHost);
+        long long sm[5] = {0, 0, 0, 0, 0}, crit = 0, nsA = 0, nsBar = 0, nsB = 0, prev_end = 0;
+        for (size_t stp = 0; stp * 8 < hs.size(); stp++) {
+          long long mx = 0;
+          for (int r = 0; r < 5; r++) { sm[r] += hs[stp * 8 + r]; mx = std::max(mx, hs[stp * 8 + r]); }
+          crit += mx;
+          const long long ga = hs[stp * 8 + 5], gr = hs[stp * 8 + 6], ge = hs[stp * 8 + 7];
+          if (ga && gr && ge) { if (prev_end) nsA += ga - prev_end; nsBar += gr - ga; nsB += ge - gr; prev_end = ge; }
+        }
+        fprintf(stderr, "[RNA_FOLD_DBG]   inside wall (globaltimer, last CTA): phase A %.3f ms, its barrier %.3f ms, phase B + barrier %.3f ms\n",
+                nsA * 1e-6, nsBar * 1e-6, nsB * 1e-6);
+        fprintf(stderr, "[RNA_FOLD_DBG]   inside phase A, sum over steps of the slowest warp: X %lld Y %lld Z-E %lld Z-M1 %lld Z-M %lld, all %lld\n",
+                sm[0], sm[1], sm[2], sm[3], sm[4], crit);
+      }
     } else if (dbg_roles) {   // debug aid: where do the cycles of one sequence go, per role and pass
       cudaStreamSynchronize(st);
       std::vector<long long> hd(2048 * 16);

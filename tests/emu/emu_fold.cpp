@@ -42,6 +42,8 @@ int run(const uint8_t* seq, int L, int allows_short, const typename Model2<CONTR
   v.mask = mask.data(); v.plist = plist.data(); v.pcnt = pcnt.data(); v.RR = RR.data(); v.LL = LL.data();
   v.C = C.data(); v.R = R.data(); v.X = X.data(); v.E = E.data(); v.M1 = M1.data(); v.Mroll = Mroll.data();
   v.E0 = E0.data(); v.EL = EL.data();
+  std::vector<float> M1rm(TRI, NEG), MB(TRI, 0.f);
+  v.M1rm = M1rm.data(); v.MB = MB.data();
   // log P either aliases sums_external (all-in-one-space modes) or is a matrix of its own (the shared-memory mode
   // keeps C and log P on chip and the dense matrices in its HBM/L2 slot)
   std::vector<float> Pown(TRI, NEG);
@@ -90,8 +92,24 @@ int run(const uint8_t* seq, int L, int allows_short, const typename Model2<CONTR
     else for (int l = n - 1; l >= 0; l--) fn(l);
   };
   auto validZ = [&](int d) { return d >= d_in0 && d < L; };
-  const bool single = (order == 2);   // one diagonal per step: the schedule of the cooperative long-sequence kernel
-  if (single) {
+  const bool pairsplit = (order == 3);   // the cooperative kernel's inside pass: pair steps, one chain per lane
+  const bool single = (order == 2) || pairsplit;   // one diagonal per step: the cooperative kernel's outside pass
+  if (pairsplit) {
+    const int nZw = (nZ + 31) / 32;
+    for (int st = 0; d_in0 + 2 * st <= L + 1; st++) {
+      const int t = d_in0 + 2 * st;
+      // phase A (roles in an arbitrary order; none reads what another writes in this phase)
+      for (int w = nZw - 1; w >= 0; w--)
+        for (int ln = 0; ln < 32; ln++) inside_chain_pair<CONTRA, 3>(v, T, lut, t, w, nZw, ln);
+      if constexpr (CONTRA) {
+        if (t + 1 < L) for (int l = 0; l < nY; l++) inside_Y_contra<3>(v, T, lut, t + 1, l, nY, 1);
+        if (t < L) for (int l = nY - 1; l >= 0; l--) inside_Y_contra<1>(v, T, lut, t, l, nY, 0);
+      }
+      for (int l = nX - 1; l >= 0; l--) inside_X<CONTRA>(v, T, lut, P, st, l, nX);
+      // phase B
+      for (int l = nt - 1; l >= 0; l--) inside_fin_pair<CONTRA>(v, T, lut, t, l, nt);
+    }
+  } else if (single) {
     // step t: X(t) whole fold | Y(t) | Z(t-1)
     for (int t = d_in0; t <= L; t++) {
       if (validZ(t - 1)) for (int l = nZ - 1; l >= 0; l--) inside_Z<CONTRA, 3>(v, T, lut, t - 1, l, nZ);
@@ -118,7 +136,16 @@ int run(const uint8_t* seq, int L, int allows_short, const typename Model2<CONTR
   const float Z = E0[L - 1];
   for (int x = 0; x < TRI; x++) { v.Pm[x] = NEG; R[x] = NEG; X[x] = NEG; }
   if (out_logz) *out_logz = Z;
-  if (single) {
+  if (pairsplit) {
+    // the cooperative kernel's outside pass: row-major probs_multibranch(2), dense Y chains on two lanes per cell
+    for (int l = nt - 1; l >= 0; l--) outside_prep<CONTRA>(v, T, l, nt);
+    const int nYw = (nY + nZ + 31) / 32;
+    for (int d = L - 1; d >= d_out0; d--) {
+      for (int w = 0; w < nYw; w++)
+        for (int ln = 31; ln >= 0; ln--) outside_Y_dense<CONTRA, 3>(v, T, lut, d, w, nYw, ln);
+      for (int l = 0; l < nX; l++) outside_X_diag_rm<CONTRA, 3>(v, T, lut, P, Z, d, l, nX);
+    }
+  } else if (single) {
     for (int d = L - 1; d >= d_out0; d--) {   // step d: X(d) whole fold | Y(d)
       const int nl = nY + nZ;
       for (int l = nX - 1; l >= 0; l--) outside_X_diag<CONTRA, 4>(v, T, lut, P, Z, d, l, nX);

@@ -81,3 +81,17 @@ def test_mid_length(emu, oracle):
     tt, ct, _ = default_tables()
     check(emu, oracle, random_seqs(31, [150, 260]), True, False, tt, ct, nX=64, nY=128, nZ=128)
     check(emu, oracle, random_seqs(32, [201]), False, False, tt, ct, order=1)
+
+
+@pytest.mark.parametrize("contra", [False, True])
+def test_pair_split_schedule(emu, oracle, contra):
+    """order = 3: the cooperative kernel's inside pass — pair steps, the three dense chains of a cell on three
+    lanes, chains of two diagonals side by side, R/Rm and sums_1ormore finished in a second phase."""
+    tt, ct, _ = default_tables()
+    seqs = load_trnas()[:2] + random_seqs(9, [1, 2, 3, 4, 5, 6, 7, 17, 40, 131])
+    check(emu, oracle, seqs, contra, False, tt, ct, order=3)
+    check(emu, oracle, seqs[:6], contra, False, tt, ct, order=3, tcap=0, nX=5, nY=3, nZ=40)
+    rt, rc = T.random_turner_tables(311), T.random_contra_tables(312)
+    check(emu, oracle, random_seqs(10, [33, 64, 90]), contra, False, rt, rc, order=3, nZ=96)
+    if contra:
+        check(emu, oracle, random_seqs(13, [2, 3, 5, 9, 33]), True, True, tt, ct, order=3)
