@@ -402,7 +402,7 @@ __global__ void __launch_bounds__(256, 2) fold_kernel2_coop(const FoldArgs a) {
   const int gtid = (int)(blockIdx.x * blockDim.x + threadIdx.x), gnt = (int)(gridDim.x * blockDim.x);
   // global warp id with consecutive ids on different SMs; role lanes are counted from the role's first warp
   const int gw = (tid >> 5) * (int)gridDim.x + (int)blockIdx.x;
-  const int nXl = a.nXw * 32, nYl = a.nYw * 32;
+  const int nXl = a.nXw * 32;
   const int lnX = gw * 32 + (tid & 31), lnY = (gw - a.nXw) * 32 + (tid & 31);
   const bool isX = gw < a.nXw, isY = !isX && gw < a.nXw + a.nYw, isZ = !isX && !isY && gw < a.nXw + a.nYw + a.nZw;
   __syncthreads();
@@ -488,6 +488,7 @@ __global__ void __launch_bounds__(256, 2) fold_kernel2_coop(const FoldArgs a) {
       }
       grid_sync();
     }
+    if constexpr (CONTRA) score_table_acc(v, T, gtid, gnt);   // accessible scores for the dense Y chains (in v.MB)
     for (size_t x = gtid; x < TRI; x += gnt) { v.C[x] = NEG; v.R[x] = NEG; v.X[x] = NEG; v.E[x] = 0.f; v.M1[x] = NEG; }
     for (int x = gtid; x < 3 * L; x += gnt) v.Mroll[x] = NEG;
     grid_sync();
@@ -496,23 +497,14 @@ __global__ void __launch_bounds__(256, 2) fold_kernel2_coop(const FoldArgs a) {
     // ---- inside, pair steps (fold_phases.cuh "PAIR-STEP schedule"): phase A = X two-loop parts of (t, t+1) |
     //      Y partial rightmost-pair sums of (t, t+1) | Z one dense chain per lane for (t-2, t-1); phase B = finish ----
     const int d_in0 = v.din0;
-    const int wZ = gw - a.nXw - a.nYw, hY = a.nYw / 2;
+    const int wZ = gw - a.nXw - a.nYw;
     long long cyc[4] = {0, 0, 0, 0};
     const bool timed = a.dbg && (tid & 31) == 0;
     for (int t = d_in0; t <= L + 1; t += 2) {
       const long long c0 = timed ? clock64() : 0;
       if (isX) inside_X<CONTRA>(v, T, lut, P, (t - d_in0) >> 1, lnX, nXl);
       else if (isY) {
-        if constexpr (CONTRA) {
-          if (hY == 0) {
-            if (t + 1 < L) inside_Y_contra<4>(v, T, lut, t + 1, lnY, nYl, 1);
-            if (t < L) inside_Y_contra<4>(v, T, lut, t, lnY, nYl, 0);
-          } else if (lnY < hY * 32) {
-            if (t + 1 < L) inside_Y_contra<4>(v, T, lut, t + 1, lnY, hY * 32, 1);
-          } else {
-            if (t < L) inside_Y_contra<4>(v, T, lut, t, lnY - hY * 32, nYl - hY * 32, 0);
-          }
-        }
+        if constexpr (CONTRA) inside_Y_dense_pair<4>(v, T, lut, t, gw - a.nXw, a.nYw, tid & 31);
       } else if (isZ) inside_chain_pair<CONTRA, 8>(v, T, lut, t, wZ, a.nZw, tid & 31);
       const long long c1 = timed ? clock64() : 0;
       unsigned long long* gslot = reinterpret_cast<unsigned long long*>(a.dbg) + 64 + (size_t)((t - d_in0) >> 1) * 8;
@@ -549,11 +541,20 @@ __global__ void __launch_bounds__(256, 2) fold_kernel2_coop(const FoldArgs a) {
     cyc[0] = cyc[1] = 0;
     for (int d = L - 1; d >= d_out0; d--) {
       const long long c0 = timed ? clock64() : 0;
-      if (isX) outside_X_diag_rm<CONTRA, 4>(v, T, lut, P, Z, d, lnX, nXl);
+      long long tsp[2] = {0, 0};
+      if (isX) outside_X_diag_rm<CONTRA, 4>(v, T, lut, P, Z, d, lnX, nXl, timed ? tsp : nullptr);
       else if (isY || isZ) outside_Y_dense<CONTRA, 4>(v, T, lut, d, gw - a.nXw, a.nYw + a.nZw, tid & 31);
       const long long c1 = timed ? clock64() : 0;
       grid_sync();
-      if (timed) { cyc[0] += c1 - c0; cyc[1] += clock64() - c1; }
+      if (timed) {
+        cyc[0] += c1 - c0; cyc[1] += clock64() - c1;
+        if (gw < a.nXw + a.nYw + a.nZw) {
+          // X: (total << 0) in slot 0; the stream part of the slowest warp rides along in slot 2 (packed with the total)
+          unsigned long long* sl = reinterpret_cast<unsigned long long*>(a.dbg) + (1 << 19) + (size_t)d * 4;
+          atomicMax(sl + (isX ? 0 : 1), (unsigned long long)(c1 - c0));
+          if (isX) atomicMax(sl + 2, ((unsigned long long)(c1 - c0) << 24) | (unsigned long long)min((long long)0xffffff, tsp[0] >> 4));
+        }
+      }
     }
     if (timed) {
       const int slot = (isX && lnX == 0) ? 20 : (!isX && lnY == 0) ? 24 : -1;

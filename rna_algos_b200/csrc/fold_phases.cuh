@@ -1017,6 +1017,13 @@ RNA_DEV void inside_Z(const SV& v, const typename Model2<CONTRA>::View& T, const
   }
 }
 
+// The chains of the cooperative kernel are pure latency (one warp per scheduler): they fold with the select-tree
+// logsumexp (numerics.cuh lse_lat, bit-identical to lse).  -DRNA_COOP_LSE_LUT switches back for A/B timing.
+#ifdef RNA_COOP_LSE_LUT
+#define RNA_COOP_LSE(sum, x, lut) lse(sum, x, lut)
+#else
+#define RNA_COOP_LSE(sum, x, lut) lse_lat(sum, x)
+#endif
 // =========================================================================================================
 // PAIR-STEP schedule of the cooperative long-sequence kernel (one sequence on the whole GPU).  There a lane is
 // cheap and latency is everything, so the three dense chains of a cell run on three different warps (one
@@ -1057,7 +1064,7 @@ RNA_DEV float chain_fold(const float* __restrict__ A, const float* __restrict__ 
     for (int u = 0; u < PF; u++) {
       const float a = pa[u], b = pb[u];
       load(pa[u], pb[u]);
-      sum = lse(sum, op(m0 + u, a, b), lut);
+      sum = RNA_COOP_LSE(sum, op(m0 + u, a, b), lut);
     }
   }
   return sum;
@@ -1112,6 +1119,61 @@ RNA_DEV void inside_chain_pair(const SV& v, const typename Model2<CONTRA>::View&
     if (g >= gB) { g -= gB; d = dA; }
     const int i = g * 32 + lane32;
     if (i < L - d) inside_chain_cell<CONTRA, PF>(v, T, lut, d, kind, i);
+  }
+}
+// CONTRAfold, Y of a pair step, DENSE: the rightmost-pair sums of cell (i, i+d) over k = i+1 .. j-1-kskip
+// (src/mccaskill_algo.rs:468-486; a non-closable (i,k) has sums_close = -inf and the fold ignores it).  kind 0:
+// external, kind 1: multibranch.  The accessible scores come from a table filled once (score_table_acc, in the buffer
+// the outside pass later reuses for the multibranch closing scores); all loads are coalesced and affine.
+template <class SV>
+RNA_DEV void score_table_acc(const SV& v, const ContraView2& T, int lane, int nl) {
+  const int L = v.L;
+  for (int d = 0; d < L; d++) {
+    const int od = doff(d, L);
+    for (int i = lane; i < L - d; i += nl)
+      v.MB[od + i] = (get32(v.mask + i * v.W2, i + d) & 1u) ? v2_acc<true>(T, v.s, L, i, i + d) : 0.f;
+  }
+}
+template <int PF, class SV>
+RNA_DEV void inside_Y_dense_cell(const SV& v, const ContraView2& T, const float4* lut, int d, int kind, int i, int kskip) {
+  const int L = v.L, n = d - 1 - kskip;   // k = i + m, m = 1 .. n
+  const float NEG = RNA_NEG_INF;
+  const DevContra* dev = T.g;
+  const float cbp = kind == 0 ? dev->ext_bp : dev->mb_bp, cun = kind == 0 ? dev->ext_unpair : dev->mb_unpair;
+  const float* pC = v.C + (L + i);     // doff(1) + i
+  const float* pS = v.MB + (L + i);
+  int sC = L - 1, mL = 1;
+  float rc[PF], rs[PF];
+  auto load = [&](float& c, float& sc) {
+    c = NEG; sc = 0.f;
+    if (mL <= n) { c = *pC; sc = *pS; }
+    pC += sC; pS += sC; sC--;          // doff(m+1) - doff(m) = L - m
+    mL++;
+  };
+#pragma unroll
+  for (int u = 0; u < PF; u++) load(rc[u], rs[u]);
+  float sum = NEG;
+  for (int m0 = 1; m0 <= n; m0 += PF) {
+#pragma unroll
+    for (int u = 0; u < PF; u++) {
+      const float av = __fadd_rn(rc[u], rs[u]);
+      load(rc[u], rs[u]);
+      sum = RNA_COOP_LSE(sum, __fadd_rn(__fadd_rn(av, cbp), __fmul_rn(cun, (float)(d - (m0 + u)))), lut);
+    }
+  }
+  (kind == 0 ? v.R : v.X)[doff(d, L) + i] = sum;
+}
+// warp tasks (diagonal, kind, 32 cells): diagonal t+1 without k = j-1 (sums_close(t) is not finished), diagonal t whole
+template <int PF, class SV>
+RNA_DEV void inside_Y_dense_pair(const SV& v, const ContraView2& T, const float4* lut, int t, int w, int nw, int lane32) {
+  const int L = v.L;
+  const int gB = (t + 1 < L) ? (L - t - 1 + 31) >> 5 : 0, gA = (t < L) ? (L - t + 31) >> 5 : 0;
+  for (int tau = w; tau < 2 * (gA + gB); tau += nw) {
+    const int kind = tau & 1;
+    int g = tau >> 1, d = t + 1, kskip = 1;
+    if (g >= gB) { g -= gB; d = t; kskip = 0; }
+    const int i = g * 32 + lane32;
+    if (i < L - d) inside_Y_dense_cell<PF>(v, T, lut, d, kind, i, kskip);
   }
 }
 // phase B of a pair step, lane = any thread of the grid
@@ -1490,7 +1552,7 @@ RNA_DEV void outside_Y_dense_cell(const SV& v, const typename Model2<CONTRA>::Vi
       if (kind == 0) y = __fadd_rn(x, m1);
       else if (CONTRA) y = __fadd_rn(x, __fmul_rn(unp, (float)(m0 + u - 1)));
       else y = x;
-      sum = lse(sum, y, lut);
+      sum = RNA_COOP_LSE(sum, y, lut);
     }
   }
   (kind == 0 ? v.R : v.X)[doff(i, L) + d] = sum;   // row-major
@@ -1538,17 +1600,17 @@ RNA_DEV float outside_cell_ml_rm(const SV& v, const typename Model2<CONTRA>::Vie
       const float x1 = bx[u], p2 = bp[u], y = by[u];
       load(bx[u], bp[u], by[u]);
       const int m = i - 1 - (k0 + u);
-      sm = lse(sm, __fadd_rn(__fadd_rn(sa, p2), x1), lut);
-      if constexpr (CONTRA) sm = lse(sm, __fadd_rn(__fadd_rn(sa, y), __fmul_rn(dev->mb_unpair, (float)m)), lut);
-      else sm = lse(sm, __fadd_rn(sa, y), lut);
-      sm = lse(sm, __fadd_rn(__fadd_rn(sa, x1), y), lut);
+      sm = RNA_COOP_LSE(sm, __fadd_rn(__fadd_rn(sa, p2), x1), lut);
+      if constexpr (CONTRA) sm = RNA_COOP_LSE(sm, __fadd_rn(__fadd_rn(sa, y), __fmul_rn(dev->mb_unpair, (float)m)), lut);
+      else sm = RNA_COOP_LSE(sm, __fadd_rn(sa, y), lut);
+      sm = RNA_COOP_LSE(sm, __fadd_rn(__fadd_rn(sa, x1), y), lut);
     }
   }
   return sm;
 }
 template <bool CONTRA, int PF, class SV>
 RNA_DEV void outside_X_diag_rm(const SV& v, const typename Model2<CONTRA>::View& T, const float4* lut,
-                               const ModelParams& P, float Z, int d, int lane, int nl) {
+                               const ModelParams& P, float Z, int d, int lane, int nl, long long* tsplit = nullptr) {
   const int L = v.L;
   if (d < v.dout0) return;
   const int st = (L - 1 - d) >> 1;
@@ -1558,7 +1620,13 @@ RNA_DEV void outside_X_diag_rm(const SV& v, const typename Model2<CONTRA>::View&
     const int i = v.plist[od + r], j = i + d;
     const float Cij = v.C[od + i];
     if (!(Cij > RNA_NEG_INF)) continue;
+#ifdef __CUDACC__
+    const long long c0 = tsplit ? clock64() : 0;
+#endif
     const float sm = outside_cell_partial<CONTRA>(v, T, lut, P, Z, st, tot, x0 + r, i, j, Cij);
+#ifdef __CUDACC__
+    if (tsplit) { tsplit[0] += clock64() - c0; tsplit[1] = i; }
+#endif
     v.Pm[od + i] = outside_cell_ml_rm<CONTRA, PF>(v, T, lut, i, j, Cij, sm);
   }
 }

@@ -67,6 +67,40 @@ RNA_DEV float lse(float sum, float x, const float4* __restrict__ lut) {
   return (z < __int_as_float(0x7f800000)) ? v : mx;
 }
 
+// Latency-optimised logsumexp, bit-identical to lse(): no shared-memory LUT — the seven breakpoint compares issue side
+// by side right after z, and each coefficient comes out of a three-level select tree (only the tree of `a` is on the
+// dependency chain; b, c, d resolve under the Horner steps).  42 instructions instead of 26, but a dependent step
+// takes 94 cycles instead of 114 on a warp that has its scheduler to itself (tools/lse_microbench.cu): used by the
+// cooperative long-sequence kernel, whose chains are pure latency; the batch kernels, which are issue-bound, keep lse().
+RNA_DEV float lse_sel8(bool q1, bool q2, bool q3, bool q4, bool q5, bool q6, bool q7, float c0, float c1, float c2,
+                       float c3, float c4, float c5, float c6, float c7) {
+  const float lo = q2 ? (q3 ? c3 : c2) : (q1 ? c1 : c0);
+  const float hi = q6 ? (q7 ? c7 : c6) : (q5 ? c5 : c4);
+  return q4 ? hi : lo;
+}
+RNA_DEV float lse_lat(float sum, float x) {
+  x = (x > RNA_NEG_INF) ? x : RNA_NEG_INF;
+  const float y = fminf(sum, x);
+  const float mx = fmaxf(sum, x);
+  const float z = __fsub_rn(mx, y);
+  // !(z < b): a NaN z lands in the last segment like in the reference's comparison tree; its result is discarded below
+  const bool q1 = !(z < 0.66153675f), q2 = !(z < 1.6320158f), q3 = !(z < 2.4912589f), q4 = !(z < 3.37925f),
+             q5 = !(z < 4.426169f), q6 = !(z < 5.789071f), q7 = !(z < 7.8162727f);
+  const float a = lse_sel8(q1, q2, q3, q4, q5, q6, q7, -0.0065591595f, -0.015515756f, -0.012890925f, -0.0072142647f,
+                           -0.0031455354f, -0.0010110698f, -0.000196278f, -0.0000113994f);
+  const float b = lse_sel8(q1, q2, q3, q4, q5, q6, q7, 0.12764427f, 0.14467756f, 0.13010283f, 0.087754086f,
+                           0.046722945f, 0.018594341f, 0.0046084408f, 0.0003734731f);
+  const float c = lse_sel8(q1, q2, q3, q4, q5, q6, q7, 0.49965546f, 0.48829398f, 0.51503986f, 0.6208708f, 0.7592532f,
+                           0.88317305f, 0.9634432f, 0.9959107f);
+  const float d = lse_sel8(q1, q2, q3, q4, q5, q6, q7, 0.6931542f, 0.6958093f, 0.6795586f, 0.5909676f, 0.43487945f,
+                           0.25236955f, 0.09831489f, 0.0149855051f);
+  float r = __fadd_rn(__fmul_rn(a, z), b);
+  r = __fadd_rn(__fmul_rn(r, z), c);
+  r = __fadd_rn(__fmul_rn(r, z), d);
+  const float v = __fadd_rn(y, (z >= RNA_LSE_THRESHOLD) ? z : r);
+  return (z < __int_as_float(0x7f800000)) ? v : mx;
+}
+
 // logsumexp into an EMPTY sum (sum == -inf): the reference takes x if it is finite (src/utils.rs:581-586)
 RNA_DEV float lse_init(float x) { return (x > RNA_NEG_INF) ? x : RNA_NEG_INF; }
 

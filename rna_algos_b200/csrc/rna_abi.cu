@@ -286,7 +286,29 @@ static int launch_fold_model(rna_handle* h, const RnaFoldBatchDev* b, cudaStream
   if (v2) {
     uint32_t n_long = 0;
     while (n_long < n && len_of(n_long) > Lsmem) n_long++;
-    if (n_long > 0 && n_long <= 4) Lcoop_min = std::max(Lsmem + 1, 384);
+    // Cost model from B200 measurements (CONTRAfold; Turner is alike): a cooperative run takes ~230 ms x (L/1024)^2
+    // (latency-bound, one sequence at a time); a wave of up to 2 x SM-count one-CTA sequences takes ~5.5 s x
+    // (L/1024)^3 when full and about half of that when nearly empty.  Sequences are sorted longest first: give the
+    // longest c of the long ones to the cooperative kernel, c chosen to minimise the sum.
+    auto coop_ms = [](int L) { const double r = L / 1024.0; return 230.0 * r * r; };
+    auto wave_ms = [&](int Lmax, uint32_t cnt) {
+      if (cnt == 0) return 0.0;
+      const double r = Lmax / 1024.0, per_wave = 2.0 * h->sm_count;
+      const double waves = cnt / per_wave;
+      return 5500.0 * r * r * r * std::max(0.5, waves);
+    };
+    uint32_t forced = 0;
+    while (forced < n_long && len_of(forced) > 1024) forced++;
+    double best = 1e300, prefix = 0;
+    uint32_t best_c = forced;
+    for (uint32_t c = 0; c <= std::min<uint32_t>(n_long, forced + 64); c++) {
+      if (c >= forced) {
+        const double cost = prefix + (c < n_long ? wave_ms(len_of(c), n_long - c) : 0.0);
+        if (cost < best) { best = cost; best_c = c; }
+      }
+      if (c < n_long) prefix += coop_ms(len_of(c));
+    }
+    if (best_c > forced) Lcoop_min = std::max(std::max(Lsmem + 1, 384), len_of(best_c - 1));
   }
   std::vector<Bucket> buckets;
   uint32_t pos = 0;
@@ -448,7 +470,7 @@ static int launch_fold_model(rna_handle* h, const RnaFoldBatchDev* b, cudaStream
 
   static const bool dbg_roles = getenv("RNA_FOLD_DBG") != nullptr;
   long long* d_dbg = nullptr;
-  if (dbg_roles) { cudaMalloc(&d_dbg, 2048 * 16 * 8); cudaMemset(d_dbg, 0, 2048 * 16 * 8); a.dbg = d_dbg; }
+  if (dbg_roles) { cudaMalloc(&d_dbg, (size_t)(1 << 20) * 8); cudaMemset(d_dbg, 0, (size_t)(1 << 20) * 8); a.dbg = d_dbg; }
   for (size_t k = 0; k < buckets.size(); k++) {
     const Bucket& bk = buckets[k];
     const int lane = (nlanes > 1 && bk.mode != MODE_COOP) ? (int)(k % nlanes) : 0;
@@ -520,7 +542,7 @@ static int launch_fold_model(rna_handle* h, const RnaFoldBatchDev* b, cudaStream
       // inside pair steps: X = closable cells of two diagonals, Y = all cells of two diagonals, Z = three chains per
       // cell of two diagonals (one lane each)
       const int full = (bk.Lcap + 31) / 32;
-      int nX = (3 * bk.Lcap / 4 + 31) / 32, nZ = 6 * full, nY = CONTRA ? 2 * full : 0;
+      int nX = (3 * bk.Lcap / 4 + 31) / 32, nZ = 6 * full, nY = CONTRA ? 4 * full : 0;
       while (nX + nY + nZ > W) { if (nZ > 1) nZ--; if (nY > 1) nY--; if (nX > 1 && nX + nY + nZ > W) nX--; if (nX + nY + nZ <= 3) break; }
       a.nXw = nX; a.nYw = nY; a.nZw = nZ;
       a.stream_ws = nullptr;
@@ -574,6 +596,16 @@ static int launch_fold_model(rna_handle* h, const RnaFoldBatchDev* b, cudaStream
         }
         fprintf(stderr, "[RNA_FOLD_DBG]   inside wall (globaltimer, last CTA): phase A %.3f ms, its barrier %.3f ms, phase B + barrier %.3f ms\n",
                 nsA * 1e-6, nsBar * 1e-6, nsB * 1e-6);
+        {
+          std::vector<long long> ho((size_t)bk.Lcap * 4);
+          cudaMemcpy(ho.data(), d_dbg + (1 << 19), ho.size() * 8, cudaMemcpyDeviceToHost);
+          long long ox = 0, oy = 0, oall = 0, ostream = 0;
+          for (int dd = 0; dd < bk.Lcap; dd++) {
+            ox += ho[(size_t)dd * 4]; oy += ho[(size_t)dd * 4 + 1]; oall += std::max(ho[(size_t)dd * 4], ho[(size_t)dd * 4 + 1]);
+            ostream += (ho[(size_t)dd * 4 + 2] & 0xffffff) << 4;
+          }
+          fprintf(stderr, "[RNA_FOLD_DBG]   outside, sum over steps of the slowest warp: X %lld (of which exterior + two-loop stream part %lld) Y %lld, all %lld\n", ox, ostream, oy, oall);
+        }
         fprintf(stderr, "[RNA_FOLD_DBG]   inside phase A, sum over steps of the slowest warp: X %lld Y %lld Z-E %lld Z-M1 %lld Z-M %lld, all %lld\n",
                 sm[0], sm[1], sm[2], sm[3], sm[4], crit);
       }

@@ -96,14 +96,21 @@ int run(const uint8_t* seq, int L, int allows_short, const typename Model2<CONTR
   const bool single = (order == 2) || pairsplit;   // one diagonal per step: the cooperative kernel's outside pass
   if (pairsplit) {
     const int nZw = (nZ + 31) / 32;
+    if constexpr (CONTRA) for (int l = 0; l < nt; l++) score_table_acc(v, T, l, nt);
     for (int st = 0; d_in0 + 2 * st <= L + 1; st++) {
       const int t = d_in0 + 2 * st;
       // phase A (roles in an arbitrary order; none reads what another writes in this phase)
       for (int w = nZw - 1; w >= 0; w--)
         for (int ln = 0; ln < 32; ln++) inside_chain_pair<CONTRA, 3>(v, T, lut, t, w, nZw, ln);
       if constexpr (CONTRA) {
-        if (t + 1 < L) for (int l = 0; l < nY; l++) inside_Y_contra<3>(v, T, lut, t + 1, l, nY, 1);
-        if (t < L) for (int l = nY - 1; l >= 0; l--) inside_Y_contra<1>(v, T, lut, t, l, nY, 0);
+        if (nX & 1) {   // (the sparse partial sums, still a valid Y of this schedule)
+          if (t + 1 < L) for (int l = 0; l < nY; l++) inside_Y_contra<3>(v, T, lut, t + 1, l, nY, 1);
+          if (t < L) for (int l = nY - 1; l >= 0; l--) inside_Y_contra<1>(v, T, lut, t, l, nY, 0);
+        } else {
+          const int nYw = (nY + 31) / 32;
+          for (int w = 0; w < nYw; w++)
+            for (int ln = 31; ln >= 0; ln--) inside_Y_dense_pair<3>(v, T, lut, t, w, nYw, ln);
+        }
       }
       for (int l = nX - 1; l >= 0; l--) inside_X<CONTRA>(v, T, lut, P, st, l, nX);
       // phase B

@@ -238,3 +238,21 @@ def test_long_cooperative_contra(handle, oracle):
     """> 1024 nt under CONTRAfold: grid-wide one-diagonal wavefront with roles spread over the SMs."""
     tt, ct, _ = default_tables()
     check_fold(handle, oracle, random_seqs(33, [1300]), True, False, [2.0, 0.5], tt, ct)
+
+
+def test_mixed_long_and_mid_routing(handle, oracle):
+    """A few long sequences next to mid-length ones: the cost model sends the longest to the cooperative kernel and
+    the rest to the one-CTA HBM-resident mode; results are bit-identical either way."""
+    tt, ct, _ = default_tables()
+    seqs = random_seqs(91, [1100, 700, 640, 300, 280, 260, 120, 76, 30])
+    check_fold(handle, oracle, seqs, True, False, [1.0, 2.0], tt, ct)
+    check_fold(handle, oracle, seqs[1:], False, False, [2.0], tt, ct)
+
+
+def test_long_cooperative_edge_lengths(handle, oracle):
+    """The cooperative kernel is also the route for a lone mid-length sequence: odd/even lengths around the warp and
+    pair-step boundaries (the last pair step handles one or two diagonals)."""
+    tt, ct, _ = default_tables()
+    for L in (384, 385, 415, 416, 449):
+        for contra in (False, True):
+            check_fold(handle, oracle, random_seqs(100 + L, [L]), contra, False, [2.0], tt, ct)
