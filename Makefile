@@ -6,7 +6,7 @@ LIB := rna_algos_b200/librna_algos_b200.so
 SRC := rna_algos_b200/csrc/rna_abi.cu
 HDR := $(wildcard rna_algos_b200/csrc/*.cuh rna_algos_b200/csrc/*.h include/*.h)
 
-all: $(LIB) oracle
+all: $(LIB) oracle cli
 
 $(LIB): $(SRC) $(HDR)
 	$(NVCC) $(NVCCFLAGS) -shared -o $@ $(SRC) -lcudart
@@ -14,7 +14,17 @@ $(LIB): $(SRC) $(HDR)
 oracle:
 	$(MAKE) -C oracle
 
+# command-line front ends with the reference's options and output formats (cli/rna_cli.cpp); one binary, three names
+CLI := bin/rna_algos_b200
+cli: $(CLI) rna_algos_b200/tables_default/turner2004.tbl
+$(CLI): cli/rna_cli.cpp include/rna_algos_b200.h $(LIB)
+	mkdir -p bin
+	g++ -std=c++17 -O2 -Wall -o $@ cli/rna_cli.cpp -Lrna_algos_b200 -lrna_algos_b200 -Wl,-rpath,'$$ORIGIN/../rna_algos_b200' -Wl,--allow-shlib-undefined
+	ln -sf rna_algos_b200 bin/mccaskill_algo && ln -sf rna_algos_b200 bin/centroid_fold && ln -sf rna_algos_b200 bin/durbin_algo
+rna_algos_b200/tables_default/turner2004.tbl: rna_algos_b200/tables.py
+	python -m rna_algos_b200.tables dump rna_algos_b200/tables_default
+
 clean:
-	rm -f $(LIB)
+	rm -rf $(LIB) bin rna_algos_b200/tables_default
 	$(MAKE) -C oracle clean
-.PHONY: all oracle clean
+.PHONY: all oracle cli clean

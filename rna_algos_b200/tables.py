@@ -454,3 +454,31 @@ def random_align_tables(seed: int) -> AlignTables:
     m = rng.uniform(-1.0, 1.0, size=(4, 4)).astype(np.float32)
     view(t, "match_scores")[...] = (m + m.T) / 2
     return t
+
+
+# ----------------------------------------------------------------------------------------------
+# Table blob files for non-Python hosts (cli/): the raw bytes of the C structs behind a 16-byte header
+#   "RNATBL01" | u32 kind (1 Turner, 2 CONTRAfold) | u32 sizeof(struct)
+# `python -m rna_algos_b200.tables dump DIR` writes the default (restated) tables; a build that has the
+# genuine rna-ss-params values writes its own files in the same format.
+# ----------------------------------------------------------------------------------------------
+def dump_table_file(path: str, kind: int, struct) -> None:
+    import struct as S
+    raw = bytes(struct)
+    with open(path, "wb") as f:
+        f.write(b"RNATBL01" + S.pack("<II", kind, len(raw)) + raw)
+
+
+def dump_default_tables(out_dir: str) -> None:
+    import os
+    os.makedirs(out_dir, exist_ok=True)
+    dump_table_file(os.path.join(out_dir, "turner2004.tbl"), 1, turner_tables())
+    dump_table_file(os.path.join(out_dir, "contrafold_v202.tbl"), 2, contra_tables())
+
+
+if __name__ == "__main__":
+    import sys
+    if len(sys.argv) == 3 and sys.argv[1] == "dump":
+        dump_default_tables(sys.argv[2])
+    else:
+        raise SystemExit("usage: python -m rna_algos_b200.tables dump DIR")
