@@ -500,6 +500,71 @@ __global__ void __launch_bounds__(MODE == MODE_SMEM ? 256 : 512) fold_kernel(con
   }
 }
 
+__device__ __forceinline__ int coop_doff(int d, int L) { return d * L - ((d * (d - 1)) >> 1); }   // diagonal-major offset
+// Grid-wide barrier of the cooperative kernel: one arrival per CTA on a counter that only grows (zeroed by the host
+// before the launch), release/acquire at GPU scope by the CTA's first thread, CTA barriers on both sides.
+__device__ __forceinline__ void coop_barrier(unsigned* ctr, unsigned& target) {
+  target += gridDim.x;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    atomicAdd(ctr, 1u);
+    unsigned seen;
+    do {
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(ctr) : "memory");
+    } while ((int)(seen - target) < 0);
+  }
+  __syncthreads();
+}
+__device__ __forceinline__ unsigned long long global_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+
+// Max-plus fill of centroid_fold (src/centroid_fold.rs:33-64) for ONE long sequence on the whole grid.  A warp task is
+// 32 neighbouring cells of the diagonal (coalesced loads) times a chunk of CENT_CHUNK split points; the partial maxima
+// meet in an integer atomicMax: every W is >= +0 and W starts at 0, so the order of the float bits as signed integers
+// is the float order wherever it matters, and a maximum does not depend on the order of its operands.
+#define RNA_CENT_CHUNK 64
+template <class GETP, class SYNC>
+__device__ __forceinline__ void centroid_fill_coop(float* W, int L, float gamma, GETP getp, SYNC sync, int gw, int nw,
+                                                   int lane32) {
+  for (int d = 1; d < L; d++) {
+    const int ncell = L - d, ng = (ncell + 31) >> 5, nch = max(1, (d - 1 + RNA_CENT_CHUNK - 1) / RNA_CENT_CHUNK);
+    const int od = coop_doff(d, L), od1 = coop_doff(d - 1, L);
+    for (int tau = gw; tau < ng * nch; tau += nw) {
+      const int g = tau % ng, ch = tau / ng, i = g * 32 + lane32;
+      if (i >= ncell) continue;
+      float wv = 0.f;
+      if (ch == 0) {
+        wv = __ldcg(&W[od1 + i + 1]);
+        float e = __ldcg(&W[od1 + i]);
+        if (e > wv) wv = e;
+        const float p = getp(d, i);
+        if (p != -1.0f) {
+          const float inner = (d >= 2) ? __ldcg(&W[coop_doff(d - 2, L) + i + 1]) : 0.f;
+          e = __fsub_rn(__fadd_rn(inner, __fmul_rn(gamma, p)), 1.0f);
+          if (e > wv) wv = e;
+        }
+      }
+      const int m_lo = 1 + ch * RNA_CENT_CHUNK, m_hi = min(d, m_lo + RNA_CENT_CHUNK);
+      const float* pa = W + (coop_doff(m_lo, L) + i);                      // W[i][i+m]
+      const float* pb = W + (coop_doff(d - m_lo - 1, L) + i + m_lo + 1);   // W[i+m+1][j]
+      int sa = L - m_lo, sb = d - m_lo - L - 1;
+#pragma unroll 8
+      for (int m = m_lo; m < m_hi; m++) {
+        const float e = __fadd_rn(__ldcg(pa), __ldcg(pb));
+        if (e > wv) wv = e;
+        pa += sa; sa--;     // coop_doff(m+1) - coop_doff(m) = L - m
+        pb += sb; sb--;     // coop_doff(d-m-2) + i+m+2 - (coop_doff(d-m-1) + i+m+1) = d - m - L - 1
+      }
+      atomicMax(reinterpret_cast<int*>(&W[od + i]), __float_as_int(wv));
+    }
+    sync();
+  }
+}
+
 // centroid_fold over packed BPP matrices that already live in device memory (rna_centroid_batch).
 // Workspace layout per slot: W (L(L+1)/2 floats) | traceback stack.
 template <int MODE>
@@ -509,6 +574,8 @@ __global__ void __launch_bounds__(MODE == MODE_SMEM ? 256 : 512) centroid_kernel
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ int s_work;
   const int tid = threadIdx.x;
+  unsigned bar_target = 0;
+  (void)bar_target;
   for (uint32_t wloop = 0;; wloop++) {
     uint32_t w;
     if (MODE == MODE_COOP) {
@@ -533,7 +600,19 @@ __global__ void __launch_bounds__(MODE == MODE_SMEM ? 256 : 512) centroid_kernel
     auto getp = [=](int d, int i) -> float {
       return __ldg(&P[(size_t)i * (size_t)(2 * L - i - 1) / 2 + (size_t)(d - 1)]);
     };
-    centroid_run<MODE>(a, sidx, sbeg, L, W, tstack, getp);
+    if constexpr (MODE == MODE_COOP) {
+      // one long sequence on the whole grid: chunked atomic-max fill, own grid barrier (a.work_counter is free here)
+      unsigned* const bar_ctr = reinterpret_cast<unsigned*>(a.work_counter);
+      auto grid_sync = [&]() { coop_barrier(bar_ctr, bar_target); };
+      const int gw = (tid >> 5) * (int)gridDim.x + (int)blockIdx.x;
+      auto fill = [&](float gamma) -> bool {
+        centroid_fill_coop(W, L, gamma, getp, grid_sync, gw, (int)(gridDim.x * (blockDim.x >> 5)), tid & 31);
+        return true;
+      };
+      centroid_run<MODE>(a, sidx, sbeg, L, W, tstack, getp, fill);
+    } else {
+      centroid_run<MODE>(a, sidx, sbeg, L, W, tstack, getp);
+    }
   }
 }
 __host__ __device__ inline size_t centroid_ws_floats(int L) {

@@ -304,70 +304,6 @@ namespace rna {
 // diagonal (whole folds, no partial sums across steps) and the barrier is grid-wide.  grid.sync() orders memory
 // for every thread of the grid, so plain loads see what other CTAs wrote in earlier steps.
 // =========================================================================================================
-// Grid-wide barrier of the cooperative kernel: one arrival per CTA on a counter that only grows (zeroed by the host
-// before the launch), release/acquire at GPU scope by the CTA's first thread, CTA barriers on both sides.
-__device__ __forceinline__ void coop_barrier(unsigned* ctr, unsigned& target) {
-  target += gridDim.x;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    __threadfence();
-    atomicAdd(ctr, 1u);
-    unsigned seen;
-    do {
-      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(ctr) : "memory");
-    } while ((int)(seen - target) < 0);
-  }
-  __syncthreads();
-}
-__device__ __forceinline__ unsigned long long global_ns() {
-  unsigned long long t;
-  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-  return t;
-}
-
-// Max-plus fill of centroid_fold (src/centroid_fold.rs:33-64) for ONE long sequence on the whole grid.  A warp task is
-// 32 neighbouring cells of the diagonal (coalesced loads) times a chunk of CENT_CHUNK split points; the partial maxima
-// meet in an integer atomicMax: every W is >= +0 and W starts at 0, so the order of the float bits as signed integers
-// is the float order wherever it matters, and a maximum does not depend on the order of its operands.
-#define RNA_CENT_CHUNK 64
-template <class GETP, class SYNC>
-__device__ __forceinline__ void centroid_fill_coop(float* W, int L, float gamma, GETP getp, SYNC sync, int gw, int nw,
-                                                   int lane32) {
-  for (int d = 1; d < L; d++) {
-    const int ncell = L - d, ng = (ncell + 31) >> 5, nch = max(1, (d - 1 + RNA_CENT_CHUNK - 1) / RNA_CENT_CHUNK);
-    const int od = doff(d, L), od1 = doff(d - 1, L);
-    for (int tau = gw; tau < ng * nch; tau += nw) {
-      const int g = tau % ng, ch = tau / ng, i = g * 32 + lane32;
-      if (i >= ncell) continue;
-      float wv = 0.f;
-      if (ch == 0) {
-        wv = __ldcg(&W[od1 + i + 1]);
-        float e = __ldcg(&W[od1 + i]);
-        if (e > wv) wv = e;
-        const float p = getp(d, i);
-        if (p != -1.0f) {
-          const float inner = (d >= 2) ? __ldcg(&W[doff(d - 2, L) + i + 1]) : 0.f;
-          e = __fsub_rn(__fadd_rn(inner, __fmul_rn(gamma, p)), 1.0f);
-          if (e > wv) wv = e;
-        }
-      }
-      const int m_lo = 1 + ch * RNA_CENT_CHUNK, m_hi = min(d, m_lo + RNA_CENT_CHUNK);
-      const float* pa = W + (doff(m_lo, L) + i);                      // W[i][i+m]
-      const float* pb = W + (doff(d - m_lo - 1, L) + i + m_lo + 1);   // W[i+m+1][j]
-      int sa = L - m_lo, sb = d - m_lo - L - 1;
-#pragma unroll 8
-      for (int m = m_lo; m < m_hi; m++) {
-        const float e = __fadd_rn(__ldcg(pa), __ldcg(pb));
-        if (e > wv) wv = e;
-        pa += sa; sa--;     // doff(m+1) - doff(m) = L - m
-        pb += sb; sb--;     // doff(d-m-2) + i+m+2 - (doff(d-m-1) + i+m+1) = d - m - L - 1
-      }
-      atomicMax(reinterpret_cast<int*>(&W[od + i]), __float_as_int(wv));
-    }
-    sync();
-  }
-}
-
 template <bool CONTRA>
 __global__ void __launch_bounds__(256, 2) fold_kernel2_coop(const FoldArgs a) {
   typedef typename Model2<CONTRA>::Dev Dev;

@@ -256,3 +256,20 @@ def test_long_cooperative_edge_lengths(handle, oracle):
     for L in (384, 385, 415, 416, 449):
         for contra in (False, True):
             check_fold(handle, oracle, random_seqs(100 + L, [L]), contra, False, [2.0], tt, ct)
+
+
+def test_centroid_batch_long_sequence(handle, oracle):
+    """rna_centroid_batch on a > 1024-nt BPP matrix: the whole-grid chunked max-plus fill (atomic integer max of
+    non-negative floats) must reproduce the reference's structures and expected accuracies."""
+    L = 1200
+    rng = np.random.default_rng(17)
+    bpp = np.full(L * (L - 1) // 2, -1.0, dtype=np.float32)
+    idx = rng.choice(bpp.shape[0], size=bpp.shape[0] // 5, replace=False)
+    bpp[idx] = (rng.uniform(0, 1, size=idx.shape[0]) ** 3).astype(np.float32)
+    offsets = np.array([0, L], dtype=np.uint32)
+    gammas = [1.0, 4.0, 64.0]
+    got = handle.centroid_batch(bpp, offsets, gammas)
+    for g, gamma in enumerate(gammas):
+        s, _, ea = oracle.centroid(bpp, L, gamma)
+        assert bytes(got["structs"][g]).decode() == s
+        assert np.float32(got["expect_acc"][g, 0]).view(np.uint32) == np.float32(ea).view(np.uint32)
