@@ -305,7 +305,7 @@ namespace rna {
 // for every thread of the grid, so plain loads see what other CTAs wrote in earlier steps.
 // =========================================================================================================
 template <bool CONTRA>
-__global__ void __launch_bounds__(256, 2) fold_kernel2_coop(const FoldArgs a) {
+__global__ void __launch_bounds__(256, 1) fold_kernel2_coop(const FoldArgs a) {
   typedef typename Model2<CONTRA>::Dev Dev;
   typedef typename Model2<CONTRA>::Small Small;
   typedef typename Model2<CONTRA>::View View;
