@@ -309,7 +309,7 @@ __global__ void __launch_bounds__(256, 1) fold_kernel2_coop(const FoldArgs a) {
   typedef typename Model2<CONTRA>::Dev Dev;
   typedef typename Model2<CONTRA>::Small Small;
   typedef typename Model2<CONTRA>::View View;
-  typedef SeqViewT<uint16_t> SV;
+  typedef CoopView SV;
   unsigned* const bar_ctr = reinterpret_cast<unsigned*>(a.work_counter);
   unsigned bar_target = 0;
   auto grid_sync = [&]() { coop_barrier(bar_ctr, bar_target); };

@@ -74,6 +74,17 @@ struct SeqViewT {
 
 RNA_DEV int doff(int d, int L) { return d * L - ((d * (d - 1)) >> 1); }
 
+// The chains of the cooperative kernel are pure latency (one warp per scheduler): they fold with the select-tree
+// logsumexp (numerics.cuh lse_lat, bit-identical to lse).  -DRNA_COOP_LSE_LUT switches back for A/B timing.
+#ifdef RNA_COOP_LSE_LUT
+#define RNA_COOP_LSE(sum, x, lut) lse(sum, x, lut)
+#else
+#define RNA_COOP_LSE(sum, x, lut) lse_lat(sum, x)
+#endif
+
+// The cooperative long-sequence kernel's view: same fields, but sums_close / log P are far away (HBM/L2).
+struct CoopView : SeqViewT<uint16_t> {};
+
 // bits [pos, pos+31] of a bit-matrix row (`row` points at the leading pad word); pos in [-32, 32*(W2-2))
 RNA_DEV uint32_t get32(const uint32_t* row, int pos) {
   const int q = (pos >> 5) + 1;
@@ -737,6 +748,51 @@ RNA_DEV float stream_chain(const SV& v, const uint2* __restrict__ st, uint32_t w
   return sum;
 }
 
+// The same fold for a view whose sums_close / log P live in HBM/L2 (the cooperative kernel: CoopView): the gathers of
+// a block are issued one whole block of logsumexp's (B x ~115 cycles) before they are consumed and the stream
+// elements two blocks ahead, so neither the stream nor the gathers are waited for (the plain version waits for its
+// gathers at the head of every block, which is fine when they are shared-memory loads).
+template <bool INSIDE, int B, class SV>
+RNA_DEV float stream_chain_deep(const SV& v, const uint2* __restrict__ st, uint32_t wd, uint32_t n, const float4* lut,
+                                float Cij, float sum) {
+  if (n == 0) return sum;
+  uint2 e2[B];
+  float c1[B], p1[B], s1[B];
+#pragma unroll
+  for (int k = 0; k < B; k++) {
+    const uint2 e = ((uint32_t)k < n) ? st[wd * k] : make_uint2(0u, 0u);
+    c1[k] = v.C[e.y]; p1[k] = INSIDE ? 0.f : v.Pm[e.y]; s1[k] = __int_as_float((int)e.x);
+  }
+#pragma unroll
+  for (int k = 0; k < B; k++) e2[k] = ((uint32_t)(B + k) < n) ? st[wd * (B + k)] : make_uint2(0u, 0u);
+  for (uint32_t pos = 0; pos < n; pos += B) {
+    float c0[B], p0[B], s0[B];
+#pragma unroll
+    for (int k = 0; k < B; k++) { c0[k] = c1[k]; p0[k] = p1[k]; s0[k] = s1[k]; }
+#pragma unroll
+    for (int k = 0; k < B; k++) {   // gathers of the next block (neutral element 0: C[0] = -inf, the fold ignores it)
+      c1[k] = v.C[e2[k].y]; p1[k] = INSIDE ? 0.f : v.Pm[e2[k].y]; s1[k] = __int_as_float((int)e2[k].x);
+    }
+#pragma unroll
+    for (int k = 0; k < B; k++) e2[k] = (pos + 2 * B + k < n) ? st[wd * (pos + 2 * B + k)] : make_uint2(0u, 0u);
+#pragma unroll
+    for (int k = 0; k < B; k += 2)
+      if (pos + 48 + k < n) RNA_PREFETCH_L2(st + wd * (pos + 48 + k));
+#pragma unroll
+    for (int k = 0; k < B; k++) sum = RNA_COOP_LSE(sum, term_operand<INSIDE>(c0[k], p0[k], Cij, s0[k]), lut);
+  }
+  return sum;
+}
+// compile-time choice by view type
+template <class SV> struct StreamDepth { static constexpr int value = 0; };   // 0: plain stream_chain
+template <> struct StreamDepth<CoopView> { static constexpr int value = 8; };
+template <bool INSIDE, class SV>
+RNA_DEV float stream_fold(const SV& v, const uint2* __restrict__ st, uint32_t wd, uint32_t n, const float4* lut,
+                          float Cij, float sum) {
+  if constexpr (StreamDepth<SV>::value > 0) return stream_chain_deep<INSIDE, StreamDepth<SV>::value>(v, st, wd, n, lut, Cij, sum);
+  else return stream_chain<INSIDE>(v, st, wd, n, lut, Cij, sum);
+}
+
 // =========================================================================================================
 // inside, role X: sums_close of the closable cells of diagonal d (src/mccaskill_algo.rs:290-343, 395-467).
 // Needs: sums_close of diagonals <= d-2, sums_multibranch of diagonal d-2.
@@ -754,7 +810,7 @@ RNA_DEV float inside_cell_partial(const SV& v, const typename Model2<CONTRA>::Vi
   }
   if (v.tin) {
     const uint32_t G = v.gcumI[st] + (x >> 5), gb = v.gbin[G], wd = group_width(tot, x >> 5);
-    sum = stream_chain<true>(v, v.tin + gb + (x & 31), wd, (v.gbin[G + 1] - gb) / wd, lut, 0.f, sum);
+    sum = stream_fold<true>(v, v.tin + gb + (x & 31), wd, (v.gbin[G + 1] - gb) / wd, lut, 0.f, sum);
   } else {
     typename LoopOf<CONTRA, true>::type lp = make_loop<CONTRA, true>(v, T, i, j);
     sum = twoloop_chain<true>(v, lp, lut, P.MAX2, i, j, 0.f, sum);
@@ -1017,13 +1073,6 @@ RNA_DEV void inside_Z(const SV& v, const typename Model2<CONTRA>::View& T, const
   }
 }
 
-// The chains of the cooperative kernel are pure latency (one warp per scheduler): they fold with the select-tree
-// logsumexp (numerics.cuh lse_lat, bit-identical to lse).  -DRNA_COOP_LSE_LUT switches back for A/B timing.
-#ifdef RNA_COOP_LSE_LUT
-#define RNA_COOP_LSE(sum, x, lut) lse(sum, x, lut)
-#else
-#define RNA_COOP_LSE(sum, x, lut) lse_lat(sum, x)
-#endif
 // =========================================================================================================
 // PAIR-STEP schedule of the cooperative long-sequence kernel (one sequence on the whole GPU).  There a lane is
 // cheap and latency is everything, so the three dense chains of a cell run on three different warps (one
@@ -1341,7 +1390,7 @@ RNA_DEV float outside_cell_partial(const SV& v, const typename Model2<CONTRA>::V
   // enclosing two-loops: k descending from i-1, l ascending from j+1
   if (v.tin) {
     const uint32_t G = v.gcumO[st] + (x >> 5), gb = v.gbout[G], wd = group_width(tot, x >> 5);
-    sm = stream_chain<false>(v, v.tout + gb + (x & 31), wd, (v.gbout[G + 1] - gb) / wd, lut, Cij, sm);
+    sm = stream_fold<false>(v, v.tout + gb + (x & 31), wd, (v.gbout[G + 1] - gb) / wd, lut, Cij, sm);
   } else {
     typename LoopOf<CONTRA, false>::type lp = make_loop<CONTRA, false>(v, T, i, j);
     sm = twoloop_chain<false>(v, lp, lut, P.MAX2, i, j, Cij, sm);

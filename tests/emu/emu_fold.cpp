@@ -94,27 +94,29 @@ int run(const uint8_t* seq, int L, int allows_short, const typename Model2<CONTR
   auto validZ = [&](int d) { return d >= d_in0 && d < L; };
   const bool pairsplit = (order == 3);   // the cooperative kernel's inside pass: pair steps, one chain per lane
   const bool single = (order == 2) || pairsplit;   // one diagonal per step: the cooperative kernel's outside pass
+  CoopView cv;
+  static_cast<SeqViewT<uint16_t>&>(cv) = v;
   if (pairsplit) {
     const int nZw = (nZ + 31) / 32;
-    if constexpr (CONTRA) for (int l = 0; l < nt; l++) score_table_acc(v, T, l, nt);
+    if constexpr (CONTRA) for (int l = 0; l < nt; l++) score_table_acc(cv, T, l, nt);
     for (int st = 0; d_in0 + 2 * st <= L + 1; st++) {
       const int t = d_in0 + 2 * st;
       // phase A (roles in an arbitrary order; none reads what another writes in this phase)
       for (int w = nZw - 1; w >= 0; w--)
-        for (int ln = 0; ln < 32; ln++) inside_chain_pair<CONTRA, 3>(v, T, lut, t, w, nZw, ln);
+        for (int ln = 0; ln < 32; ln++) inside_chain_pair<CONTRA, 3>(cv, T, lut, t, w, nZw, ln);
       if constexpr (CONTRA) {
         if (nX & 1) {   // (the sparse partial sums, still a valid Y of this schedule)
-          if (t + 1 < L) for (int l = 0; l < nY; l++) inside_Y_contra<3>(v, T, lut, t + 1, l, nY, 1);
-          if (t < L) for (int l = nY - 1; l >= 0; l--) inside_Y_contra<1>(v, T, lut, t, l, nY, 0);
+          if (t + 1 < L) for (int l = 0; l < nY; l++) inside_Y_contra<3>(cv, T, lut, t + 1, l, nY, 1);
+          if (t < L) for (int l = nY - 1; l >= 0; l--) inside_Y_contra<1>(cv, T, lut, t, l, nY, 0);
         } else {
           const int nYw = (nY + 31) / 32;
           for (int w = 0; w < nYw; w++)
-            for (int ln = 31; ln >= 0; ln--) inside_Y_dense_pair<3>(v, T, lut, t, w, nYw, ln);
+            for (int ln = 31; ln >= 0; ln--) inside_Y_dense_pair<3>(cv, T, lut, t, w, nYw, ln);
         }
       }
-      for (int l = nX - 1; l >= 0; l--) inside_X<CONTRA>(v, T, lut, P, st, l, nX);
+      for (int l = nX - 1; l >= 0; l--) inside_X<CONTRA>(cv, T, lut, P, st, l, nX);
       // phase B
-      for (int l = nt - 1; l >= 0; l--) inside_fin_pair<CONTRA>(v, T, lut, t, l, nt);
+      for (int l = nt - 1; l >= 0; l--) inside_fin_pair<CONTRA>(cv, T, lut, t, l, nt);
     }
   } else if (single) {
     // step t: X(t) whole fold | Y(t) | Z(t-1)
@@ -145,12 +147,12 @@ int run(const uint8_t* seq, int L, int allows_short, const typename Model2<CONTR
   if (out_logz) *out_logz = Z;
   if (pairsplit) {
     // the cooperative kernel's outside pass: row-major probs_multibranch(2), dense Y chains on two lanes per cell
-    for (int l = nt - 1; l >= 0; l--) outside_prep<CONTRA>(v, T, l, nt);
+    for (int l = nt - 1; l >= 0; l--) outside_prep<CONTRA>(cv, T, l, nt);
     const int nYw = (nY + nZ + 31) / 32;
     for (int d = L - 1; d >= d_out0; d--) {
       for (int w = 0; w < nYw; w++)
-        for (int ln = 31; ln >= 0; ln--) outside_Y_dense<CONTRA, 3>(v, T, lut, d, w, nYw, ln);
-      for (int l = 0; l < nX; l++) outside_X_diag_rm<CONTRA, 3>(v, T, lut, P, Z, d, l, nX);
+        for (int ln = 31; ln >= 0; ln--) outside_Y_dense<CONTRA, 3>(cv, T, lut, d, w, nYw, ln);
+      for (int l = 0; l < nX; l++) outside_X_diag_rm<CONTRA, 3>(cv, T, lut, P, Z, d, l, nX);
     }
   } else if (single) {
     for (int d = L - 1; d >= d_out0; d--) {   // step d: X(d) whole fold | Y(d)
