@@ -1121,7 +1121,7 @@ RNA_DEV float chain_fold(const float* __restrict__ A, const float* __restrict__ 
 // one dense chain (kind 0: sums_external, 1: sums_1ormore_basepairs without its last term, 2: sums_multibranch) of
 // cell (i, i+d).  Needs the finished R (/Rm) of diagonal d.  src/mccaskill_algo.rs:352-374, 487-512.
 template <bool CONTRA, int PF, class SV>
-RNA_DEV void inside_chain_cell(const SV& v, const typename Model2<CONTRA>::View& T, const float4* lut, int d, int kind,
+RNA_DEV_CALL void inside_chain_cell(const SV& v, const typename Model2<CONTRA>::View& T, const float4* lut, int d, int kind,
                                int i) {
   const int L = v.L, od = doff(d, L);
   const typename Model2<CONTRA>::Dev* dev = T.g;
@@ -1566,7 +1566,7 @@ RNA_DEV void outside_prep(const SV& v, const typename Model2<CONTRA>::View& T, i
 }
 // kind 0: probs_multibranch[i][j], kind 1: probs_multibranch2[i][j]   (src/mccaskill_algo.rs:540-557, 641-661)
 template <bool CONTRA, int PF, class SV>
-RNA_DEV void outside_Y_dense_cell(const SV& v, const typename Model2<CONTRA>::View& T, const float4* lut, int d,
+RNA_DEV_CALL void outside_Y_dense_cell(const SV& v, const typename Model2<CONTRA>::View& T, const float4* lut, int d,
                                   int kind, int i) {
   const int L = v.L, j = i + d, n = L - 1 - j;   // k = j + m, m = 1 .. n
   const float NEG = RNA_NEG_INF;
@@ -1618,7 +1618,7 @@ RNA_DEV void outside_Y_dense(const SV& v, const typename Model2<CONTRA>::View& T
 // enclosing multiloops of log P(i,j) from the row-major matrices, k ascending 0 .. i-1
 // (src/mccaskill_algo.rs:594-601, 701-714)
 template <bool CONTRA, int PF, class SV>
-RNA_DEV float outside_cell_ml_rm(const SV& v, const typename Model2<CONTRA>::View& T, const float4* lut, int i, int j,
+RNA_DEV_CALL float outside_cell_ml_rm(const SV& v, const typename Model2<CONTRA>::View& T, const float4* lut, int i, int j,
                                  float Cij, float sm) {
   const int L = v.L;
   const float NEG = RNA_NEG_INF;

@@ -13,6 +13,12 @@
 #define RNA_DEVM __device__ __forceinline__   // member functions
 #define RNA_CONST_TABLE __device__ __constant__
 #define RNA_PREFETCH_L2(p) asm volatile("prefetch.global.L2 [%0];" ::"l"(p))
+// chains of the cooperative kernel; compiled as separate functions with -DRNA_COOP_NOINLINE (measured slower)
+#ifdef RNA_COOP_NOINLINE
+#define RNA_DEV_CALL __device__ __noinline__
+#else
+#define RNA_DEV_CALL __device__ __forceinline__
+#endif
 #else
 #include <math.h>
 #include <string.h>
@@ -20,6 +26,7 @@
 #define RNA_DEVM inline
 #define RNA_CONST_TABLE static const
 #define RNA_PREFETCH_L2(p) ((void)(p))
+#define RNA_DEV_CALL static inline
 #define __restrict__ __restrict
 struct float4 { float x, y, z, w; };
 struct uint2 { unsigned x, y; };
