@@ -59,6 +59,7 @@ enum { RNA_MODEL_TURNER = 0, RNA_MODEL_CONTRA = 1 };
 #define RNA_BASE_U 3
 #define RNA_PSEUDO_BASE 4        /* src/utils.rs:122 — only ever at Durbin sentinel positions       */
 #define RNA_MAX_SEQ_LEN 65535u   /* u16 HashIndex domain, src/bin/centroid_fold.rs:85-101           */
+/* (mccaskill/centroid entry points of this build: RNA_ERR_TOO_LONG beyond 46340 nt — 32-bit matrix offsets) */
 #define RNA_LOOP_TABLE_LEN 31    /* lengths 0..30                                                   */
 #define RNA_MAX_SPECIAL_HAIRPINS 128
 #define RNA_MAX_SPECIAL_HAIRPIN_LEN 12

@@ -317,6 +317,8 @@ static int launch_fold_model(rna_handle* h, const RnaFoldBatchDev* b, cudaStream
     Bucket bk;
     bk.begin = pos;
     if (L >= Lcoop_min) {
+      // the cooperative kernel indexes its triangular matrices with 32-bit offsets (d * L must not overflow)
+      if (v2 && L > 46340) { h->err = "sequences longer than 46340 nt are not supported by this build"; return RNA_ERR_TOO_LONG; }
       bk.mode = MODE_COOP; bk.Lcap = L; bk.end = pos + 1;
     } else if (L > Lsmem) {
       bk.mode = MODE_GLOBAL; bk.Lcap = L;
