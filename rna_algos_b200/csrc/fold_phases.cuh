@@ -81,6 +81,12 @@ RNA_DEV int doff(int d, int L) { return d * L - ((d * (d - 1)) >> 1); }
 #else
 #define RNA_COOP_LSE(sum, x, lut) lse_lat(sum, x)
 #endif
+// the same for operands that are sums of finite or -inf values (no subtraction, no +inf): they cannot be NaN
+#ifdef RNA_COOP_LSE_LUT
+#define RNA_COOP_LSE_NN(sum, x, lut) lse(sum, x, lut)
+#else
+#define RNA_COOP_LSE_NN(sum, x, lut) lse_lat<false>(sum, x)
+#endif
 
 // The cooperative long-sequence kernel's view: same fields, but sums_close / log P are far away (HBM/L2).
 struct CoopView : SeqViewT<uint16_t> {};
@@ -1113,7 +1119,7 @@ RNA_DEV float chain_fold(const float* __restrict__ A, const float* __restrict__ 
     for (int u = 0; u < PF; u++) {
       const float a = pa[u], b = pb[u];
       load(pa[u], pb[u]);
-      sum = RNA_COOP_LSE(sum, op(m0 + u, a, b), lut);
+      sum = RNA_COOP_LSE_NN(sum, op(m0 + u, a, b), lut);
     }
   }
   return sum;
@@ -1207,7 +1213,7 @@ RNA_DEV void inside_Y_dense_cell(const SV& v, const ContraView2& T, const float4
     for (int u = 0; u < PF; u++) {
       const float av = __fadd_rn(rc[u], rs[u]);
       load(rc[u], rs[u]);
-      sum = RNA_COOP_LSE(sum, __fadd_rn(__fadd_rn(av, cbp), __fmul_rn(cun, (float)(d - (m0 + u)))), lut);
+      sum = RNA_COOP_LSE_NN(sum, __fadd_rn(__fadd_rn(av, cbp), __fmul_rn(cun, (float)(d - (m0 + u)))), lut);
     }
   }
   (kind == 0 ? v.R : v.X)[doff(d, L) + i] = sum;
@@ -1649,10 +1655,10 @@ RNA_DEV_CALL float outside_cell_ml_rm(const SV& v, const typename Model2<CONTRA>
       const float x1 = bx[u], p2 = bp[u], y = by[u];
       load(bx[u], bp[u], by[u]);
       const int m = i - 1 - (k0 + u);
-      sm = RNA_COOP_LSE(sm, __fadd_rn(__fadd_rn(sa, p2), x1), lut);
-      if constexpr (CONTRA) sm = RNA_COOP_LSE(sm, __fadd_rn(__fadd_rn(sa, y), __fmul_rn(dev->mb_unpair, (float)m)), lut);
-      else sm = RNA_COOP_LSE(sm, __fadd_rn(sa, y), lut);
-      sm = RNA_COOP_LSE(sm, __fadd_rn(__fadd_rn(sa, x1), y), lut);
+      sm = RNA_COOP_LSE_NN(sm, __fadd_rn(__fadd_rn(sa, p2), x1), lut);
+      if constexpr (CONTRA) sm = RNA_COOP_LSE_NN(sm, __fadd_rn(__fadd_rn(sa, y), __fmul_rn(dev->mb_unpair, (float)m)), lut);
+      else sm = RNA_COOP_LSE_NN(sm, __fadd_rn(sa, y), lut);
+      sm = RNA_COOP_LSE_NN(sm, __fadd_rn(__fadd_rn(sa, x1), y), lut);
     }
   }
   return sm;

@@ -78,8 +78,10 @@ RNA_DEV float lse_sel8(bool q1, bool q2, bool q3, bool q4, bool q5, bool q6, boo
   const float hi = q6 ? (q7 ? c7 : c6) : (q5 ? c5 : c4);
   return q4 ? hi : lo;
 }
+// NORM = false: the caller guarantees that x is finite or -inf (never NaN), which saves the normalising select
+template <bool NORM = true>
 RNA_DEV float lse_lat(float sum, float x) {
-  x = (x > RNA_NEG_INF) ? x : RNA_NEG_INF;
+  if (NORM) x = (x > RNA_NEG_INF) ? x : RNA_NEG_INF;
   const float y = fminf(sum, x);
   const float mx = fmaxf(sum, x);
   const float z = __fsub_rn(mx, y);
