@@ -95,3 +95,23 @@ def test_pair_split_schedule(emu, oracle, contra):
     check(emu, oracle, random_seqs(10, [33, 64, 90]), contra, False, rt, rc, order=3, nZ=96)
     if contra:
         check(emu, oracle, random_seqs(13, [2, 3, 5, 9, 33]), True, True, tt, ct, order=3)
+
+
+def test_phases_are_address_sanitizer_clean(tmp_path):
+    """compute-sanitizer is not available on the GPU pool; the same phase code runs here on exactly-sized host
+    buffers under AddressSanitizer instead (all schedules, both models)."""
+    import os
+    import subprocess
+    import sys
+    from emu_lib import SRC
+    from common import ROOT
+    asan = subprocess.run(["g++", "-print-file-name=libasan.so"], capture_output=True, text=True).stdout.strip()
+    if not asan or not os.path.isabs(asan) or not os.path.exists(asan):
+        pytest.skip("libasan not available")
+    lib = str(tmp_path / "_emu_asan.so")
+    subprocess.run(["g++", "-O1", "-g", "-std=c++17", "-ffp-contract=off", "-fno-fast-math", "-fsanitize=address",
+                    "-fno-omit-frame-pointer", "-shared", "-fPIC", "-o", lib, SRC], check=True, capture_output=True)
+    env = dict(os.environ, LD_PRELOAD=asan, ASAN_OPTIONS="detect_leaks=0")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "emu", "asan_run.py"), ROOT, lib], env=env,
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "asan-clean" in r.stdout, r.stderr[-3000:]
