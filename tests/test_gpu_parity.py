@@ -273,3 +273,13 @@ def test_centroid_batch_long_sequence(handle, oracle):
         s, _, ea = oracle.centroid(bpp, L, gamma)
         assert bytes(got["structs"][g]).decode() == s
         assert np.float32(got["expect_acc"][g, 0]).view(np.uint32) == np.float32(ea).view(np.uint32)
+
+
+def test_too_long_for_32bit_offsets_is_an_error(handle):
+    """Beyond 46340 nt the cooperative kernel's 32-bit matrix offsets would overflow: the call must fail with
+    RNA_ERR_TOO_LONG before touching the device, not corrupt memory."""
+    from rna_algos_b200.api import RnaError
+    seq = np.zeros(46341, dtype=np.uint8)
+    with pytest.raises(RnaError) as e:
+        handle.fold_batch(seq, np.array([0, 46341], dtype=np.uint32), False, False, [1.0])
+    assert e.value.code == 4 and "46340" in str(e.value)   # RNA_ERR_TOO_LONG
