@@ -56,6 +56,7 @@ struct FoldArgs {
   unsigned long long stream_stride;   // bytes per slot
   uint32_t tcap;             // terms per stream a slot can hold
   long long* dbg;            // optional per-step per-warp cycle counts of CTA 0's first sequence (RNA_FOLD_DBG)
+  int no_ml_split;           // cooperative kernel: A/B switch, multiloop chain without the producer warp
 };
 
 template <int MODE>

@@ -304,6 +304,118 @@ namespace rna {
 // diagonal (whole folds, no partial sums across steps) and the barrier is grid-wide.  grid.sync() orders memory
 // for every thread of the grid, so plain loads see what other CTAs wrote in earlier steps.
 // =========================================================================================================
+// =========================================================================================================
+// Producer / consumer split of the multiloop part of log P (cooperative kernel, outside pass).  That chain is three
+// dependent logsumexp's per split point and it is the critical path of the whole pass; a warp issues at most one
+// instruction every other cycle, so every load, address step and operand add that sits in the chain's warp costs two
+// cycles of critical path.  Here a PRODUCER warp (same CTA, another scheduler) walks the row-major matrices, forms
+// the three operands of each split point and leaves them in a shared-memory double buffer; the CONSUMER warp's loop
+// is nothing but LDS + logsumexp.  One named barrier (64 threads) per batch of RNA_ML_BATCH split points hands a
+// buffer over; buffers alternate on a running batch counter that both warps advance identically, across cell groups
+// and diagonals, so the producer is always exactly one batch ahead and never touches the buffer being read.
+// =========================================================================================================
+#define RNA_ML_BATCH 8
+#define RNA_ML_RING_FLOATS (2 * RNA_ML_BATCH * 3 * 32)
+// The consumer's folds of one batch, as a function of its own: inside the big kernel ptxas has two predicate registers
+// left for the seven breakpoint compares (the rest hold long-lived flags), so it interleaves the four coefficient select
+// trees level by level and re-materialises their sixteen register-side constants for every fold — 45 instructions and
+// ~142 cycles per fold.  A separate function starts with all predicates and registers free.  The loop is NOT unrolled
+// beyond four folds: the body stays inside the L0 instruction cache.
+__device__ __noinline__ float ml_consume_batch(const float4* buf, float sm, const float4* lut) {
+  float4 nx = buf[0];
+#pragma unroll 1
+  for (int q4 = 0; q4 < 3 * RNA_ML_BATCH / 4; q4++) {
+    const float4 x = nx;
+    if (q4 + 1 < 3 * RNA_ML_BATCH / 4) nx = buf[(q4 + 1) * 32];
+    sm = RNA_COOP_LSE_NN(sm, x.x, lut);
+    sm = RNA_COOP_LSE_NN(sm, x.y, lut);
+    sm = RNA_COOP_LSE_NN(sm, x.z, lut);
+    sm = RNA_COOP_LSE_NN(sm, x.w, lut);
+  }
+  return sm;
+}
+
+// Called through a pointer read from device memory: an indirect call obeys the full ABI, so the callee is compiled with
+// every predicate and register at its disposal instead of the few the big kernel leaves over.
+typedef float (*MlConsumeFn)(const float4*, float, const float4*);
+__device__ MlConsumeFn g_ml_consume = ml_consume_batch;
+
+template <bool CONTRA, class SV>
+__device__ __forceinline__ void outside_X_diag_split(const SV& v, const typename Model2<CONTRA>::View& T, const float4* lut,
+                                                     const ModelParams& P, float Z, int d, int lane, int nl, bool producer,
+                                                     float* ring, unsigned& gbatch, long long* tsplit) {
+  constexpr int B = RNA_ML_BATCH;
+  const MlConsumeFn consume = *reinterpret_cast<MlConsumeFn volatile*>(&g_ml_consume);
+  const int L = v.L;
+  if (d < v.dout0) return;
+  const float NEG = RNA_NEG_INF;
+  const int st = (L - 1 - d) >> 1;
+  const StepCells sc = step_cells<false>(v, st);
+  const int tot = sc.cA + sc.cB, x0 = (d == sc.dA) ? 0 : sc.cA, cnt = v.pcnt[d], od = doff(d, L);
+  const int lane32 = lane & 31;
+  const typename Model2<CONTRA>::Dev* dev = T.g;
+  for (int r0 = lane - lane32; r0 < cnt; r0 += nl) {   // warp-uniform: both warps of a pair see the same groups
+    const int r = r0 + lane32;
+    bool act = r < cnt;
+    int i = 0, j = 0;
+    float Cij = NEG;
+    if (act) { i = v.plist[od + r]; j = i + d; Cij = v.C[od + i]; act = Cij > NEG; }
+    const int ie = act ? i : 0;                                      // split points of this lane
+    const int nb = (__reduce_max_sync(0xffffffffu, ie) + B - 1) / B;   // batches of this group (warp-uniform)
+    if (producer) {
+      float sa = NEG, unp = 0.f;
+      if (act) {
+        const float Aij = __fadd_rn(Cij, v2_acc<CONTRA>(T, v.s, L, i, j));
+        if constexpr (CONTRA) sa = __fadd_rn(Aij, dev->mb_bp); else sa = __fadd_rn(Aij, dev->coeff_num_branches);
+      }
+      if constexpr (CONTRA) unp = dev->mb_unpair;
+      const float* pX = v.X + j;                // probs_multibranch2[k][j], row-major, row k = 0
+      const float* pR = v.R + j;                // probs_multibranch[k][j]
+      const float* pM = v.M1rm + (L + i - 2);   // sums_1ormore[k+1][i-1], row 1
+      int sQ = L - 1, sM = L - 2;
+      for (int b = 0; b < nb; b++) {
+        float p2[B], y[B], x1[B];
+#pragma unroll
+        for (int u = 0; u < B; u++) {           // all loads of the batch in flight before the first use
+          const int kk = b * B + u;
+          p2[u] = NEG; y[u] = NEG; x1[u] = NEG;
+#ifndef RNA_ML_FAKE_PRODUCER
+          if (kk < ie) { p2[u] = *pX; y[u] = *pR; if (kk < ie - 1) x1[u] = *pM; }
+#endif
+          pX += sQ; pR += sQ; sQ--;
+          pM += sM; sM--;
+        }
+        // operands q = 3 u + {0,1,2} in fold order, four to a 16-byte shared-memory word per lane
+        float4* buf = reinterpret_cast<float4*>(ring) + ((gbatch + (unsigned)b) & 1u) * (B * 3 / 4 * 32) + lane32;
+        float o[3 * B];
+#pragma unroll
+        for (int u = 0; u < B; u++)
+          ml_operands<CONTRA>(sa, unp, ie - 1 - (b * B + u), p2[u], y[u], x1[u], o[3 * u], o[3 * u + 1], o[3 * u + 2]);
+#pragma unroll
+        for (int q4 = 0; q4 < 3 * B / 4; q4++) buf[q4 * 32] = make_float4(o[4 * q4], o[4 * q4 + 1], o[4 * q4 + 2], o[4 * q4 + 3]);
+        asm volatile("bar.sync 1, 64;" ::: "memory");
+      }
+    } else {
+      const long long c0 = tsplit ? clock64() : 0;
+      float sm = NEG;
+      if (act) sm = outside_cell_partial<CONTRA>(v, T, lut, P, Z, st, tot, x0 + r, i, j, Cij);
+      if (tsplit) tsplit[0] += clock64() - c0;
+      for (int b = 0; b < nb; b++) {
+        asm volatile("bar.sync 1, 64;" ::: "memory");
+        // LDS.128: ptxas sinks each shared-memory load in front of its first use (in-order issue puts that latency on
+        // the chain), so the operands come four at a time
+        const float4* buf = reinterpret_cast<const float4*>(ring) + ((gbatch + (unsigned)b) & 1u) * (B * 3 / 4 * 32) + lane32;
+        // NOT unrolled: the body (four folds, ~170 instructions) must stay inside the ~6 KB L0 instruction cache — a
+        // lone warp that streams a 16 KB straight-line body pays an instruction-fetch miss per cache line, measured
+        // 142 cycles per fold against 95 for a compact loop
+        sm = consume(buf, sm, lut);
+      }
+      if (act) v.Pm[od + i] = sm;
+    }
+    gbatch += (unsigned)nb;
+  }
+}
+
 template <bool CONTRA>
 __global__ void __launch_bounds__(256, 1) fold_kernel2_coop(const FoldArgs a) {
   typedef typename Model2<CONTRA>::Dev Dev;
@@ -318,6 +430,8 @@ __global__ void __launch_bounds__(256, 1) fold_kernel2_coop(const FoldArgs a) {
   float4* lut = reinterpret_cast<float4*>(smem_raw);
   Small* small = reinterpret_cast<Small*>(smem_raw + 128);
   uint8_t* sseq = smem_raw + 128 + align16(sizeof(Small));
+  float* ml_ring = reinterpret_cast<float*>(smem_raw + fold2_fixed_bytes<CONTRA>(a.Lcap));   // RNA_ML_RING_FLOATS
+  unsigned ml_batches = 0;
 
   const Dev* dev = reinterpret_cast<const Dev*>(a.tables);
   const int tid = threadIdx.x;
@@ -475,10 +589,19 @@ __global__ void __launch_bounds__(256, 1) fold_kernel2_coop(const FoldArgs a) {
     // ---- outside, one diagonal per step: X(d) | Y(d) --------------------------------------------------------------
     const int d_out0 = v.dout0;
     cyc[0] = cyc[1] = 0;
+    // the producer/consumer split needs every X warp to be warp 0 of its CTA and 8 warps per CTA
+    const bool ml_split = a.nXw <= (int)gridDim.x && blockDim.x == 256 && !a.no_ml_split;
     for (int d = L - 1; d >= d_out0; d--) {
       const long long c0 = timed ? clock64() : 0;
       long long tsp[2] = {0, 0};
-      if (isX) outside_X_diag_rm<CONTRA, 4>(v, T, lut, P, Z, d, lnX, nXl, timed ? tsp : nullptr);
+      if (ml_split) {
+        // consumers: warp 0 of the first nXw CTAs (the X lanes as before); producers: warp 1 of the same CTAs;
+        // probs_multibranch(2): every warp from index 2 up
+        const int wi = tid >> 5;
+        if (isX) outside_X_diag_split<CONTRA>(v, T, lut, P, Z, d, lnX, nXl, false, ml_ring, ml_batches, timed ? tsp : nullptr);
+        else if (wi == 1 && (int)blockIdx.x < a.nXw) outside_X_diag_split<CONTRA>(v, T, lut, P, Z, d, (int)blockIdx.x * 32 + (tid & 31), nXl, true, ml_ring, ml_batches, nullptr);
+        else if (wi >= 2) outside_Y_dense<CONTRA, 4>(v, T, lut, d, (wi - 2) * (int)gridDim.x + (int)blockIdx.x, 6 * (int)gridDim.x, tid & 31);
+      } else if (isX) outside_X_diag_rm<CONTRA, 4>(v, T, lut, P, Z, d, lnX, nXl, timed ? tsp : nullptr);
       else if (isY || isZ) outside_Y_dense<CONTRA, 4>(v, T, lut, d, gw - a.nXw, a.nYw + a.nZw, tid & 31);
       const long long c1 = timed ? clock64() : 0;
       grid_sync();

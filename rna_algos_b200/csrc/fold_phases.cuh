@@ -1621,6 +1621,14 @@ RNA_DEV void outside_Y_dense(const SV& v, const typename Model2<CONTRA>::View& T
     if (i < L - d) outside_Y_dense_cell<CONTRA, PF>(v, T, lut, d, kind, i);
   }
 }
+// the three operands of split point k of the multiloop part of log P(i,j) (src/mccaskill_algo.rs:596-600, 703-713):
+// sa = A(i,j) + branch score, p2 = probs_multibranch2[k][j], y = probs_multibranch[k][j], x1 = sums_1ormore[k+1][i-1]
+template <bool CONTRA>
+RNA_DEV void ml_operands(float sa, float unp, int m, float p2, float y, float x1, float& a, float& b, float& c) {
+  a = __fadd_rn(__fadd_rn(sa, p2), x1);
+  if (CONTRA) b = __fadd_rn(__fadd_rn(sa, y), __fmul_rn(unp, (float)m)); else b = __fadd_rn(sa, y);
+  c = __fadd_rn(__fadd_rn(sa, x1), y);
+}
 // enclosing multiloops of log P(i,j) from the row-major matrices, k ascending 0 .. i-1
 // (src/mccaskill_algo.rs:594-601, 701-714)
 template <bool CONTRA, int PF, class SV>
@@ -1631,7 +1639,8 @@ RNA_DEV_CALL float outside_cell_ml_rm(const SV& v, const typename Model2<CONTRA>
   const typename Model2<CONTRA>::Dev* dev = T.g;
   const float Aij = __fadd_rn(Cij, v2_acc<CONTRA>(T, v.s, L, i, j));
   float sa;
-  if constexpr (CONTRA) sa = __fadd_rn(Aij, dev->mb_bp); else sa = __fadd_rn(Aij, dev->coeff_num_branches);
+  float unp = 0.f;
+  if constexpr (CONTRA) { sa = __fadd_rn(Aij, dev->mb_bp); unp = dev->mb_unpair; } else sa = __fadd_rn(Aij, dev->coeff_num_branches);
   const float* pX = v.X + j;                 // probs_multibranch2[k][j], row k = 0
   const float* pR = v.R + j;                 // probs_multibranch[k][j]
   const float* pM = v.M1rm + (L + i - 2);    // sums_1ormore[k+1][i-1], row 1: doff(1) + (i-1) - 1
@@ -1654,11 +1663,11 @@ RNA_DEV_CALL float outside_cell_ml_rm(const SV& v, const typename Model2<CONTRA>
     for (int u = 0; u < PF; u++) {
       const float x1 = bx[u], p2 = bp[u], y = by[u];
       load(bx[u], bp[u], by[u]);
-      const int m = i - 1 - (k0 + u);
-      sm = RNA_COOP_LSE_NN(sm, __fadd_rn(__fadd_rn(sa, p2), x1), lut);
-      if constexpr (CONTRA) sm = RNA_COOP_LSE_NN(sm, __fadd_rn(__fadd_rn(sa, y), __fmul_rn(dev->mb_unpair, (float)m)), lut);
-      else sm = RNA_COOP_LSE_NN(sm, __fadd_rn(sa, y), lut);
-      sm = RNA_COOP_LSE_NN(sm, __fadd_rn(__fadd_rn(sa, x1), y), lut);
+      float oa, ob, oc;
+      ml_operands<CONTRA>(sa, unp, i - 1 - (k0 + u), p2, y, x1, oa, ob, oc);
+      sm = RNA_COOP_LSE_NN(sm, oa, lut);
+      sm = RNA_COOP_LSE_NN(sm, ob, lut);
+      sm = RNA_COOP_LSE_NN(sm, oc, lut);
     }
   }
   return sm;

@@ -535,7 +535,9 @@ static int launch_fold_model(rna_handle* h, const RnaFoldBatchDev* b, cudaStream
     } else if (v2) {
       // long sequence: cooperative grid, roles spread over the SMs
       const int nt = 256;
-      const size_t smem = fold2_fixed_bytes<CONTRA>(bk.Lcap);
+      const size_t smem = fold2_fixed_bytes<CONTRA>(bk.Lcap) + RNA_ML_RING_FLOATS * 4;
+      static const bool no_split = getenv("RNA_COOP_NOSPLIT") != nullptr;
+      a.no_ml_split = no_split ? 1 : 0;
       int occ = 1;
       TRY(set_smem_attr(h, fold_kernel2_coop<CONTRA>, smem));
       CU(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fold_kernel2_coop<CONTRA>, nt, smem));
