@@ -87,6 +87,16 @@ RNA_DEV int doff(int d, int L) { return d * L - ((d * (d - 1)) >> 1); }
 #else
 #define RNA_COOP_LSE_NN(sum, x, lut) lse_lat<false>(sum, x)
 #endif
+// (see "The long chains of the cooperative kernel ..." below)
+#ifdef __CUDACC__
+#define RNA_CHAIN_FN __device__ __noinline__
+#define RNA_CHAIN_PTR(name) __device__ decltype(&name) g_##name = name;
+#define RNA_CHAIN_CALL(name) (*reinterpret_cast<decltype(&name) volatile*>(&g_##name))
+#else
+#define RNA_CHAIN_FN static inline
+#define RNA_CHAIN_PTR(name)
+#define RNA_CHAIN_CALL(name) name
+#endif
 
 // The cooperative long-sequence kernel's view: same fields, but sums_close / log P are far away (HBM/L2).
 struct CoopView : SeqViewT<uint16_t> {};
@@ -758,26 +768,27 @@ RNA_DEV float stream_chain(const SV& v, const uint2* __restrict__ st, uint32_t w
 // a block are issued one whole block of logsumexp's (B x ~115 cycles) before they are consumed and the stream
 // elements two blocks ahead, so neither the stream nor the gathers are waited for (the plain version waits for its
 // gathers at the head of every block, which is fine when they are shared-memory loads).
-template <bool INSIDE, int B, class SV>
-RNA_DEV float stream_chain_deep(const SV& v, const uint2* __restrict__ st, uint32_t wd, uint32_t n, const float4* lut,
-                                float Cij, float sum) {
+template <bool INSIDE, int B>
+RNA_DEV float stream_chain_deep(const float* __restrict__ C, const float* __restrict__ Pm, const uint2* __restrict__ st,
+                                uint32_t wd, uint32_t n, const float4* lut, float Cij, float sum) {
   if (n == 0) return sum;
   uint2 e2[B];
   float c1[B], p1[B], s1[B];
 #pragma unroll
   for (int k = 0; k < B; k++) {
     const uint2 e = ((uint32_t)k < n) ? st[wd * k] : make_uint2(0u, 0u);
-    c1[k] = v.C[e.y]; p1[k] = INSIDE ? 0.f : v.Pm[e.y]; s1[k] = __int_as_float((int)e.x);
+    c1[k] = C[e.y]; p1[k] = INSIDE ? 0.f : Pm[e.y]; s1[k] = __int_as_float((int)e.x);
   }
 #pragma unroll
   for (int k = 0; k < B; k++) e2[k] = ((uint32_t)(B + k) < n) ? st[wd * (B + k)] : make_uint2(0u, 0u);
+#pragma unroll 1
   for (uint32_t pos = 0; pos < n; pos += B) {
     float c0[B], p0[B], s0[B];
 #pragma unroll
     for (int k = 0; k < B; k++) { c0[k] = c1[k]; p0[k] = p1[k]; s0[k] = s1[k]; }
 #pragma unroll
     for (int k = 0; k < B; k++) {   // gathers of the next block (neutral element 0: C[0] = -inf, the fold ignores it)
-      c1[k] = v.C[e2[k].y]; p1[k] = INSIDE ? 0.f : v.Pm[e2[k].y]; s1[k] = __int_as_float((int)e2[k].x);
+      c1[k] = C[e2[k].y]; p1[k] = INSIDE ? 0.f : Pm[e2[k].y]; s1[k] = __int_as_float((int)e2[k].x);
     }
 #pragma unroll
     for (int k = 0; k < B; k++) e2[k] = (pos + 2 * B + k < n) ? st[wd * (pos + 2 * B + k)] : make_uint2(0u, 0u);
@@ -789,13 +800,19 @@ RNA_DEV float stream_chain_deep(const SV& v, const uint2* __restrict__ st, uint3
   }
   return sum;
 }
+RNA_CHAIN_FN float coop_stream_fold(const float* C, const float* Pm, const uint2* st, uint32_t wd, uint32_t n,
+                                    const float4* lut, float Cij, float sum, int inside) {
+  if (inside) return stream_chain_deep<true, 8>(C, Pm, st, wd, n, lut, Cij, sum);
+  return stream_chain_deep<false, 8>(C, Pm, st, wd, n, lut, Cij, sum);
+}
+RNA_CHAIN_PTR(coop_stream_fold)
 // compile-time choice by view type
 template <class SV> struct StreamDepth { static constexpr int value = 0; };   // 0: plain stream_chain
 template <> struct StreamDepth<CoopView> { static constexpr int value = 8; };
 template <bool INSIDE, class SV>
 RNA_DEV float stream_fold(const SV& v, const uint2* __restrict__ st, uint32_t wd, uint32_t n, const float4* lut,
                           float Cij, float sum) {
-  if constexpr (StreamDepth<SV>::value > 0) return stream_chain_deep<INSIDE, StreamDepth<SV>::value>(v, st, wd, n, lut, Cij, sum);
+  if constexpr (StreamDepth<SV>::value > 0) return RNA_CHAIN_CALL(coop_stream_fold)(v.C, v.Pm, st, wd, n, lut, Cij, sum, INSIDE ? 1 : 0);
   else return stream_chain<INSIDE>(v, st, wd, n, lut, Cij, sum);
 }
 
@@ -1114,6 +1131,7 @@ RNA_DEV float chain_fold(const float* __restrict__ A, const float* __restrict__ 
   };
 #pragma unroll
   for (int u = 0; u < PF; u++) load(pa[u], pb[u]);
+#pragma unroll 1
   for (int m0 = 1; m0 < d; m0 += PF) {
 #pragma unroll
     for (int u = 0; u < PF; u++) {
@@ -1124,38 +1142,53 @@ RNA_DEV float chain_fold(const float* __restrict__ A, const float* __restrict__ 
   }
   return sum;
 }
+// ---------------------------------------------------------------------------------------------------------
+// The long chains of the cooperative kernel are compiled as functions of their own and CALLED THROUGH A POINTER read
+// from device memory.  Inlined into the big kernel, ptxas has two predicate registers left for the seven breakpoint
+// compares of the logsumexp (the others hold long-lived flags): it then interleaves the four coefficient select
+// trees level by level and re-materialises their constants per fold — 142 cycles per dependent fold instead of
+// ~100.  An indirect call obeys the full ABI, so the callee gets every predicate and register.  Arguments are plain
+// pointers and scalars; the host build (tests/emu) calls the same functions directly.
+// ---------------------------------------------------------------------------------------------------------
+
+// dense inside chain over split points m = 1 .. d-1; opk 0: A + B, 1: A + c1*m, 2: A + c0, 3: B + (A + c0)
+RNA_CHAIN_FN float coop_chain_fold(const float* A, const float* B, int L, int d, int i, float sum, int opk, float c0,
+                                   float c1, const float4* lut) {
+  switch (opk) {
+    case 0: return chain_fold<4, true>(A, B, L, d, i, sum, lut, [](int, float a, float b) { return __fadd_rn(a, b); });
+    case 1: return chain_fold<4, false>(A, B, L, d, i, sum, lut, [c1](int m, float a, float) { return __fadd_rn(a, __fmul_rn(c1, (float)m)); });
+    case 2: return chain_fold<4, false>(A, B, L, d, i, sum, lut, [c0](int, float a, float) { return __fadd_rn(a, c0); });
+    default: return chain_fold<4, true>(A, B, L, d, i, sum, lut, [c0](int, float a, float b) { return __fadd_rn(b, __fadd_rn(a, c0)); });
+  }
+}
+RNA_CHAIN_PTR(coop_chain_fold)
+
 // one dense chain (kind 0: sums_external, 1: sums_1ormore_basepairs without its last term, 2: sums_multibranch) of
 // cell (i, i+d).  Needs the finished R (/Rm) of diagonal d.  src/mccaskill_algo.rs:352-374, 487-512.
 template <bool CONTRA, int PF, class SV>
-RNA_DEV_CALL void inside_chain_cell(const SV& v, const typename Model2<CONTRA>::View& T, const float4* lut, int d, int kind,
+RNA_DEV void inside_chain_cell(const SV& v, const typename Model2<CONTRA>::View& T, const float4* lut, int d, int kind,
                                int i) {
   const int L = v.L, od = doff(d, L);
   const typename Model2<CONTRA>::Dev* dev = T.g;
+  (void)PF;
   if (kind == 0) {
     float sE;
     if constexpr (CONTRA) sE = __fmul_rn(dev->ext_unpair, (float)(d + 1)); else sE = 0.f;
     sE = lse(sE, __fadd_rn(v.R[od + i], 0.f), lut);   // k = i: E[i][i-1] = 0
-    v.E[od + i] = chain_fold<PF, true>(v.R, v.E, L, d, i, sE, lut, [](int, float r, float e) { return __fadd_rn(r, e); });
+    v.E[od + i] = RNA_CHAIN_CALL(coop_chain_fold)(v.R, v.E, L, d, i, sE, 0, 0.f, 0.f, lut);          // R[k][j] + E[i][k-1]
   } else if (kind == 1) {
-    if constexpr (CONTRA) {
-      const float u = dev->mb_unpair;
-      v.M1[od + i] = chain_fold<PF, false>(v.X, nullptr, L, d, i, v.X[od + i], lut,
-                                           [u](int m, float rm, float) { return __fadd_rn(rm, __fmul_rn(u, (float)m)); });
-    } else {
+    if constexpr (CONTRA)   // Rm[k][j] + multibranch_score_unpair * (k - i)
+      v.M1[od + i] = RNA_CHAIN_CALL(coop_chain_fold)(v.X, nullptr, L, d, i, v.X[od + i], 1, 0.f, dev->mb_unpair, lut);
+    else {                  // R[k][j] + COEFF_NUM_BRANCHES
       const float cb = dev->coeff_num_branches;
-      v.M1[od + i] = chain_fold<PF, false>(v.R, nullptr, L, d, i, __fadd_rn(v.R[od + i], cb), lut,
-                                           [cb](int, float r, float) { return __fadd_rn(r, cb); });
+      v.M1[od + i] = RNA_CHAIN_CALL(coop_chain_fold)(v.R, nullptr, L, d, i, __fadd_rn(v.R[od + i], cb), 2, cb, 0.f, lut);
     }
   } else {
     float* Mcur = v.Mroll + (d % 3) * L;
-    if constexpr (CONTRA) {
-      Mcur[i] = chain_fold<PF, true>(v.X, v.M1, L, d, i, RNA_NEG_INF, lut,
-                                     [](int, float rm, float m1) { return __fadd_rn(m1, rm); });
-    } else {
-      const float cb = dev->coeff_num_branches;
-      Mcur[i] = chain_fold<PF, true>(v.R, v.M1, L, d, i, RNA_NEG_INF, lut,
-                                     [cb](int, float r, float m1) { return __fadd_rn(m1, __fadd_rn(r, cb)); });
-    }
+    if constexpr (CONTRA)   // M1[i][k-1] + Rm[k][j]  (IEEE addition commutes bit for bit)
+      Mcur[i] = RNA_CHAIN_CALL(coop_chain_fold)(v.X, v.M1, L, d, i, RNA_NEG_INF, 0, 0.f, 0.f, lut);
+    else                    // M1[i][k-1] + (R[k][j] + COEFF_NUM_BRANCHES)
+      Mcur[i] = RNA_CHAIN_CALL(coop_chain_fold)(v.R, v.M1, L, d, i, RNA_NEG_INF, 3, dev->coeff_num_branches, 0.f, lut);
   }
 }
 // Z of a pair step: warp-sized tasks (chain kind x 32 cells) of the diagonals t-2 and t-1, the longer diagonal first;
@@ -1189,14 +1222,13 @@ RNA_DEV void score_table_acc(const SV& v, const ContraView2& T, int lane, int nl
       v.MB[od + i] = (get32(v.mask + i * v.W2, i + d) & 1u) ? v2_acc<true>(T, v.s, L, i, i + d) : 0.f;
   }
 }
-template <int PF, class SV>
-RNA_DEV void inside_Y_dense_cell(const SV& v, const ContraView2& T, const float4* lut, int d, int kind, int i, int kskip) {
-  const int L = v.L, n = d - 1 - kskip;   // k = i + m, m = 1 .. n
+// fold over k = i + m, m = 1 .. n, of (sums_close + accessible score + cbp) + cun * (d - m)
+RNA_CHAIN_FN float coop_in_y_dense(const float* C, const float* S, int L, int d, int i, int n, float cbp, float cun,
+                                   const float4* lut) {
+  constexpr int PF = 4;
   const float NEG = RNA_NEG_INF;
-  const DevContra* dev = T.g;
-  const float cbp = kind == 0 ? dev->ext_bp : dev->mb_bp, cun = kind == 0 ? dev->ext_unpair : dev->mb_unpair;
-  const float* pC = v.C + (L + i);     // doff(1) + i
-  const float* pS = v.MB + (L + i);
+  const float* pC = C + (L + i);     // doff(1) + i
+  const float* pS = S + (L + i);
   int sC = L - 1, mL = 1;
   float rc[PF], rs[PF];
   auto load = [&](float& c, float& sc) {
@@ -1208,6 +1240,7 @@ RNA_DEV void inside_Y_dense_cell(const SV& v, const ContraView2& T, const float4
 #pragma unroll
   for (int u = 0; u < PF; u++) load(rc[u], rs[u]);
   float sum = NEG;
+#pragma unroll 1
   for (int m0 = 1; m0 <= n; m0 += PF) {
 #pragma unroll
     for (int u = 0; u < PF; u++) {
@@ -1216,7 +1249,15 @@ RNA_DEV void inside_Y_dense_cell(const SV& v, const ContraView2& T, const float4
       sum = RNA_COOP_LSE_NN(sum, __fadd_rn(__fadd_rn(av, cbp), __fmul_rn(cun, (float)(d - (m0 + u)))), lut);
     }
   }
-  (kind == 0 ? v.R : v.X)[doff(d, L) + i] = sum;
+  return sum;
+}
+RNA_CHAIN_PTR(coop_in_y_dense)
+template <int PF, class SV>
+RNA_DEV void inside_Y_dense_cell(const SV& v, const ContraView2& T, const float4* lut, int d, int kind, int i, int kskip) {
+  (void)PF;
+  const DevContra* dev = T.g;
+  const float cbp = kind == 0 ? dev->ext_bp : dev->mb_bp, cun = kind == 0 ? dev->ext_unpair : dev->mb_unpair;
+  (kind == 0 ? v.R : v.X)[doff(d, v.L) + i] = RNA_CHAIN_CALL(coop_in_y_dense)(v.C, v.MB, v.L, d, i, d - 1 - kskip, cbp, cun, lut);
 }
 // warp tasks (diagonal, kind, 32 cells): diagonal t+1 without k = j-1 (sums_close(t) is not finished), diagonal t whole
 template <int PF, class SV>
@@ -1571,22 +1612,24 @@ RNA_DEV void outside_prep(const SV& v, const typename Model2<CONTRA>::View& T, i
   }
 }
 // kind 0: probs_multibranch[i][j], kind 1: probs_multibranch2[i][j]   (src/mccaskill_algo.rs:540-557, 641-661)
-template <bool CONTRA, int PF, class SV>
-RNA_DEV_CALL void outside_Y_dense_cell(const SV& v, const typename Model2<CONTRA>::View& T, const float4* lut, int d,
-                                  int kind, int i) {
-  const int L = v.L, j = i + d, n = L - 1 - j;   // k = j + m, m = 1 .. n
+// opk 0: probs_multibranch (x + sums_1ormore[j+1][k-1]), 1: probs_multibranch2 CONTRAfold (x + unp * (m-1)), 2: Turner (x)
+// with x = (log P(i,k) + closing score(i,k)) - sums_close(i,k), k = j + m, m = 1 .. L-1-j
+RNA_CHAIN_FN float coop_out_y_dense(const float* Pm, const float* C, const float* S, const float* M1, int L, int d, int i,
+                                    int opk, float unp, const float4* lut) {
+  constexpr int PF = 4;
+  const int j = i + d, n = L - 1 - j;
   const float NEG = RNA_NEG_INF;
-  const float* pP = v.Pm + (doff(d + 1, L) + i);   // (i, j+1): same offset in Pm, C, MB
-  const float* pC = v.C + (doff(d + 1, L) + i);
-  const float* pS = v.MB + (doff(d + 1, L) + i);
-  const float* pM = v.M1 + (j + 1);                // M1[j+1][k-1] for m = 2: diagonal 0
+  const float* pP = Pm + (doff(d + 1, L) + i);   // (i, j+1): same offset in Pm, C, S
+  const float* pC = C + (doff(d + 1, L) + i);
+  const float* pS = S + (doff(d + 1, L) + i);
+  const float* pM = M1 + (j + 1);                // M1[j+1][k-1] for m = 2: diagonal 0
   int sP = L - d - 1, sM = L, mL = 1;
   float rp[PF], rc[PF], rs[PF], rm[PF];
   auto load = [&](float& a, float& c, float& sc, float& m1) {
     a = NEG; c = NEG; sc = 0.f; m1 = NEG;
     if (mL <= n) {
       a = *pP; c = *pC; sc = *pS;
-      if (kind == 0 && mL >= 2) m1 = *pM;
+      if (opk == 0 && mL >= 2) m1 = *pM;
     }
     pP += sP; pC += sP; pS += sP; sP--;          // doff(d+m+1) - doff(d+m) = L - (d+m)
     if (mL >= 2) { pM += sM; sM--; }             // doff(m-1) - doff(m-2) = L - (m-2)
@@ -1595,8 +1638,7 @@ RNA_DEV_CALL void outside_Y_dense_cell(const SV& v, const typename Model2<CONTRA
 #pragma unroll
   for (int u = 0; u < PF; u++) load(rp[u], rc[u], rs[u], rm[u]);
   float sum = NEG;
-  float unp = 0.f;
-  if constexpr (CONTRA) unp = T.g->mb_unpair;
+#pragma unroll 1
   for (int m0 = 1; m0 <= n; m0 += PF) {
 #pragma unroll
     for (int u = 0; u < PF; u++) {
@@ -1604,13 +1646,24 @@ RNA_DEV_CALL void outside_Y_dense_cell(const SV& v, const typename Model2<CONTRA
       load(rp[u], rc[u], rs[u], rm[u]);
       const float x = __fsub_rn(__fadd_rn(a, sc), c);
       float y;
-      if (kind == 0) y = __fadd_rn(x, m1);
-      else if (CONTRA) y = __fadd_rn(x, __fmul_rn(unp, (float)(m0 + u - 1)));
+      if (opk == 0) y = __fadd_rn(x, m1);
+      else if (opk == 1) y = __fadd_rn(x, __fmul_rn(unp, (float)(m0 + u - 1)));
       else y = x;
-      sum = RNA_COOP_LSE(sum, y, lut);
+      sum = RNA_COOP_LSE(sum, y, lut);   // (x is NaN for a non-closable (i,k): the normalising fold)
     }
   }
-  (kind == 0 ? v.R : v.X)[doff(i, L) + d] = sum;   // row-major
+  return sum;
+}
+RNA_CHAIN_PTR(coop_out_y_dense)
+// kind 0: probs_multibranch[i][j], kind 1: probs_multibranch2[i][j]   (src/mccaskill_algo.rs:540-557, 641-661)
+template <bool CONTRA, int PF, class SV>
+RNA_DEV void outside_Y_dense_cell(const SV& v, const typename Model2<CONTRA>::View& T, const float4* lut, int d,
+                                  int kind, int i) {
+  (void)PF;
+  float unp = 0.f;
+  if constexpr (CONTRA) unp = T.g->mb_unpair;
+  const int opk = kind == 0 ? 0 : (CONTRA ? 1 : 2);
+  (kind == 0 ? v.R : v.X)[doff(i, v.L) + d] = RNA_CHAIN_CALL(coop_out_y_dense)(v.Pm, v.C, v.MB, v.M1, v.L, d, i, opk, unp, lut);   // row-major
 }
 template <bool CONTRA, int PF, class SV>
 RNA_DEV void outside_Y_dense(const SV& v, const typename Model2<CONTRA>::View& T, const float4* lut, int d, int w, int nw,
@@ -1632,7 +1685,7 @@ RNA_DEV void ml_operands(float sa, float unp, int m, float p2, float y, float x1
 // enclosing multiloops of log P(i,j) from the row-major matrices, k ascending 0 .. i-1
 // (src/mccaskill_algo.rs:594-601, 701-714)
 template <bool CONTRA, int PF, class SV>
-RNA_DEV_CALL float outside_cell_ml_rm(const SV& v, const typename Model2<CONTRA>::View& T, const float4* lut, int i, int j,
+RNA_DEV float outside_cell_ml_rm(const SV& v, const typename Model2<CONTRA>::View& T, const float4* lut, int i, int j,
                                  float Cij, float sm) {
   const int L = v.L;
   const float NEG = RNA_NEG_INF;
