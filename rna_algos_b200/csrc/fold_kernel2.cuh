@@ -314,7 +314,7 @@ namespace rna {
 // buffer over; buffers alternate on a running batch counter that both warps advance identically, across cell groups
 // and diagonals, so the producer is always exactly one batch ahead and never touches the buffer being read.
 // =========================================================================================================
-#define RNA_ML_BATCH 16
+#define RNA_ML_BATCH 32
 #define RNA_ML_RING_FLOATS (2 * RNA_ML_BATCH * 3 * 32)
 // The consumer's folds of one batch, as a function of its own: inside the big kernel ptxas has two predicate registers
 // left for the seven breakpoint compares (the rest hold long-lived flags), so it interleaves the four coefficient select
