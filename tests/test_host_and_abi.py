@@ -39,6 +39,34 @@ def test_library_exports_every_declared_symbol():
     assert lib.rna_sizeof_align_tables() == C.sizeof(T.AlignTables)
 
 
+def test_rust_shim_binds_only_exported_symbols_with_matching_blob_sizes():
+    """rust/rna_algos_b200_shim cannot be compiled here (no Rust toolchain): at least every extern "C" name it declares
+    must be exported by the library, and the #[repr(C)] table structs must add up to the C sizes."""
+    lib = _lib.load()
+    src = open(os.path.join(ROOT, "rust", "rna_algos_b200_shim", "src", "ffi.rs")).read()
+    names = re.findall(r"pub fn (rna_[a-z0-9_]+)\s*\(", src)
+    assert len(names) >= 20
+    for name in names:
+        assert hasattr(lib, name), name
+
+    def struct_bytes(name):
+        body = re.search(r"pub struct %s \{(.*?)\n\}" % name, src, re.S).group(1)
+        alias = {"T4": 256 * 4, "T3": 64 * 4, "f32": 4, "i32": 4, "u8": 1, "RnaSpecialHairpin": 20}
+
+        def size(t):
+            t = t.strip()
+            m = re.match(r"\[(.*);\s*([A-Z_0-9a-z]+)\]$", t)
+            if m:
+                n = {"RNA_LOOP_TABLE_LEN": 31, "RNA_MAX_SPECIAL_HAIRPINS": 128, "RNA_MAX_SPECIAL_HAIRPIN_LEN": 12}.get(m.group(2))
+                return size(m.group(1)) * (n if n is not None else int(m.group(2)))
+            return alias[t]
+        return sum(size(f.split(":", 1)[1].strip().rstrip(",")) for f in body.split(",\n") if ":" in f)
+
+    assert struct_bytes("RnaTurnerTables") == lib.rna_sizeof_turner_tables()
+    assert struct_bytes("RnaContraTables") == lib.rna_sizeof_contra_tables()
+    assert struct_bytes("RnaAlignTables") == lib.rna_sizeof_align_tables()
+
+
 def test_no_cpu_fallback_without_device():
     """Without a CUDA device the product refuses to compute (RNA_ERR_NO_DEVICE), it never falls back."""
     import torch
