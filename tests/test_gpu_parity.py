@@ -283,3 +283,23 @@ def test_too_long_for_32bit_offsets_is_an_error(handle):
     with pytest.raises(RnaError) as e:
         handle.fold_batch(seq, np.array([0, 46341], dtype=np.uint32), False, False, [1.0])
     assert e.value.code == 4 and "46340" in str(e.value)   # RNA_ERR_TOO_LONG
+
+
+def test_cooperative_random_lengths_stress(handle, oracle):
+    """The cooperative kernel synchronises warps four ways (grid barrier, named producer/consumer barrier, CTA barriers,
+    atomic-max centroid): a spread of lengths — odd and even, around warp (32) and batch (32 split points) multiples —
+    one sequence per call so that each takes the cooperative route, each run twice to catch order-dependent results."""
+    tt, ct, _ = default_tables()
+    rng = np.random.default_rng(4242)
+    lens = [384, 415, 448, 449, 511, 512, 513, 640, 777, 1025]
+    for L in lens:
+        contra = bool(rng.integers(0, 2))
+        seq = rng.integers(0, 4, size=L).astype(np.uint8)
+        bases, offsets = pack([seq])
+        want = oracle.fold_batch(bases, offsets, contra, False, tt, ct, [0.5, 4.0], n_threads=8)
+        for _ in range(2):
+            got = handle.fold_batch(bases, offsets, contra, False, [0.5, 4.0])
+            assert_bits_equal(got["bpp"], want["bpp"], f"BPP L={L} contra={contra}")
+            assert_bits_equal(got["logz"], want["logz"], f"logZ L={L}")
+            assert (got["structs"] == want["structs"]).all(), L
+            assert_bits_equal(got["expect_acc"], want["expect_acc"], f"expected accuracy L={L}")
