@@ -436,11 +436,15 @@ static int launch_fold_model(rna_handle* h, const RnaFoldBatchDev* b, cudaStream
   // leave most SMs idle, and the tails of big ones overlap).  Kernels of one lane are stream-ordered, so the
   // scratch is one region per lane, each sized for the largest bucket.
   static const bool serial = getenv("RNA_FOLD_SERIAL") != nullptr || getenv("RNA_FOLD_DBG") != nullptr;
-  // (only when some buckets cannot fill the GPU by themselves: full-size launches run best one after the other)
-  size_t small_buckets = 0;
+  // Also full-size launches gain from it: the next bucket's CTAs take over SMs as the last CTAs of the previous one
+  // drain (default bench, four buckets of 4096-12288 sequences: 164.0 k -> 173.3 k seq/s).
+  size_t batch_buckets = 0;
   for (size_t k = 0; k < buckets.size(); k++)
-    if (buckets[k].mode != MODE_COOP && (size_t)(buckets[k].end - buckets[k].begin) < (size_t)2 * h->sm_count) small_buckets++;
-  const int nlanes = (serial || small_buckets < 2) ? 1 : (int)std::min<size_t>(rna_handle::kLanes, buckets.size());
+    if (buckets[k].mode != MODE_COOP) batch_buckets++;
+  static const int force_lanes = getenv("RNA_FOLD_LANES") ? atoi(getenv("RNA_FOLD_LANES")) : 0;   // A/B switch
+  const int nlanes = serial ? 1
+                     : (int)std::max<size_t>(1, std::min<size_t>(force_lanes > 0 ? (size_t)std::min(force_lanes, (int)rna_handle::kLanes)
+                                                                              : (size_t)rna_handle::kLanes, batch_buckets));
   ws_floats = (ws_floats + 63) / 64 * 64;
   stream_bytes = (stream_bytes + 255) / 256 * 256;
   if (stream_bytes) TRY(ensure(h, h->stream_ws, stream_bytes * nlanes));
