@@ -725,12 +725,33 @@ extern "C" int rna_mccaskill_centroid_batch(rna_handle* h, const uint8_t* bases,
   b.d_bases = (const uint8_t*)h->b_bases.p;
   b.d_offsets = (const uint32_t*)h->b_offsets.p;
   size_t bpp_total = 0;
+  bool bpp_zero_copy = false;
   if (out_bpp) {
     bpp_total = bpp_offsets[n_seqs];
     TRY(h2d(h, h->b_bppoff, bpp_offsets, sizeof(uint64_t) * ((size_t)n_seqs + 1), st));
-    TRY(ensure(h, h->b_bpp, bpp_total * 4));
     b.d_bpp_offsets = (const uint64_t*)h->b_bppoff.p;
-    b.d_out_bpp = (float*)h->b_bpp.p;
+    // The packed BPP matrices are by far the largest output (11 KB per tRNA) and the kernels only ever WRITE them, in
+    // coalesced row segments.  When the caller's buffer is page-locked (cudaHostAlloc / cudaHostRegister) the kernels
+    // write it directly over PCIe while they compute, instead of staging in HBM and copying after the last kernel;
+    // a pageable buffer takes the staged path.  (RNA_NO_ZERO_COPY=1 forces staging.)
+    static const bool no_zc = getenv("RNA_NO_ZERO_COPY") != nullptr;
+    cudaPointerAttributes pat;
+    memset(&pat, 0, sizeof pat);
+    if (!no_zc && cudaPointerGetAttributes(&pat, out_bpp) == cudaSuccess && pat.type == cudaMemoryTypeHost && pat.devicePointer) {
+      // (the whole range must be page-locked: probe its last byte too)
+      cudaPointerAttributes pend;
+      memset(&pend, 0, sizeof pend);
+      if (cudaPointerGetAttributes(&pend, reinterpret_cast<const char*>(out_bpp) + bpp_total * 4 - 1) == cudaSuccess &&
+          pend.type == cudaMemoryTypeHost && pend.devicePointer) {
+        bpp_zero_copy = true;
+        b.d_out_bpp = reinterpret_cast<float*>(pat.devicePointer);
+      }
+    }
+    cudaGetLastError();   // (older drivers report an unregistered pointer as an error)
+    if (!bpp_zero_copy) {
+      TRY(ensure(h, h->b_bpp, bpp_total * 4));
+      b.d_out_bpp = (float*)h->b_bpp.p;
+    }
   }
   if (n_gammas) {
     TRY(h2d(h, h->b_gammas, gammas, sizeof(float) * n_gammas, st));
@@ -747,7 +768,8 @@ extern "C" int rna_mccaskill_centroid_batch(rna_handle* h, const uint8_t* bases,
   b.n_gammas = n_gammas;
   TRY(rna_mccaskill_centroid_batch_dev(h, &b, st));
   if (out_logz) TRY(d2h(h, out_logz, h->b_logz, sizeof(float) * n_seqs, st));
-  if (out_bpp) TRY(d2h(h, out_bpp, h->b_bpp, bpp_total * 4, st));
+  if (out_bpp && !bpp_zero_copy) TRY(d2h(h, out_bpp, h->b_bpp, bpp_total * 4, st));
+  if (out_bpp && bpp_zero_copy) h->stats.d2h_bytes += bpp_total * 4;   // written to host memory by the kernels
   if (n_gammas && out_structs) TRY(d2h(h, out_structs, h->b_structs, (size_t)n_gammas * total, st));
   if (n_gammas && out_expect_acc) TRY(d2h(h, out_expect_acc, h->b_ea, sizeof(float) * (size_t)n_gammas * n_seqs, st));
   CU(h, cudaStreamSynchronize(st));

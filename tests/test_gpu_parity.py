@@ -303,3 +303,23 @@ def test_cooperative_random_lengths_stress(handle, oracle):
             assert_bits_equal(got["logz"], want["logz"], f"logZ L={L}")
             assert (got["structs"] == want["structs"]).all(), L
             assert_bits_equal(got["expect_acc"], want["expect_acc"], f"expected accuracy L={L}")
+
+
+def test_zero_copy_bpp_into_pinned_host_buffer(handle, oracle):
+    """A page-locked output buffer is written by the kernels directly (no staging copy); a pageable one is staged.
+    Both must hold the same bits, in the batch path and in the cooperative path, and a buffer that is only partly
+    page-locked must take the staged path."""
+    import torch
+    tt, ct, _ = default_tables()
+    for seqs in (load_trnas() + random_seqs(55, [40, 120, 300]), random_seqs(56, [600])):
+        bases, offsets = pack(seqs)
+        want = handle.fold_batch(bases, offsets, True, False, [2.0])                 # pageable numpy outputs
+        nbpp = want["bpp"].shape[0]
+        pinned = torch.full((nbpp + 8,), 7.0, dtype=torch.float32).pin_memory().numpy()
+        got = handle.fold_batch(bases, offsets, True, False, [2.0], out={"bpp": pinned[:nbpp]})
+        assert got["bpp"] is not None and np.shares_memory(got["bpp"], pinned)
+        assert_bits_equal(got["bpp"], want["bpp"], "zero-copy BPP")
+        assert (pinned[nbpp:] == 7.0).all()                                          # nothing written past the end
+        assert (got["structs"] == want["structs"]).all()
+    ref = oracle.fold_batch(bases, offsets, True, False, tt, ct, [2.0], n_threads=8)
+    assert_bits_equal(got["bpp"], ref["bpp"], "zero-copy BPP vs oracle")
