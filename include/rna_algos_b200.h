@@ -199,7 +199,9 @@ static inline uint64_t rna_bpp_index(uint64_t L, uint64_t i, uint64_t j) {
 
 /* mccaskill_algo over a batch (+ optionally centroid_fold for n_gammas thresholds, fused on device).
  *   out_logz        [n_seqs]                  sums_external[0][L-1]   (may be NULL)
- *   out_bpp         concatenated packed BPPs, sequence s at bpp_offsets[s] (floats)  (may be NULL)
+ *   out_bpp         concatenated packed BPPs, sequence s at bpp_offsets[s] (floats)  (may be NULL).  If the buffer is
+ *                   page-locked (cudaHostAlloc / cudaHostRegister) the kernels write it directly while they compute;
+ *                   a pageable buffer is filled by a copy after the last kernel.  Same bits either way.
  *   bpp_offsets     [n_seqs+1] or NULL => offsets are the running sum of rna_bpp_len(L_s)
  *   gammas          [n_gammas] centroid thresholds (src/centroid_fold.rs:28)          (n_gammas may be 0)
  *   out_structs     [n_gammas][total_len] dot-bracket bytes '.', '(', ')'; sequence s of gamma g at
