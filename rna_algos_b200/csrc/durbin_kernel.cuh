@@ -2,9 +2,11 @@
 //
 // Reference: src/durbin_algo.rs:79-199 (get_align_sums), :201-242 (get_match_probs).  One thread per
 // row i of the current anti-diagonal s = i + j.  Only three anti-diagonals of each state are live, so
-// F_I/F_D/B_M/B_I/B_D roll through 3 x n buffers; F_M (needed by the posterior) is parked in the output
-// matrix itself and overwritten by the match probability when the backward sweep reaches (i+1, j+1).
-// The posterior is fused into the backward sweep.  All folds are in the reference's order, so the
+// F_I/F_D/B_M/B_I/B_D roll through 3 x n buffers; F_M (needed by the posterior) is parked in an n x m matrix
+// of the CTA's own (shared memory when it fits, else a global slot) and overwritten there by the match probability
+// when the backward sweep reaches (i+1, j+1).  The posterior is fused into the backward sweep.  The output matrix is
+// written ONCE at the end, whole rows at a time (write-only and coalesced: it may be the caller's page-locked host
+// buffer, so the device-to-host transfer runs under the kernel).  All folds are in the reference's order, so the
 // result is bit-identical to the reference.
 #pragma once
 #include "dev_tables.h"
@@ -26,12 +28,16 @@ struct DurbinArgs {
   int* work_counter;
   int ncap, mcap;              // shared-memory capacity (padded lengths)
   int roll_in_smem;
+  int park_in_smem;            // the n x m forward / posterior matrix lives in shared memory
+  float* park_ws;              // else: one slot of park_stride floats per CTA
+  unsigned long long park_stride;
 };
 
-__host__ __device__ inline size_t durbin_smem_bytes(int ncap, int mcap, bool roll_in_smem) {
+__host__ __device__ inline size_t durbin_smem_bytes(int ncap, int mcap, bool roll_in_smem, bool park_in_smem = false) {
   size_t b = 128 + 128;   // LSE LUT + DevAlign copy
   b += ((size_t)ncap + (size_t)mcap + 8 + 15) / 16 * 16;
   if (roll_in_smem) b += (size_t)9 * (size_t)ncap * 4;
+  if (park_in_smem) b += (size_t)ncap * (size_t)mcap * 4;
   return b;
 }
 
@@ -68,6 +74,8 @@ __global__ void __launch_bounds__(256, 6) durbin_kernel(const DurbinArgs a) {
     float* RI = roll + 3 * (size_t)n;
     float* RD = roll + 6 * (size_t)n;
     float* out = a.out_probs + a.prob_offsets[pidx];
+    float* park = a.park_in_smem ? sroll + (a.roll_in_smem ? (size_t)9 * a.ncap : 0)
+                                 : a.park_ws + (size_t)blockIdx.x * a.park_stride;
     for (int x = tid; x < 9 * n; x += nt) roll[x] = NEG;
     __syncthreads();
 
@@ -102,7 +110,7 @@ __global__ void __launch_bounds__(256, 6) durbin_kernel(const DurbinArgs a) {
           }
         }
         RM[b0 + i] = fm; RI[b0 + i] = fi; RD[b0 + i] = fd;
-        out[(size_t)i * m + j] = fm;      // park forward_sums_match for the posterior
+        park[(size_t)i * m + j] = fm;     // park forward_sums_match for the posterior
       }
       __syncthreads();
     }
@@ -156,15 +164,17 @@ __global__ void __launch_bounds__(256, 6) durbin_kernel(const DurbinArgs a) {
           t = lse(t, __fadd_rn(m2i, bi), lut);
           t = lse(t, __fadd_rn(m2i, bd), lut);
           const size_t q = (size_t)(i - 1) * m + (j - 1);
-          const float fwd = out[q];
-          out[q] = approx_expf(__fsub_rn(__fadd_rn(fwd, t), Z));
+          const float fwd = park[q];
+          park[q] = approx_expf(__fsub_rn(__fadd_rn(fwd, t), Z));
         }
       }
       __syncthreads();
     }
-    // zero border (rows 0, n-1; columns 0, m-1)
-    for (int x = tid; x < m; x += nt) { out[x] = 0.f; out[(size_t)(n - 1) * m + x] = 0.f; }
-    for (int x = tid; x < n; x += nt) { out[(size_t)x * m] = 0.f; out[(size_t)x * m + m - 1] = 0.f; }
+    // the output, row-major n x m with a zero border (rows 0, n-1; columns 0, m-1), in one coalesced sweep
+    for (int x = tid; x < n * m; x += nt) {
+      const int i = x / m, j = x - i * m;
+      out[x] = (i == 0 || i == n - 1 || j == 0 || j == m - 1) ? 0.f : park[x];
+    }
   }
 }
 

@@ -900,17 +900,27 @@ extern "C" int rna_durbin_batch_dev(rna_handle* h, const RnaDurbinBatchDev* b, v
   a.ncap = ncap;
   a.mcap = mcap;
   a.roll_in_smem = durbin_smem_bytes(ncap, mcap, true) + 1024 <= h->smem_optin;
-  const size_t smem = durbin_smem_bytes(ncap, mcap, a.roll_in_smem != 0);
+  // the n x m forward / posterior matrix on chip when at least 6 CTAs per SM still fit (tRNA-length pairs)
+  // (on chip it would cap the residency at 6 CTAs of 3 warps per SM for tRNA-length pairs — measured 3.07 M pairs/s
+  // against 4.4 M with a global slot per CTA, which stays L2-resident: 2 x SM-count x ~20 CTAs x 33 KB)
+  static const bool park_smem = getenv("RNA_DURBIN_PARK_SMEM") != nullptr;
+  a.park_in_smem = park_smem && a.roll_in_smem && 6 * (durbin_smem_bytes(ncap, mcap, true, true) + 1024) <= (size_t)233472;
+  const size_t smem = durbin_smem_bytes(ncap, mcap, a.roll_in_smem != 0, a.park_in_smem != 0);
   if (smem + 1024 > h->smem_optin) { h->err = "sequence too long for the Durbin kernel"; return RNA_ERR_TOO_LONG; }
   const int nt = std::min(256, std::max(32, (ncap + 31) / 32 * 32));
   TRY(set_smem_attr(h, durbin_kernel, smem));
   int occ = 1;
   CU(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, durbin_kernel, nt, smem));
   const int grid = (int)std::min<size_t>(np, (size_t)std::max(1, occ) * h->sm_count);
-  if (!a.roll_in_smem) {
-    a.ws_stride = (size_t)9 * ncap + 32;
-    TRY(ensure(h, h->ws, (size_t)grid * a.ws_stride * 4));
-    a.workspace = (float*)h->ws.p;
+  {
+    a.ws_stride = a.roll_in_smem ? 0 : (size_t)9 * ncap + 32;
+    a.park_stride = a.park_in_smem ? 0 : ((size_t)ncap * mcap + 31) / 32 * 32;
+    const size_t per = a.ws_stride + a.park_stride;
+    if (per) {
+      TRY(ensure(h, h->ws, (size_t)grid * per * 4));
+      a.workspace = (float*)h->ws.p;
+      a.park_ws = (float*)h->ws.p + (size_t)grid * a.ws_stride;
+    }
   }
   durbin_kernel<<<grid, nt, smem, st>>>(a);
   CU(h, cudaGetLastError());
@@ -948,7 +958,23 @@ extern "C" int rna_durbin_batch(rna_handle* h, const uint8_t* bases, const uint3
   TRY(h2d(h, h->b_offsets, offsets, sizeof(uint32_t) * ((size_t)n_seqs + 1), st));
   TRY(h2d(h, h->b_pairs, pairs, sizeof(uint32_t) * 2 * (size_t)n_pairs, st));
   TRY(h2d(h, h->b_proboff, prob_offsets, sizeof(uint64_t) * ((size_t)n_pairs + 1), st));
-  TRY(ensure(h, h->b_probs, tot * 4));
+  // the kernel writes the match-probability matrices once, whole rows at a time: straight into the caller's buffer when
+  // it is page-locked (see rna_mccaskill_centroid_batch), else staged in HBM and copied afterwards
+  bool zero_copy = false;
+  float* d_target = nullptr;
+  {
+    static const bool no_zc = getenv("RNA_NO_ZERO_COPY") != nullptr;
+    cudaPointerAttributes p0, p1;
+    memset(&p0, 0, sizeof p0); memset(&p1, 0, sizeof p1);
+    if (!no_zc && tot && cudaPointerGetAttributes(&p0, out_probs) == cudaSuccess && p0.type == cudaMemoryTypeHost && p0.devicePointer &&
+        cudaPointerGetAttributes(&p1, reinterpret_cast<const char*>(out_probs) + tot * 4 - 1) == cudaSuccess &&
+        p1.type == cudaMemoryTypeHost && p1.devicePointer) {
+      zero_copy = true;
+      d_target = reinterpret_cast<float*>(p0.devicePointer);
+    }
+    cudaGetLastError();
+  }
+  if (!zero_copy) TRY(ensure(h, h->b_probs, tot * 4));
   RnaDurbinBatchDev b;
   memset(&b, 0, sizeof b);
   b.h_offsets = offsets;
@@ -959,9 +985,10 @@ extern "C" int rna_durbin_batch(rna_handle* h, const uint8_t* bases, const uint3
   b.d_prob_offsets = (const uint64_t*)h->b_proboff.p;
   b.n_seqs = n_seqs;
   b.n_pairs = n_pairs;
-  b.d_out_probs = (float*)h->b_probs.p;
+  b.d_out_probs = zero_copy ? d_target : (float*)h->b_probs.p;
   TRY(rna_durbin_batch_dev(h, &b, st));
-  TRY(d2h(h, out_probs, h->b_probs, tot * 4, st));
+  if (!zero_copy) TRY(d2h(h, out_probs, h->b_probs, tot * 4, st));
+  else h->stats.d2h_bytes += tot * 4;   // written to host memory by the kernel
   CU(h, cudaStreamSynchronize(st));
   return RNA_OK;
 }
