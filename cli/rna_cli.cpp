@@ -85,24 +85,34 @@ Fasta read_fasta(const std::string& path) {
 }
 
 // Rust's `{}` for f32: the shortest decimal string that parses back to the same f32, never in exponent form.
-std::string f32_display(float x) {
-  if (std::isnan(x)) return "NaN";
-  if (std::isinf(x)) return x < 0 ? "-inf" : "inf";
+// Appends to `out` without temporaries (the output files run to gigabytes).
+void append_f32(std::string& out, float x) {
+  if (std::isnan(x)) { out += "NaN"; return; }
+  if (std::isinf(x)) { out += x < 0 ? "-inf" : "inf"; return; }
   // shortest round-trip digits d.ddd e±xx, laid out positionally (zero padding instead of exact integer digits)
-  char buf[64];
-  auto r = std::to_chars(buf, buf + sizeof buf, x, std::chars_format::scientific);
-  std::string sci(buf, r.ptr), out;
-  size_t p = 0;
-  if (sci[0] == '-') { out = "-"; p = 1; }
-  const size_t e = sci.find('e');
-  std::string digits;
-  for (size_t k = p; k < e; k++) if (sci[k] != '.') digits += sci[k];
-  const int exp10 = atoi(sci.c_str() + e + 1);   // value = 0.d1d2... x 10^(exp10+1)
-  if (digits.find_first_not_of('0') == std::string::npos) return out + "0";
-  const int point = exp10 + 1;                     // digits before the decimal point
-  if (point <= 0) return out + "0." + std::string((size_t)(-point), '0') + digits;
-  if ((size_t)point >= digits.size()) return out + digits + std::string((size_t)point - digits.size(), '0');
-  return out + digits.substr(0, (size_t)point) + "." + digits.substr((size_t)point);
+  char buf[48];
+  const auto r = std::to_chars(buf, buf + sizeof buf, x, std::chars_format::scientific);
+  const char* p = buf;
+  if (*p == '-') { out += '-'; p++; }
+  char digits[16];
+  int nd = 0;
+  const char* e = p;
+  for (; e < r.ptr && *e != 'e'; e++) if (*e != '.') digits[nd++] = *e;
+  int exp10 = 0;
+  std::from_chars(e + 1 + (e[1] == '+' ? 1 : 0), r.ptr, exp10);   // value = d1.d2d3... x 10^exp10
+  bool all_zero = true;
+  for (int k = 0; k < nd; k++) if (digits[k] != '0') all_zero = false;
+  if (all_zero) { out += '0'; return; }
+  const int point = exp10 + 1;                                     // digits before the decimal point
+  if (point <= 0) { out += "0."; out.append((size_t)(-point), '0'); out.append(digits, (size_t)nd); }
+  else if (point >= nd) { out.append(digits, (size_t)nd); out.append((size_t)(point - nd), '0'); }
+  else { out.append(digits, (size_t)point); out += '.'; out.append(digits + point, (size_t)(nd - point)); }
+}
+std::string f32_display(float x) { std::string s; append_f32(s, x); return s; }
+void append_uint(std::string& out, uint64_t v) {
+  char buf[24];
+  const auto r = std::to_chars(buf, buf + sizeof buf, v);
+  out.append(buf, (size_t)(r.ptr - buf));
 }
 
 struct Opts {
@@ -236,7 +246,7 @@ int main_mccaskill(int argc, char** argv, int first) {
       for (uint64_t j = i + 1; j < L; j++) {
         const float x = p[rna_bpp_index(L, i, j)];
         if (x == RNA_BPP_ABSENT) continue;   // key not in the reference's SparseProbMat (a present 0.0 is written)
-        buf += std::to_string(i) + "," + std::to_string(j) + "," + f32_display(x) + " ";
+        append_uint(buf, i); buf += ','; append_uint(buf, j); buf += ','; append_f32(buf, x); buf += ' ';
       }
   }
   write_file(o.out, buf);
@@ -299,7 +309,7 @@ int main_durbin(int argc, char** argv, int first) {
     const float* x = probs.data() + poff[p];
     for (uint64_t i = 0; i < n; i++)
       for (uint64_t j = 0; j < m; j++)
-        if (x[i * m + j] > 0.f) buf += std::to_string(i - 1) + "," + std::to_string(j - 1) + "," + f32_display(x[i * m + j]) + " ";
+        if (x[i * m + j] > 0.f) { append_uint(buf, i - 1); buf += ','; append_uint(buf, j - 1); buf += ','; append_f32(buf, x[i * m + j]); buf += ' '; }
   }
   write_file(o.out, buf);
   return 0;
