@@ -104,6 +104,77 @@ __host__ __device__ inline size_t fold_smem_bytes(int Lcap, bool smem_mats) {
 // centroid_fold: src/centroid_fold.rs:25-105.  W (max_expect_accuracies) is diagonal-major in `W`;
 // getp(d, i) returns the base-pairing probability of (i, i+d) or -1 when the key is absent.
 // ---------------------------------------------------------------------------------------------------
+// Traceback of one threshold (src/centroid_fold.rs:65-102) by ONE warp (all 32 lanes call it); the k-scan is
+// lane-parallel (first match wins).  W, tstack: this threshold's matrix and stack.
+template <int MODE, class PF>
+__device__ __forceinline__ void centroid_traceback(const FoldArgs& a, uint32_t sidx, uint32_t sbeg, int L, const float* W,
+                                                   int* tstack, PF getp, uint32_t g) {
+  typedef Ctx<MODE> X;
+  const float gamma = a.gammas[g];
+  const int tid = threadIdx.x & 31;
+  uint8_t* ostr = a.out_structs ? a.out_structs + (size_t)g * a.total_len + sbeg : nullptr;
+  {
+    const int lane = tid;
+    int sp = 0;
+    uint32_t np = 0;
+    uint16_t* opairs = a.out_pairs ? a.out_pairs + 2 * ((size_t)g * a.total_len + sbeg) : nullptr;
+    if (lane == 0) { tstack[0] = 0; tstack[1] = L - 1; }
+    sp = 1;
+    __syncwarp();
+    while (sp > 0) {
+      sp--;
+      const int i = tstack[2 * sp], j = tstack[2 * sp + 1];
+      __syncwarp();
+      if (j <= i) continue;
+      const int d = j - i;
+      const float wv = X::ld(&W[X::off(d, L) + i]);
+      if (wv == 0.f) continue;
+      const float wi1 = X::ld(&W[X::off(d - 1, L) + i + 1]);
+      const float wj1 = X::ld(&W[X::off(d - 1, L) + i]);
+      const float p = getp(d, i);
+      const float inner = (d >= 2) ? X::ld(&W[X::off(d - 2, L) + i + 1]) : 0.f;
+      if (wv == wi1) {
+        if (lane == 0) { tstack[2 * sp] = i + 1; tstack[2 * sp + 1] = j; }
+        sp++;
+      } else if (wv == wj1) {
+        if (lane == 0) { tstack[2 * sp] = i; tstack[2 * sp + 1] = j - 1; }
+        sp++;
+      } else if (p != -1.0f && wv == __fsub_rn(__fadd_rn(inner, __fmul_rn(gamma, p)), 1.0f)) {
+        if (lane == 0) {
+          tstack[2 * sp] = i + 1; tstack[2 * sp + 1] = j - 1;
+          if (ostr) { ostr[i] = '('; ostr[j] = ')'; }
+          if (opairs) { opairs[2 * np] = (uint16_t)i; opairs[2 * np + 1] = (uint16_t)j; }
+        }
+        sp++;
+        np++;
+      } else {
+        for (int m0 = 1; m0 < d; m0 += 32) {
+          const int m = m0 + lane;
+          bool hit = false;
+          if (m < d) {
+            hit = (wv == __fadd_rn(X::ld(&W[X::off(m, L) + i]), X::ld(&W[X::off(d - m - 1, L) + i + m + 1])));
+          }
+          const unsigned bal = __ballot_sync(0xffffffffu, hit);
+          if (bal) {
+            const int k = i + m0 + (__ffs(bal) - 1);
+            if (lane == 0) {
+              tstack[2 * sp] = i; tstack[2 * sp + 1] = k;
+              tstack[2 * sp + 2] = k + 1; tstack[2 * sp + 3] = j;
+            }
+            sp += 2;
+            break;
+          }
+        }
+      }
+      __syncwarp();
+    }
+    if (lane == 0) {
+      if (a.out_ea) a.out_ea[(size_t)g * a.n_seqs + sidx] = X::ld(&W[X::off(L - 1, L)]);
+      if (a.out_npairs) a.out_npairs[(size_t)g * a.n_seqs + sidx] = np;
+    }
+  }
+}
+
 struct NoCentroidFill { __device__ __forceinline__ bool operator()(float) const { return false; } };
 // fill(gamma): optional replacement of the max-plus fill (W is zeroed and a barrier has passed; it must end with a
 // barrier); returns false to get the built-in thread-per-cell fill.
@@ -145,67 +216,8 @@ __device__ __forceinline__ void centroid_run(const FoldArgs& a, uint32_t sidx, u
       }
       X::sync();
     }
-    // traceback by the first warp of the (first) CTA; the k-scan is lane-parallel (first match wins)
-    if ((MODE != MODE_COOP || blockIdx.x == 0) && tid < 32) {
-      const int lane = tid;
-      int sp = 0;
-      uint32_t np = 0;
-      uint16_t* opairs = a.out_pairs ? a.out_pairs + 2 * ((size_t)g * a.total_len + sbeg) : nullptr;
-      if (lane == 0) { tstack[0] = 0; tstack[1] = L - 1; }
-      sp = 1;
-      __syncwarp();
-      while (sp > 0) {
-        sp--;
-        const int i = tstack[2 * sp], j = tstack[2 * sp + 1];
-        __syncwarp();
-        if (j <= i) continue;
-        const int d = j - i;
-        const float wv = X::ld(&W[X::off(d, L) + i]);
-        if (wv == 0.f) continue;
-        const float wi1 = X::ld(&W[X::off(d - 1, L) + i + 1]);
-        const float wj1 = X::ld(&W[X::off(d - 1, L) + i]);
-        const float p = getp(d, i);
-        const float inner = (d >= 2) ? X::ld(&W[X::off(d - 2, L) + i + 1]) : 0.f;
-        if (wv == wi1) {
-          if (lane == 0) { tstack[2 * sp] = i + 1; tstack[2 * sp + 1] = j; }
-          sp++;
-        } else if (wv == wj1) {
-          if (lane == 0) { tstack[2 * sp] = i; tstack[2 * sp + 1] = j - 1; }
-          sp++;
-        } else if (p != -1.0f && wv == __fsub_rn(__fadd_rn(inner, __fmul_rn(gamma, p)), 1.0f)) {
-          if (lane == 0) {
-            tstack[2 * sp] = i + 1; tstack[2 * sp + 1] = j - 1;
-            if (ostr) { ostr[i] = '('; ostr[j] = ')'; }
-            if (opairs) { opairs[2 * np] = (uint16_t)i; opairs[2 * np + 1] = (uint16_t)j; }
-          }
-          sp++;
-          np++;
-        } else {
-          for (int m0 = 1; m0 < d; m0 += 32) {
-            const int m = m0 + lane;
-            bool hit = false;
-            if (m < d) {
-              hit = (wv == __fadd_rn(X::ld(&W[X::off(m, L) + i]), X::ld(&W[X::off(d - m - 1, L) + i + m + 1])));
-            }
-            const unsigned bal = __ballot_sync(0xffffffffu, hit);
-            if (bal) {
-              const int k = i + m0 + (__ffs(bal) - 1);
-              if (lane == 0) {
-                tstack[2 * sp] = i; tstack[2 * sp + 1] = k;
-                tstack[2 * sp + 2] = k + 1; tstack[2 * sp + 3] = j;
-              }
-              sp += 2;
-              break;
-            }
-          }
-        }
-        __syncwarp();
-      }
-      if (lane == 0) {
-        if (a.out_ea) a.out_ea[(size_t)g * a.n_seqs + sidx] = X::ld(&W[X::off(L - 1, L)]);
-        if (a.out_npairs) a.out_npairs[(size_t)g * a.n_seqs + sidx] = np;
-      }
-    }
+    // traceback by the first warp of the (first) CTA
+    if ((MODE != MODE_COOP || blockIdx.x == 0) && tid < 32) centroid_traceback<MODE>(a, sidx, sbeg, L, W, tstack, getp, g);
     X::sync();
   }
 }
@@ -528,15 +540,20 @@ __device__ __forceinline__ unsigned long long global_ns() {
 // meet in an integer atomicMax: every W is >= +0 and W starts at 0, so the order of the float bits as signed integers
 // is the float order wherever it matters, and a maximum does not depend on the order of its operands.
 #define RNA_CENT_CHUNK 64
+// All thresholds are filled in the same sweep over the diagonals (tasks = threshold x cell group x chunk): the number
+// of grid barriers does not grow with the number of thresholds (the reference's default is a sweep of 18).
 template <class GETP, class SYNC>
-__device__ __forceinline__ void centroid_fill_coop(float* W, int L, float gamma, GETP getp, SYNC sync, int gw, int nw,
-                                                   int lane32) {
+__device__ __forceinline__ void centroid_fill_coop(float* Wall, size_t wstride, int L, const float* gammas, int ngam, GETP getp,
+                                                   SYNC sync, int gw, int nw, int lane32) {
   for (int d = 1; d < L; d++) {
     const int ncell = L - d, ng = (ncell + 31) >> 5, nch = max(1, (d - 1 + RNA_CENT_CHUNK - 1) / RNA_CENT_CHUNK);
     const int od = coop_doff(d, L), od1 = coop_doff(d - 1, L);
-    for (int tau = gw; tau < ng * nch; tau += nw) {
-      const int g = tau % ng, ch = tau / ng, i = g * 32 + lane32;
+    for (int tau = gw; tau < ngam * ng * nch; tau += nw) {
+      const int gi = tau / (ng * nch), rest = tau - gi * (ng * nch);
+      const int g = rest % ng, ch = rest / ng, i = g * 32 + lane32;
       if (i >= ncell) continue;
+      float* W = Wall + (size_t)gi * wstride;
+      const float gamma = gammas[gi];
       float wv = 0.f;
       if (ch == 0) {
         wv = __ldcg(&W[od1 + i + 1]);
@@ -566,6 +583,33 @@ __device__ __forceinline__ void centroid_fill_coop(float* W, int L, float gamma,
   }
 }
 
+// centroid_fold for every threshold of the call, one long sequence on the whole grid: zero, one fill sweep, then the
+// traceback of threshold g by the first warp of CTA g (mod grid).  Wall: n_gammas matrices wstride floats apart;
+// tstacks: n_gammas stacks of 2 (L + 2) ints.
+template <class PF, class SYNC>
+__device__ __forceinline__ void centroid_coop_all(const FoldArgs& a, uint32_t sidx, uint32_t sbeg, int L, float* Wall,
+                                                  size_t wstride, int* tstacks, PF getp, SYNC sync) {
+  const int tid = threadIdx.x;
+  const size_t gtid = (size_t)blockIdx.x * blockDim.x + tid, gnt = (size_t)gridDim.x * blockDim.x;
+  const size_t TRI = (size_t)L * (L + 1) / 2;
+  const int ngam = (int)a.n_gammas;
+  if (ngam == 0) return;
+  for (int g = 0; g < ngam; g++) {
+    float* W = Wall + (size_t)g * wstride;
+    for (size_t x = gtid; x < TRI; x += gnt) W[x] = 0.f;
+    if (a.out_structs) {
+      uint8_t* ostr = a.out_structs + (size_t)g * a.total_len + sbeg;
+      for (size_t x = gtid; x < (size_t)L; x += gnt) ostr[x] = '.';
+    }
+  }
+  sync();
+  const int gw = (tid >> 5) * (int)gridDim.x + (int)blockIdx.x;
+  centroid_fill_coop(Wall, wstride, L, a.gammas, ngam, getp, sync, gw, (int)(gridDim.x * (blockDim.x >> 5)), tid & 31);
+  if (tid < 32)
+    for (int g = (int)blockIdx.x; g < ngam; g += (int)gridDim.x)
+      centroid_traceback<MODE_COOP>(a, sidx, sbeg, L, Wall + (size_t)g * wstride, tstacks + (size_t)g * 2 * (L + 2), getp, (uint32_t)g);
+  sync();
+}
 // centroid_fold over packed BPP matrices that already live in device memory (rna_centroid_batch).
 // Workspace layout per slot: W (L(L+1)/2 floats) | traceback stack.
 template <int MODE>
@@ -602,15 +646,13 @@ __global__ void __launch_bounds__(MODE == MODE_SMEM ? 256 : 512) centroid_kernel
       return __ldg(&P[(size_t)i * (size_t)(2 * L - i - 1) / 2 + (size_t)(d - 1)]);
     };
     if constexpr (MODE == MODE_COOP) {
-      // one long sequence on the whole grid: chunked atomic-max fill, own grid barrier (a.work_counter is free here)
+      // one long sequence on the whole grid: all thresholds in one chunked atomic-max fill sweep, own grid barrier
+      // (a.work_counter is free here); workspace = n_gammas x (W | traceback stack)
       unsigned* const bar_ctr = reinterpret_cast<unsigned*>(a.work_counter);
       auto grid_sync = [&]() { coop_barrier(bar_ctr, bar_target); };
-      const int gw = (tid >> 5) * (int)gridDim.x + (int)blockIdx.x;
-      auto fill = [&](float gamma) -> bool {
-        centroid_fill_coop(W, L, gamma, getp, grid_sync, gw, (int)(gridDim.x * (blockDim.x >> 5)), tid & 31);
-        return true;
-      };
-      centroid_run<MODE>(a, sidx, sbeg, L, W, tstack, getp, fill);
+      const size_t wstride = (size_t)TRI;
+      int* tstacks = reinterpret_cast<int*>(a.workspace + (size_t)a.n_gammas * wstride);
+      centroid_coop_all(a, sidx, sbeg, L, a.workspace, wstride, tstacks, getp, grid_sync);
     } else {
       centroid_run<MODE>(a, sidx, sbeg, L, W, tstack, getp);
     }

@@ -635,12 +635,10 @@ __global__ void __launch_bounds__(256, 1) fold_kernel2_coop(const FoldArgs a) {
     {
       const float* Pm = v.Pm;
       auto getp = [=](int d, int i) -> float { return __ldcg(&Pm[doff(d, L) + i]); };
-      float* W = v.C;
-      auto fill = [&](float gamma) -> bool {
-        centroid_fill_coop(W, L, gamma, getp, grid_sync, gw, (int)(gridDim.x * (blockDim.x >> 5)), tid & 31);
-        return true;
-      };
-      centroid_run<MODE_COOP>(a, sidx, sbeg, L, W, tstack, getp, fill);
+      // every threshold's W matrix behind the two extra matrices of the outside pass, then the traceback stacks
+      float* Wall = v.MB + TRI;
+      int* tstacks = reinterpret_cast<int*>(Wall + (size_t)a.n_gammas * TRI);
+      centroid_coop_all(a, sidx, sbeg, L, Wall, TRI, tstacks, getp, grid_sync);
     }
     mark(3);   // BPP + centroid
   }

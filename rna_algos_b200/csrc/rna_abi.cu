@@ -355,7 +355,10 @@ static int launch_fold_model(rna_handle* h, const RnaFoldBatchDev* b, cudaStream
     stride_of[k] = per;
     if (bk.mode == MODE_COOP) {
       // + row-major sums_1ormore and the multibranch closing-score table of the cooperative kernel's outside pass
-      ws_floats = std::max(ws_floats, per + (v2 ? (size_t)bk.Lcap * (bk.Lcap + 1) + 64 : 0));
+      // + one max-plus matrix and traceback stack per centroid threshold (all thresholds are filled in one sweep)
+      const size_t Tc = (size_t)bk.Lcap * (bk.Lcap + 1) / 2;
+      const size_t cent = (size_t)std::max<uint32_t>(1, b->n_gammas) * (Tc + 2 * ((size_t)bk.Lcap + 2)) + 64;
+      ws_floats = std::max(ws_floats, centroid_only ? cent + 64 : per + (v2 ? 2 * Tc + 64 + cent : 0));
     } else {
       size_t freeb = 0, totb = 0;
       cudaMemGetInfo(&freeb, &totb);
