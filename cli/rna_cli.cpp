@@ -330,6 +330,16 @@ int main(int argc, char** argv) {
     prog = argv[1];
     first = 2;
   }
+  if (prog == "_parse") {   // test hook: print the records the FASTA reader produces (no GPU needed)
+    if (argc <= first) return 1;
+    const Fasta fa = read_fasta(argv[first]);
+    for (uint32_t q = 0; q < fa.n(); q++) {
+      printf("%s %u ", fa.ids[q].c_str(), fa.len(q));
+      for (uint32_t x = fa.offsets[q]; x < fa.offsets[q + 1]; x++) putchar("ACGU"[fa.bases[x]]);
+      putchar('\n');
+    }
+    return 0;
+  }
   if (prog == "_fmt") {   // test hook: print f32 bit patterns (hex) the way the output files do
     for (int k = first; k < argc; k++) {
       const uint32_t b = (uint32_t)strtoul(argv[k], nullptr, 16);

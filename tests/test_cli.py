@@ -59,6 +59,28 @@ def test_bad_base_is_an_error_not_a_crash(cli, tmp_path):
     assert r.returncode == 1 and "cannot open" in r.stderr
 
 
+def test_fasta_reader_semantics(cli, tmp_path):
+    """bio::io::fasta as the reference uses it: id = first word of the header, the sequence is every following line up
+    to the next header with line ends removed, a/c/g/u in either case (src/utils.rs:562-577)."""
+    fa = tmp_path / "in.fa"
+    fa.write_bytes(b">first some description\nACGU\nacgu\r\n\nGG\n>second\tx\nu\n>third\nAcGuAcGu")
+    r = run(cli, "_parse", str(fa))
+    assert r.returncode == 0, r.stderr
+    assert r.stdout.splitlines() == ["first 10 ACGUACGUGG", "second 1 U", "third 8 ACGUACGU"]
+    empty = tmp_path / "empty.fa"
+    empty.write_text(">only_header\n")
+    r = run(cli, "_parse", str(empty))
+    assert r.returncode == 1 and "has no sequence" in r.stderr
+    nohdr = tmp_path / "nohdr.fa"
+    nohdr.write_text("ACGU\n")
+    r = run(cli, "_parse", str(nohdr))
+    assert r.returncode == 1 and "before the first" in r.stderr
+    t = tmp_path / "t.fa"
+    t.write_text(">dna\nACGT\n")
+    r = run(cli, "_parse", str(t))
+    assert r.returncode == 1 and "'T'" in r.stderr      # the reference panics on T as well
+
+
 def test_no_device_fails_loudly(cli, tmp_path):
     import torch
     if torch.cuda.is_available():
