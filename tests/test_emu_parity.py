@@ -97,9 +97,9 @@ def test_pair_split_schedule(emu, oracle, contra):
         check(emu, oracle, random_seqs(13, [2, 3, 5, 9, 33]), True, True, tt, ct, order=3)
 
 
-def test_phases_are_address_sanitizer_clean(tmp_path):
+def test_phases_are_sanitizer_clean(tmp_path):
     """compute-sanitizer is not available on the GPU pool; the same phase code runs here on exactly-sized host
-    buffers under AddressSanitizer instead (all schedules, both models)."""
+    buffers under AddressSanitizer + UndefinedBehaviorSanitizer instead (all schedules, both models)."""
     import os
     import subprocess
     import sys
@@ -109,8 +109,8 @@ def test_phases_are_address_sanitizer_clean(tmp_path):
     if not asan or not os.path.isabs(asan) or not os.path.exists(asan):
         pytest.skip("libasan not available")
     lib = str(tmp_path / "_emu_asan.so")
-    subprocess.run(["g++", "-O1", "-g", "-std=c++17", "-ffp-contract=off", "-fno-fast-math", "-fsanitize=address",
-                    "-fno-omit-frame-pointer", "-shared", "-fPIC", "-o", lib, SRC], check=True, capture_output=True)
+    subprocess.run(["g++", "-O1", "-g", "-std=c++17", "-ffp-contract=off", "-fno-fast-math", "-fsanitize=address,undefined",
+                    "-fno-sanitize-recover=undefined", "-fno-omit-frame-pointer", "-shared", "-fPIC", "-o", lib, SRC], check=True, capture_output=True)
     env = dict(os.environ, LD_PRELOAD=asan, ASAN_OPTIONS="detect_leaks=0")
     r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "emu", "asan_run.py"), ROOT, lib], env=env,
                        capture_output=True, text=True, timeout=600)
