@@ -16,15 +16,16 @@ oracle:
 
 # command-line front ends with the reference's options and output formats (cli/rna_cli.cpp); one binary, three names
 CLI := bin/rna_algos_b200
-cli: $(CLI) rna_algos_b200/tables_default/turner2004.tbl
+cli: $(CLI) rna_algos_b200/tables_standin/standin_turner.tbl
 $(CLI): cli/rna_cli.cpp include/rna_algos_b200.h $(LIB)
 	mkdir -p bin
 	g++ -std=c++17 -O2 -Wall -o $@ cli/rna_cli.cpp -Lrna_algos_b200 -lrna_algos_b200 -Wl,-rpath,'$$ORIGIN/../rna_algos_b200' -Wl,--allow-shlib-undefined
 	ln -sf rna_algos_b200 bin/mccaskill_algo && ln -sf rna_algos_b200 bin/centroid_fold && ln -sf rna_algos_b200 bin/durbin_algo
-rna_algos_b200/tables_default/turner2004.tbl: rna_algos_b200/tables.py
-	python -m rna_algos_b200.tables dump rna_algos_b200/tables_default
+# (stand-in score tables for --standin-tables; the genuine blobs come from tools/ref_dump)
+rna_algos_b200/tables_standin/standin_turner.tbl: rna_algos_b200/tables.py
+	python -m rna_algos_b200.tables dump rna_algos_b200/tables_standin
 
 clean:
-	rm -rf $(LIB) bin rna_algos_b200/tables_default
+	rm -rf $(LIB) bin rna_algos_b200/tables_standin build
 	$(MAKE) -C oracle clean
 .PHONY: all oracle cli clean

@@ -7,7 +7,7 @@
 // (the reference iterates hashbrown maps, whose order is unspecified); -t is accepted and ignored (the GPU batches
 // the sequences); a non-ACGU base or an unreadable file ends the program with a message and exit status 1 instead
 // of a panic.  Score tables are run-time blobs: --tables DIR, else $RNA_ALGOS_B200_TABLES, else ../rna_algos_b200/
-// tables_default next to the executable (written by `python -m rna_algos_b200.tables dump`).
+// tables_standin next to the executable (written by `python -m rna_algos_b200.tables dump`; --standin-tables only).
 #include <charconv>
 #include <cmath>
 #include <cstdint>
@@ -117,7 +117,7 @@ void append_uint(std::string& out, uint64_t v) {
 
 struct Opts {
   std::string in, out, tables;
-  bool contra = false, has_gamma = false, help = false;
+  bool contra = false, has_gamma = false, help = false, standin = false;
   float gamma = 0.f;
 };
 
@@ -128,7 +128,9 @@ void usage(const char* prog, bool with_gamma, bool with_model) {
   if (with_gamma) printf("    -g, --centroid_threshold FLOAT  A specific centroid threshold rather than a range of centroid thresholds\n");
   printf("    -t, --num_threads UINT      Accepted for compatibility; the GPU batches all sequences\n");
   if (with_model) printf("    -c, --uses_contra_model     Use the CONTRAfold model instead of Turner's model to score RNA secondary structures\n");
-  printf("        --tables DIR            Directory with turner2004.tbl / contrafold_v202.tbl score-table blobs\n");
+  printf("        --tables DIR            Directory with the genuine turner2004.tbl / contrafold_v202.tbl score-table blobs\n");
+  printf("                                (written from rna-ss-params by tools/ref_dump; default: $RNA_ALGOS_B200_TABLES)\n");
+  printf("        --standin-tables        Run on the in-repo STAND-IN tables instead (NOT the reference's numbers)\n");
   printf("    -h, --help                  Print a help menu\n");
 }
 
@@ -151,6 +153,7 @@ Opts parse(int argc, char** argv, int first, bool with_gamma, bool with_model) {
       if (end == v.c_str() || *end) die("cannot parse centroid threshold '" + v + "'");
       o.has_gamma = true;
     } else if (a == "--tables") o.tables = val();
+    else if (a == "--standin-tables") o.standin = true;
     else if (a == "-h" || a == "--help") o.help = true;
     else die("unknown option " + a);
   }
@@ -171,7 +174,7 @@ template <class T>
 void load_table(const std::string& dir, const char* name, uint32_t kind, T* out) {
   const std::string path = dir + "/" + name;
   std::ifstream in(path, std::ios::binary);
-  if (!in) die("cannot open score table " + path + " (write it with `python -m rna_algos_b200.tables dump DIR`)");
+  if (!in) die("cannot open score table " + path + " (genuine blobs: tools/ref_dump; stand-ins: `python -m rna_algos_b200.tables dump DIR`)");
   char magic[8];
   uint32_t hdr[2];
   in.read(magic, 8);
@@ -188,21 +191,33 @@ struct Session {
     if (rc != RNA_OK) die(std::string(what) + ": " + (h ? rna_last_error(h) : "no handle") + " (status " + std::to_string(rc) + ")");
   }
   void open(const Opts& o, bool need_fold_tables) {
-    const int rc = rna_create(0, &h);
-    if (rc != RNA_OK) die("no usable CUDA device (status " + std::to_string(rc) + "); this program has no CPU path");
+    // score tables first (an argument error must not depend on the machine)
+    static RnaContraTables ct;
+    static RnaTurnerTables tt;
     if (need_fold_tables) {
       std::string dir = o.tables;
       if (dir.empty() && getenv("RNA_ALGOS_B200_TABLES")) dir = getenv("RNA_ALGOS_B200_TABLES");
-      if (dir.empty()) dir = exe_dir() + "/../rna_algos_b200/tables_default";
-      if (o.contra) {
-        static RnaContraTables ct;
-        load_table(dir, "contrafold_v202.tbl", 2, &ct);
-        check(rna_set_contra_tables(h, &ct), "rna_set_contra_tables");
-      } else {
-        static RnaTurnerTables tt;
-        load_table(dir, "turner2004.tbl", 1, &tt);
-        check(rna_set_turner_tables(h, &tt), "rna_set_turner_tables");
+      // The file names turner2004.tbl / contrafold_v202.tbl are reserved for the genuine rna-ss-params values.  The
+      // stand-in tables of this repository give results that differ from the reference's: explicit opt-in only.
+      const char* tname = "turner2004.tbl";
+      const char* cname = "contrafold_v202.tbl";
+      if (o.standin) {
+        dir = exe_dir() + "/../rna_algos_b200/tables_standin";
+        tname = "standin_turner.tbl";
+        cname = "standin_contrafold.tbl";
+        fprintf(stderr, "WARNING: --standin-tables: these are NOT the Turner 2004 / CONTRAfold v2.02 parameters of rna-ss-params; "
+                        "probabilities and structures differ from the reference's.\n");
+      } else if (dir.empty()) {
+        die("no score tables: pass --tables DIR (or set RNA_ALGOS_B200_TABLES) with the genuine turner2004.tbl / "
+            "contrafold_v202.tbl written by tools/ref_dump, or opt in to the stand-in tables with --standin-tables");
       }
+      if (o.contra) load_table(dir, cname, 2, &ct); else load_table(dir, tname, 1, &tt);
+    }
+    const int rc = rna_create(0, &h);
+    if (rc != RNA_OK) die("no usable CUDA device (status " + std::to_string(rc) + "); this program has no CPU path");
+    if (need_fold_tables) {
+      if (o.contra) check(rna_set_contra_tables(h, &ct), "rna_set_contra_tables");
+      else check(rna_set_turner_tables(h, &tt), "rna_set_turner_tables");
     } else {
       RnaAlignTables at;
       rna_align_tables_contralign_v201(&at);

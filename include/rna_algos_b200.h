@@ -42,7 +42,7 @@ enum {
   RNA_ERR_BAD_ARG = 1,       /* null pointer, inconsistent offsets, bad enum                       */
   RNA_ERR_INVALID_BASE = 2,  /* a base code outside 0..3 (reference: bytes2seq panic)              */
   RNA_ERR_EMPTY_SEQ = 3,     /* L == 0 (reference underflows seq_len - 1, src/mccaskill_algo.rs:526) */
-  RNA_ERR_TOO_LONG = 4,      /* L > RNA_MAX_SEQ_LEN (u16 index domain of the reference)            */
+  RNA_ERR_TOO_LONG = 4,      /* L > RNA_MAX_SEQ_LEN (u16 index domain of the reference), or > RNA_MAX_FOLD_LEN for folding */
   RNA_ERR_NO_TABLES = 5,     /* the table blob for the requested model was never set               */
   RNA_ERR_BAD_TABLES = 6,    /* caps in the blob exceed the fixed array sizes below                */
   RNA_ERR_CUDA = 7,          /* a CUDA runtime call failed; see rna_last_error()                   */
@@ -58,8 +58,10 @@ enum { RNA_MODEL_TURNER = 0, RNA_MODEL_CONTRA = 1 };
 #define RNA_BASE_G 2
 #define RNA_BASE_U 3
 #define RNA_PSEUDO_BASE 4        /* src/utils.rs:122 — only ever at Durbin sentinel positions       */
-#define RNA_MAX_SEQ_LEN 65535u   /* u16 HashIndex domain, src/bin/centroid_fold.rs:85-101           */
-/* (mccaskill/centroid entry points of this build: RNA_ERR_TOO_LONG beyond 46340 nt — 32-bit matrix offsets) */
+#define RNA_MAX_SEQ_LEN 65535u   /* u16 HashIndex domain, src/bin/centroid_fold.rs:85-101 (Durbin inputs) */
+#define RNA_MAX_FOLD_LEN 46340   /* mccaskill / centroid inputs: triangular matrices are indexed with 32-bit
+                                    offsets (46340^2 < 2^31); longer sequences get RNA_ERR_TOO_LONG from
+                                    rna_validate_fold_lengths and from every fold entry point, before any copy */
 #define RNA_LOOP_TABLE_LEN 31    /* lengths 0..30                                                   */
 #define RNA_MAX_SPECIAL_HAIRPINS 128
 #define RNA_MAX_SPECIAL_HAIRPIN_LEN 12
@@ -254,7 +256,9 @@ int rna_durbin_algo(rna_handle *h, const uint8_t *seq_a, uint32_t len_a, const u
 
 /* ------------------------------------------------------------------------------------------------
  * Device-resident variants: every pointer is a DEVICE pointer on the handle's GPU, work is enqueued
- * on `stream` (a cudaStream_t passed as void*; NULL = default stream) and NOT synchronised.  Inputs
+ * on `stream` (a cudaStream_t passed as void*; NULL = the handle's own non-blocking stream) and NOT synchronised.
+ * Calls of one handle share its scratch memory: each call is ordered behind the previous call of the same handle
+ * (an event wait on `stream`), whatever streams they use; rna_set_*_tables waits for the calls in flight.  Inputs
  * must have been validated by the caller (or by rna_validate_bases).  Used for HBM-resident timing
  * and for pipelines that keep the BPPs on the GPU.
  * ---------------------------------------------------------------------------------------------- */
@@ -297,6 +301,8 @@ int rna_durbin_batch_dev(rna_handle *h, const RnaDurbinBatchDev *b, void *stream
 
 /* Host-side validation used by all host entry points; exposed for callers of the *_dev variants. */
 int rna_validate_bases(const uint8_t *bases, const uint32_t *offsets, uint32_t n_seqs);
+/* RNA_ERR_TOO_LONG if a sequence exceeds RNA_MAX_FOLD_LEN (checked by the fold / centroid entry points). */
+int rna_validate_fold_lengths(const uint32_t *offsets, uint32_t n_seqs);
 
 /* Length-balanced partition of work units over n_parts GPUs (longest-processing-time-first on the
  * cost model c(L) = L^3 + 500 L^2 for folding, n*m for pairs).  part_of[u] receives

@@ -45,34 +45,26 @@ static __thread uint64_t g_lse_terms;
  * Numerics: src/utils.rs:579-655
  * ------------------------------------------------------------------------------------------- */
 
-/* src/utils.rs:603-627 */
+/* src/utils.rs:603-627.  The reference's comparison tree picks one of eight cubic segments; here the segment index
+ * is counted from the same seven breakpoints (`!(x < b)`, so a NaN lands in the last segment like in the tree) and
+ * the Horner form is evaluated with that segment's coefficients: same operations, same order, no data-dependent
+ * branch (the tree mispredicts on random operands and dominated the run time of long sequences). */
+#ifndef ORC_EXACT
+static const float kLnExp1pBreaks[7] = {0.66153675f, 1.6320158f, 2.4912589f, 3.37925f, 4.426169f, 5.789071f, 7.8162727f};
+static const float kLnExp1pCoef[8][4] = {
+    {-0.0065591595f, 0.12764427f, 0.49965546f, 0.6931542f},   {-0.015515756f, 0.14467756f, 0.48829398f, 0.6958093f},
+    {-0.012890925f, 0.13010283f, 0.51503986f, 0.6795586f},    {-0.0072142647f, 0.087754086f, 0.6208708f, 0.5909676f},
+    {-0.0031455354f, 0.046722945f, 0.7592532f, 0.43487945f},  {-0.0010110698f, 0.018594341f, 0.88317305f, 0.25236955f},
+    {-0.000196278f, 0.0046084408f, 0.9634432f, 0.09831489f},  {-0.0000113994f, 0.0003734731f, 0.9959107f, 0.0149855051f}};
+#endif
 static inline real ln_exp_1p(real x) {
 #ifdef ORC_EXACT
   return log1p(exp(x));
 #else
-  if (x < 3.37925f) {
-    if (x < 1.6320158f) {
-      if (x < 0.66153675f) {
-        return ((-0.0065591595f * x + 0.12764427f) * x + 0.49965546f) * x + 0.6931542f;
-      } else {
-        return ((-0.015515756f * x + 0.14467756f) * x + 0.48829398f) * x + 0.6958093f;
-      }
-    } else if (x < 2.4912589f) {
-      return ((-0.012890925f * x + 0.13010283f) * x + 0.51503986f) * x + 0.6795586f;
-    } else {
-      return ((-0.0072142647f * x + 0.087754086f) * x + 0.6208708f) * x + 0.5909676f;
-    }
-  } else if (x < 5.789071f) {
-    if (x < 4.426169f) {
-      return ((-0.0031455354f * x + 0.046722945f) * x + 0.7592532f) * x + 0.43487945f;
-    } else {
-      return ((-0.0010110698f * x + 0.018594341f) * x + 0.88317305f) * x + 0.25236955f;
-    }
-  } else if (x < 7.8162727f) {
-    return ((-0.000196278f * x + 0.0046084408f) * x + 0.9634432f) * x + 0.09831489f;
-  } else {
-    return ((-0.0000113994f * x + 0.0003734731f) * x + 0.9959107f) * x + 0.0149855051f;
-  }
+  int seg = 0;
+  for (int b = 0; b < 7; b++) seg += !(x < kLnExp1pBreaks[b]);
+  const float *c = kLnExp1pCoef[seg];
+  return ((c[0] * x + c[1]) * x + c[2]) * x + c[3];
 #endif
 }
 
@@ -334,7 +326,112 @@ static real c_twoloop_score(const uint8_t *s, int i, int j, int k, int l, CT *t)
 /* ---------------------------------------------------------------------------------------------
  * Inside / outside state: FoldSums, src/mccaskill_algo.rs:3-11, 213-226
  * ------------------------------------------------------------------------------------------- */
+
+/* ---------------------------------------------------------------------------------------------
+ * Optional parallelism INSIDE one sequence (long sequences: the 2048 / 4096 nt parity checks).  The cells of one span
+ * (anti-diagonal) are independent of one another — each reads only cells of other spans and writes its own — so
+ * span_for() spreads them over a small persistent pthread team.  Every cell's folds run exactly as in the serial
+ * loop (same operands, same order), so all values are bit-identical to the serial run.  Off by default: the
+ * reference is serial per sequence (src/mccaskill_algo.rs:282-723) and so is the CPU baseline;
+ * orc_set_inner_threads(n) turns it on for single-sequence calls of the calling process.
+ * ------------------------------------------------------------------------------------------- */
+typedef void (*span_cell_fn)(void *ctx, int i);
+static int g_inner_threads = 1;
+static struct {
+  pthread_mutex_t mu;
+  pthread_cond_t go, done;
+  pthread_t *th;
+  int n_workers;          /* helper threads (the caller works too) */
+  uint64_t epoch;         /* bumped per parallel span */
+  int running;            /* helpers still inside the current span */
+  span_cell_fn fn;
+  void *ctx;
+  int ncells;
+  volatile int next;      /* next chunk start */
+  uint64_t terms;         /* LSE-terms counted by the helpers in the current span */
+  int quit;
+} g_team = {PTHREAD_MUTEX_INITIALIZER, PTHREAD_COND_INITIALIZER, PTHREAD_COND_INITIALIZER, NULL, 0, 0, 0, NULL, NULL, 0, 0, 0, 0};
+#define SPAN_CHUNK 4
+
+static void span_drain(void) {
+  for (;;) {
+    int b = __atomic_fetch_add(&g_team.next, SPAN_CHUNK, __ATOMIC_RELAXED);
+    if (b >= g_team.ncells) break;
+    int e = b + SPAN_CHUNK < g_team.ncells ? b + SPAN_CHUNK : g_team.ncells;
+    for (int i = b; i < e; i++) g_team.fn(g_team.ctx, i);
+  }
+}
+static void *span_helper(void *arg) {
+  (void)arg;
+  uint64_t seen = 0;
+  pthread_mutex_lock(&g_team.mu);
+  for (;;) {
+    while (g_team.epoch == seen && !g_team.quit) pthread_cond_wait(&g_team.go, &g_team.mu);
+    if (g_team.quit) break;
+    seen = g_team.epoch;
+    pthread_mutex_unlock(&g_team.mu);
+    const uint64_t t0 = g_lse_terms;
+    span_drain();
+    const uint64_t dt = g_lse_terms - t0;
+    pthread_mutex_lock(&g_team.mu);
+    g_team.terms += dt;
+    if (--g_team.running == 0) pthread_cond_signal(&g_team.done);
+  }
+  pthread_mutex_unlock(&g_team.mu);
+  return NULL;
+}
+void orc_set_inner_threads(int n) {
+  if (n < 1) n = 1;
+  pthread_mutex_lock(&g_team.mu);
+  if (g_team.th) {   /* stop the old team */
+    g_team.quit = 1;
+    pthread_cond_broadcast(&g_team.go);
+    pthread_mutex_unlock(&g_team.mu);
+    for (int x = 0; x < g_team.n_workers; x++) pthread_join(g_team.th[x], NULL);
+    pthread_mutex_lock(&g_team.mu);
+    free(g_team.th);
+    g_team.th = NULL; g_team.n_workers = 0; g_team.quit = 0;
+  }
+  g_inner_threads = n;
+  if (n > 1) {
+    g_team.n_workers = n - 1;
+    g_team.th = (pthread_t *)malloc(sizeof(pthread_t) * (size_t)(n - 1));
+    for (int x = 0; x < n - 1; x++) pthread_create(&g_team.th[x], NULL, span_helper, NULL);
+  }
+  pthread_mutex_unlock(&g_team.mu);
+}
+/* fn(ctx, i) for i = 0 .. ncells-1: serial, or over the team (the caller takes part and returns when all are done) */
+static void span_for(int ncells, span_cell_fn fn, void *ctx) {
+  if (g_inner_threads <= 1 || ncells < 4 * SPAN_CHUNK) {
+    for (int i = 0; i < ncells; i++) fn(ctx, i);
+    return;
+  }
+  pthread_mutex_lock(&g_team.mu);
+  g_team.fn = fn; g_team.ctx = ctx; g_team.ncells = ncells; g_team.next = 0; g_team.terms = 0;
+  g_team.running = g_team.n_workers;
+  g_team.epoch++;
+  pthread_cond_broadcast(&g_team.go);
+  pthread_mutex_unlock(&g_team.mu);
+  span_drain();
+  pthread_mutex_lock(&g_team.mu);
+  while (g_team.running > 0) pthread_cond_wait(&g_team.done, &g_team.mu);
+  g_lse_terms += g_team.terms;
+  pthread_mutex_unlock(&g_team.mu);
+}
+
+/* what a cell function sees */
 typedef struct {
+  const uint8_t *s;
+  int L, span, allows_short;
+  const RnaTurnerTables *tt;
+  const RnaContraTables *ct;
+  struct FoldSums_ *f;
+  float gamma_unused;
+  void *bp, *pm, *pm2;     /* real* */
+  double global_sum;       /* holds a `real` exactly */
+} SpanCtx;
+
+typedef struct FoldSums_ {
   int L;
   real *ext;    /* sums_external                          init 0.0 (incl. lower triangle) */
   real *rbe;    /* sums_rightmost_basepairs_external      init -inf */
@@ -344,6 +441,9 @@ typedef struct {
   real *mb;     /* sums_multibranch                       init -inf */
   real *m1;     /* sums_1ormore_basepairs                 init -inf */
   real *mbc;    /* fold_scores.multibranch_close_scores (memo, :333-335) */
+  /* Transposed mirrors (xT[j][i] == x[i][j], written together with x) of the matrices the recurrences walk DOWN A
+   * COLUMN (`[k][j]`, k running): the same values read from contiguous memory.  Layout only — no arithmetic differs. */
+  real *rbeT, *rbmT, *m1T;
 } FoldSums;
 
 static real *alloc_mat(int L, real v) {
@@ -363,21 +463,29 @@ static void fold_sums_new(FoldSums *f, int L) {
   f->mb = alloc_mat(L, NEG_INF);
   f->m1 = alloc_mat(L, NEG_INF);
   f->mbc = alloc_mat(L, (real)0.);
+  f->rbeT = alloc_mat(L, NEG_INF);
+  f->rbmT = alloc_mat(L, NEG_INF);
+  f->m1T = alloc_mat(L, NEG_INF);
 }
 
 static void fold_sums_free(FoldSums *f) {
   free(f->ext); free(f->rbe); free(f->rbm); free(f->close); free(f->acc); free(f->mb); free(f->m1);
-  free(f->mbc);
+  free(f->mbc); free(f->rbeT); free(f->rbmT); free(f->m1T);
 }
 
 #define AT(m, i, j) (m)[(size_t)(i) * (size_t)L + (size_t)(j)]
 
-/* get_fold_sums: src/mccaskill_algo.rs:282-378 */
-static void get_fold_sums(const uint8_t *s, int L, TT *t, FoldSums *f) {
+/* get_fold_sums: src/mccaskill_algo.rs:282-378 (one cell of the span loop; the loops are in get_fold_sums below) */
+static void fold_sums_cell(void *vc, int i) {
+  const SpanCtx *c = (const SpanCtx *)vc;
+  const uint8_t *s = c->s;
+  const int L = c->L, span = c->span;
+  TT *t = c->tt;
+  FoldSums *f = c->f;
   const int MINSPAN = t->min_span_hairpin_close, MAX2 = t->max_2loop_len;
   const real CNB = (real)t->coeff_num_branches;
-  for (int span = MINSPAN; span <= L; span++) {
-    for (int i = 0; i <= L - span; i++) {
+  {
+    {
       int j = i + span - 1;
       real sum = NEG_INF;
       if (j - i + 1 >= MINSPAN && canonical(s[i], s[j])) {
@@ -410,9 +518,10 @@ static void get_fold_sums(const uint8_t *s, int L, TT *t, FoldSums *f) {
         if (x > NEG_INF) lse(&sum, x);
       }
       AT(f->rbe, i, j) = sum;
+      AT(f->rbeT, j, i) = sum;
       sum = (real)0.;
       for (int k = i; k < j; k++) {
-        real x = AT(f->rbe, k, j);
+        real x = AT(f->rbeT, j, k);
         real y = (i == 0 && k == 0) ? (real)0. : AT(f->ext, i, k - 1);
         y = x + y;
         lse(&sum, y);
@@ -421,7 +530,7 @@ static void get_fold_sums(const uint8_t *s, int L, TT *t, FoldSums *f) {
       sum = AT(f->rbe, i, j) + CNB;
       real sum2 = NEG_INF;
       for (int k = i + 1; k < j; k++) {
-        real x = AT(f->rbe, k, j) + CNB;
+        real x = AT(f->rbeT, j, k) + CNB;
         lse(&sum, x);
         real y = AT(f->m1, i, k - 1) + x;
         lse(&sum2, y);
@@ -429,15 +538,30 @@ static void get_fold_sums(const uint8_t *s, int L, TT *t, FoldSums *f) {
       AT(f->mb, i, j) = sum2;
       lse(&sum, sum2);
       AT(f->m1, i, j) = sum;
+      AT(f->m1T, j, i) = sum;
     }
   }
 }
+static void get_fold_sums(const uint8_t *s, int L, TT *t, FoldSums *f) {
+  SpanCtx c;
+  memset(&c, 0, sizeof c);
+  c.s = s; c.L = L; c.tt = t; c.f = f;
+  for (int span = t->min_span_hairpin_close; span <= L; span++) {   /* i ascending within a span, :283-284 */
+    c.span = span;
+    span_for(L - span + 1, fold_sums_cell, &c);
+  }
+}
 
-/* get_fold_sums_contra: src/mccaskill_algo.rs:380-516 */
-static void get_fold_sums_contra(const uint8_t *s, int L, int allows_short, CT *t, FoldSums *f) {
+/* get_fold_sums_contra: src/mccaskill_algo.rs:380-516 (one cell) */
+static void fold_sums_contra_cell(void *vc, int i) {
+  const SpanCtx *c = (const SpanCtx *)vc;
+  const uint8_t *s = c->s;
+  const int L = c->L, span = c->span, allows_short = c->allows_short;
+  CT *t = c->ct;
+  FoldSums *f = c->f;
   const int MINSPAN = t->min_span_hairpin_close, MAXL = t->max_loop_len;
-  for (int span = 1; span <= L; span++) {
-    for (int i = 0; i <= L - span; i++) {
+  {
+    {
       int j = i + span - 1;
       real sum = NEG_INF;
       if (canonical(s[i], s[j]) && (allows_short || j - i + 1 >= MINSPAN)) {
@@ -478,10 +602,12 @@ static void get_fold_sums_contra(const uint8_t *s, int L, int allows_short, CT *
         }
       }
       AT(f->rbe, i, j) = sum;
+      AT(f->rbeT, j, i) = sum;
       AT(f->rbm, i, j) = sum2;
+      AT(f->rbmT, j, i) = sum2;
       sum = (real)t->external_score_unpair * (real)span;
       for (int k = i; k < j; k++) {
-        real x = AT(f->rbe, k, j);
+        real x = AT(f->rbeT, j, k);
         real y = (i == 0 && k == 0) ? (real)0. : AT(f->ext, i, k - 1);
         y = x + y;
         lse(&sum, y);
@@ -490,7 +616,7 @@ static void get_fold_sums_contra(const uint8_t *s, int L, int allows_short, CT *
       sum = AT(f->rbm, i, j);
       sum2 = NEG_INF;
       for (int k = i + 1; k < j; k++) {
-        real x = AT(f->rbm, k, j);
+        real x = AT(f->rbmT, j, k);
         lse(&sum, x + (real)t->multibranch_score_unpair * (real)(k - i));
         real y = AT(f->m1, i, k - 1) + x;
         lse(&sum2, y);
@@ -498,18 +624,33 @@ static void get_fold_sums_contra(const uint8_t *s, int L, int allows_short, CT *
       AT(f->mb, i, j) = sum2;
       lse(&sum, sum2);
       AT(f->m1, i, j) = sum;
+      AT(f->m1T, j, i) = sum;
     }
   }
 }
+static void get_fold_sums_contra(const uint8_t *s, int L, int allows_short, CT *t, FoldSums *f) {
+  SpanCtx c;
+  memset(&c, 0, sizeof c);
+  c.s = s; c.L = L; c.ct = t; c.f = f; c.allows_short = allows_short;
+  for (int span = 1; span <= L; span++) {
+    c.span = span;
+    span_for(L - span + 1, fold_sums_contra_cell, &c);
+  }
+}
 
-/* get_basepair_probs: src/mccaskill_algo.rs:518-610.  Returns log-probs in `bp` (dense, -inf = absent). */
-static void get_basepair_probs(const uint8_t *s, int L, TT *t, const FoldSums *f, real *bp) {
-  const int MINSPAN = t->min_span_hairpin_close, MAX2 = t->max_2loop_len;
+/* get_basepair_probs: src/mccaskill_algo.rs:518-610 (one cell).  Log-probs go to `bp` (dense, -inf = absent). */
+static void basepair_probs_cell(void *vc, int i) {
+  const SpanCtx *c = (const SpanCtx *)vc;
+  const uint8_t *s = c->s;
+  const int L = c->L, span = c->span;
+  TT *t = c->tt;
+  const FoldSums *f = c->f;
+  real *bp = (real *)c->bp, *pm = (real *)c->pm, *pm2 = (real *)c->pm2;
+  const int MAX2 = t->max_2loop_len;
   const real CNB = (real)t->coeff_num_branches;
-  real global_sum = AT(f->ext, 0, L - 1);
-  real *pm = alloc_mat(L, NEG_INF), *pm2 = alloc_mat(L, NEG_INF);
-  for (int span = L; span >= MINSPAN; span--) {
-    for (int i = 0; i <= L - span; i++) {
+  const real global_sum = (real)c->global_sum;
+  {
+    {
       int j = i + span - 1;
       real sum = NEG_INF, sum2 = NEG_INF;
       for (int k = j + 1; k < L; k++) {
@@ -522,8 +663,8 @@ static void get_basepair_probs(const uint8_t *s, int L, TT *t, const FoldSums *f
           lse(&sum2, x);
         }
       }
-      AT(pm, i, j) = sum;
-      AT(pm2, i, j) = sum2;
+      AT(pm, j, i) = sum;     /* probs_multibranch[i][j], stored transposed: read as [k][j], k running */
+      AT(pm2, j, i) = sum2;
       real sum_close = AT(f->close, i, j);
       if (sum_close > NEG_INF) {
         real sum_acc = AT(f->acc, i, j);
@@ -542,9 +683,9 @@ static void get_basepair_probs(const uint8_t *s, int L, TT *t, const FoldSums *f
         }
         sum_acc = sum_acc + CNB;
         for (int k = 0; k < i; k++) {
-          real x = AT(f->m1, k + 1, i - 1);
-          lse(&sm, sum_acc + AT(pm2, k, j) + x);
-          real y = AT(pm, k, j);
+          real x = AT(f->m1T, i - 1, k + 1);
+          lse(&sm, sum_acc + AT(pm2, j, k) + x);
+          real y = AT(pm, j, k);
           lse(&sm, sum_acc + y);
           lse(&sm, sum_acc + x + y);
         }
@@ -552,18 +693,34 @@ static void get_basepair_probs(const uint8_t *s, int L, TT *t, const FoldSums *f
       }
     }
   }
+}
+static void get_basepair_probs(const uint8_t *s, int L, TT *t, const FoldSums *f, real *bp) {
+  const int MINSPAN = t->min_span_hairpin_close;
+  real *pm = alloc_mat(L, NEG_INF), *pm2 = alloc_mat(L, NEG_INF);
+  SpanCtx c;
+  memset(&c, 0, sizeof c);
+  c.s = s; c.L = L; c.tt = t; c.f = (FoldSums *)f; c.bp = bp; c.pm = pm; c.pm2 = pm2;
+  c.global_sum = (double)AT(f->ext, 0, L - 1);
+  for (int span = L; span >= MINSPAN; span--) {
+    c.span = span;
+    span_for(L - span + 1, basepair_probs_cell, &c);
+  }
   free(pm);
   free(pm2);
 }
 
-/* get_basepair_probs_contra: src/mccaskill_algo.rs:612-723 */
-static void get_basepair_probs_contra(const uint8_t *s, int L, int allows_short, CT *t,
-                                      const FoldSums *f, real *bp) {
-  const int MINSPAN = allows_short ? 2 : t->min_span_hairpin_close, MAXL = t->max_loop_len;
-  real global_sum = AT(f->ext, 0, L - 1);
-  real *pm = alloc_mat(L, NEG_INF), *pm2 = alloc_mat(L, NEG_INF);
-  for (int span = L; span >= MINSPAN; span--) {
-    for (int i = 0; i <= L - span; i++) {
+/* get_basepair_probs_contra: src/mccaskill_algo.rs:612-723 (one cell) */
+static void basepair_probs_contra_cell(void *vc, int i) {
+  const SpanCtx *c = (const SpanCtx *)vc;
+  const uint8_t *s = c->s;
+  const int L = c->L, span = c->span;
+  CT *t = c->ct;
+  const FoldSums *f = c->f;
+  real *bp = (real *)c->bp, *pm = (real *)c->pm, *pm2 = (real *)c->pm2;
+  const int MAXL = t->max_loop_len;
+  const real global_sum = (real)c->global_sum;
+  {
+    {
       int j = i + span - 1;
       real sum = NEG_INF, sum2 = NEG_INF;
       for (int k = j + 1; k < L; k++) {
@@ -576,8 +733,8 @@ static void get_basepair_probs_contra(const uint8_t *s, int L, int allows_short,
           lse(&sum2, x + (real)t->multibranch_score_unpair * (real)(k - j - 1));
         }
       }
-      AT(pm, i, j) = sum;
-      AT(pm2, i, j) = sum2;
+      AT(pm, j, i) = sum;     /* probs_multibranch[i][j], stored transposed: read as [k][j], k running */
+      AT(pm2, j, i) = sum2;
       real sum_close = AT(f->close, i, j);
       if (sum_close > NEG_INF) {
         real sp0 = i < 1 ? (real)0. : AT(f->ext, 0, i - 1);
@@ -595,15 +752,28 @@ static void get_basepair_probs_contra(const uint8_t *s, int L, int allows_short,
         }
         real sum_acc = AT(f->acc, i, j) + (real)t->multibranch_score_basepair;
         for (int k = 0; k < i; k++) {
-          real x = AT(f->m1, k + 1, i - 1);
-          lse(&sm, sum_acc + AT(pm2, k, j) + x);
-          real y = AT(pm, k, j);
+          real x = AT(f->m1T, i - 1, k + 1);
+          lse(&sm, sum_acc + AT(pm2, j, k) + x);
+          real y = AT(pm, j, k);
           lse(&sm, sum_acc + y + (real)t->multibranch_score_unpair * (real)(i - k - 1));
           lse(&sm, sum_acc + x + y);
         }
         if (sm > NEG_INF) AT(bp, i, j) = sm;
       }
     }
+  }
+}
+static void get_basepair_probs_contra(const uint8_t *s, int L, int allows_short, CT *t,
+                                      const FoldSums *f, real *bp) {
+  const int MINSPAN = allows_short ? 2 : t->min_span_hairpin_close;
+  real *pm = alloc_mat(L, NEG_INF), *pm2 = alloc_mat(L, NEG_INF);
+  SpanCtx c;
+  memset(&c, 0, sizeof c);
+  c.s = s; c.L = L; c.ct = t; c.f = (FoldSums *)f; c.bp = bp; c.pm = pm; c.pm2 = pm2; c.allows_short = allows_short;
+  c.global_sum = (double)AT(f->ext, 0, L - 1);
+  for (int span = L; span >= MINSPAN; span--) {
+    c.span = span;
+    span_for(L - span + 1, basepair_probs_contra_cell, &c);
   }
   free(pm);
   free(pm2);
@@ -649,20 +819,20 @@ int orc_mccaskill_algo(const uint8_t *seq, int L, int uses_contra_model, int all
   return RNA_OK;
 }
 
-/* ---------------------------------------------------------------------------------------------
- * centroid_fold: src/centroid_fold.rs:25-105.  `bpp` is the packed matrix (absent = RNA_BPP_ABSENT).
- * ------------------------------------------------------------------------------------------- */
-int orc_centroid_fold(const float *bpp, int L, float centroid_threshold, uint8_t *out_fold_str,
-                      uint16_t *out_pairs, uint32_t *out_num_pairs, float *out_expect_accuracy) {
-  if (L < 1) return RNA_ERR_EMPTY_SEQ;
-  real g = (real)centroid_threshold;
-  real *W = alloc_mat(L, (real)0.);
+/* the max-plus fill of centroid_fold, src/centroid_fold.rs:33-64 (one cell) */
+typedef struct { const float *bpp; int L, span; real g; real *W, *WT; } CentroidCtx;
 #define HAS(i, j) (bpp[rna_bpp_index((uint64_t)L, (uint64_t)(i), (uint64_t)(j))] != RNA_BPP_ABSENT)
 #define PR(i, j) ((real)bpp[rna_bpp_index((uint64_t)L, (uint64_t)(i), (uint64_t)(j))])
-  for (int span = 1; span <= L; span++) {
-    for (int i = 0; i <= L - span; i++) {
+static void centroid_cell(void *vc, int i) {
+  const CentroidCtx *c = (const CentroidCtx *)vc;
+  const float *bpp = c->bpp;
+  const int L = c->L, span = c->span;
+  const real g = c->g;
+  real *W = c->W, *WT = c->WT;   /* WT[j][i] == W[i][j]: the split loop reads W[k+1][j] down a column */
+  {
+    {
       int j = i + span - 1;
-      if (i == j) continue;
+      if (i == j) return;
       real w = AT(W, i + 1, j);
       real e = AT(W, i, j - 1);
       if (e > w) w = e;
@@ -671,10 +841,32 @@ int orc_centroid_fold(const float *bpp, int L, float centroid_threshold, uint8_t
         if (e > w) w = e;
       }
       for (int k = i + 1; k < j; k++) {
-        e = AT(W, i, k) + AT(W, k + 1, j);
+        e = AT(W, i, k) + AT(WT, j, k + 1);
         if (e > w) w = e;
       }
       AT(W, i, j) = w;
+      AT(WT, j, i) = w;
+    }
+  }
+}
+#undef HAS
+#undef PR
+
+/* ---------------------------------------------------------------------------------------------
+ * centroid_fold: src/centroid_fold.rs:25-105.  `bpp` is the packed matrix (absent = RNA_BPP_ABSENT).
+ * ------------------------------------------------------------------------------------------- */
+int orc_centroid_fold(const float *bpp, int L, float centroid_threshold, uint8_t *out_fold_str,
+                      uint16_t *out_pairs, uint32_t *out_num_pairs, float *out_expect_accuracy) {
+  if (L < 1) return RNA_ERR_EMPTY_SEQ;
+  real g = (real)centroid_threshold;
+  real *W = alloc_mat(L, (real)0.), *WT = alloc_mat(L, (real)0.);
+#define HAS(i, j) (bpp[rna_bpp_index((uint64_t)L, (uint64_t)(i), (uint64_t)(j))] != RNA_BPP_ABSENT)
+#define PR(i, j) ((real)bpp[rna_bpp_index((uint64_t)L, (uint64_t)(i), (uint64_t)(j))])
+  {
+    CentroidCtx cc = {bpp, L, 0, g, W, WT};
+    for (int span = 1; span <= L; span++) {
+      cc.span = span;
+      span_for(L - span + 1, centroid_cell, &cc);
     }
   }
   uint32_t np = 0;
@@ -711,6 +903,7 @@ int orc_centroid_fold(const float *bpp, int L, float centroid_threshold, uint8_t
   if (out_expect_accuracy) *out_expect_accuracy = (float)AT(W, 0, L - 1);
   free(stack);
   free(W);
+  free(WT);
 #undef HAS
 #undef PR
   return RNA_OK;
@@ -918,6 +1111,7 @@ int orc_mccaskill_centroid_batch(const uint8_t *bases, const uint32_t *offsets, 
   jb.total_len = offsets[n_seqs];
   pthread_mutex_init(&jb.mu, NULL);
   if (n_threads < 1) n_threads = 1;
+  if (g_inner_threads > 1) n_threads = 1;   /* the span team is one per process: sequences one after the other */
   pthread_t *th = (pthread_t *)malloc(sizeof(pthread_t) * (size_t)n_threads);
   for (int x = 0; x < n_threads; x++) pthread_create(&th[x], NULL, fold_worker, &jb);
   for (int x = 0; x < n_threads; x++) pthread_join(th[x], NULL);

@@ -10,7 +10,8 @@ import os
 from .tables import AlignTables, ContraTables, TurnerTables
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "librna_algos_b200.so")
+# RNA_B200_LIB: development override (A/B builds of the same library); the product is the in-tree library
+LIB_PATH = os.environ.get("RNA_B200_LIB") or os.path.join(_HERE, "librna_algos_b200.so")
 
 u8p = C.POINTER(C.c_uint8)
 u16p = C.POINTER(C.c_uint16)

@@ -254,24 +254,64 @@ class Handle:
 
 
 _default: Optional[Handle] = None
+_by_tables: Dict[bytes, Handle] = {}
 
 
 def default_handle() -> Handle:
+    """The handle behind the module-level functions.  Score tables: the genuine rna-ss-params blobs
+    (`turner2004.tbl`, `contrafold_v202.tbl`, written by tools/ref_dump) from the directory named by
+    $RNA_ALGOS_B200_TABLES.  The in-repo STAND-IN tables are not the reference's numbers: they are used only when
+    $RNA_ALGOS_B200_ALLOW_STANDIN=1 opts in, with a warning; otherwise this raises RNA_ERR_NO_TABLES."""
     global _default
     if _default is None:
+        import os
+        import warnings
         lib = _lib.load()
-        _default = Handle(0, T.turner_tables(), T.contra_tables(lib), T.contralign_tables())
+        d = os.environ.get("RNA_ALGOS_B200_TABLES")
+        if d:
+            tt, ct = T.load_genuine_tables(d)
+        elif os.environ.get("RNA_ALGOS_B200_ALLOW_STANDIN") == "1":
+            warnings.warn("rna_algos_b200: using the STAND-IN Turner / CONTRAfold tables; results differ from the "
+                          "reference's (set RNA_ALGOS_B200_TABLES to a directory with the genuine blobs)", stacklevel=2)
+            tt, ct = T.standin_turner_tables(), T.standin_contra_tables(lib)
+        else:
+            raise RnaError(5, "no score tables: set RNA_ALGOS_B200_TABLES to a directory holding turner2004.tbl and "
+                              "contrafold_v202.tbl (tools/ref_dump writes them from rna-ss-params), pass a Handle, or "
+                              "opt in to the stand-in tables with RNA_ALGOS_B200_ALLOW_STANDIN=1")
+        _default = Handle(0, tt, ct, T.contralign_tables())
     return _default
+
+
+def _handle_for(handle: Optional[Handle], contra: Optional[T.ContraTables] = None,
+                align: Optional[T.AlignTables] = None) -> Handle:
+    """The reference takes `&FoldScoreSets` / `&AlignScores` PER CALL (src/mccaskill_algo.rs:247-255,
+    src/durbin_algo.rs:73).  A call that passes its own tables gets a handle of its own, cached by the blob's bytes,
+    so the tables of the shared default handle are never changed behind other callers' backs."""
+    if handle is not None:
+        if contra is not None or align is not None:
+            handle.set_tables(contra=contra, align=align)
+        return handle
+    if contra is None and align is None:
+        return default_handle()
+    key = (bytes(contra) if contra is not None else b"") + b"|" + (bytes(align) if align is not None else b"")
+    h = _by_tables.get(key)
+    if h is None:
+        if len(_by_tables) >= 8:   # bounded: drop the oldest
+            _by_tables.pop(next(iter(_by_tables))).close()
+        h = Handle(0, None, contra, align if align is not None else T.contralign_tables())
+        _by_tables[key] = h
+    return h
 
 
 def mccaskill_algo(seq, uses_contra_model: bool, allows_short_hairpins: bool = False,
                    fold_score_sets: Optional[T.ContraTables] = None, handle: Optional[Handle] = None):
     """mccaskill_algo(seq, uses_contra_model, allows_short_hairpins, &fold_score_sets) ->
-    SparseProbMat (as a dict; FoldScores<T>, the second tuple element, is not produced: no in-tree
-    caller reads it — src/bin/centroid_fold.rs:129, tests/tests.rs:31)."""
-    h = handle or default_handle()
-    if fold_score_sets is not None:
-        h.set_tables(contra=fold_score_sets)
+    SparseProbMat (as a dict).  `fold_score_sets` is read only by the CONTRAfold model, as in the reference; the Turner
+    model reads the handle's Turner blob (rna-ss-params consts in the reference)."""
+    if uses_contra_model and fold_score_sets is not None:
+        h = _handle_for(handle, contra=fold_score_sets)
+    else:
+        h = handle or default_handle()
     bpp, _ = h.mccaskill_algo(seq, uses_contra_model, allows_short_hairpins)
     return sparse_prob_mat(bpp, len(seq))
 
@@ -303,9 +343,7 @@ def durbin_algo(seq_pair, align_scores: Optional[T.AlignTables] = None, handle: 
     """durbin_algo(&(seq_a, seq_b), &align_scores) -> ProbMat.  The reference's callers pad both
     sequences with PSEUDO_BASE first (src/bin/durbin_algo.rs:48-50); pass them either way — sentinels
     are stripped and re-added by the library, and the result is the same sentinel-indexed matrix."""
-    h = handle or default_handle()
-    if align_scores is not None:
-        h.set_tables(align=align_scores)
+    h = _handle_for(handle, align=align_scores)
     a, b = (np.asarray(s, dtype=np.uint8) for s in seq_pair)
     if len(a) >= 2 and a[0] == PSEUDO_BASE and a[-1] == PSEUDO_BASE:
         a = a[1:-1]

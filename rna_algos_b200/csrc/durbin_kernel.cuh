@@ -171,8 +171,10 @@ __global__ void __launch_bounds__(256, 6) durbin_kernel(const DurbinArgs a) {
       __syncthreads();
     }
     // the output, row-major n x m with a zero border (rows 0, n-1; columns 0, m-1), in one coalesced sweep
-    for (int x = tid; x < n * m; x += nt) {
-      const int i = x / m, j = x - i * m;
+    // (64-bit cell count: n * m exceeds 2^31 when both sequences are longer than 46340 nt)
+    const size_t nm = (size_t)n * (size_t)m;
+    for (size_t x = tid; x < nm; x += nt) {
+      const int i = (int)(x / (unsigned)m), j = (int)(x - (size_t)i * m);
       out[x] = (i == 0 || i == n - 1 || j == 0 || j == m - 1) ? 0.f : park[x];
     }
   }

@@ -1,22 +1,14 @@
-// fold_kernel.cuh — McCaskill inside/outside + BPP + centroid estimator as an anti-diagonal wavefront.
+// fold_kernel.cuh — what the fold kernels share: launch arguments, storage modes, the grid-wide barrier of the
+// cooperative kernel, and centroid_fold (src/centroid_fold.rs:25-105: max-plus fill + traceback) both fused behind
+// the McCaskill passes (fold_kernel2.cuh) and as kernels of its own over packed BPP matrices (rna_centroid_batch).
 //
-// One thread per DP cell of the current diagonal ("span"); every cell's fold over split points /
-// interior loops is evaluated sequentially IN THE REFERENCE'S ORDER with the reference's polynomial
-// logsumexp, so all values are bit-identical to the reference algorithm.
-// All matrices are stored DIAGONAL-MAJOR (index(i,j) = off(j-i) + i): the cells of one diagonal are
-// contiguous, so for every operand of every recurrence the 32 lanes of a warp (cells i..i+31 of the same
-// diagonal) touch 32 consecutive words — conflict-free in shared memory, fully coalesced in HBM/L2.
-// Loop-type branches (stack / bulge / 1x1 / ... / generic interior) depend only on the offsets
-// (a,b) = (k-i-1, j-l-1), which are identical for all lanes: the scoring code is warp-uniform.
-//
-// Three storage/synchronisation modes share this one body:
-//   MODE_SMEM   one CTA per sequence, matrices resident in shared memory      (tRNA .. ~145 nt)
-//   MODE_GLOBAL one CTA per sequence, matrices in an HBM/L2 workspace slot    (Rfam-length batches)
-//   MODE_COOP   the whole grid works on one sequence, grid-wide barrier per diagonal (1k-4k nt)
-//
-// Reference recurrences: src/mccaskill_algo.rs:282-378 (Turner inside), :380-516 (CONTRAfold inside),
-// :518-610 / :612-723 (outside + BPP), src/centroid_fold.rs:25-105 (centroid + traceback),
-// scorers src/utils.rs:166-556.
+// Matrices are DIAGONAL-MAJOR (index(i,j) = off(j-i) + i): the cells of one diagonal are contiguous, so the 32 lanes
+// of a warp (cells i..i+31 of one diagonal) touch 32 consecutive words for every operand of every recurrence.
+//   MODE_SMEM   one CTA per sequence, working set in shared memory
+//   MODE_GLOBAL one CTA per sequence, working set in an HBM/L2 workspace slot
+//   MODE_COOP   the whole grid works on one sequence, grid-wide barrier per diagonal
+// (The first kernel of round 1, a thread-per-cell wavefront over these modes, is gone from the product: see git
+// history, commit ed704ea.)
 #pragma once
 #include <cooperative_groups.h>
 
@@ -77,28 +69,6 @@ struct Ctx {
     return (ofs_t)d * (ofs_t)L - (((ofs_t)d * (ofs_t)(d - 1)) >> 1);
   }
 };
-
-// Shared-memory footprint (bytes) of the fixed part and of the SMEM-mode matrices for capacity Lcap.
-template <bool CONTRA>
-__host__ __device__ inline size_t fold_smem_fixed_bytes(int Lcap) {
-  size_t b = 128;                                            // LSE coefficient LUT
-  b += (sizeof(typename ModelTraits<CONTRA>::Small) + 15) / 16 * 16;
-  b += ((size_t)Lcap + 8 + 15) / 16 * 16;                    // sequence bytes (+ guard)
-  return b;
-}
-template <bool CONTRA>
-__host__ __device__ inline size_t fold_ws_floats(int L) {
-  const size_t T = (size_t)L * ((size_t)L + 1) / 2;
-  const size_t nm = CONTRA ? 6 : 5;
-  // matrices | Mroll 3L | E0 L | EL L | traceback stack 2(L+2) ints
-  return nm * T + 3 * (size_t)L + 2 * (size_t)L + 2 * ((size_t)L + 2) + 8;
-}
-template <bool CONTRA>
-__host__ __device__ inline size_t fold_smem_bytes(int Lcap, bool smem_mats) {
-  size_t b = fold_smem_fixed_bytes<CONTRA>(Lcap);
-  if (smem_mats) b += fold_ws_floats<CONTRA>(Lcap) * 4;
-  return b;
-}
 
 // ---------------------------------------------------------------------------------------------------
 // centroid_fold: src/centroid_fold.rs:25-105.  W (max_expect_accuracies) is diagonal-major in `W`;
@@ -219,297 +189,6 @@ __device__ __forceinline__ void centroid_run(const FoldArgs& a, uint32_t sidx, u
     // traceback by the first warp of the (first) CTA
     if ((MODE != MODE_COOP || blockIdx.x == 0) && tid < 32) centroid_traceback<MODE>(a, sidx, sbeg, L, W, tstack, getp, g);
     X::sync();
-  }
-}
-
-// ---------------------------------------------------------------------------------------------------
-// The kernel
-// ---------------------------------------------------------------------------------------------------
-template <bool CONTRA, int MODE>
-__global__ void __launch_bounds__(MODE == MODE_SMEM ? 256 : 512) fold_kernel(const FoldArgs a) {
-  typedef Ctx<MODE> X;
-  typedef typename X::ofs_t ofs_t;
-  typedef typename ModelTraits<CONTRA>::Dev Dev;
-  typedef typename ModelTraits<CONTRA>::Small Small;
-  typedef typename ModelTraits<CONTRA>::View View;
-
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  float4* lut = reinterpret_cast<float4*>(smem_raw);
-  Small* small = reinterpret_cast<Small*>(smem_raw + 128);
-  uint8_t* sseq = smem_raw + 128 + (sizeof(Small) + 15) / 16 * 16;
-  float* smats = reinterpret_cast<float*>(smem_raw + fold_smem_fixed_bytes<CONTRA>(a.Lcap));
-  __shared__ int s_work;
-
-  const Dev* dev = reinterpret_cast<const Dev*>(a.tables);
-  const int tid = threadIdx.x;
-  load_lse_lut(lut);
-  for (int x = tid; x < (int)(sizeof(Small) / 4); x += blockDim.x)
-    reinterpret_cast<float*>(small)[x] = reinterpret_cast<const float*>(&dev->small)[x];
-  View T;
-  T.g = dev;
-  T.sm = small;
-  __syncthreads();
-
-  const float NEG = RNA_NEG_INF;
-  const int MINSPAN = dev->min_span;
-  int MAX2;
-  if constexpr (CONTRA) MAX2 = dev->max_loop_len; else MAX2 = dev->max_2loop_len;
-
-  for (uint32_t wloop = 0;; wloop++) {
-    uint32_t w;
-    if (MODE == MODE_COOP) {
-      w = wloop;
-    } else {
-      __syncthreads();
-      if (tid == 0) s_work = atomicAdd(a.work_counter, 1);
-      __syncthreads();
-      w = (uint32_t)s_work;
-    }
-    if (w >= a.n_launch) break;
-    const uint32_t sidx = a.order ? a.order[w] : w;
-    const uint32_t sbeg = a.offsets[sidx];
-    const int L = (int)(a.offsets[sidx + 1] - sbeg);
-    const ofs_t TRI = (ofs_t)L * (ofs_t)(L + 1) / 2;
-
-    float* base;
-    if (MODE == MODE_SMEM) base = smats;
-    else if (MODE == MODE_GLOBAL) base = a.workspace + (size_t)blockIdx.x * a.ws_stride;
-    else base = a.workspace;
-    float* mC = base;
-    float* mR = mC + TRI;       // R -> PM -> W (centroid)
-    float* mE = mR + TRI;       // E -> P (log) -> prob
-    float* mM1 = mE + TRI;
-    float* mX = mM1 + TRI;      // Turner: PM2 (outside only); CONTRAfold: Rm -> PM2
-    float* mA = mX + TRI;       // CONTRAfold only: A
-    float* Mroll = CONTRA ? mA + TRI : mX + TRI;   // sums_multibranch: only diagonals d, d-1, d-2 are live
-    float* E0 = Mroll + 3 * (size_t)L;             // sums_external[0][x]
-    float* EL = E0 + L;                            // sums_external[x][L-1]
-    int* tstack = reinterpret_cast<int*>(EL + L);
-
-    uint8_t* s = sseq + 4;
-    for (int x = tid; x < L; x += blockDim.x) s[x] = a.bases[sbeg + x];
-    if (tid < 4) { sseq[tid] = 0; s[L + tid] = 0; }
-
-    const int c0 = X::first(), cs = X::stride();
-    // ---- init (FoldSums::new, src/mccaskill_algo.rs:213-226) ---------------------------------------
-    for (ofs_t x = c0; x < TRI; x += cs) {
-      mC[x] = NEG; mR[x] = NEG; mE[x] = 0.f; mM1[x] = NEG; mX[x] = NEG;
-      if (CONTRA) mA[x] = NEG;
-    }
-    for (int x = c0; x < 3 * L; x += cs) Mroll[x] = NEG;
-    X::sync();
-
-    // ================================ inside =======================================================
-    const int d_in0 = CONTRA ? 0 : (MINSPAN - 1);
-    for (int d = d_in0; d < L; d++) {
-      const int ncell = L - d;
-      const ofs_t od = X::off(d, L);
-      float* Mcur = Mroll + (size_t)(d % 3) * L;
-      const float* Mm2 = Mroll + (size_t)((d + 1) % 3) * L;   // diagonal d-2
-      for (int i = c0; i < ncell; i += cs) {
-        const int j = i + d;
-        const int si = s[i], sj = s[j];
-        bool pairable = canonical_pair(si, sj);
-        if (CONTRA) pairable = pairable && (a.allows_short || d + 1 >= MINSPAN);
-        float sumC = NEG;
-        // (1) sums_close
-        if (__any_sync(__activemask(), pairable)) {
-          if (pairable) {
-            if constexpr (CONTRA) {
-              if (d - 1 <= MAX2) sumC = lse(sumC, c_hairpin(T, s, i, j), lut);
-            } else {
-              sumC = lse(sumC, t_hairpin(T, s, i, j), lut);
-            }
-          }
-          const int amax = min(MAX2, d - 3);
-          for (int aa = 0; aa <= amax; aa++) {
-            const int k = i + 1 + aa;
-            const int bmax = min(MAX2 - aa, d - 3 - aa);
-            for (int bb = 0; bb <= bmax; bb++) {
-              const int l = j - 1 - bb;
-              const float c = X::ld(&mC[X::off(d - 2 - aa - bb, L) + k]);
-              const bool on = pairable && (c > NEG);
-              if (__any_sync(__activemask(), on)) {
-                const float y = __fadd_rn(c, m_twoloop<CONTRA>(T, s, i, j, k, l, aa, bb));
-                sumC = lse_if(on, sumC, y, lut);
-              }
-            }
-          }
-          if (pairable) {
-            const float mbc = m_mbclose<CONTRA>(T, s, L, i, j);
-            const float mb = (d >= 2) ? X::ld(&Mm2[i + 1]) : NEG;
-            sumC = lse(sumC, __fadd_rn(mb, mbc), lut);
-          }
-        }
-        float accv = NEG;
-        if (sumC > NEG) {
-          mC[od + i] = sumC;
-          accv = __fadd_rn(sumC, m_acc<CONTRA>(T, s, L, i, j));
-          if (CONTRA) mA[od + i] = accv;
-        }
-        // (2) sums_rightmost_basepairs_external (/ _multibranch)
-        float Rij, Rmij = NEG;
-        if constexpr (!CONTRA) {
-          // prefix property of the left-to-right fold: R[i][j] = R[i][j-1] (+) A(i,j)
-          const float prev = (d >= 1) ? X::ld(&mR[X::off(d - 1, L) + i]) : NEG;
-          Rij = lse(prev, accv, lut);
-        } else {
-          Rij = NEG;
-          for (int m = 1; m <= d; m++) {
-            const float av = (m == d) ? accv : X::ld(&mA[X::off(m, L) + i]);
-            const float n = (float)(d - m);
-            Rij = lse(Rij, __fadd_rn(__fadd_rn(av, dev->ext_bp), __fmul_rn(dev->ext_unpair, n)), lut);
-            Rmij = lse(Rmij, __fadd_rn(__fadd_rn(av, dev->mb_bp), __fmul_rn(dev->mb_unpair, n)), lut);
-          }
-          mX[od + i] = Rmij;
-        }
-        mR[od + i] = Rij;
-        // (3) sums_external, (4) sums_multibranch / sums_1ormore_basepairs — three independent chains
-        float sE, sM1, sM = NEG;
-        if constexpr (CONTRA) {
-          sE = __fmul_rn(dev->ext_unpair, (float)(d + 1));
-          sM1 = Rmij;
-        } else {
-          sE = 0.f;
-          sM1 = __fadd_rn(Rij, dev->coeff_num_branches);
-        }
-        sE = lse(sE, __fadd_rn(Rij, 0.f), lut);   // k = i: E[i][i-1] = 0 (lower triangle / literal 0)
-        for (int m = 1; m < d; m++) {
-          const float r = X::ld(&mR[X::off(d - m, L) + i + m]);
-          const float e = X::ld(&mE[X::off(m - 1, L) + i]);
-          const float m1 = X::ld(&mM1[X::off(m - 1, L) + i]);
-          sE = lse(sE, __fadd_rn(r, e), lut);
-          if constexpr (CONTRA) {
-            const float rm = X::ld(&mX[X::off(d - m, L) + i + m]);
-            sM1 = lse(sM1, __fadd_rn(rm, __fmul_rn(dev->mb_unpair, (float)m)), lut);
-            sM = lse(sM, __fadd_rn(m1, rm), lut);
-          } else {
-            const float xx = __fadd_rn(r, dev->coeff_num_branches);
-            sM1 = lse(sM1, xx, lut);
-            sM = lse(sM, __fadd_rn(m1, xx), lut);
-          }
-        }
-        mE[od + i] = sE;
-        Mcur[i] = sM;
-        sM1 = lse(sM1, sM, lut);
-        mM1[od + i] = sM1;
-      }
-      X::sync();
-    }
-
-    // ================================ outside ======================================================
-    // keep sums_external[0][*] and [*][L-1], then recycle: E -> P, R -> PM, X -> PM2
-    for (int x = c0; x < L; x += cs) {
-      E0[x] = X::ld(&mE[X::off(x, L)]);
-      EL[x] = X::ld(&mE[X::off(L - 1 - x, L) + x]);
-    }
-    X::sync();
-    const float Z = X::ld(&E0[L - 1]);
-    for (ofs_t x = c0; x < TRI; x += cs) { mE[x] = NEG; mR[x] = NEG; mX[x] = NEG; }
-    if (c0 == 0 && a.out_logz) a.out_logz[sidx] = Z;
-    X::sync();
-
-    const int d_out0 = CONTRA ? (a.allows_short ? 1 : MINSPAN - 1) : (MINSPAN - 1);
-    for (int d = L - 1; d >= d_out0; d--) {
-      const int ncell = L - d;
-      const ofs_t od = X::off(d, L);
-      for (int i = c0; i < ncell; i += cs) {
-        const int j = i + d;
-        // (1) probs_multibranch / probs_multibranch2  (src/mccaskill_algo.rs:540-557, 641-661)
-        float pm = NEG, pm2 = NEG;
-        const int mmax = L - 1 - d;   // largest k - j over the diagonal (lane i = 0)
-        for (int m = 1; m <= mmax; m++) {
-          const int k = j + m;
-          const bool inr = k < L;
-          const ofs_t q = X::off(d + m, L) + i;
-          const float c = inr ? X::ld(&mC[q]) : NEG;
-          const bool on = c > NEG;
-          if (__any_sync(__activemask(), on)) {
-            const int kk = inr ? k : j;
-            const float p = inr ? X::ld(&mE[q]) : NEG;
-            const float x = __fsub_rn(__fadd_rn(p, m_mbclose<CONTRA>(T, s, L, i, kk)), c);
-            const float m1 = (m >= 2 && inr) ? X::ld(&mM1[X::off(m - 2, L) + j + 1]) : NEG;
-            pm = lse_if(on, pm, __fadd_rn(x, m1), lut);
-            if constexpr (CONTRA) pm2 = lse_if(on, pm2, __fadd_rn(x, __fmul_rn(dev->mb_unpair, (float)(m - 1))), lut);
-            else pm2 = lse_if(on, pm2, x, lut);
-          }
-        }
-        mR[od + i] = pm;
-        mX[od + i] = pm2;
-        // (2) the pair (i,j) itself
-        const float Cij = X::ld(&mC[od + i]);
-        const bool has = Cij > NEG;
-        if (__any_sync(__activemask(), has)) {
-          const float Aij = has ? __fadd_rn(Cij, m_acc<CONTRA>(T, s, L, i, j)) : NEG;
-          const float El = (i < 1) ? 0.f : X::ld(&E0[i - 1]);
-          const float Er = (j > L - 2) ? 0.f : X::ld(&EL[j + 1]);
-          float sm;
-          if constexpr (CONTRA) {
-            sm = __fsub_rn(__fadd_rn(__fadd_rn(__fadd_rn(El, Er), Aij), dev->ext_bp), Z);
-          } else {
-            sm = __fsub_rn(__fadd_rn(__fadd_rn(El, Aij), Er), Z);
-          }
-          if (!has) sm = NEG;
-          // enclosing two-loops: k descending from i-1, l ascending from j+1
-          const int cap = min(MAX2, L - d - 3);
-          for (int aa = 0; aa <= cap; aa++) {
-            const int k = i - 1 - aa;
-            for (int bb = 0; aa + bb <= cap; bb++) {
-              const int l = j + 1 + bb;
-              const bool inr = (k >= 0) && (l < L);
-              const ofs_t q = X::off(d + 2 + aa + bb, L) + k;
-              const float c = inr ? X::ld(&mC[q]) : NEG;
-              const bool on = has && (c > NEG);
-              if (__any_sync(__activemask(), on)) {
-                const int kk = inr ? k : i, ll = inr ? l : j;
-                const float p = inr ? X::ld(&mE[q]) : NEG;
-                const float tl = on ? m_twoloop<CONTRA>(T, s, kk, ll, i, j, aa, bb) : 0.f;
-                const float y = __fadd_rn(__fsub_rn(__fadd_rn(p, Cij), c), tl);
-                sm = lse_if(on, sm, y, lut);
-              }
-            }
-          }
-          // enclosing multiloops: k ascending 0..i-1  <=>  m = i-1-k descending
-          float sa;
-          if constexpr (CONTRA) sa = __fadd_rn(Aij, dev->mb_bp); else sa = __fadd_rn(Aij, dev->coeff_num_branches);
-          for (int m = ncell - 2; m >= 0; m--) {
-            const bool on = has && (m <= i - 1);
-            const int k = on ? (i - 1 - m) : 0;
-            const ofs_t q = X::off(d + 1 + m, L) + k;
-            const float x = (on && m >= 1) ? X::ld(&mM1[X::off(m - 1, L) + k + 1]) : NEG;
-            const float p2 = on ? X::ld(&mX[q]) : NEG;
-            const float y = on ? X::ld(&mR[q]) : NEG;
-            sm = lse_if(on, sm, __fadd_rn(__fadd_rn(sa, p2), x), lut);
-            if constexpr (CONTRA) sm = lse_if(on, sm, __fadd_rn(__fadd_rn(sa, y), __fmul_rn(dev->mb_unpair, (float)m)), lut);
-            else sm = lse_if(on, sm, __fadd_rn(sa, y), lut);
-            sm = lse_if(on, sm, __fadd_rn(__fadd_rn(sa, x), y), lut);
-          }
-          if (has && sm > NEG) mE[od + i] = sm;
-        }
-      }
-      X::sync();
-    }
-
-    // ================================ BPP = expf(P) ================================================
-    for (ofs_t x = c0; x < TRI; x += cs) {
-      const float v = X::ld(&mE[x]);
-      mE[x] = (v > NEG) ? approx_expf(v) : -1.0f;
-    }
-    X::sync();
-    if (a.out_bpp) {
-      float* ob = a.out_bpp + a.bpp_offsets[sidx];
-      for (int i = 0; i < L - 1; i++) {
-        const size_t rowoff = (size_t)i * (size_t)(2 * L - i - 1) / 2;
-        for (int x = c0; x < L - 1 - i; x += cs) ob[rowoff + x] = X::ld(&mE[X::off(x + 1, L) + i]);
-      }
-    }
-
-    // ================================ centroid (src/centroid_fold.rs:25-105) =======================
-    {
-      const float* P = mE;
-      auto getp = [=](int d, int i) -> float { return X::ld(&P[X::off(d, L) + i]); };
-      centroid_run<MODE>(a, sidx, sbeg, L, mR, tstack, getp);
-    }
   }
 }
 

@@ -7,6 +7,18 @@
 #include "fold_kernel.cuh"
 #include "fold_phases.cuh"
 
+// prefetch depths of the shared-memory mode's chains whose operands live in the CTA's L2 slot (split points / terms
+// in flight ahead of the fold)
+#ifndef RNA_Z_PF
+#define RNA_Z_PF 2
+#endif
+#ifndef RNA_ML_PF
+#define RNA_ML_PF 2
+#endif
+#ifndef RNA_Y_CH
+#define RNA_Y_CH 1
+#endif
+
 namespace rna {
 
 template <int MODE> struct PIdxOf { typedef uint16_t type; };
@@ -227,11 +239,11 @@ __global__ void __launch_bounds__(REGS48 ? 256 : 512, REGS48 ? 5 : 2) fold_kerne
         inside_X<CONTRA>(v, T, lut, P, st, tid, nXl);
       } else if (!helper) {
         const bool isY = warp < a.nXw + a.nYw;
-        if (isY) { if constexpr (CONTRA) { if (t - 1 >= d_in0 && t - 1 < L) inside_Y_contra<(MODE == MODE_SMEM ? 1 : 4)>(v, T, lut, t - 1, tid - nXl, nYl); } }
-        else if (t - 2 >= d_in0 && t - 2 < L) inside_Z<CONTRA, (MODE == MODE_SMEM ? 2 : 4)>(v, T, lut, t - 2, tid - nXl - nYl, nZl);
+        if (isY) { if constexpr (CONTRA) { if (t - 1 >= d_in0 && t - 1 < L) inside_Y_contra<(MODE == MODE_SMEM ? RNA_Y_CH : 4)>(v, T, lut, t - 1, tid - nXl, nYl); } }
+        else if (t - 2 >= d_in0 && t - 2 < L) inside_Z<CONTRA, (MODE == MODE_SMEM ? RNA_Z_PF : 4)>(v, T, lut, t - 2, tid - nXl - nYl, nZl);
         asm volatile("bar.sync 1, %0;" ::"r"(nYZl) : "memory");
-        if (isY) { if constexpr (CONTRA) { if (t < L) inside_Y_contra<(MODE == MODE_SMEM ? 1 : 4)>(v, T, lut, t, tid - nXl, nYl); } }
-        else if (t - 1 >= d_in0 && t - 1 < L) inside_Z<CONTRA, (MODE == MODE_SMEM ? 2 : 4)>(v, T, lut, t - 1, tid - nXl - nYl, nZl);
+        if (isY) { if constexpr (CONTRA) { if (t < L) inside_Y_contra<(MODE == MODE_SMEM ? RNA_Y_CH : 4)>(v, T, lut, t, tid - nXl, nYl); } }
+        else if (t - 1 >= d_in0 && t - 1 < L) inside_Z<CONTRA, (MODE == MODE_SMEM ? RNA_Z_PF : 4)>(v, T, lut, t - 1, tid - nXl - nYl, nZl);
       }
       if (dbg_on && (tid & 31) == 0 && !helper) a.dbg[(size_t)t * 16 + warp] = clock64() - c0;
       __syncthreads();
@@ -258,13 +270,13 @@ __global__ void __launch_bounds__(REGS48 ? 256 : 512, REGS48 ? 5 : 2) fold_kerne
       if (warp < a.nXw) {
         outside_X<CONTRA>(v, T, lut, P, Z, st, tid, nXl);
       } else if (!helper) {
-        if (d + 1 < L) outside_Y<CONTRA, (MODE == MODE_SMEM ? 1 : 4)>(v, T, lut, d + 1, tid - nXl, nYZl);
-        outside_Y<CONTRA, (MODE == MODE_SMEM ? 1 : 4)>(v, T, lut, d, tid - nXl, nYZl);
+        if (d + 1 < L) outside_Y<CONTRA, (MODE == MODE_SMEM ? RNA_Y_CH : 4)>(v, T, lut, d + 1, tid - nXl, nYZl);
+        outside_Y<CONTRA, (MODE == MODE_SMEM ? RNA_Y_CH : 4)>(v, T, lut, d, tid - nXl, nYZl);
       }
       if (dbg_on && (tid & 31) == 0 && !helper) a.dbg[(size_t)(1024 + d) * 16 + warp] = clock64() - c0;
       __syncthreads();
       const long long c1 = dbg_on ? clock64() : 0;
-      if (warp < a.nXw) outside_X_ml<CONTRA, (MODE == MODE_SMEM ? 2 : 3)>(v, T, lut, st, tid, nXl);
+      if (warp < a.nXw) outside_X_ml<CONTRA, (MODE == MODE_SMEM ? RNA_ML_PF : 3)>(v, T, lut, st, tid, nXl);
       if (dbg_on && (tid & 31) == 0 && warp < a.nXw) a.dbg[(size_t)(1024 + d) * 16 + 8 + warp] = clock64() - c1;
       __syncthreads();
     }

@@ -636,7 +636,7 @@ RNA_DEV uint32_t stream_fill_rows(const SV& v, const LOOP& lp, const Windows<INS
         t1.c = 0.f; t1.pv = 0.f; t1.q = q; t1.code = code; t1.a = a; t1.b = b;
         sc = lp.score(lp.stage2(t1));
       }
-      out[wd * n] = make_uint2((unsigned)__float_as_int(sc), (unsigned)q);
+      RNA_ST_STREAM(&out[wd * n], make_uint2((unsigned)__float_as_int(sc), (unsigned)q));
       n++;
     }
   }
@@ -665,7 +665,7 @@ RNA_DEV uint32_t stream_fill_rows_flat(const SV& v, const LOOP& lp, const Window
     const int q = doff(l - k, L) + k;
     const int code = INSIDE ? v.RR[l] * 16 + kcode : kcode + v.LL[l];
     const float sc = lp.fast(a, b, code);
-    if (has) out[wd * n] = make_uint2((unsigned)__float_as_int(sc), (unsigned)q);
+    if (has) RNA_ST_STREAM(&out[wd * n], make_uint2((unsigned)__float_as_int(sc), (unsigned)q));
     n += has ? 1u : 0u;
     // next row when this one is exhausted (its window was loaded one row ahead)
     const bool adv = w == 0;
@@ -685,7 +685,7 @@ RNA_DEV void stream_fill_cell(const SV& v, const typename Model2<CONTRA>::View& 
   uint32_t n = 0;
   n = stream_fill_rows<CONTRA, INSIDE, false>(v, lp, window, i, j, 0, min(LOOP::kFastFrom - 1, window.amax), out, wd, n);
   n = stream_fill_rows_flat<CONTRA, INSIDE>(v, lp, window, i, j, LOOP::kFastFrom, window.amax, out, wd, n);
-  for (; n < nmax; n++) out[wd * n] = make_uint2(0u, 0u);   // neutral padding
+  for (; n < nmax; n++) RNA_ST_STREAM(&out[wd * n], make_uint2(0u, 0u));   // neutral padding
 }
 // fill tasks: chunks of 32 consecutive cells of a pass; task tau -> (pass, chunk), longest partner lists first
 template <class SV>
@@ -731,7 +731,15 @@ RNA_DEV void stream_fill_task(const SV& v, const typename Model2<CONTRA>::View& 
 // the latency-critical fold over a lane's column of its group's block.  Every step of the warp touches a new
 // 256-byte line pair, so the stream is read a block of 8 steps ahead (>= 800 cycles of logsumexp), and the
 // gathers of a block are issued before its chain starts.
+#ifndef RNA_STREAM_BLOCK
 #define RNA_STREAM_BLOCK 4
+#endif
+#ifndef RNA_STREAM_PF_STEP
+#define RNA_STREAM_PF_STEP 2
+#endif
+#ifndef RNA_STREAM_PF_DIST
+#define RNA_STREAM_PF_DIST 32
+#endif
 template <bool INSIDE, class SV>
 RNA_DEV float stream_chain(const SV& v, const uint2* __restrict__ st, uint32_t wd, uint32_t n, const float4* lut,
                            float Cij, float sum) {
@@ -739,19 +747,19 @@ RNA_DEV float stream_chain(const SV& v, const uint2* __restrict__ st, uint32_t w
   if (n == 0) return sum;
   uint2 nx[B];
 #pragma unroll
-  for (int k = 0; k < B; k++) nx[k] = ((uint32_t)k < n) ? st[wd * k] : make_uint2(0u, 0u);
+  for (int k = 0; k < B; k++) nx[k] = ((uint32_t)k < n) ? RNA_LD_STREAM(&st[wd * k]) : make_uint2(0u, 0u);
   for (uint32_t pos = 0; pos < n; pos += B) {
     uint2 cur[B];
     float c[B], p[B];
 #pragma unroll
     for (int k = 0; k < B; k++) cur[k] = nx[k];
 #pragma unroll
-    for (int k = 0; k < B; k++) nx[k] = (pos + B + k < n) ? st[wd * (pos + B + k)] : make_uint2(0u, 0u);
+    for (int k = 0; k < B; k++) nx[k] = (pos + B + k < n) ? RNA_LD_STREAM(&st[wd * (pos + B + k)]) : make_uint2(0u, 0u);
     // HBM latency exceeds a block of logsumexp's: pull the lines into L2 well ahead (one 8-byte element per
     // lane and step => a warp's step covers at most 256 bytes; every other step touches all lines)
 #pragma unroll
-    for (int k = 0; k < B; k += 2)
-      if (pos + 32 + k < n) RNA_PREFETCH_L2(st + wd * (pos + 32 + k));
+    for (int k = 0; k < B; k += RNA_STREAM_PF_STEP)
+      if (pos + RNA_STREAM_PF_DIST + k < n) RNA_PREFETCH_L2(st + wd * (pos + RNA_STREAM_PF_DIST + k));
 #pragma unroll
     for (int k = 0; k < B; k++) {
       c[k] = v.C[cur[k].y];                    // neutral element: C[0] = -inf => operand -inf => no-op
@@ -776,11 +784,11 @@ RNA_DEV float stream_chain_deep(const float* __restrict__ C, const float* __rest
   float c1[B], p1[B], s1[B];
 #pragma unroll
   for (int k = 0; k < B; k++) {
-    const uint2 e = ((uint32_t)k < n) ? st[wd * k] : make_uint2(0u, 0u);
+    const uint2 e = ((uint32_t)k < n) ? RNA_LD_STREAM(&st[wd * k]) : make_uint2(0u, 0u);
     c1[k] = C[e.y]; p1[k] = INSIDE ? 0.f : Pm[e.y]; s1[k] = __int_as_float((int)e.x);
   }
 #pragma unroll
-  for (int k = 0; k < B; k++) e2[k] = ((uint32_t)(B + k) < n) ? st[wd * (B + k)] : make_uint2(0u, 0u);
+  for (int k = 0; k < B; k++) e2[k] = ((uint32_t)(B + k) < n) ? RNA_LD_STREAM(&st[wd * (B + k)]) : make_uint2(0u, 0u);
 #pragma unroll 1
   for (uint32_t pos = 0; pos < n; pos += B) {
     float c0[B], p0[B], s0[B];
@@ -791,7 +799,7 @@ RNA_DEV float stream_chain_deep(const float* __restrict__ C, const float* __rest
       c1[k] = C[e2[k].y]; p1[k] = INSIDE ? 0.f : Pm[e2[k].y]; s1[k] = __int_as_float((int)e2[k].x);
     }
 #pragma unroll
-    for (int k = 0; k < B; k++) e2[k] = (pos + 2 * B + k < n) ? st[wd * (pos + 2 * B + k)] : make_uint2(0u, 0u);
+    for (int k = 0; k < B; k++) e2[k] = (pos + 2 * B + k < n) ? RNA_LD_STREAM(&st[wd * (pos + 2 * B + k)]) : make_uint2(0u, 0u);
 #pragma unroll
     for (int k = 0; k < B; k += 2)
       if (pos + 48 + k < n) RNA_PREFETCH_L2(st + wd * (pos + 48 + k));

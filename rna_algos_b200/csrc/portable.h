@@ -13,6 +13,9 @@
 #define RNA_DEVM __device__ __forceinline__   // member functions
 #define RNA_CONST_TABLE __device__ __constant__
 #define RNA_PREFETCH_L2(p) asm volatile("prefetch.global.L2 [%0];" ::"l"(p))
+// the two-loop term streams (st.global.cs / ld.global.cs measured 9 % SLOWER on the default bench: plain accesses)
+#define RNA_ST_STREAM(p, v) (*(p) = (v))
+#define RNA_LD_STREAM(p) (*(p))
 // chains of the cooperative kernel; compiled as separate functions with -DRNA_COOP_NOINLINE (measured slower)
 #ifdef RNA_COOP_NOINLINE
 #define RNA_DEV_CALL __device__ __noinline__
@@ -26,6 +29,8 @@
 #define RNA_DEVM inline
 #define RNA_CONST_TABLE static const
 #define RNA_PREFETCH_L2(p) ((void)(p))
+#define RNA_ST_STREAM(p, v) (*(p) = (v))
+#define RNA_LD_STREAM(p) (*(p))
 #define RNA_DEV_CALL static inline
 #define __restrict__ __restrict
 struct float4 { float x, y, z, w; };

@@ -44,8 +44,22 @@ struct rna_handle {
   DevBuf ws, counters, order, stream_ws;                           // kernel scratch
   DevBuf b_bases, b_offsets, b_bppoff, b_gammas, b_logz, b_bpp, b_structs, b_ea, b_pairs, b_probs, b_proboff;
   RnaCallStats stats{};
-  bool attrs_set = false;
+  // cached answers of the CUDA runtime about kernel configurations (kern_prepare)
+  struct OccEntry { const void* fn; int nt; size_t smem; int occ; };
+  std::vector<OccEntry> occ_cache;
+  std::vector<const void*> attr_set;
+  int lsmem[2] = {-1, -1};                       // largest shared-memory-mode length per model
+  cudaEvent_t ev_done = nullptr;                 // end of the last enqueued call: calls of one handle share its scratch
+  bool ev_done_valid = false;
 };
+
+// Development switches (A/B timing, role timers) are read from the environment only in builds made with
+// -DRNA_DEV_SWITCHES (make EXTRA=-DRNA_DEV_SWITCHES); the product build has none.
+#ifdef RNA_DEV_SWITCHES
+static inline const char* dev_env(const char* name) { return getenv(name); }
+#else
+static inline const char* dev_env(const char*) { return nullptr; }
+#endif
 
 #define CU(h, call)                                                                                  \
   do {                                                                                               \
@@ -91,6 +105,7 @@ extern "C" int rna_create(int device, rna_handle** out) {
   h->smem_optin = prop.sharedMemPerBlockOptin;
   if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) { delete h; return RNA_ERR_CUDA; }
   bool ok = cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming) == cudaSuccess;
+  ok = ok && cudaEventCreateWithFlags(&h->ev_done, cudaEventDisableTiming) == cudaSuccess;
   for (int x = 0; x < rna_handle::kLanes; x++) {
     ok = ok && cudaStreamCreateWithFlags(&h->aux[x], cudaStreamNonBlocking) == cudaSuccess;
     ok = ok && cudaEventCreateWithFlags(&h->ev_join[x], cudaEventDisableTiming) == cudaSuccess;
@@ -113,6 +128,7 @@ extern "C" int rna_destroy(rna_handle* h) {
   cudaFree(h->d_hp_ext); cudaFree(h->d_int11); cudaFree(h->d_int12); cudaFree(h->d_int22);
   for (int x = 0; x < rna_handle::kLanes; x++) { cudaStreamSynchronize(h->aux[x]); cudaStreamDestroy(h->aux[x]); cudaEventDestroy(h->ev_join[x]); }
   cudaEventDestroy(h->ev_fork);
+  cudaEventDestroy(h->ev_done);
   cudaStreamDestroy(h->stream);
   delete h;
   return RNA_OK;
@@ -129,6 +145,14 @@ extern "C" int rna_get_stats(const rna_handle* h, RnaCallStats* out) {
 // ---------------------------------------------------------------------------------------------------
 // table packing (host, plain IEEE f32 — compiled with -ffp-contract=off)
 // ---------------------------------------------------------------------------------------------------
+// A table upload must not overtake a call that is still reading the old tables (the *_dev entry points return
+// before their kernels have run, on streams that a blocking cudaMemcpy does not order against).
+static int tables_quiesce(rna_handle* h) {
+  CU(h, cudaSetDevice(h->device));
+  if (h->ev_done_valid) CU(h, cudaEventSynchronize(h->ev_done));
+  return RNA_OK;
+}
+
 extern "C" void rna_contra_tables_accumulate(RnaContraTables* t) {
   // FoldScoreSets::accumulate, reference src/mccaskill_algo.rs:60-86
   struct { const float* src; float* dst; int n; } jobs[] = {
@@ -165,7 +189,7 @@ extern "C" int rna_set_turner_tables(rna_handle* h, const RnaTurnerTables* t) {
   DevTurner d;
   std::vector<float> hp;
   TRY(pack_turner(t, &d, &hp, &h->err));
-  CU(h, cudaSetDevice(h->device));
+  TRY(tables_quiesce(h));
   if (!h->d_turner) {
     CU(h, cudaMalloc(&h->d_turner, sizeof(DevTurner)));
     CU(h, cudaMalloc(&h->d_hp_ext, sizeof(float) * RNA_HAIRPIN_EXT_LEN));
@@ -190,7 +214,7 @@ extern "C" int rna_set_contra_tables(rna_handle* h, const RnaContraTables* t) {
   if (!h || !t) return RNA_ERR_BAD_ARG;
   DevContra d;
   TRY(pack_contra(t, &d, &h->err));
-  CU(h, cudaSetDevice(h->device));
+  TRY(tables_quiesce(h));
   if (!h->d_contra) CU(h, cudaMalloc(&h->d_contra, sizeof(DevContra)));
   CU(h, cudaMemcpy(h->d_contra, &d, sizeof d, cudaMemcpyHostToDevice));
   h->has_contra = true;
@@ -199,9 +223,9 @@ extern "C" int rna_set_contra_tables(rna_handle* h, const RnaContraTables* t) {
 
 extern "C" int rna_set_align_tables(rna_handle* h, const RnaAlignTables* t) {
   if (!h || !t) return RNA_ERR_BAD_ARG;
-  CU(h, cudaSetDevice(h->device));
   DevAlign d;
-  pack_align(t, &d);
+  TRY(pack_align(t, &d, &h->err));
+  TRY(tables_quiesce(h));
   if (!h->d_align) CU(h, cudaMalloc(&h->d_align, sizeof(DevAlign)));
   CU(h, cudaMemcpy(h->d_align, &d, sizeof d, cudaMemcpyHostToDevice));
   h->has_align = true;
@@ -225,6 +249,13 @@ extern "C" int rna_validate_bases(const uint8_t* bases, const uint32_t* offsets,
   return RNA_OK;
 }
 
+extern "C" int rna_validate_fold_lengths(const uint32_t* offsets, uint32_t n_seqs) {
+  if (!offsets) return RNA_ERR_BAD_ARG;
+  for (uint32_t s = 0; s < n_seqs; s++)
+    if (offsets[s + 1] >= offsets[s] && offsets[s + 1] - offsets[s] > (uint32_t)RNA_MAX_FOLD_LEN) return RNA_ERR_TOO_LONG;
+  return RNA_OK;
+}
+
 extern "C" int rna_partition_lpt(const uint64_t* costs, uint32_t n_units, uint32_t n_parts, uint32_t* part_of) {
   if (!costs || !part_of || n_parts == 0) return RNA_ERR_BAD_ARG;
   std::vector<uint32_t> idx(n_units);
@@ -245,9 +276,22 @@ extern "C" int rna_partition_lpt(const uint64_t* costs, uint32_t n_units, uint32
 // ---------------------------------------------------------------------------------------------------
 // fold launcher
 // ---------------------------------------------------------------------------------------------------
-template <class K>
-static int set_smem_attr(rna_handle* h, K kernel, size_t bytes) {
-  CU(h, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+// Per-handle cache of what the CUDA runtime is asked about a kernel configuration (a batch call used to repeat these
+// queries for every bucket of every call: cudaFuncSetAttribute + occupancy query cost ~10 us each).
+static int kern_prepare(rna_handle* h, const void* fn, int nt, size_t smem, int* occ_out) {
+  bool attr_done = false;
+  for (const void* f : h->attr_set) attr_done = attr_done || f == fn;
+  if (!attr_done) {
+    CU(h, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_optin - 1024));   // (static shared memory comes out of the same budget)
+    h->attr_set.push_back(fn);
+  }
+  if (!occ_out) return RNA_OK;
+  for (const rna_handle::OccEntry& e : h->occ_cache)
+    if (e.fn == fn && e.nt == nt && e.smem == smem) { *occ_out = e.occ; return RNA_OK; }
+  int occ = 1;
+  CU(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, nt, smem));
+  h->occ_cache.push_back(rna_handle::OccEntry{fn, nt, smem, occ});
+  *occ_out = occ;
   return RNA_OK;
 }
 
@@ -257,33 +301,226 @@ struct Bucket {
   uint32_t begin, end;   // range in the sorted order array
 };
 
-template <bool CONTRA>
-static int launch_fold_model(rna_handle* h, const RnaFoldBatchDev* b, cudaStream_t st, bool centroid_only,
-                             const float* d_bpp_in) {
+// sequence indices by length, longest first (LPT inside each launch's work queue); stable, O(n + max length)
+static void order_by_length(const uint32_t* ho, uint32_t n, std::vector<uint32_t>& order) {
+  uint32_t maxlen = 0;
+  for (uint32_t i = 0; i < n; i++) maxlen = std::max(maxlen, ho[i + 1] - ho[i]);
+  std::vector<uint32_t> start((size_t)maxlen + 2, 0);
+  for (uint32_t i = 0; i < n; i++) start[maxlen - (ho[i + 1] - ho[i]) + 1]++;
+  for (size_t x = 1; x < start.size(); x++) start[x] += start[x - 1];
+  order.resize(n);
+  for (uint32_t i = 0; i < n; i++) order[start[maxlen - (ho[i + 1] - ho[i])]++] = i;
+}
+
+// Every call of a handle uses the same scratch (workspace, work counters, order array): calls are stream-ordered
+// behind one another whatever stream they were enqueued on.
+static int call_begin(rna_handle* h, cudaStream_t st) {
+  if (h->ev_done_valid) CU(h, cudaStreamWaitEvent(st, h->ev_done, 0));
+  return RNA_OK;
+}
+static int call_end(rna_handle* h, cudaStream_t st) {
+  CU(h, cudaEventRecord(h->ev_done, st));
+  h->ev_done_valid = true;
+  return RNA_OK;
+}
+
+// centroid_fold over packed BPP matrices (rna_centroid_batch): buckets by length, one CTA per sequence; sequences
+// beyond 1024 nt one at a time on the whole grid
+static int launch_centroid(rna_handle* h, const RnaFoldBatchDev* b, cudaStream_t st, const float* d_bpp_in) {
   const uint32_t n = b->n_seqs;
   const uint32_t* ho = b->h_offsets;
-  // sort by length, longest first (LPT inside each launch's work queue)
-  std::vector<uint32_t> order(n);
-  for (uint32_t i = 0; i < n; i++) order[i] = i;
-  std::stable_sort(order.begin(), order.end(),
-                   [&](uint32_t x, uint32_t y) { return ho[x + 1] - ho[x] > ho[y + 1] - ho[y]; });
+  std::vector<uint32_t> order;
+  order_by_length(ho, n, order);
+  auto len_of = [&](uint32_t pos) { return (int)(ho[order[pos] + 1] - ho[order[pos]]); };
+  const int gran = 8;
+  int Lsmem = 0;
+  for (int L = 16; L <= 1024; L += gran) { if (centroid_ws_floats(L) * 4 + 1024 <= h->smem_optin) Lsmem = L; else break; }
+  std::vector<Bucket> buckets;
+  for (uint32_t pos = 0; pos < n;) {
+    const int L = len_of(pos);
+    Bucket bk;
+    bk.begin = pos;
+    if (L > 1024) {
+      if (L > RNA_MAX_FOLD_LEN) { h->err = "sequence longer than RNA_MAX_FOLD_LEN (46340 nt)"; return RNA_ERR_TOO_LONG; }
+      bk.mode = MODE_COOP; bk.Lcap = L; bk.end = pos + 1;
+    } else if (L > Lsmem) {
+      bk.mode = MODE_GLOBAL; bk.Lcap = L;
+      uint32_t e = pos;
+      while (e < n && len_of(e) > Lsmem) e++;
+      bk.end = e;
+    } else {
+      bk.mode = MODE_SMEM;
+      bk.Lcap = std::max(16, (L + gran - 1) / gran * gran);
+      const int lo = bk.Lcap > 16 ? bk.Lcap - gran : 0;
+      uint32_t e = pos;
+      while (e < n && len_of(e) > lo) e++;
+      bk.end = e;
+    }
+    buckets.push_back(bk);
+    pos = bk.end;
+  }
+  TRY(ensure(h, h->order, sizeof(uint32_t) * (size_t)std::max<uint32_t>(n, 1)));
+  TRY(ensure(h, h->counters, sizeof(int) * buckets.size()));
+  CU(h, cudaMemcpyAsync(h->order.p, order.data(), sizeof(uint32_t) * n, cudaMemcpyHostToDevice, st));
+  CU(h, cudaMemsetAsync(h->counters.p, 0, sizeof(int) * buckets.size(), st));
+  h->stats.h2d_bytes += sizeof(uint32_t) * n;
+  size_t ws_floats = 0;
+  std::vector<int> grid_of(buckets.size(), 0);
+  for (size_t k = 0; k < buckets.size(); k++) {
+    const Bucket& bk = buckets[k];
+    const size_t per = centroid_ws_floats(bk.Lcap) + 32;
+    if (bk.mode == MODE_COOP) {
+      const size_t Tc = (size_t)bk.Lcap * (bk.Lcap + 1) / 2;
+      ws_floats = std::max(ws_floats, (size_t)std::max<uint32_t>(1, b->n_gammas) * (Tc + 2 * ((size_t)bk.Lcap + 2)) + 128);
+    } else if (bk.mode == MODE_GLOBAL) {
+      size_t freeb = 0, totb = 0;
+      cudaMemGetInfo(&freeb, &totb);
+      const size_t budget = (freeb + h->ws.cap) / 2;
+      int g = (int)std::min<size_t>(bk.end - bk.begin, (size_t)h->sm_count * 2);
+      while (g > 1 && (size_t)g * per * 4 > budget) g--;
+      if ((size_t)g * per * 4 > budget) { h->err = "sequence too long for device memory"; return RNA_ERR_NOMEM; }
+      grid_of[k] = g;
+      ws_floats = std::max(ws_floats, (size_t)g * per);
+    }
+  }
+  if (ws_floats) TRY(ensure(h, h->ws, ws_floats * 4));
+  FoldArgs a;
+  memset(&a, 0, sizeof a);
+  a.offsets = b->d_offsets;
+  a.n_seqs = n;
+  a.total_len = b->total_len;
+  a.gammas = b->d_gammas;
+  a.n_gammas = b->n_gammas;
+  a.bpp_offsets = b->d_bpp_offsets;
+  a.out_structs = b->d_out_structs;
+  a.out_ea = b->d_out_expect_acc;
+  a.out_pairs = b->d_out_pairs;
+  a.out_npairs = b->d_out_num_pairs;
+  a.workspace = (float*)h->ws.p;
+  for (size_t k = 0; k < buckets.size(); k++) {
+    const Bucket& bk = buckets[k];
+    a.order = (const uint32_t*)h->order.p + bk.begin;
+    a.n_launch = bk.end - bk.begin;
+    a.work_counter = (int*)h->counters.p + k;
+    a.Lcap = bk.Lcap;
+    a.ws_stride = centroid_ws_floats(bk.Lcap) + 32;
+    if (bk.mode == MODE_SMEM) {
+      const int nt = std::min(256, std::max(32, (bk.Lcap + 31) / 32 * 32));
+      const size_t smem = centroid_ws_floats(bk.Lcap) * 4;
+      int occ = 1;
+      TRY(kern_prepare(h, (const void*)centroid_kernel<MODE_SMEM>, nt, smem, &occ));
+      const int grid = (int)std::min<size_t>(a.n_launch, (size_t)std::max(1, occ) * h->sm_count);
+      centroid_kernel<MODE_SMEM><<<grid, nt, smem, st>>>(a, d_bpp_in);
+    } else if (bk.mode == MODE_GLOBAL) {
+      const int nt = std::min(512, std::max(32, (bk.Lcap + 31) / 32 * 32));
+      centroid_kernel<MODE_GLOBAL><<<grid_of[k], nt, 16, st>>>(a, d_bpp_in);
+    } else {
+      const int nt = 128;
+      int occ = 1;
+      TRY(kern_prepare(h, (const void*)centroid_kernel<MODE_COOP>, nt, 16, &occ));
+      const int grid = std::max(1, std::min(std::max(1, occ) * h->sm_count, (bk.Lcap + nt - 1) / nt));
+      void* params[] = {(void*)&a, (void*)&d_bpp_in};
+      CU(h, cudaLaunchCooperativeKernel((void*)centroid_kernel<MODE_COOP>, dim3(grid), dim3(nt), params, 16, st));
+    }
+    CU(h, cudaGetLastError());
+    h->stats.kernel_launches++;
+  }
+  return RNA_OK;
+}
+
+#ifdef RNA_DEV_SWITCHES
+// RNA_FOLD_DBG=1 (development builds): where do the cycles of one sequence go, per role and pass
+static void fold_dbg_report(int mode, int Lcap, const FoldArgs& a, long long* d_dbg, cudaStream_t st, int nt, int grid, size_t smem) {
+    if (mode == MODE_COOP) {
+      cudaStreamSynchronize(st);
+      long long hd[32];
+      cudaMemcpy(hd, d_dbg, sizeof hd, cudaMemcpyDeviceToHost);
+      fprintf(stderr, "[RNA_FOLD_DBG] coop L=%d roles %d/%d/%d: setup+streams=%lld inside=%lld outside=%lld bpp+centroid=%lld cycles\n", Lcap,
+              a.nXw, a.nYw, a.nZw, hd[0], hd[1], hd[2], hd[3]);
+      fprintf(stderr, "[RNA_FOLD_DBG]   inside, first warp of a role (work, wait A, phase B): X %lld %lld %lld | Y %lld %lld %lld | Z %lld %lld %lld\n",
+              hd[8], hd[9], hd[10], hd[12], hd[13], hd[14], hd[16], hd[17], hd[18]);
+      fprintf(stderr, "[RNA_FOLD_DBG]   outside, first warp of a role (work, wait): X %lld %lld | Y %lld %lld\n", hd[20], hd[21], hd[24], hd[25]);
+      {
+        std::vector<long long> hs((size_t)(Lcap / 2 + 2) * 8);
+        cudaMemcpy(hs.data(), d_dbg + 64, hs.size() * 8, cudaMemcpyDeviceToHost);
+        long long sm[5] = {0, 0, 0, 0, 0}, crit = 0, nsA = 0, nsBar = 0, nsB = 0, prev_end = 0;
+        for (size_t stp = 0; stp * 8 < hs.size(); stp++) {
+          long long mx = 0;
+          for (int r = 0; r < 5; r++) { sm[r] += hs[stp * 8 + r]; mx = std::max(mx, hs[stp * 8 + r]); }
+          crit += mx;
+          const long long ga = hs[stp * 8 + 5], gr = hs[stp * 8 + 6], ge = hs[stp * 8 + 7];
+          if (ga && gr && ge) { if (prev_end) nsA += ga - prev_end; nsBar += gr - ga; nsB += ge - gr; prev_end = ge; }
+        }
+        fprintf(stderr, "[RNA_FOLD_DBG]   inside wall (globaltimer, last CTA): phase A %.3f ms, its barrier %.3f ms, phase B + barrier %.3f ms\n",
+                nsA * 1e-6, nsBar * 1e-6, nsB * 1e-6);
+        {
+          std::vector<long long> ho((size_t)Lcap * 4);
+          cudaMemcpy(ho.data(), d_dbg + (1 << 19), ho.size() * 8, cudaMemcpyDeviceToHost);
+          long long ox = 0, oy = 0, oall = 0, ostream = 0;
+          for (int dd = 0; dd < Lcap; dd++) {
+            ox += ho[(size_t)dd * 4]; oy += ho[(size_t)dd * 4 + 1]; oall += std::max(ho[(size_t)dd * 4], ho[(size_t)dd * 4 + 1]);
+            ostream += (ho[(size_t)dd * 4 + 2] & 0xffffff) << 4;
+          }
+          fprintf(stderr, "[RNA_FOLD_DBG]   outside, sum over steps of the slowest warp: X %lld (of which exterior + two-loop stream part %lld) Y %lld, all %lld\n", ox, ostream, oy, oall);
+        }
+        fprintf(stderr, "[RNA_FOLD_DBG]   inside phase A, sum over steps of the slowest warp: X %lld Y %lld Z-E %lld Z-M1 %lld Z-M %lld, all %lld\n",
+                sm[0], sm[1], sm[2], sm[3], sm[4], crit);
+      }
+    } else {   // debug aid: where do the cycles of one sequence go, per role and pass
+      cudaStreamSynchronize(st);
+      std::vector<long long> hd(2048 * 16);
+      cudaMemcpy(hd.data(), d_dbg, hd.size() * 8, cudaMemcpyDeviceToHost);
+      for (int pass = 0; pass < 2; pass++) {
+        long long role[3] = {0, 0, 0}, crit = 0, critrole[3] = {0, 0, 0};
+        for (int t = 0; t < 1000; t++) {
+          long long m[3] = {0, 0, 0};
+          for (int wv = 0; wv < 16; wv++) {
+            const int r = wv < a.nXw ? 0 : wv < a.nXw + a.nYw ? 1 : 2;
+            m[r] = std::max(m[r], hd[(size_t)(pass * 1024 + t) * 16 + wv]);
+          }
+          const long long mx = std::max(m[0], std::max(m[1], m[2]));
+          crit += mx;
+          for (int r = 0; r < 3; r++) { role[r] += m[r]; if (m[r] == mx && mx) critrole[r] += mx; }
+        }
+        fprintf(stderr, "[RNA_FOLD_DBG] bucket Lcap=%d pass=%s roles X/Y/Z warps %d/%d/%d: sum of per-step max cycles X=%lld Y=%lld Z=%lld, "
+                "critical path=%lld (X %lld, Y %lld, Z %lld)\n", Lcap, pass ? "outside" : "inside", a.nXw, a.nYw, a.nZw,
+                role[0], role[1], role[2], crit, critrole[0], critrole[1], critrole[2]);
+      }
+      for (int t = 1024; t < 1024; t++) {
+        long long my = 0, mx = 0;
+        for (int wv = 0; wv < 16; wv++) { (wv < a.nXw ? mx : my) = std::max(wv < a.nXw ? mx : my, hd[(size_t)t * 16 + wv]); }
+        if (my > 200000) fprintf(stderr, "[RNA_FOLD_DBG]   outside d=%d: X=%lld Y=%lld\n", t - 1024, mx, my);
+      }
+      fprintf(stderr, "[RNA_FOLD_DBG]   setup=%lld count=%lld scan=%lld fill=%lld cycles, terms=%lld\n", hd[2047 * 16], hd[2047 * 16 + 1],
+              hd[2047 * 16 + 2], hd[2047 * 16 + 3], hd[2047 * 16 + 4]);
+      fprintf(stderr, "[RNA_FOLD_DBG]   L=%lld: output+centroid=%lld cycles, whole sequence=%lld cycles; launch: %d threads, grid %d, smem %zu\n",
+              hd[2047 * 16 + 7], hd[2047 * 16 + 5], hd[2047 * 16 + 6], nt, grid, smem);
+      if (!hd[2047 * 16 + 3]) fprintf(stderr, "[RNA_FOLD_DBG]   (streams did not fit: scored on the fly)\n");
+      cudaMemset(d_dbg, 0, 2048 * 16 * 8);
+    }
+}
+#endif
+
+template <bool CONTRA>
+static int launch_fold_model(rna_handle* h, const RnaFoldBatchDev* b, cudaStream_t st) {
+  const uint32_t n = b->n_seqs;
+  const uint32_t* ho = b->h_offsets;
+  std::vector<uint32_t> order;
+  order_by_length(ho, n, order);
   auto len_of = [&](uint32_t pos) { return (int)(ho[order[pos] + 1] - ho[order[pos]]); };
   const size_t smem_cap = h->smem_optin;
-  static const bool use_v1 = getenv("RNA_FOLD_V1") != nullptr;   // A/B switch: the thread-per-cell kernel
-  const bool v2 = !centroid_only && !use_v1;
-  const int gran = v2 ? 4 : 8;                                     // bucket width in nt
-  auto smem_need = [&](int Lcap) -> size_t {
-    if (centroid_only) return centroid_ws_floats(Lcap) * 4;
-    if (v2) return fold2_fixed_bytes<CONTRA>(Lcap) + fold2_seq_bytes(Lcap, 1, 2);
-    return fold_smem_bytes<CONTRA>(Lcap, true);
-  };
-  // largest L whose matrices fit in shared memory (v2 keeps u8 cell lists there: L <= 252)
-  int Lsmem = 0;
-  for (int L = 16; L <= (v2 ? 252 : 1024); L += gran) { if (smem_need(L) + 1024 <= smem_cap) Lsmem = L; else break; }
+  const int gran = 4;                                     // bucket width in nt
+  auto smem_need = [&](int Lcap) -> size_t { return fold2_fixed_bytes<CONTRA>(Lcap) + fold2_seq_bytes(Lcap, 1, 2); };
+  // largest L whose shared-memory working set fits (the u8 cell lists cap it at 252)
+  int& Lsmem = h->lsmem[CONTRA ? 1 : 0];
+  if (Lsmem < 0) {
+    Lsmem = 0;
+    for (int L = 16; L <= 252; L += gran) { if (smem_need(L) + 1024 <= smem_cap) Lsmem = L; else break; }
+  }
   // Sequences beyond 1024 nt get the whole grid, one at a time.  So do the few sequences that are too long for the
-  // shared-memory mode when there are not enough of them to occupy the GPU one CTA each (v2 only).
+  // shared-memory mode when there are not enough of them to occupy the GPU one CTA each.
   int Lcoop_min = 1025;
-  if (v2) {
+  {
     uint32_t n_long = 0;
     while (n_long < n && len_of(n_long) > Lsmem) n_long++;
     // Cost model from B200 measurements (CONTRAfold; Turner is alike): a cooperative run takes ~230 ms x (L/1024)^2
@@ -311,14 +548,13 @@ static int launch_fold_model(rna_handle* h, const RnaFoldBatchDev* b, cudaStream
     if (best_c > forced) Lcoop_min = std::max(std::max(Lsmem + 1, 384), len_of(best_c - 1));
   }
   std::vector<Bucket> buckets;
-  uint32_t pos = 0;
-  while (pos < n) {
+  for (uint32_t pos = 0; pos < n;) {
     const int L = len_of(pos);
     Bucket bk;
     bk.begin = pos;
     if (L >= Lcoop_min) {
       // the cooperative kernel indexes its triangular matrices with 32-bit offsets (d * L must not overflow)
-      if (v2 && L > 46340) { h->err = "sequences longer than 46340 nt are not supported by this build"; return RNA_ERR_TOO_LONG; }
+      if (L > RNA_MAX_FOLD_LEN) { h->err = "sequence longer than RNA_MAX_FOLD_LEN (46340 nt)"; return RNA_ERR_TOO_LONG; }
       bk.mode = MODE_COOP; bk.Lcap = L; bk.end = pos + 1;
     } else if (L > Lsmem) {
       bk.mode = MODE_GLOBAL; bk.Lcap = L;
@@ -346,22 +582,22 @@ static int launch_fold_model(rna_handle* h, const RnaFoldBatchDev* b, cudaStream
   size_t ws_floats = 0;
   std::vector<int> grid_of(buckets.size(), 0);
   std::vector<size_t> stride_of(buckets.size(), 0);
+  size_t freeb = 0, totb = 0;
+  bool have_meminfo = false;
+  auto meminfo = [&]() { if (!have_meminfo) { cudaMemGetInfo(&freeb, &totb); have_meminfo = true; } };
   for (size_t k = 0; k < buckets.size(); k++) {
     const Bucket& bk = buckets[k];
-    if (bk.mode == MODE_SMEM) continue;   // (v2: sized below, once the grid is known)
-    const size_t per = (centroid_only ? centroid_ws_floats(bk.Lcap)
-                        : v2 ? fold2_seq_bytes(bk.Lcap, 2, 5) / 4 + 64
-                             : fold_ws_floats<CONTRA>(bk.Lcap)) + 32;
+    if (bk.mode == MODE_SMEM) continue;   // (sized below, once the grid is known)
+    const size_t per = fold2_seq_bytes(bk.Lcap, 2, 5) / 4 + 64 + 32;
     stride_of[k] = per;
     if (bk.mode == MODE_COOP) {
       // + row-major sums_1ormore and the multibranch closing-score table of the cooperative kernel's outside pass
       // + one max-plus matrix and traceback stack per centroid threshold (all thresholds are filled in one sweep)
       const size_t Tc = (size_t)bk.Lcap * (bk.Lcap + 1) / 2;
       const size_t cent = (size_t)std::max<uint32_t>(1, b->n_gammas) * (Tc + 2 * ((size_t)bk.Lcap + 2)) + 64;
-      ws_floats = std::max(ws_floats, centroid_only ? cent + 64 : per + (v2 ? 2 * Tc + 64 + cent : 0));
+      ws_floats = std::max(ws_floats, per + 2 * Tc + 64 + cent);
     } else {
-      size_t freeb = 0, totb = 0;
-      cudaMemGetInfo(&freeb, &totb);
+      meminfo();
       const size_t budget = (freeb + h->ws.cap) / 2;
       int g = (int)std::min<size_t>(bk.end - bk.begin, (size_t)h->sm_count * 2);
       while (g > 1 && (size_t)g * per * 4 > budget) g--;
@@ -370,81 +606,66 @@ static int launch_fold_model(rna_handle* h, const RnaFoldBatchDev* b, cudaStream
       ws_floats = std::max(ws_floats, (size_t)g * per);
     }
   }
-  // v2 shared-memory buckets: grid size and the per-CTA slots of the two-loop term streams
+  // shared-memory buckets: grid size and the per-CTA slots of the two-loop term streams
   std::vector<size_t> stream_stride_of(buckets.size(), 0);
   std::vector<uint32_t> tcap_of(buckets.size(), 0);
-  static const bool no_streams = getenv("RNA_FOLD_NOSTREAMS") != nullptr;   // A/B switches
-  static const bool no_helpers = getenv("RNA_FOLD_NOHELPERS") != nullptr;
+  static const bool no_streams = dev_env("RNA_FOLD_NOSTREAMS") != nullptr;   // A/B switches (RNA_DEV_SWITCHES builds)
+  static const bool no_helpers = dev_env("RNA_FOLD_NOHELPERS") != nullptr;
   std::vector<int> nt_of(buckets.size(), 0);
   std::vector<Roles> ro_of(buckets.size());
-  std::vector<char> regs48_of(buckets.size(), 0);
   size_t stream_bytes = 0;
-  if (v2) {
-    for (size_t k = 0; k < buckets.size(); k++) {
-      const Bucket& bk = buckets[k];
-      if (bk.mode == MODE_COOP && !no_streams) {
-        // one sequence on the whole GPU: a single stream slot, as large as memory comfortably allows (else the kernel
-        // scores on the fly)
-        const size_t Tc = (size_t)bk.Lcap * (bk.Lcap + 1) / 2;
-        size_t freeb = 0, totb = 0;
-        cudaMemGetInfo(&freeb, &totb);
-        size_t cap = std::min<size_t>(96 * Tc, (size_t)0xfffffff0u);
-        const size_t budget = (freeb + h->stream_ws.cap) / 3;
-        if (cap * 16 > budget) cap = budget / 16;
-        tcap_of[k] = (uint32_t)cap;
-        stream_stride_of[k] = fold2_stream_bytes(bk.Lcap, tcap_of[k]);
-        stream_bytes = std::max(stream_bytes, stream_stride_of[k]);
-      }
-      if (bk.mode != MODE_SMEM) continue;
-      // CTAs per SM: bounded by shared memory (C, log P and the small per-sequence tables) and by 1024 threads per SM
-      // at 64 registers.  The chains are latency-bound, so residency is what fills the SM: take all the CTAs that
-      // fit (<= 4, measured best) and give each 1024 / CTAs threads: roles first, the rest help in the all-thread phases.
-      const size_t smem = smem_need(bk.Lcap);
-      static const int occ_cap = getenv("RNA_FOLD_OCC") ? atoi(getenv("RNA_FOLD_OCC")) : 4;   // measured best on tRNA-length batches
-      int occ_s = (int)std::min<size_t>((size_t)std::max(1, occ_cap), (size_t)233472 / (smem + 1024 + 64));
-      occ_s = std::max(1, occ_s);
-      occ_s = std::min(occ_s, std::max(1, 32 / fold2_min_warps(bk.Lcap, CONTRA)));
-      int warps = std::min(16, 32 / occ_s);
-      // a fifth CTA of 8 warps fits when shared memory allows it and the kernel is built under a 48-register cap
-      static const bool allow48 = getenv("RNA_FOLD_REGS48") != nullptr;
-      regs48_of[k] = allow48 && (size_t)233472 / (smem + 1024 + 64) >= 5 && warps == 8 && occ_cap >= 4;
-      if (no_helpers) { const Roles fr = fold2_roles(bk.Lcap, CONTRA, 16); warps = std::min(warps, fr.nX + fr.nY + fr.nZ); }
-      const Roles ro = fold2_roles(bk.Lcap, CONTRA, warps);
-      ro_of[k] = ro;
-      int nt = 32 * warps;
-      int occ = 1;
-      if (regs48_of[k]) {
-        TRY(set_smem_attr(h, fold_kernel2<CONTRA, MODE_SMEM, true>, smem));
-        CU(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fold_kernel2<CONTRA, MODE_SMEM, true>, nt, smem));
-        occ = std::max(1, std::min(occ, 5));
-      } else {
-        TRY(set_smem_attr(h, fold_kernel2<CONTRA, MODE_SMEM>, smem));
-        CU(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fold_kernel2<CONTRA, MODE_SMEM>, nt, smem));
-        occ = std::max(1, std::min(occ, occ_cap));
-      }
-      nt_of[k] = nt;
-      grid_of[k] = (int)std::min<size_t>(bk.end - bk.begin, (size_t)std::max(1, occ) * h->sm_count);
-      stride_of[k] = 4 * ((size_t)bk.Lcap * (bk.Lcap + 1) / 2) + 32;   // R X E M1 of one CTA
-      ws_floats = std::max(ws_floats, (size_t)grid_of[k] * stride_of[k]);
-      if (!no_streams) {
-        // room for 128 stream elements per cell (random sequences need ~50 incl. padding); sequences with longer
-        // lists score on the fly
-        tcap_of[k] = (uint32_t)(128 * ((size_t)bk.Lcap * (bk.Lcap + 1) / 2));
-        stream_stride_of[k] = fold2_stream_bytes(bk.Lcap, tcap_of[k]);
-        stream_bytes = std::max(stream_bytes, (size_t)grid_of[k] * stream_stride_of[k]);
-      }
+  for (size_t k = 0; k < buckets.size(); k++) {
+    const Bucket& bk = buckets[k];
+    if (bk.mode == MODE_COOP && !no_streams) {
+      // one sequence on the whole GPU: a single stream slot, as large as memory comfortably allows (else the kernel
+      // scores on the fly)
+      const size_t Tc = (size_t)bk.Lcap * (bk.Lcap + 1) / 2;
+      meminfo();
+      size_t cap = std::min<size_t>(96 * Tc, (size_t)0xfffffff0u);
+      const size_t budget = (freeb + h->stream_ws.cap) / 3;
+      if (cap * 16 > budget) cap = budget / 16;
+      tcap_of[k] = (uint32_t)cap;
+      stream_stride_of[k] = fold2_stream_bytes(bk.Lcap, tcap_of[k]);
+      stream_bytes = std::max(stream_bytes, stream_stride_of[k]);
+    }
+    if (bk.mode != MODE_SMEM) continue;
+    // CTAs per SM: bounded by shared memory (C, log P and the small per-sequence tables) and by 1024 threads per SM
+    // at 64 registers.  The chains are latency-bound, so residency is what fills the SM: take all the CTAs that
+    // fit (<= 4, measured best) and give each 1024 / CTAs threads: roles first, the rest help in the all-thread phases.
+    const size_t smem = smem_need(bk.Lcap);
+    static const int occ_cap = dev_env("RNA_FOLD_OCC") ? atoi(dev_env("RNA_FOLD_OCC")) : 4;   // measured best on tRNA-length batches
+    int occ_s = (int)std::min<size_t>((size_t)std::max(1, occ_cap), (size_t)233472 / (smem + 1024 + 64));
+    occ_s = std::max(1, occ_s);
+    occ_s = std::min(occ_s, std::max(1, 32 / fold2_min_warps(bk.Lcap, CONTRA)));
+    int warps = std::min(16, 32 / occ_s);
+    if (no_helpers) { const Roles fr = fold2_roles(bk.Lcap, CONTRA, 16); warps = std::min(warps, fr.nX + fr.nY + fr.nZ); }
+    ro_of[k] = fold2_roles(bk.Lcap, CONTRA, warps);
+    const int nt = 32 * warps;
+    int occ = 1;
+    TRY(kern_prepare(h, (const void*)fold_kernel2<CONTRA, MODE_SMEM>, nt, smem, &occ));
+    occ = std::max(1, std::min(occ, occ_cap));
+    nt_of[k] = nt;
+    grid_of[k] = (int)std::min<size_t>(bk.end - bk.begin, (size_t)occ * h->sm_count);
+    stride_of[k] = 4 * ((size_t)bk.Lcap * (bk.Lcap + 1) / 2) + 32;   // R X E M1 of one CTA
+    ws_floats = std::max(ws_floats, (size_t)grid_of[k] * stride_of[k]);
+    if (!no_streams) {
+      // room for 128 stream elements per cell (random sequences need ~50 incl. padding); sequences with longer
+      // lists score on the fly
+      tcap_of[k] = (uint32_t)(128 * ((size_t)bk.Lcap * (bk.Lcap + 1) / 2));
+      stream_stride_of[k] = fold2_stream_bytes(bk.Lcap, tcap_of[k]);
+      stream_bytes = std::max(stream_bytes, (size_t)grid_of[k] * stream_stride_of[k]);
     }
   }
   // Buckets run concurrently on up to kLanes streams (bucket k on lane k % kLanes; small buckets would otherwise
-  // leave most SMs idle, and the tails of big ones overlap).  Kernels of one lane are stream-ordered, so the
-  // scratch is one region per lane, each sized for the largest bucket.
-  static const bool serial = getenv("RNA_FOLD_SERIAL") != nullptr || getenv("RNA_FOLD_DBG") != nullptr;
-  // Also full-size launches gain from it: the next bucket's CTAs take over SMs as the last CTAs of the previous one
-  // drain (default bench, four buckets of 4096-12288 sequences: 164.0 k -> 173.3 k seq/s).
+  // leave most SMs idle, and the tails of big ones overlap: the next bucket's CTAs take over SMs as the last CTAs of
+  // the previous one drain).  Kernels of one lane are stream-ordered, so the scratch is one region per lane, each
+  // sized for the largest bucket.
+  static const bool dbg_roles = dev_env("RNA_FOLD_DBG") != nullptr;
+  static const bool serial = dev_env("RNA_FOLD_SERIAL") != nullptr || dbg_roles;
   size_t batch_buckets = 0;
   for (size_t k = 0; k < buckets.size(); k++)
     if (buckets[k].mode != MODE_COOP) batch_buckets++;
-  static const int force_lanes = getenv("RNA_FOLD_LANES") ? atoi(getenv("RNA_FOLD_LANES")) : 0;   // A/B switch
+  static const int force_lanes = dev_env("RNA_FOLD_LANES") ? atoi(dev_env("RNA_FOLD_LANES")) : 0;
   const int nlanes = serial ? 1
                      : (int)std::max<size_t>(1, std::min<size_t>(force_lanes > 0 ? (size_t)std::min(force_lanes, (int)rna_handle::kLanes)
                                                                               : (size_t)rna_handle::kLanes, batch_buckets));
@@ -477,7 +698,6 @@ static int launch_fold_model(rna_handle* h, const RnaFoldBatchDev* b, cudaStream
   }
   cudaStream_t st_main = st;
 
-  static const bool dbg_roles = getenv("RNA_FOLD_DBG") != nullptr;
   long long* d_dbg = nullptr;
   if (dbg_roles) { cudaMalloc(&d_dbg, (size_t)(1 << 20) * 8); cudaMemset(d_dbg, 0, (size_t)(1 << 20) * 8); a.dbg = d_dbg; }
   for (size_t k = 0; k < buckets.size(); k++) {
@@ -495,59 +715,32 @@ static int launch_fold_model(rna_handle* h, const RnaFoldBatchDev* b, cudaStream
     a.work_counter = (int*)h->counters.p + k;
     a.Lcap = bk.Lcap;
     a.ws_stride = stride_of[k];
-    if (v2 && bk.mode != MODE_COOP) {
+    if (bk.mode != MODE_COOP) {
       const Roles ro = (bk.mode == MODE_SMEM) ? ro_of[k] : fold2_roles(bk.Lcap, CONTRA, 16);
       a.nXw = ro.nX; a.nYw = ro.nY; a.nZw = ro.nZ;
       const int nt = (bk.mode == MODE_SMEM) ? nt_of[k] : 32 * (ro.nX + ro.nY + ro.nZ);
       a.stream_ws = nullptr;
       if (bk.mode == MODE_SMEM) {
         const size_t smem = smem_need(bk.Lcap);
-        if (regs48_of[k]) TRY(set_smem_attr(h, (fold_kernel2<CONTRA, MODE_SMEM, true>), smem));
-        else TRY(set_smem_attr(h, fold_kernel2<CONTRA, MODE_SMEM>, smem));
         if (stream_stride_of[k]) {
           a.tcap = tcap_of[k];
           a.stream_stride = stream_stride_of[k];
           a.stream_ws = (unsigned char*)h->stream_ws.p + (size_t)lane * stream_bytes;
         }
-        if (regs48_of[k]) fold_kernel2<CONTRA, MODE_SMEM, true><<<grid_of[k], nt, smem, st>>>(a);
-        else fold_kernel2<CONTRA, MODE_SMEM><<<grid_of[k], nt, smem, st>>>(a);
+        fold_kernel2<CONTRA, MODE_SMEM><<<grid_of[k], nt, smem, st>>>(a);
       } else {
         const size_t smem = fold2_fixed_bytes<CONTRA>(bk.Lcap);
-        TRY(set_smem_attr(h, fold_kernel2<CONTRA, MODE_GLOBAL>, smem));
+        TRY(kern_prepare(h, (const void*)fold_kernel2<CONTRA, MODE_GLOBAL>, nt, smem, nullptr));
         fold_kernel2<CONTRA, MODE_GLOBAL><<<grid_of[k], nt, smem, st>>>(a);
       }
-    } else if (bk.mode == MODE_SMEM) {
-      const int nt = std::min(256, std::max(32, (bk.Lcap + 31) / 32 * 32));
-      const size_t smem = smem_need(bk.Lcap);
-      int occ = 1;
-      if (centroid_only) {
-        TRY(set_smem_attr(h, centroid_kernel<MODE_SMEM>, smem));
-        CU(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, centroid_kernel<MODE_SMEM>, nt, smem));
-      } else {
-        TRY(set_smem_attr(h, fold_kernel<CONTRA, MODE_SMEM>, smem));
-        CU(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fold_kernel<CONTRA, MODE_SMEM>, nt, smem));
-      }
-      const int grid = (int)std::min<size_t>(a.n_launch, (size_t)std::max(1, occ) * h->sm_count);
-      if (centroid_only) centroid_kernel<MODE_SMEM><<<grid, nt, smem, st>>>(a, d_bpp_in);
-      else fold_kernel<CONTRA, MODE_SMEM><<<grid, nt, smem, st>>>(a);
-    } else if (bk.mode == MODE_GLOBAL) {
-      const int nt = std::min(512, std::max(32, (bk.Lcap + 31) / 32 * 32));
-      const size_t smem = centroid_only ? 16 : fold_smem_bytes<CONTRA>(bk.Lcap, false);
-      if (centroid_only) {
-        centroid_kernel<MODE_GLOBAL><<<grid_of[k], nt, smem, st>>>(a, d_bpp_in);
-      } else {
-        TRY(set_smem_attr(h, fold_kernel<CONTRA, MODE_GLOBAL>, smem));
-        fold_kernel<CONTRA, MODE_GLOBAL><<<grid_of[k], nt, smem, st>>>(a);
-      }
-    } else if (v2) {
+    } else {
       // long sequence: cooperative grid, roles spread over the SMs
       const int nt = 256;
       const size_t smem = fold2_fixed_bytes<CONTRA>(bk.Lcap) + RNA_ML_RING_FLOATS * 4;
-      static const bool no_split = getenv("RNA_COOP_NOSPLIT") != nullptr;
+      static const bool no_split = dev_env("RNA_COOP_NOSPLIT") != nullptr;
       a.no_ml_split = no_split ? 1 : 0;
       int occ = 1;
-      TRY(set_smem_attr(h, fold_kernel2_coop<CONTRA>, smem));
-      CU(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fold_kernel2_coop<CONTRA>, nt, smem));
+      TRY(kern_prepare(h, (const void*)fold_kernel2_coop<CONTRA>, nt, smem, &occ));
       const int grid = std::max(1, std::min(occ, 2)) * h->sm_count;
       const int W = grid * (nt / 32);
       // inside pair steps: X = closable cells of two diagonals, Y = all cells of two diagonals, Z = three chains per
@@ -564,94 +757,12 @@ static int launch_fold_model(rna_handle* h, const RnaFoldBatchDev* b, cudaStream
       }
       void* params[] = {(void*)&a};
       CU(h, cudaLaunchCooperativeKernel((void*)fold_kernel2_coop<CONTRA>, dim3(grid), dim3(nt), params, smem, st));
-    } else {
-      const int nt = 128;
-      const size_t smem = centroid_only ? 16 : fold_smem_bytes<CONTRA>(bk.Lcap, false);
-      int occ = 1;
-      void* kern;
-      if (centroid_only) {
-        kern = (void*)centroid_kernel<MODE_COOP>;
-        CU(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, centroid_kernel<MODE_COOP>, nt, smem));
-      } else {
-        kern = (void*)fold_kernel<CONTRA, MODE_COOP>;
-        TRY(set_smem_attr(h, fold_kernel<CONTRA, MODE_COOP>, smem));
-        CU(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fold_kernel<CONTRA, MODE_COOP>, nt, smem));
-      }
-      const int maxg = std::max(1, occ) * h->sm_count;
-      const int grid = std::max(1, std::min(maxg, (bk.Lcap + nt - 1) / nt));
-      void* params_fold[] = {(void*)&a};
-      void* params_cent[] = {(void*)&a, (void*)&d_bpp_in};
-      CU(h, cudaLaunchCooperativeKernel(kern, dim3(grid), dim3(nt), centroid_only ? params_cent : params_fold, smem, st));
     }
     CU(h, cudaGetLastError());
     h->stats.kernel_launches++;
-    if (dbg_roles && v2 && bk.mode == MODE_COOP) {
-      cudaStreamSynchronize(st);
-      long long hd[32];
-      cudaMemcpy(hd, d_dbg, sizeof hd, cudaMemcpyDeviceToHost);
-      fprintf(stderr, "[RNA_FOLD_DBG] coop L=%d roles %d/%d/%d: setup+streams=%lld inside=%lld outside=%lld bpp+centroid=%lld cycles\n", bk.Lcap,
-              a.nXw, a.nYw, a.nZw, hd[0], hd[1], hd[2], hd[3]);
-      fprintf(stderr, "[RNA_FOLD_DBG]   inside, first warp of a role (work, wait A, phase B): X %lld %lld %lld | Y %lld %lld %lld | Z %lld %lld %lld\n",
-              hd[8], hd[9], hd[10], hd[12], hd[13], hd[14], hd[16], hd[17], hd[18]);
-      fprintf(stderr, "[RNA_FOLD_DBG]   outside, first warp of a role (work, wait): X %lld %lld | Y %lld %lld\n", hd[20], hd[21], hd[24], hd[25]);
-      {
-        std::vector<long long> hs((size_t)(bk.Lcap / 2 + 2) * 8);
-        cudaMemcpy(hs.data(), d_dbg + 64, hs.size() * 8, cudaMemcpyDeviceToHost);
-        long long sm[5] = {0, 0, 0, 0, 0}, crit = 0, nsA = 0, nsBar = 0, nsB = 0, prev_end = 0;
-        for (size_t stp = 0; stp * 8 < hs.size(); stp++) {
-          long long mx = 0;
-          for (int r = 0; r < 5; r++) { sm[r] += hs[stp * 8 + r]; mx = std::max(mx, hs[stp * 8 + r]); }
-          crit += mx;
-          const long long ga = hs[stp * 8 + 5], gr = hs[stp * 8 + 6], ge = hs[stp * 8 + 7];
-          if (ga && gr && ge) { if (prev_end) nsA += ga - prev_end; nsBar += gr - ga; nsB += ge - gr; prev_end = ge; }
-        }
-        fprintf(stderr, "[RNA_FOLD_DBG]   inside wall (globaltimer, last CTA): phase A %.3f ms, its barrier %.3f ms, phase B + barrier %.3f ms\n",
-                nsA * 1e-6, nsBar * 1e-6, nsB * 1e-6);
-        {
-          std::vector<long long> ho((size_t)bk.Lcap * 4);
-          cudaMemcpy(ho.data(), d_dbg + (1 << 19), ho.size() * 8, cudaMemcpyDeviceToHost);
-          long long ox = 0, oy = 0, oall = 0, ostream = 0;
-          for (int dd = 0; dd < bk.Lcap; dd++) {
-            ox += ho[(size_t)dd * 4]; oy += ho[(size_t)dd * 4 + 1]; oall += std::max(ho[(size_t)dd * 4], ho[(size_t)dd * 4 + 1]);
-            ostream += (ho[(size_t)dd * 4 + 2] & 0xffffff) << 4;
-          }
-          fprintf(stderr, "[RNA_FOLD_DBG]   outside, sum over steps of the slowest warp: X %lld (of which exterior + two-loop stream part %lld) Y %lld, all %lld\n", ox, ostream, oy, oall);
-        }
-        fprintf(stderr, "[RNA_FOLD_DBG]   inside phase A, sum over steps of the slowest warp: X %lld Y %lld Z-E %lld Z-M1 %lld Z-M %lld, all %lld\n",
-                sm[0], sm[1], sm[2], sm[3], sm[4], crit);
-      }
-    } else if (dbg_roles) {   // debug aid: where do the cycles of one sequence go, per role and pass
-      cudaStreamSynchronize(st);
-      std::vector<long long> hd(2048 * 16);
-      cudaMemcpy(hd.data(), d_dbg, hd.size() * 8, cudaMemcpyDeviceToHost);
-      for (int pass = 0; pass < 2; pass++) {
-        long long role[3] = {0, 0, 0}, crit = 0, critrole[3] = {0, 0, 0};
-        for (int t = 0; t < 1000; t++) {
-          long long m[3] = {0, 0, 0};
-          for (int wv = 0; wv < 16; wv++) {
-            const int r = wv < a.nXw ? 0 : wv < a.nXw + a.nYw ? 1 : 2;
-            m[r] = std::max(m[r], hd[(size_t)(pass * 1024 + t) * 16 + wv]);
-          }
-          const long long mx = std::max(m[0], std::max(m[1], m[2]));
-          crit += mx;
-          for (int r = 0; r < 3; r++) { role[r] += m[r]; if (m[r] == mx && mx) critrole[r] += mx; }
-        }
-        fprintf(stderr, "[RNA_FOLD_DBG] bucket Lcap=%d pass=%s roles X/Y/Z warps %d/%d/%d: sum of per-step max cycles X=%lld Y=%lld Z=%lld, "
-                "critical path=%lld (X %lld, Y %lld, Z %lld)\n", bk.Lcap, pass ? "outside" : "inside", a.nXw, a.nYw, a.nZw,
-                role[0], role[1], role[2], crit, critrole[0], critrole[1], critrole[2]);
-      }
-      for (int t = 1024; t < 1024; t++) {
-        long long my = 0, mx = 0;
-        for (int wv = 0; wv < 16; wv++) { (wv < a.nXw ? mx : my) = std::max(wv < a.nXw ? mx : my, hd[(size_t)t * 16 + wv]); }
-        if (my > 200000) fprintf(stderr, "[RNA_FOLD_DBG]   outside d=%d: X=%lld Y=%lld\n", t - 1024, mx, my);
-      }
-      fprintf(stderr, "[RNA_FOLD_DBG]   setup=%lld count=%lld scan=%lld fill=%lld cycles, terms=%lld\n", hd[2047 * 16], hd[2047 * 16 + 1],
-              hd[2047 * 16 + 2], hd[2047 * 16 + 3], hd[2047 * 16 + 4]);
-      fprintf(stderr, "[RNA_FOLD_DBG]   L=%lld: output+centroid=%lld cycles, whole sequence=%lld cycles; launch: %d threads, grid %d, smem %zu\n",
-              hd[2047 * 16 + 7], hd[2047 * 16 + 5], hd[2047 * 16 + 6], nt_of[k], grid_of[k], smem_need(bk.Lcap));
-      if (!hd[2047 * 16 + 3]) fprintf(stderr, "[RNA_FOLD_DBG]   (streams did not fit: scored on the fly)\n");
-      cudaMemset(d_dbg, 0, 2048 * 16 * 8);
-    }
+#ifdef RNA_DEV_SWITCHES
+    if (dbg_roles) fold_dbg_report(bk.mode, bk.Lcap, a, d_dbg, st, nt_of[k], grid_of[k], bk.mode == MODE_SMEM ? smem_need(bk.Lcap) : 0);
+#endif
   }
   if (nlanes > 1) {
     for (int x = 0; x < nlanes; x++) { CU(h, cudaEventRecord(h->ev_join[x], h->aux[x])); CU(h, cudaStreamWaitEvent(st_main, h->ev_join[x], 0)); }
@@ -669,6 +780,7 @@ static int check_fold_args(rna_handle* h, const RnaFoldBatchDev* b) {
   if (b->model == RNA_MODEL_CONTRA && !h->has_contra) { h->err = "CONTRAfold tables not set"; return RNA_ERR_NO_TABLES; }
   if (b->d_out_bpp && !b->d_bpp_offsets) { h->err = "d_bpp_offsets required"; return RNA_ERR_BAD_ARG; }
   if (b->n_gammas && !b->d_gammas) { h->err = "d_gammas required"; return RNA_ERR_BAD_ARG; }
+  if (rna_validate_fold_lengths(b->h_offsets, b->n_seqs) != RNA_OK) { h->err = "sequence longer than RNA_MAX_FOLD_LEN (46340 nt)"; return RNA_ERR_TOO_LONG; }
   return RNA_OK;
 }
 
@@ -677,8 +789,10 @@ extern "C" int rna_mccaskill_centroid_batch_dev(rna_handle* h, const RnaFoldBatc
   if (b->n_seqs == 0) return RNA_OK;
   CU(h, cudaSetDevice(h->device));
   cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
-  if (b->model == RNA_MODEL_CONTRA) return launch_fold_model<true>(h, b, st, false, nullptr);
-  return launch_fold_model<false>(h, b, st, false, nullptr);
+  TRY(call_begin(h, st));
+  if (b->model == RNA_MODEL_CONTRA) TRY(launch_fold_model<true>(h, b, st));
+  else TRY(launch_fold_model<false>(h, b, st));
+  return call_end(h, st);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -705,7 +819,8 @@ extern "C" int rna_mccaskill_centroid_batch(rna_handle* h, const uint8_t* bases,
   h->stats = RnaCallStats{};
   if (n_seqs == 0) return RNA_OK;
   int rc = rna_validate_bases(bases, offsets, n_seqs);
-  if (rc != RNA_OK) { h->err = "input validation failed"; return rc; }
+  if (rc == RNA_OK) rc = rna_validate_fold_lengths(offsets, n_seqs);
+  if (rc != RNA_OK) { h->err = rc == RNA_ERR_TOO_LONG ? "sequence longer than RNA_MAX_FOLD_LEN (46340 nt)" : "input validation failed"; return rc; }
   if (offsets[0] != 0) { h->err = "offsets[0] must be 0"; return RNA_ERR_BAD_ARG; }
   if (n_gammas && !gammas) return RNA_ERR_BAD_ARG;
   CU(h, cudaSetDevice(h->device));
@@ -737,7 +852,7 @@ extern "C" int rna_mccaskill_centroid_batch(rna_handle* h, const uint8_t* bases,
     // coalesced row segments.  When the caller's buffer is page-locked (cudaHostAlloc / cudaHostRegister) the kernels
     // write it directly over PCIe while they compute, instead of staging in HBM and copying after the last kernel;
     // a pageable buffer takes the staged path.  (RNA_NO_ZERO_COPY=1 forces staging.)
-    static const bool no_zc = getenv("RNA_NO_ZERO_COPY") != nullptr;
+    static const bool no_zc = dev_env("RNA_NO_ZERO_COPY") != nullptr;
     cudaPointerAttributes pat;
     memset(&pat, 0, sizeof pat);
     if (!no_zc && cudaPointerGetAttributes(&pat, out_bpp) == cudaSuccess && pat.type == cudaMemoryTypeHost && pat.devicePointer) {
@@ -796,7 +911,7 @@ static int centroid_host(rna_handle* h, const float* bpp, const uint64_t* bpp_of
   if (offsets[0] != 0) { h->err = "offsets[0] must be 0"; return RNA_ERR_BAD_ARG; }
   for (uint32_t s = 0; s < n_seqs; s++) {
     if (offsets[s + 1] <= offsets[s]) return RNA_ERR_EMPTY_SEQ;
-    if (offsets[s + 1] - offsets[s] > RNA_MAX_SEQ_LEN) return RNA_ERR_TOO_LONG;
+    if (offsets[s + 1] - offsets[s] > (uint32_t)RNA_MAX_FOLD_LEN) return RNA_ERR_TOO_LONG;
   }
   CU(h, cudaSetDevice(h->device));
   cudaStream_t st = h->stream;
@@ -826,7 +941,9 @@ static int centroid_host(rna_handle* h, const float* bpp, const uint64_t* bpp_of
   if (out_expect_acc) { TRY(ensure(h, h->b_ea, sizeof(float) * (size_t)n_gammas * n_seqs)); b.d_out_expect_acc = (float*)h->b_ea.p; }
   if (out_pairs) { TRY(ensure(h, h->b_pairs, sizeof(uint16_t) * 2 * (size_t)n_gammas * total)); b.d_out_pairs = (uint16_t*)h->b_pairs.p; }
   if (out_num_pairs) { TRY(ensure(h, h->b_logz, sizeof(uint32_t) * (size_t)n_gammas * n_seqs)); b.d_out_num_pairs = (uint32_t*)h->b_logz.p; }
-  TRY(launch_fold_model<false>(h, &b, st, true, (const float*)h->b_bpp.p));
+  TRY(call_begin(h, st));
+  TRY(launch_centroid(h, &b, st, (const float*)h->b_bpp.p));
+  TRY(call_end(h, st));
   if (out_structs) TRY(d2h(h, out_structs, h->b_structs, (size_t)n_gammas * total, st));
   if (out_expect_acc) TRY(d2h(h, out_expect_acc, h->b_ea, sizeof(float) * (size_t)n_gammas * n_seqs, st));
   if (out_pairs) TRY(d2h(h, out_pairs, h->b_pairs, sizeof(uint16_t) * 2 * (size_t)n_gammas * total, st));
@@ -868,6 +985,7 @@ extern "C" int rna_durbin_batch_dev(rna_handle* h, const RnaDurbinBatchDev* b, v
       !b->d_out_probs) { h->err = "null pointer"; return RNA_ERR_BAD_ARG; }
   CU(h, cudaSetDevice(h->device));
   cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
+  TRY(call_begin(h, st));
   const uint32_t np = b->n_pairs;
   const uint32_t* ho = b->h_offsets;
   std::vector<uint32_t> order(np);
@@ -906,14 +1024,13 @@ extern "C" int rna_durbin_batch_dev(rna_handle* h, const RnaDurbinBatchDev* b, v
   // the n x m forward / posterior matrix on chip when at least 6 CTAs per SM still fit (tRNA-length pairs)
   // (on chip it would cap the residency at 6 CTAs of 3 warps per SM for tRNA-length pairs — measured 3.07 M pairs/s
   // against 4.4 M with a global slot per CTA, which stays L2-resident: 2 x SM-count x ~20 CTAs x 33 KB)
-  static const bool park_smem = getenv("RNA_DURBIN_PARK_SMEM") != nullptr;
+  static const bool park_smem = dev_env("RNA_DURBIN_PARK_SMEM") != nullptr;
   a.park_in_smem = park_smem && a.roll_in_smem && 6 * (durbin_smem_bytes(ncap, mcap, true, true) + 1024) <= (size_t)233472;
   const size_t smem = durbin_smem_bytes(ncap, mcap, a.roll_in_smem != 0, a.park_in_smem != 0);
   if (smem + 1024 > h->smem_optin) { h->err = "sequence too long for the Durbin kernel"; return RNA_ERR_TOO_LONG; }
   const int nt = std::min(256, std::max(32, (ncap + 31) / 32 * 32));
-  TRY(set_smem_attr(h, durbin_kernel, smem));
   int occ = 1;
-  CU(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, durbin_kernel, nt, smem));
+  TRY(kern_prepare(h, (const void*)durbin_kernel, nt, smem, &occ));
   const int grid = (int)std::min<size_t>(np, (size_t)std::max(1, occ) * h->sm_count);
   {
     a.ws_stride = a.roll_in_smem ? 0 : (size_t)9 * ncap + 32;
@@ -928,7 +1045,7 @@ extern "C" int rna_durbin_batch_dev(rna_handle* h, const RnaDurbinBatchDev* b, v
   durbin_kernel<<<grid, nt, smem, st>>>(a);
   CU(h, cudaGetLastError());
   h->stats.kernel_launches++;
-  return RNA_OK;
+  return call_end(h, st);
 }
 
 extern "C" int rna_durbin_batch(rna_handle* h, const uint8_t* bases, const uint32_t* offsets, uint32_t n_seqs,
@@ -966,7 +1083,7 @@ extern "C" int rna_durbin_batch(rna_handle* h, const uint8_t* bases, const uint3
   bool zero_copy = false;
   float* d_target = nullptr;
   {
-    static const bool no_zc = getenv("RNA_NO_ZERO_COPY") != nullptr;
+    static const bool no_zc = dev_env("RNA_NO_ZERO_COPY") != nullptr;
     cudaPointerAttributes p0, p1;
     memset(&p0, 0, sizeof p0); memset(&p1, 0, sizeof p1);
     if (!no_zc && tot && cudaPointerGetAttributes(&p0, out_probs) == cudaSuccess && p0.type == cudaMemoryTypeHost && p0.devicePointer &&

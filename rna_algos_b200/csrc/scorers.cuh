@@ -32,7 +32,12 @@ RNA_DEV float t_hairpin(const TV& T, const uint8_t* s, int i, int j) {
     for (int p = 0; p < span; p++) key |= (unsigned)s[i + p] << (2 * p);
     const int n = T.g->num_special;
     for (int x = 0; x < n; x++) {
-      if ((int)T.g->special_len[x] == span && T.g->special_key[x] == key) return T.g->special_score[x];
+      if ((int)T.g->special_len[x] == span && T.g->special_key[x] == key) {
+        // first match decides (src/utils.rs:198-205); a listed score of -inf falls through to the generic
+        // hairpin (`if special_hairpin_score > NEG_INFINITY`, src/utils.rs:169)
+        if (T.g->special_score[x] > RNA_NEG_INF) return T.g->special_score[x];
+        break;
+      }
     }
   }
   const int len = j - i - 1;

@@ -18,6 +18,14 @@ namespace rna {
 static inline float f32_add(float a, float b) { volatile float r = a + b; return r; }
 static inline float f32_mul(float a, float b) { volatile float r = a * b; return r; }
 
+// Scores must be finite or -inf ("forbidden"): a NaN or +inf entry would leave the domain in which the kernels'
+// branch-free logsumexp equals the reference's `if !x.is_finite() { return }` (src/utils.rs:581-586).
+static inline bool scores_ok(const void* first, const void* end) {
+  for (const float* p = static_cast<const float*>(first); p < static_cast<const float*>(end); p++)
+    if (!(*p < INFINITY)) return false;   // NaN or +inf
+  return true;
+}
+
 // Fills everything of DevTurner except the four device pointers; hp_ext receives the hairpin-initiation
 // table for every loop length (table value, or the f32 ln-extrapolation of src/utils.rs:178-184).
 static inline int pack_turner(const RnaTurnerTables* t, DevTurner* d, std::vector<float>* hp_ext, std::string* err) {
@@ -27,6 +35,10 @@ static inline int pack_turner(const RnaTurnerTables* t, DevTurner* d, std::vecto
       t->min_hairpin_len_extrapolation > 31 || t->num_special_hairpins < 0 ||
       t->num_special_hairpins > RNA_MAX_SPECIAL_HAIRPINS) {
     *err = "Turner blob: caps out of range";
+    return RNA_ERR_BAD_TABLES;
+  }
+  if (!scores_ok(&t->coeff_hairpin_len_extrapolation, &t->hairpin_scores_special[0])) {
+    *err = "Turner blob: a score is NaN or +inf";
     return RNA_ERR_BAD_TABLES;
   }
   memset(d, 0, sizeof *d);
@@ -52,6 +64,7 @@ static inline int pack_turner(const RnaTurnerTables* t, DevTurner* d, std::vecto
   for (int x = 0; x < t->num_special_hairpins; x++) {
     const RnaSpecialHairpin& e = t->hairpin_scores_special[x];
     if (e.len < 2 || e.len > RNA_MAX_SPECIAL_HAIRPIN_LEN) { *err = "Turner blob: special hairpin length"; return RNA_ERR_BAD_TABLES; }
+    if (!(e.score < INFINITY)) { *err = "Turner blob: a special hairpin score is NaN or +inf"; return RNA_ERR_BAD_TABLES; }
     unsigned key = 0;
     for (int p = 0; p < e.len; p++) {
       if (e.seq[p] > 3) { *err = "Turner blob: special hairpin base"; return RNA_ERR_BAD_TABLES; }
@@ -105,6 +118,10 @@ static inline int pack_contra(const RnaContraTables* t, DevContra* d, std::strin
   if (t->max_loop_len != RNA_CONTRA_MAX_LOOP_LEN || t->min_span_hairpin_close < 2 ||
       t->max_interior_explicit < 0 || t->max_interior_explicit > RNA_CONTRA_MAX_INTERIOR_EXPLICIT) {
     *err = "CONTRAfold blob: caps out of range";
+    return RNA_ERR_BAD_TABLES;
+  }
+  if (!scores_ok(&t->hairpin_scores_len[0], t + 1)) {
+    *err = "CONTRAfold blob: a score is NaN or +inf";
     return RNA_ERR_BAD_TABLES;
   }
   memset(d, 0, sizeof *d);
@@ -172,7 +189,11 @@ static inline int pack_contra(const RnaContraTables* t, DevContra* d, std::strin
   return RNA_OK;
 }
 
-static inline void pack_align(const RnaAlignTables* t, DevAlign* d) {
+static inline int pack_align(const RnaAlignTables* t, DevAlign* d, std::string* err) {
+  if (!scores_ok(t, t + 1)) {
+    *err = "align blob: a score is NaN or +inf";
+    return RNA_ERR_BAD_TABLES;
+  }
   d->m2m = t->match2match_score;
   d->m2i = t->match2insert_score;
   d->iex = t->insert_extend_score;
@@ -180,6 +201,7 @@ static inline void pack_align(const RnaAlignTables* t, DevAlign* d) {
   d->ini = t->init_insert_score;
   memcpy(d->insert, t->insert_scores, 16);
   memcpy(d->match, t->match_scores, 64);
+  return RNA_OK;
 }
 
 }  // namespace rna

@@ -7,13 +7,17 @@ arguments of the C ABI; a Rust shim fills them from the genuine crate (INTEGRATI
 module offers:
 
 * ``contralign_tables()``   – the genuine CONTRAlign v2.01 numbers (in-tree: src/compiled_align_scores.rs:2-19).
-* ``turner_tables()``       – "restated" Turner 2004 set: stacking, loop-initiation, multiloop, Ninio,
-  terminal-AU and a few special hairpins are restated from the public nearest-neighbour parameters;
-  mismatch / dangle / 1x1 / 1x2 / 2x2 tables are deterministic, physically plausible STAND-INS.
-  They are NOT guaranteed to equal upstream values (parity vs upstream tables is unpinned).
-* ``contra_tables()``       – same status for CONTRAfold v2.02 (scalars restated, tables stand-ins),
-  materialised exactly like FoldScoreSets::new(0.).transfer() (src/mccaskill_algo.rs:25-210): only
-  canonical entries are written, everything else keeps init_val = 0.
+* ``standin_turner_tables()`` – a STAND-IN of the shape of the Turner 2004 set, NOT the upstream numbers: stacking,
+  loop-initiation, multiloop, Ninio, terminal-AU and a few special hairpins are restated from the public
+  nearest-neighbour parameters from memory; mismatch / dangle / 1x1 / 1x2 / 2x2 tables are deterministic
+  pseudo-values.  Results computed with it differ from the reference's.  It exists so that kernels,
+  oracle and benchmarks have a realistic table set to run on.
+* ``standin_contra_tables()`` – same status for CONTRAfold v2.02, materialised exactly like
+  FoldScoreSets::new(0.).transfer() (src/mccaskill_algo.rs:25-210): only canonical entries are written,
+  everything else keeps init_val = 0.
+* ``load_table_file()`` / ``load_genuine_tables(dir)`` – read ``turner2004.tbl`` / ``contrafold_v202.tbl`` blobs
+  written from the genuine crate by ``tools/ref_dump`` (a machine with cargo); these names are reserved for
+  genuine values — the stand-ins are dumped as ``standin_turner.tbl`` / ``standin_contrafold.tbl``.
 * ``random_*_tables(seed)`` – fuzz tables for bit-parity tests of kernels vs oracle.
 """
 from __future__ import annotations
@@ -233,7 +237,7 @@ def _pair_strength(x, y) -> float:
     return 0.2
 
 
-def turner_tables() -> TurnerTables:
+def standin_turner_tables() -> TurnerTables:
     t = TurnerTables()
     t.max_2loop_len = 30
     t.min_span_hairpin_close = 5
@@ -309,7 +313,7 @@ def turner_tables() -> TurnerTables:
 # ----------------------------------------------------------------------------------------------
 # CONTRAfold v2.02 — restated scalars / stand-in tables, materialised like FoldScoreSets::transfer
 # ----------------------------------------------------------------------------------------------
-def contra_tables(lib=None) -> ContraTables:
+def standin_contra_tables(lib=None) -> ContraTables:
     t = ContraTables()  # FoldScoreSets::new(0.)
     t.max_loop_len = CONTRA_MAX_LOOP_LEN
     t.min_span_hairpin_close = 5
@@ -457,11 +461,17 @@ def random_align_tables(seed: int) -> AlignTables:
 
 
 # ----------------------------------------------------------------------------------------------
-# Table blob files for non-Python hosts (cli/): the raw bytes of the C structs behind a 16-byte header
-#   "RNATBL01" | u32 kind (1 Turner, 2 CONTRAfold) | u32 sizeof(struct)
-# `python -m rna_algos_b200.tables dump DIR` writes the default (restated) tables; a build that has the
-# genuine rna-ss-params values writes its own files in the same format.
+# Table blob files: the raw bytes of the C structs behind a 16-byte header
+#   "RNATBL01" | u32 kind (1 Turner, 2 CONTRAfold, 3 align) | u32 sizeof(struct)
+# File names `turner2004.tbl` / `contrafold_v202.tbl` are RESERVED for the genuine rna-ss-params values (written by
+# tools/ref_dump on a machine with cargo); `python -m rna_algos_b200.tables dump DIR` writes the stand-ins as
+# `standin_turner.tbl` / `standin_contrafold.tbl`.
 # ----------------------------------------------------------------------------------------------
+GENUINE_TURNER, GENUINE_CONTRA = "turner2004.tbl", "contrafold_v202.tbl"
+STANDIN_TURNER, STANDIN_CONTRA = "standin_turner.tbl", "standin_contrafold.tbl"
+_KIND_STRUCT = {1: TurnerTables, 2: ContraTables, 3: AlignTables}
+
+
 def dump_table_file(path: str, kind: int, struct) -> None:
     import struct as S
     raw = bytes(struct)
@@ -469,16 +479,37 @@ def dump_table_file(path: str, kind: int, struct) -> None:
         f.write(b"RNATBL01" + S.pack("<II", kind, len(raw)) + raw)
 
 
-def dump_default_tables(out_dir: str) -> None:
+def load_table_file(path: str, kind: int):
+    import struct as S
+    with open(path, "rb") as f:
+        head = f.read(16)
+        raw = f.read()
+    if len(head) != 16 or head[:8] != b"RNATBL01":
+        raise ValueError(f"{path}: not an RNATBL01 table blob")
+    k, size = S.unpack("<II", head[8:])
+    cls = _KIND_STRUCT[kind]
+    if k != kind or size != C.sizeof(cls) or len(raw) != size:
+        raise ValueError(f"{path}: kind/size mismatch (kind {k}, {size} bytes; expected kind {kind}, {C.sizeof(cls)} bytes)")
+    return cls.from_buffer_copy(raw)
+
+
+def load_genuine_tables(directory: str):
+    """(TurnerTables, ContraTables) from the reserved file names in `directory`."""
+    import os
+    return (load_table_file(os.path.join(directory, GENUINE_TURNER), 1),
+            load_table_file(os.path.join(directory, GENUINE_CONTRA), 2))
+
+
+def dump_standin_tables(out_dir: str) -> None:
     import os
     os.makedirs(out_dir, exist_ok=True)
-    dump_table_file(os.path.join(out_dir, "turner2004.tbl"), 1, turner_tables())
-    dump_table_file(os.path.join(out_dir, "contrafold_v202.tbl"), 2, contra_tables())
+    dump_table_file(os.path.join(out_dir, STANDIN_TURNER), 1, standin_turner_tables())
+    dump_table_file(os.path.join(out_dir, STANDIN_CONTRA), 2, standin_contra_tables())
 
 
 if __name__ == "__main__":
     import sys
     if len(sys.argv) == 3 and sys.argv[1] == "dump":
-        dump_default_tables(sys.argv[2])
+        dump_standin_tables(sys.argv[2])
     else:
-        raise SystemExit("usage: python -m rna_algos_b200.tables dump DIR")
+        raise SystemExit("usage: python -m rna_algos_b200.tables dump DIR   (writes the STAND-IN blobs)")

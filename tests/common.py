@@ -41,7 +41,7 @@ _tables_cache = {}
 
 def default_tables():
     if "d" not in _tables_cache:
-        _tables_cache["d"] = (T.turner_tables(), T.contra_tables(), T.contralign_tables())
+        _tables_cache["d"] = (T.standin_turner_tables(), T.standin_contra_tables(), T.contralign_tables())
     return _tables_cache["d"]
 
 

@@ -67,8 +67,13 @@ class Oracle:
         L.orc_durbin_batch.restype = C.c_int
         L.orc_durbin_batch.argtypes = [u8p, u32p, u32p, C.c_uint32, C.POINTER(AlignTables), f32p, u64p,
                                        C.c_int, u64p]
+        L.orc_set_inner_threads.argtypes = [C.c_int]
         L.orc_is_exact_flavour.restype = C.c_int
         assert bool(L.orc_is_exact_flavour()) == exact
+
+    def set_inner_threads(self, n: int) -> None:
+        """Spread the cells of one span of ONE sequence over n host threads (bit-identical; long-sequence checks)."""
+        self.lib.orc_set_inner_threads(int(n))
 
     # ---- single-item calls --------------------------------------------------------------------
     def mccaskill(self, seq: np.ndarray, contra: bool, allows_short: bool, tt, ct, debug: bool = False):
@@ -108,7 +113,15 @@ class Oracle:
 
     # ---- batch calls (threaded; the CPU baseline) ---------------------------------------------
     def fold_batch(self, bases, offsets, contra, allows_short, tt, ct, gammas, n_threads=1,
-                   want_bpp=True):
+                   want_bpp=True, inner_threads=1):
+        """n_threads: one sequence per task (the CPU baseline's shape).  inner_threads > 1: sequences one after the
+        other, the cells of each span spread over that many threads (long sequences; bit-identical)."""
+        if inner_threads > 1:
+            self.set_inner_threads(inner_threads)
+            try:
+                return self.fold_batch(bases, offsets, contra, allows_short, tt, ct, gammas, 1, want_bpp, 1)
+            finally:
+                self.set_inner_threads(1)
         bases = np.ascontiguousarray(bases, dtype=np.uint8)
         offsets = np.ascontiguousarray(offsets, dtype=np.uint32)
         gammas = np.ascontiguousarray(gammas, dtype=np.float32)

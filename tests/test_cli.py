@@ -85,8 +85,16 @@ def test_no_device_fails_loudly(cli, tmp_path):
     import torch
     if torch.cuda.is_available():
         pytest.skip("a GPU is present")
-    r = run(cli, "centroid_fold", "-i", TRNA_FASTA, "-o", str(tmp_path / "out"))
+    r = run(cli, "centroid_fold", "-i", TRNA_FASTA, "-o", str(tmp_path / "out"), "--standin-tables")
     assert r.returncode == 1 and "no CPU path" in r.stderr
+
+
+def test_standin_tables_need_an_explicit_opt_in(cli, tmp_path):
+    """turner2004.tbl / contrafold_v202.tbl are names reserved for the genuine rna-ss-params values: without --tables
+    (or $RNA_ALGOS_B200_TABLES) and without --standin-tables the fold programs refuse to run."""
+    env = {k: v for k, v in os.environ.items() if k != "RNA_ALGOS_B200_TABLES"}
+    r = subprocess.run([cli, "mccaskill_algo", "-i", TRNA_FASTA, "-o", str(tmp_path / "o.dat")], capture_output=True, text=True, env=env)
+    assert r.returncode == 1 and "no score tables" in r.stderr and "--standin-tables" in r.stderr
 
 
 # ---- GPU: whole-file parity -----------------------------------------------------------------------------------
@@ -96,7 +104,7 @@ def test_mccaskill_algo_output(cli, tmp_path, contra):
     from oracle_lib import Oracle
     tt, ct, _ = default_tables()
     out = tmp_path / "bpp.dat"
-    r = run(cli, "mccaskill_algo", "-i", TRNA_FASTA, "-o", str(out), *(["-c"] if contra else []), "-t", "3")
+    r = run(cli, "mccaskill_algo", "-i", TRNA_FASTA, "-o", str(out), *(["-c"] if contra else []), "-t", "3", "--standin-tables")
     assert r.returncode == 0, r.stderr
     seqs = load_trnas()
     want = ("# Format = >{RNA sequence id} {line break} {basepairing left nucleotide}, {basepairing right nucleotide}, "
@@ -124,7 +132,7 @@ def test_centroid_fold_output(cli, tmp_path):
     orc = Oracle()
     # the reference's sweep 2^-7 .. 2^10 (no -g), CONTRAfold
     outdir = tmp_path / "sweep"
-    r = run(cli, "centroid_fold", "-i", TRNA_FASTA, "-o", str(outdir), "-c")
+    r = run(cli, "centroid_fold", "-i", TRNA_FASTA, "-o", str(outdir), "-c", "--standin-tables")
     assert r.returncode == 0, r.stderr
     gammas = [float(np.float32(2.0) ** p) for p in range(-7, 11)]
     want = orc.fold_batch(bases, offsets, True, False, tt, ct, gammas, n_threads=4)
@@ -135,7 +143,7 @@ def test_centroid_fold_output(cli, tmp_path):
         assert (outdir / f"centroid_threshold={rust_f32(gamma)}.fa").read_text() == text
     # one threshold, Turner
     outdir = tmp_path / "one"
-    r = run(cli, "centroid_fold", "-i", TRNA_FASTA, "-o", str(outdir), "-g", "2")
+    r = run(cli, "centroid_fold", "-i", TRNA_FASTA, "-o", str(outdir), "-g", "2", "--standin-tables")
     assert r.returncode == 0, r.stderr
     assert os.listdir(outdir) == ["centroid_threshold=2.fa"]
     want = orc.fold_batch(bases, offsets, False, False, tt, ct, [2.0], n_threads=4)

@@ -240,6 +240,26 @@ def test_long_cooperative_contra(handle, oracle):
     check_fold(handle, oracle, random_seqs(33, [1300]), True, False, [2.0, 0.5], tt, ct)
 
 
+@pytest.mark.parametrize("L,seed", [(1024, 1), (2048, 2), (4096, 3)])
+@pytest.mark.parametrize("contra", [False, True])
+def test_config3_long_single_sequences(handle, oracle, L, seed, contra):
+    """BASELINE configs[3]: one i.i.d.-uniform sequence at 1024 / 2048 / 4096 nt, seeds 1/2/3,
+    both models, through the cooperative multi-CTA wavefront: logZ, every BPP entry, expected accuracies and
+    structures bit-equal to the oracle (whose span loops run on all host cores here: same folds, same order)."""
+    import os
+    tt, ct, _ = default_tables()
+    seq = np.random.default_rng(seed).integers(0, 4, size=L).astype(np.uint8)
+    bases, offsets = pack([seq])
+    gammas = [1.0, 2.0, 8.0]
+    got = handle.fold_batch(bases, offsets, contra, False, gammas)
+    want = oracle.fold_batch(bases, offsets, contra, False, tt, ct, gammas, inner_threads=max(2, os.cpu_count() or 2))
+    assert_bits_equal(got["logz"], want["logz"], f"logZ L={L}")
+    assert_bits_equal(got["bpp"], want["bpp"], f"BPP L={L}")
+    assert_bits_equal(got["expect_acc"], want["expect_acc"], f"expect_accuracy L={L}")
+    assert (got["structs"] == want["structs"]).all(), f"dot-bracket structures differ at L={L}"
+    assert (got["structs"][1] == ord("(")).sum() > 10   # gamma = 2: a real structure, not all dots
+
+
 def test_mixed_long_and_mid_routing(handle, oracle):
     """A few long sequences next to mid-length ones: the cost model sends the longest to the cooperative kernel and
     the rest to the one-CTA HBM-resident mode; results are bit-identical either way."""

@@ -189,7 +189,7 @@ def test_real_tables_small():
     ox = Oracle(exact=True)
     for contra in (False, True):
         seq = _biased_seq(rng, 17)
-        tt, ct = T.turner_tables(), T.contra_tables()
+        tt, ct = T.standin_turner_tables(), T.standin_contra_tables()
         m = Model(ox, seq, contra, False, tt, ct)
         logz, bpp, n = brute(m)
         got, got_logz = ox.mccaskill(seq, contra, False, tt, ct)
