@@ -6,18 +6,6 @@
 
 namespace rna {
 
-// Base-indexed Turner tables that the kernels gather with per-lane indices (staged in shared memory).
-struct TurnerSmall {
-  float tm_hairpin[256];   // TERMINAL_MISMATCH_SCORES_HAIRPIN[i][j][i+1][j-1]
-  float stack[256];        // STACK_SCORES[i][j][k][l]
-  float tm_1xmany[256];
-  float tm_2x3[256];
-  float tm_interior[256];
-  float tm_multi[256];     // TERMINAL_MISMATCH_SCORES_MULTIBRANCH
-  float d5[64];            // DANGLING_SCORES_5PRIME[i][j][i-1]
-  float d3[64];            // DANGLING_SCORES_3PRIME[i][j][j+1]
-};
-
 // v2 kernels: the three interior-mismatch tables re-indexed by the per-position base codes
 //   RR[p] = s[p]*4 + s[p+1],  LL[p] = s[p]*4 + s[p-1]:   tm2[X][RR*16 + LL] = TERMINAL_MISMATCH_X[x][y][x1][y1]
 // (X = 0: 1xMANY, 1: 2x3, 2: INTERIOR), so one byte per partner position addresses them.
@@ -48,24 +36,12 @@ struct DevTurner {
   unsigned special_key[128];        // 2 bits per base, base p at bits 2p (slice incl. closing pair)
   unsigned char special_len[128];
   float special_score[128];
-  TurnerSmall small;
   TurnerSmall2 small2;
   // device-global arrays
   const float* hairpin_init_ext;    // [RNA_HAIRPIN_EXT_LEN]: INIT[len] or the ln-extrapolation (src/utils.rs:178-184)
   const float* int11;               // [4^6]
   const float* int12;               // [4^7]
   const float* int22;               // [4^8]
-};
-
-struct ContraSmall {
-  float stack[256];
-  float tm[256];          // terminal_mismatch_scores
-  float dl[64];           // dangling_scores_left
-  float dr[64];           // dangling_scores_right
-  float hc[16];           // helix_close_scores
-  float bp[16];           // basepair_scores
-  float bulge0x1[4];
-  float int1x1[16];
 };
 
 // v2 kernels (fold_phases.cuh): per-lane gathers.  js / b1 / i11 / ptab are host-precomputed combinations;
@@ -101,7 +77,6 @@ struct DevContra {
   float sym_cum[15];
   float asym_cum[28];
   float explicit_[16];
-  ContraSmall small;
   ContraSmall2 small2;
 };
 

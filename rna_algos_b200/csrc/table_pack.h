@@ -75,14 +75,6 @@ static inline int pack_turner(const RnaTurnerTables* t, DevTurner* d, std::vecto
     d->special_score[x] = e.score;
     d->special_len_mask |= 1u << e.len;
   }
-  memcpy(d->small.tm_hairpin, t->terminal_mismatch_scores_hairpin, 1024);
-  memcpy(d->small.stack, t->stack_scores, 1024);
-  memcpy(d->small.tm_1xmany, t->terminal_mismatch_scores_1xmany, 1024);
-  memcpy(d->small.tm_2x3, t->terminal_mismatch_scores_2x3, 1024);
-  memcpy(d->small.tm_interior, t->terminal_mismatch_scores_interior, 1024);
-  memcpy(d->small.tm_multi, t->terminal_mismatch_scores_multibranch, 1024);
-  memcpy(d->small.d5, t->dangling_scores_5prime, 256);
-  memcpy(d->small.d3, t->dangling_scores_3prime, 256);
   memcpy(d->small2.stack, t->stack_scores, 1024);
   memcpy(d->small2.tm_hairpin, t->terminal_mismatch_scores_hairpin, 1024);
   memcpy(d->small2.tm_multi, t->terminal_mismatch_scores_multibranch, 1024);
@@ -140,14 +132,6 @@ static inline int pack_contra(const RnaContraTables* t, DevContra* d, std::strin
   memcpy(d->sym_cum, t->interior_scores_symmetric_cumulative, sizeof d->sym_cum);
   memcpy(d->asym_cum, t->interior_scores_asymmetric_cumulative, sizeof d->asym_cum);
   memcpy(d->explicit_, t->interior_scores_explicit, sizeof d->explicit_);
-  memcpy(d->small.stack, t->stack_scores, 1024);
-  memcpy(d->small.tm, t->terminal_mismatch_scores, 1024);
-  memcpy(d->small.dl, t->dangling_scores_left, 256);
-  memcpy(d->small.dr, t->dangling_scores_right, 256);
-  memcpy(d->small.hc, t->helix_close_scores, 64);
-  memcpy(d->small.bp, t->basepair_scores, 64);
-  memcpy(d->small.bulge0x1, t->bulge_scores_0x1, 16);
-  memcpy(d->small.int1x1, t->interior_scores_1x1, 64);
   // ---- v2 combinations --------------------------------------------------------------------------
   ContraSmall2& s2 = d->small2;
   memcpy(s2.dl, t->dangling_scores_left, 256);

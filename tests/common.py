@@ -15,7 +15,7 @@ _CODE = {"A": 0, "C": 1, "G": 2, "U": 3}
 def load_trnas():
     """The 6 tRNAs of the reference's assets/sampled_trnas.fa (L = 84, 74, 73, 73, 68, 89)."""
     seqs, cur = [], None
-    for line in open(TRNA_FASTA):
+    for line in open(TRNA_FASTA).read().splitlines():
         line = line.strip()
         if line.startswith(">"):
             seqs.append([])
