@@ -3,10 +3,10 @@ NVCC ?= nvcc
 NVCCFLAGS := $(EXTRA) -std=c++17 -O3 -gencode arch=compute_100a,code=sm_100a -lineinfo -fmad=false \
              -Xcompiler -fPIC,-ffp-contract=off,-fno-fast-math -Xptxas -v
 LIB := rna_algos_b200/librna_algos_b200.so
-SRC := rna_algos_b200/csrc/rna_abi.cu
+SRC := rna_algos_b200/csrc/rna_abi.cu rna_algos_b200/csrc/rna_multi.cpp rna_algos_b200/csrc/rna_queue.cpp
 HDR := $(wildcard rna_algos_b200/csrc/*.cuh rna_algos_b200/csrc/*.h include/*.h)
 
-all: $(LIB) oracle cli
+all: $(LIB) oracle cli peaks
 
 $(LIB): $(SRC) $(HDR)
 	$(NVCC) $(NVCCFLAGS) -shared -o $@ $(SRC) -lcudart
@@ -25,7 +25,14 @@ $(CLI): cli/rna_cli.cpp include/rna_algos_b200.h $(LIB)
 rna_algos_b200/tables_standin/standin_turner.tbl: rna_algos_b200/tables.py
 	python -m rna_algos_b200.tables dump rna_algos_b200/tables_standin
 
+# measured roofline denominators for bench.py (FP32 non-FMA issue, MUFU, shared-memory bandwidth): measurement
+# infrastructure, not linked by the product library
+peaks: tools/_build/libpeaks.so
+tools/_build/libpeaks.so: tools/peak_microbench.cu
+	mkdir -p tools/_build
+	$(NVCC) -O3 -gencode arch=compute_100a,code=sm_100a -fmad=false -shared -Xcompiler -fPIC -o $@ $< -lcudart
+
 clean:
-	rm -rf $(LIB) bin rna_algos_b200/tables_standin build
+	rm -rf $(LIB) bin rna_algos_b200/tables_standin build tools/_build
 	$(MAKE) -C oracle clean
-.PHONY: all oracle cli clean
+.PHONY: all oracle cli peaks clean

@@ -16,9 +16,14 @@ independent (no collective on the data path).
              CUDA events on the launching stream, max over ranks.
   e2e        sequences/s through the host-buffer C-ABI call (pinned host memory in, pinned host memory out;
              H2D + kernels + D2H inside the timed region).
-  roofline   HBM roofline of the fold kernel (algorithmic bytes / measured kernel time / measured peak) —
-             plus the FP32-issue view that actually bounds this path ("compute").
+  roofline   the roof that binds this path: FP32 NON-FMA issue (counted logsumexp terms x 14 FP32 instructions / s against
+             the rate a micro-kernel reaches in the same process, tools/peak_microbench.cu); the HBM view (algorithmic
+             bytes / time / MEASURED_PEAKS.json hbm_gbs) rides along under "hbm".
   cpu_baseline  the oracle port (tests-only code) on all host cores over a bounded sample.
+  configs    (N = 1) short legs for every BASELINE.json config, each with a bit-parity spot check against the oracle:
+             Turner tRNAs, gamma = 2 and the 18-threshold sweep, the seeded Rfam-like families, single long sequences
+             (1k / 2k / 4k nt, both models, reference-exact and FAST), Durbin on the intra-family pairs.
+  strong     (N > 1) strong scaling of the fixed Rfam-like global batch, LPT-partitioned, with per-rank busy time.
 """
 from __future__ import annotations
 
@@ -73,6 +78,44 @@ def make_workload(name: str, nseq: int, seed: int = 20251018, length: int = 76):
     else:
         raise SystemExit(f"unknown workload {name}")
     return seqs, contra, desc
+
+
+def make_families(n_families: int, seed: int = 20251019):
+    """Stand-in for assets/rfam_seed_stas_v14.3.sth (missing from the reference tree): SURVEY.md §8(d) config 3 —
+    per family a random parent of length ~ log-uniform[50, 500] and 2-10 members derived from it by 15 %
+    substitutions + 5 % indels (members of a family have similar lengths)."""
+    rng = np.random.default_rng(seed)
+    fams = []
+    for _ in range(n_families):
+        L = int(np.exp(rng.uniform(np.log(50), np.log(500))))
+        parent = rng.integers(0, 4, size=L).astype(np.uint8)
+        members = []
+        for _m in range(int(rng.integers(2, 11))):
+            out = []
+            for b in parent:
+                r = rng.random()
+                if r < 0.025:
+                    continue                                   # deletion
+                if r < 0.05:
+                    out.append(int(rng.integers(0, 4)))        # insertion before the base
+                if rng.random() < 0.15:
+                    b = (int(b) + int(rng.integers(1, 4))) % 4  # substitution by a different base
+                out.append(int(b))
+            members.append(np.array(out if out else [0], dtype=np.uint8))
+        fams.append(members)
+    return fams
+
+
+def family_batch(n_seqs_target: int):
+    """Sequences of the first families up to ~n_seqs_target, and all intra-family pairs (a < b) among them."""
+    seqs, pairs = [], []
+    for members in make_families(max(8, n_seqs_target // 4)):
+        if len(seqs) >= n_seqs_target:
+            break
+        base = len(seqs)
+        seqs.extend(members)
+        pairs.extend((base + a, base + b) for a in range(len(members)) for b in range(a + 1, len(members)))
+    return seqs, np.array(pairs, dtype=np.uint32).reshape(-1, 2)
 
 
 def cells_of(lens: np.ndarray) -> int:
@@ -205,6 +248,206 @@ def reference_arm(args):
 
 
 # ----------------------------------------------------------------------------------------------------
+# measured peaks of this process's GPU (tools/peak_microbench.cu): FP32 non-FMA issue, MUFU, shared memory
+# ----------------------------------------------------------------------------------------------------
+def measure_peaks(device: int):
+    path = os.path.join(ROOT, "tools", "_build", "libpeaks.so")
+    if not os.path.exists(path):
+        return None
+    lib = C.CDLL(path)
+    lib.peaks_measure.restype = C.c_int
+    lib.peaks_measure.argtypes = [C.c_int, C.POINTER(C.c_double)]
+    out = (C.c_double * 4)()
+    if lib.peaks_measure(device, out) != 0:
+        return None
+    return {"fp32_nofma_ginstr_s": out[0] / 1e9, "mufu_ginstr_s": out[1] / 1e9, "smem_gbs": out[2] / 1e9, "sms": int(out[3])}
+
+
+# ----------------------------------------------------------------------------------------------------
+# a batch resident in HBM + the *_dev entry point, timed with CUDA events on the launching stream
+# ----------------------------------------------------------------------------------------------------
+class FoldRunner:
+    def __init__(self, h, seqs, contra, gammas, dev, stream):
+        import torch
+        from common import pack
+        from rna_algos_b200 import _lib
+        from rna_algos_b200.api import bpp_offsets_of
+        self.h, self.stream, self.torch = h, stream, torch
+        self.bases, self.offsets = pack(seqs)
+        self.n = len(seqs)
+        self.lens = np.diff(self.offsets.astype(np.int64))
+        self.total = int(self.offsets[-1])
+        self.bpp_off = bpp_offsets_of(self.offsets)
+        self.bpp_total = int(self.bpp_off[-1])
+        self.ng = len(gammas)
+        t = self.t = {}
+        t["bases"] = torch.from_numpy(self.bases).to(dev)
+        t["offsets"] = torch.from_numpy(self.offsets.view(np.int32)).to(dev)
+        t["bppoff"] = torch.from_numpy(self.bpp_off.view(np.int64)).to(dev)
+        t["gammas"] = torch.tensor(list(gammas) or [1.0], dtype=torch.float32, device=dev)
+        t["logz"] = torch.empty(self.n, dtype=torch.float32, device=dev)
+        t["bpp"] = torch.empty(max(self.bpp_total, 1), dtype=torch.float32, device=dev)
+        t["structs"] = torch.empty(max(self.ng * self.total, 1), dtype=torch.uint8, device=dev)
+        t["ea"] = torch.empty(max(self.ng * self.n, 1), dtype=torch.float32, device=dev)
+        fb = self.fb = _lib.FoldBatchDev()
+        fb.h_offsets = self.offsets.ctypes.data
+        fb.d_bases = t["bases"].data_ptr(); fb.d_offsets = t["offsets"].data_ptr(); fb.d_bpp_offsets = t["bppoff"].data_ptr()
+        fb.n_seqs = self.n; fb.total_len = self.total; fb.max_len = int(self.lens.max())
+        fb.model = _lib.MODEL_CONTRA if contra else _lib.MODEL_TURNER
+        fb.allows_short_hairpins = 0
+        fb.d_gammas = t["gammas"].data_ptr(); fb.n_gammas = self.ng
+        fb.d_out_logz = t["logz"].data_ptr(); fb.d_out_bpp = t["bpp"].data_ptr()
+        fb.d_out_structs = t["structs"].data_ptr(); fb.d_out_expect_acc = t["ea"].data_ptr()
+        self.sptr = C.c_void_p(stream.cuda_stream)
+
+    def step(self):
+        lib = self.h.lib
+        rc = lib.rna_mccaskill_centroid_batch_dev(self.h.h, C.byref(self.fb), self.sptr)
+        if rc:
+            raise RuntimeError(f"rna_mccaskill_centroid_batch_dev rc={rc}: {lib.rna_last_error(self.h.h)}")
+
+    def timed(self, steps, warmup):
+        torch = self.torch
+        for _ in range(warmup):
+            self.step()
+        torch.cuda.synchronize()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record(self.stream)
+        for _ in range(steps):
+            self.step()
+        ev1.record(self.stream)
+        torch.cuda.synchronize()
+        return ev0.elapsed_time(ev1) / steps
+
+    def results(self, idx):
+        """(logz, packed bpp list, structs [ng][...]) of the sequences `idx`, copied back from HBM."""
+        logz = self.t["logz"].cpu().numpy()
+        bpp = self.t["bpp"].cpu().numpy()
+        st = self.t["structs"].cpu().numpy()[: self.ng * self.total].reshape(self.ng, self.total) if self.ng else None
+        out = []
+        for s in idx:
+            lo, hi = int(self.bpp_off[s]), int(self.bpp_off[s + 1])
+            out.append((logz[s], bpp[lo:hi], None if st is None else st[:, self.offsets[s]:self.offsets[s + 1]]))
+        return out
+
+
+def parity_sample(runner, seqs, contra, gammas, idx, inner_threads=1):
+    """Bit-compare the device-resident results of the sequences `idx` with the oracle (test infrastructure: checker only)."""
+    from common import default_tables, pack
+    from oracle_lib import Oracle
+    tt, ct, _ = default_tables()
+    orc = parity_sample.orc = getattr(parity_sample, "orc", None) or Oracle()
+    sub = [seqs[i] for i in idx]
+    b, o = pack(sub)
+    cores = os.cpu_count() or 1
+    if inner_threads > 1:
+        want = orc.fold_batch(b, o, contra, False, tt, ct, gammas, inner_threads=inner_threads)
+    else:
+        want = orc.fold_batch(b, o, contra, False, tt, ct, gammas, n_threads=cores)
+    ok = True
+    for k, (logz, bpp, st) in enumerate(runner.results(idx)):
+        lo, hi = int(want["bpp_offsets"][k]), int(want["bpp_offsets"][k + 1])
+        ok = ok and np.float32(logz).view(np.uint32) == want["logz"][k].view(np.uint32)
+        ok = ok and bool((bpp.view(np.uint32) == want["bpp"][lo:hi].view(np.uint32)).all())
+        if st is not None:
+            ok = ok and bool((st == want["structs"][:, o[k]:o[k + 1]]).all())
+    return bool(ok)
+
+
+def config_legs(h, dev, stream, args):
+    """Short legs for every BASELINE.json config on one GPU, each with a bit-parity spot check (N = 1 only)."""
+    import torch
+    from common import default_tables, load_trnas, pack
+    from oracle_lib import Oracle
+    from rna_algos_b200 import _lib
+    cores = os.cpu_count() or 1
+    out = {}
+    trnas = load_trnas()
+    tiled = [trnas[i % 6] for i in range(args.nseq)]
+    sweep = [float(np.float32(2.0) ** p) for p in range(-7, 11)]   # src/bin/centroid_fold.rs:9-11
+    # configs[0]: Turner 2004 on the tRNA set; gamma = 2 and the reference's default sweep under CONTRAfold
+    for key, contra, gam in (("c0_trna_turner_g1", False, [1.0]), ("c1_trna_contra_g2", True, [2.0]),
+                             ("c1_trna_contra_sweep18", True, sweep)):
+        r = FoldRunner(h, tiled, contra, gam, dev, stream)
+        ms = r.timed(2, 1)
+        out[key] = {"seq_s": round(r.n / ms * 1e3), "ms": round(ms, 1), "parity_ok": parity_sample(r, tiled, contra, gam, range(6))}
+        del r
+    # configs[2]: the seeded Rfam-like families (50-500 nt), one GPU's share
+    fam_seqs, fam_pairs = family_batch(args.rfam_nseq)
+    r = FoldRunner(h, fam_seqs, True, [1.0], dev, stream)
+    ms = r.timed(1, 1)
+    lens = r.lens
+    pick = [int(np.argmax(lens)), int(np.argmin(lens)), 0, len(fam_seqs) // 2, len(fam_seqs) - 1]
+    out["c2_rfam_like_contra"] = {"seq_s": round(r.n / ms * 1e3), "ms": round(ms, 1), "n": r.n, "len": [int(lens.min()), int(lens.max())],
+                                  "cells_s": round(cells_of(lens) / ms * 1e3), "parity_ok": parity_sample(r, fam_seqs, True, [1.0], pick)}
+    del r
+    # configs[3]: one random sequence at 1k / 2k / 4k nt, both models; parity at 1024 here, 2048 / 4096 in tests/
+    longs = {}
+    for L, seed in ((1024, 1), (2048, 2), (4096, 3)):
+        seq = np.random.default_rng(seed).integers(0, 4, size=L).astype(np.uint8)
+        ent = {}
+        for contra in (False, True):
+            r = FoldRunner(h, [seq], contra, [1.0], dev, stream)
+            ent["contra_ms" if contra else "turner_ms"] = round(r.timed(1, 1), 1)
+            if L == 1024:
+                ent["parity_ok"] = ent.get("parity_ok", True) and parity_sample(r, [seq], contra, [1.0], [0], inner_threads=cores)
+            if contra:   # FAST numeric mode on the same sequence (f32 warp-shuffle reductions), with its deviation
+                exact_logz = float(r.t["logz"][0])
+                h.set_numeric_mode("fast")
+                try:
+                    ent["fast_ms"] = round(r.timed(1, 1), 1)
+                    ent["fast_dlogz"] = float(f"{abs(float(r.t['logz'][0]) - exact_logz):.3g}")
+                finally:
+                    h.set_numeric_mode("exact")
+            del r
+        longs[str(L)] = ent
+    out["c3_long"] = longs
+    # configs[4]: Durbin forward-backward on the intra-family pairs
+    b, o = pack(fam_seqs)
+    _, _, at = default_tables()
+    host = torch.empty(1, dtype=torch.float32)
+    t0 = time.perf_counter()
+    res = h.durbin_batch(b, o, fam_pairs)
+    torch.cuda.synchronize()
+    t1 = time.perf_counter()
+    res = h.durbin_batch(b, o, fam_pairs)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t1
+    k = min(len(fam_pairs), 48)
+    want = Oracle().durbin_batch(b, o, fam_pairs[:k], at, n_threads=cores)
+    hi = int(res["prob_offsets"][k])
+    lens64 = np.diff(o.astype(np.int64))
+    dcells = int(((lens64[fam_pairs[:, 0]] + 2) * (lens64[fam_pairs[:, 1]] + 2)).sum())
+    out["c4_durbin_family_pairs"] = {"pairs_s": round(len(fam_pairs) / dt), "n": int(len(fam_pairs)), "cells_s": round(dcells / dt),
+                                     "path": "host buffers", "parity_ok": bool((res["probs"][:hi].view(np.uint32) == want["probs"].view(np.uint32)).all())}
+    return out
+
+
+def strong_leg(h, dev, stream, args, world, rank, dist):
+    """Strong scaling on a ragged batch: the fixed seeded Rfam-like global batch, LPT-partitioned over the ranks."""
+    import torch
+    from rna_algos_b200.api import fold_cost, partition_lpt
+    seqs_all, _ = family_batch(args.rfam_nseq)
+    part = partition_lpt(fold_cost([len(s) for s in seqs_all]), world)
+    mine = [s for s, p in zip(seqs_all, part) if p == rank]
+    r = FoldRunner(h, mine, True, [1.0], dev, stream)
+    r.timed(1, 0)
+    if world > 1:
+        dist.barrier()
+    ms = r.timed(1, 0)
+    busy = torch.tensor([ms], dtype=torch.float64, device=dev)
+    allb = [torch.zeros_like(busy) for _ in range(world)]
+    if world > 1:
+        dist.all_gather(allb, busy)
+    else:
+        allb = [busy]
+    busy_ms = [float(x.item()) for x in allb]
+    return {"workload": f"{len(seqs_all)} seeded Rfam-like sequences (50-500 nt), fixed global batch, LPT on L^3+500L^2",
+            "seq_s": round(len(seqs_all) / max(busy_ms) * 1e3), "busy_ms": [round(x, 1) for x in busy_ms],
+            "imbalance_max_over_mean": round(max(busy_ms) / (sum(busy_ms) / len(busy_ms)), 3)}
+
+
+# ----------------------------------------------------------------------------------------------------
 # GPU arm
 # ----------------------------------------------------------------------------------------------------
 def gpu_arm(args):
@@ -331,6 +574,14 @@ def gpu_arm(args):
     ms, e2e_dt = (float(x) for x in red.tolist())
     n_all, cells_all, abytes_all, launches_all, h2d_all, d2h_all = (float(x) for x in cnt.tolist())
 
+    strong = None
+    if world > 1 and not args.no_configs:
+        strong = strong_leg(h, dev, stream, args, world, rank, dist)
+    own_peaks = measure_peaks(local) if rank == 0 else None
+    configs = None
+    if world == 1 and not args.no_configs:
+        configs = config_legs(h, dev, stream, args)
+
     if rank == 0:
         try:
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -349,39 +600,49 @@ def gpu_arm(args):
                    "sample": f"first {cn} sequences of the same workload, {cdt:.1f} s wall (oracle/oracle.c port of the "
                              f"reference algorithm, one sequence per task on {cores} threads)"}
         per_gpu_bytes = abytes_all / world
-        achieved = per_gpu_bytes / sec_per_step / 1e9
+        hbm_ach = per_gpu_bytes / sec_per_step / 1e9
         # DRAM bytes per step of the same command, from the committed ncu capture (profiles/), if it matches
         traffic = None
-        try:
-            tj = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))
-            if tj.get("workload") == args.workload and tj.get("nseq_per_gpu") == args.nseq and tj.get("gammas") == gammas:
-                traffic = tj["dram_bytes_per_step"]
-        except Exception:
-            pass
-        roof = {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                "traffic": traffic, "peak_source": peak_src, "kernel": f"fold_kernel2<{'CONTRA' if contra else 'TURNER'}, SMEM>",
-                "algorithmic_bytes_per_step": per_gpu_bytes,
-                "note": "achieved = algorithmic bytes per step (bases+offsets in, packed BPP+logZ+structures out) / CUDA-event "
-                        "time of the step's fold_kernel2 launches; traffic = DRAM bytes per step from the ncu capture in "
-                        "profiles/ (two-loop term streams dominate it); the path is bound by the latency of the "
-                        "reference-exact logsumexp chains and FP32/ALU issue, see 'compute' and DESIGN.md 3.3"}
-        comp = None
+        for tname in ("r2_traffic.json", "r1_traffic.json"):
+            try:
+                tj = json.load(open(os.path.join(ROOT, "profiles", tname)))
+                if tj.get("workload") == args.workload and tj.get("nseq_per_gpu") == args.nseq and tj.get("gammas") == gammas:
+                    traffic = tj["dram_bytes_per_step"]
+                    break
+            except Exception:
+                pass
+        # algorithmic work: logsumexp terms per sequence, counted by the instrumented oracle (exact for the tiled tRNA
+        # workload: its 6 distinct sequences; else from the CPU sample above)
+        if lse_per_seq is None and args.workload in ("trna_contra", "trna_turner"):
+            from common import load_trnas
+            _, r6 = cpu_run(load_trnas(), contra, gammas, min(6, os.cpu_count() or 1))
+            lse_per_seq = r6["lse_terms"] / 6
+        roof = {"bound": "fp32_issue", "achieved": None, "peak": None, "unit": "G FP32 thread-instr/s per GPU", "frac": None,
+                "traffic": traffic, "kernel": f"fold_kernel2<{'CONTRA' if contra else 'TURNER'}, SMEM>"}
         if lse_per_seq is not None:
-            sm_mhz = (clocks or {}).get("sm_mhz") or 1965.0
-            peak_instr = 148 * 128 * sm_mhz * 1e6   # FP32 lanes x clock (thread-instructions/s)
-            ach = lse_per_seq * value / world * FP32_INSTR_PER_LSE
-            comp = {"lse_terms_per_seq": lse_per_seq, "lse_terms_per_s": lse_per_seq * value,
-                    "fp32_instr_per_lse": FP32_INSTR_PER_LSE, "achieved_ginstr_per_s_per_gpu": ach / 1e9,
-                    "peak_ginstr_per_s_per_gpu": peak_instr / 1e9, "frac": ach / peak_instr,
-                    "peak_source": f"nominal 148 SM x 128 FP32 lanes x {sm_mhz:.0f} MHz (median SM clock under load)"}
+            ach = lse_per_seq * value / world * FP32_INSTR_PER_LSE / 1e9
+            if own_peaks:
+                peak, src = own_peaks["fp32_nofma_ginstr_s"], "measured in-run (tools/peak_microbench.cu: separate FMUL/FADD, no FMA)"
+            else:
+                sm_mhz = (clocks or {}).get("sm_mhz") or 1965.0
+                peak, src = 148 * 128 * sm_mhz * 1e-3, "nominal 148 SM x 128 lanes x clock (libpeaks.so missing)"
+            roof.update({"achieved": ach, "peak": peak, "frac": ach / peak, "peak_source": src,
+                         "lse_terms_per_seq": lse_per_seq, "fp32_instr_per_lse": FP32_INSTR_PER_LSE,
+                         "note": "achieved = counted logsumexp terms/s x 14 FP32 instructions (SURVEY 8(d)); the reference-exact "
+                                 "chains are latency-bound, see DESIGN.md 3.3"})
+        roof["hbm"] = {"achieved": hbm_ach, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_ach / hbm_peak, "peak_source": peak_src,
+                       "algorithmic_bytes_per_step": per_gpu_bytes}
+        if own_peaks:
+            roof["measured_peaks"] = {k: round(v, 1) for k, v in own_peaks.items()}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic (bundled tRNAs tiled)",
-            "config": {"workload": desc, "gammas": gammas, "nseq_per_gpu": args.nseq, "numeric_mode": "reference-exact f32",
-                       "l2": f"per-step output working set {4 * bpp_total / 1e6:.0f} MB/GPU vs 126 MB L2 "
-                             f"({'exceeds L2, no flush needed' if 4 * bpp_total > 126e6 else 'smaller than L2'})",
-                       "partition": "LPT on L^3+500L^2 over ranks, no collective"},
+            "config": {"workload": desc, "gammas": gammas, "nseq_per_gpu": args.nseq},
+            "notes": {"numeric_mode": "reference-exact f32",
+                      "l2": f"per-step output working set {4 * bpp_total / 1e6:.0f} MB/GPU vs 126 MB L2 "
+                            f"({'exceeds L2, no flush needed' if 4 * bpp_total > 126e6 else 'smaller than L2'})",
+                      "partition": "LPT on L^3+500L^2 over ranks, no collective"},
             "cells_per_s": cells_all * args.steps / (ms / 1e3),
             "e2e": {"value": n_all * e2e_steps / e2e_dt, "unit": UNIT, "h2d_bytes_per_step": h2d_all,
                     "d2h_bytes_per_step": d2h_all, "steps": e2e_steps,
@@ -389,9 +650,12 @@ def gpu_arm(args):
             "gpu_launches": int(launches_all),
             "clocks": clocks,
             "roofline": roof,
-            "compute": comp,
             "cpu_baseline": cpu,
         }
+        if strong is not None:
+            line["strong"] = strong
+        if configs is not None:
+            line["configs"] = configs   # (last key: the driver keeps the tail of the line)
         print(json.dumps(line), flush=True)
     h.close()
     if world > 1:
@@ -513,6 +777,8 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--ref-step-seconds", type=float, default=3.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-configs", action="store_true", help="skip the per-config legs (N=1) / the strong-scaling leg (N>1)")
+    ap.add_argument("--rfam-nseq", type=int, default=4096, help="sequences of the seeded Rfam-like batch (configs[2], [4], strong)")
     args = ap.parse_args()
     if args.impl == "reference":
         reference_arm(args)

@@ -4,8 +4,8 @@
 //   centroid_fold   -i FASTA -o DIR  [-g GAMMA] [-c] [-t N]       src/bin/centroid_fold.rs:13-207
 //   durbin_algo     -i FASTA -o FILE [-t N]                        src/bin/durbin_algo.rs:6-90
 // Differences that cannot be observed in a reference run: records of a hash map are written in sorted key order
-// (the reference iterates hashbrown maps, whose order is unspecified); -t is accepted and ignored (the GPU batches
-// the sequences); a non-ACGU base or an unreadable file ends the program with a message and exit status 1 instead
+// (the reference iterates hashbrown maps, whose order is unspecified); -t limits the number of GPUs the sequences are
+// fanned out over (default: all visible); a non-ACGU base or an unreadable file ends the program with a message and exit status 1 instead
 // of a panic.  Score tables are run-time blobs: --tables DIR, else $RNA_ALGOS_B200_TABLES, else ../rna_algos_b200/
 // tables_standin next to the executable (written by `python -m rna_algos_b200.tables dump`; --standin-tables only).
 #include <charconv>
@@ -118,6 +118,7 @@ void append_uint(std::string& out, uint64_t v) {
 struct Opts {
   std::string in, out, tables;
   bool contra = false, has_gamma = false, help = false, standin = false;
+  int num_gpus = 0;   // 0 = all visible
   float gamma = 0.f;
 };
 
@@ -126,7 +127,7 @@ void usage(const char* prog, bool with_gamma, bool with_model) {
   printf("    -i, --input_file_path STR   An input FASTA file path containing RNA sequences\n");
   printf("    -o, --output_%s STR  An output %s path\n", with_gamma ? "dir_path " : "file_path", with_gamma ? "directory" : "file");
   if (with_gamma) printf("    -g, --centroid_threshold FLOAT  A specific centroid threshold rather than a range of centroid thresholds\n");
-  printf("    -t, --num_threads UINT      Accepted for compatibility; the GPU batches all sequences\n");
+  printf("    -t, --num_threads UINT      The number of GPUs to fan the sequences out over (default: all visible GPUs)\n");
   if (with_model) printf("    -c, --uses_contra_model     Use the CONTRAfold model instead of Turner's model to score RNA secondary structures\n");
   printf("        --tables DIR            Directory with the genuine turner2004.tbl / contrafold_v202.tbl score-table blobs\n");
   printf("                                (written from rna-ss-params by tools/ref_dump; default: $RNA_ALGOS_B200_TABLES)\n");
@@ -144,7 +145,13 @@ Opts parse(int argc, char** argv, int first, bool with_gamma, bool with_model) {
     };
     if (a == "-i" || a == "--input_file_path") o.in = val();
     else if (a == "-o" || a == "--output_file_path" || a == "--output_dir_path") o.out = val();
-    else if (a == "-t" || a == "--num_threads") (void)val();
+    else if (a == "-t" || a == "--num_threads") {
+      const std::string v = val();
+      char* end = nullptr;
+      const long t = strtol(v.c_str(), &end, 10);
+      if (end == v.c_str() || *end || t < 1) die("cannot parse the number of threads '" + v + "'");
+      o.num_gpus = (int)std::min<long>(t, 64);
+    }
     else if (with_model && (a == "-c" || a == "--uses_contra_model")) o.contra = true;
     else if (with_gamma && (a == "-g" || a == "--centroid_threshold")) {
       const std::string v = val();
@@ -185,10 +192,12 @@ void load_table(const std::string& dir, const char* name, uint32_t kind, T* out)
   if (!in) die(path + ": truncated");
 }
 
+// All visible GPUs behind one rna_multi (the reference fans its units out over a thread pool inside the binary,
+// src/bin/centroid_fold.rs:104-161; here the library partitions them over the devices).
 struct Session {
-  rna_handle* h = nullptr;
+  rna_multi* h = nullptr;
   void check(int rc, const char* what) {
-    if (rc != RNA_OK) die(std::string(what) + ": " + (h ? rna_last_error(h) : "no handle") + " (status " + std::to_string(rc) + ")");
+    if (rc != RNA_OK) die(std::string(what) + ": " + (h ? rna_multi_last_error(h) : "no handle") + " (status " + std::to_string(rc) + ")");
   }
   void open(const Opts& o, bool need_fold_tables) {
     // score tables first (an argument error must not depend on the machine)
@@ -213,18 +222,22 @@ struct Session {
       }
       if (o.contra) load_table(dir, cname, 2, &ct); else load_table(dir, tname, 1, &tt);
     }
-    const int rc = rna_create(0, &h);
+    // every visible device, or the first -t / --num_threads of them (a GPU is this implementation's unit of fan-out)
+    std::vector<int> devs;
+    for (int d = 0; d < o.num_gpus; d++) devs.push_back(d);
+    int rc = rna_multi_create(devs.empty() ? nullptr : devs.data(), (int)devs.size(), &h);
+    if (rc == RNA_ERR_BAD_ARG && !devs.empty()) rc = rna_multi_create(nullptr, 0, &h);   // (-t beyond the device count)
     if (rc != RNA_OK) die("no usable CUDA device (status " + std::to_string(rc) + "); this program has no CPU path");
     if (need_fold_tables) {
-      if (o.contra) check(rna_set_contra_tables(h, &ct), "rna_set_contra_tables");
-      else check(rna_set_turner_tables(h, &tt), "rna_set_turner_tables");
+      if (o.contra) check(rna_multi_set_contra_tables(h, &ct), "rna_set_contra_tables");
+      else check(rna_multi_set_turner_tables(h, &tt), "rna_set_turner_tables");
     } else {
       RnaAlignTables at;
       rna_align_tables_contralign_v201(&at);
-      check(rna_set_align_tables(h, &at), "rna_set_align_tables");
+      check(rna_multi_set_align_tables(h, &at), "rna_set_align_tables");
     }
   }
-  ~Session() { if (h) rna_destroy(h); }
+  ~Session() { if (h) rna_multi_destroy(h); }
 };
 
 void write_file(const std::string& path, const std::string& data) {
@@ -250,8 +263,8 @@ int main_mccaskill(int argc, char** argv, int first) {
   S.open(o, true);
   const std::vector<uint64_t> off = bpp_offsets_of(fa);
   std::vector<float> bpp(off.back());
-  S.check(rna_mccaskill_batch(S.h, fa.bases.data(), fa.offsets.data(), fa.n(), o.contra ? RNA_MODEL_CONTRA : RNA_MODEL_TURNER,
-                              0, nullptr, bpp.data(), off.data()), "rna_mccaskill_batch");
+  S.check(rna_multi_mccaskill_centroid_batch(S.h, fa.bases.data(), fa.offsets.data(), fa.n(), o.contra ? RNA_MODEL_CONTRA : RNA_MODEL_TURNER,
+                                             0, nullptr, 0, nullptr, bpp.data(), off.data(), nullptr, nullptr), "rna_multi_mccaskill_centroid_batch");
   std::string buf = "# Format = >{RNA sequence id} {line break} {basepairing left nucleotide}, {basepairing right nucleotide}, {basepairing probability} ...";
   for (uint32_t s = 0; s < fa.n(); s++) {
     buf += "\n\n>" + std::to_string(s) + "\n";
@@ -281,7 +294,7 @@ int main_centroid(int argc, char** argv, int first) {
   S.open(o, true);
   const size_t total = fa.bases.size();
   std::vector<uint8_t> structs(gammas.size() * total);
-  S.check(rna_mccaskill_centroid_batch(S.h, fa.bases.data(), fa.offsets.data(), fa.n(), o.contra ? RNA_MODEL_CONTRA : RNA_MODEL_TURNER, 0,
+  S.check(rna_multi_mccaskill_centroid_batch(S.h, fa.bases.data(), fa.offsets.data(), fa.n(), o.contra ? RNA_MODEL_CONTRA : RNA_MODEL_TURNER, 0,
                                        gammas.data(), (uint32_t)gammas.size(), nullptr, nullptr, nullptr, structs.data(), nullptr),
           "rna_mccaskill_centroid_batch");
   struct stat st;
@@ -315,7 +328,7 @@ int main_durbin(int argc, char** argv, int first) {
     }
   const uint32_t np = (uint32_t)(pairs.size() / 2);
   std::vector<float> probs(poff.back());
-  if (np) S.check(rna_durbin_batch(S.h, fa.bases.data(), fa.offsets.data(), fa.n(), pairs.data(), np, probs.data(), poff.data()), "rna_durbin_batch");
+  if (np) S.check(rna_multi_durbin_batch(S.h, fa.bases.data(), fa.offsets.data(), fa.n(), pairs.data(), np, probs.data(), poff.data()), "rna_durbin_batch");
   std::string buf = "# Format = >{RNA sequence id 1},{RNA sequence id 2} {line break} {nucleotide 1}, {nucleotide 2}, {nucletide matching probability} ...";
   for (uint32_t p = 0; p < np; p++) {
     const uint32_t a = pairs[2 * p], b = pairs[2 * p + 1];

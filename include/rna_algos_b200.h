@@ -52,6 +52,16 @@ enum {
 
 enum { RNA_MODEL_TURNER = 0, RNA_MODEL_CONTRA = 1 };
 
+/* Numeric modes of the McCaskill passes (rna_set_numeric_mode).
+ *   RNA_NUMERIC_REF_EXACT  (default) every fold in the reference's order with its piecewise-cubic logsumexp / expf
+ *                          (src/utils.rs:579-655): results bit-identical to the reference algorithm.
+ *   RNA_NUMERIC_FAST_F32   the same recurrences in exact log-space arithmetic, re-associated into warp-shuffle
+ *                          max / sum-of-exp reductions (ex2.approx / lg2.approx), f32 state.
+ *   RNA_NUMERIC_FAST_F64   the same with f64 state and libdevice exp / log.
+ * The FAST modes do NOT reproduce the reference's approximation error (<= 7.6e-6 per logsumexp): they agree with an
+ * exact-math evaluation to the tolerances of DESIGN.md §2 and with the reference only to ~1e-3 in a probability. */
+enum { RNA_NUMERIC_REF_EXACT = 0, RNA_NUMERIC_FAST_F32 = 1, RNA_NUMERIC_FAST_F64 = 2 };
+
 #define RNA_NUM_BASES 4
 #define RNA_BASE_A 0
 #define RNA_BASE_C 1
@@ -182,6 +192,9 @@ int rna_destroy(rna_handle *h);
 const char *rna_last_error(const rna_handle *h);    /* human-readable detail of the last failure   */
 int rna_device(const rna_handle *h);
 
+int rna_set_numeric_mode(rna_handle *h, int mode);  /* RNA_NUMERIC_*; applies to the mccaskill entry points   */
+int rna_get_numeric_mode(const rna_handle *h);
+
 int rna_set_turner_tables(rna_handle *h, const RnaTurnerTables *t);
 int rna_set_contra_tables(rna_handle *h, const RnaContraTables *t);
 int rna_set_align_tables(rna_handle *h, const RnaAlignTables *t);
@@ -238,6 +251,31 @@ int rna_durbin_batch(rna_handle *h, const uint8_t *bases, const uint32_t *offset
                      const uint32_t *pairs, uint32_t n_pairs, float *out_probs,
                      const uint64_t *prob_offsets);
 
+/* get_fold_sums / get_fold_sums_contra stand-alone (src/mccaskill_algo.rs:282-516), plus the per-pair score memo
+ * FoldScores<T> (:13-22, the second value mccaskill_algo returns) — what downstream crates read besides the BPPs.
+ * Sequence s receives RNA_SUMS_PLANES planes of rna_sums_len(L_s) floats at sums_offsets[s] (NULL => running sum of
+ * RNA_SUMS_PLANES * rna_sums_len(L)); a plane is the upper triangle INCLUDING the diagonal, row-major:
+ *   index(i,j) = i*L - i*(i-1)/2 + (j-i),  i <= j.
+ * Hash-map members of the reference (sums_close, sums_accessible and the three score maps) hold -inf where the key
+ * is absent; dense members hold the reference's values (sums_external is 0.0 on spans the recurrences never visit). */
+enum {
+  RNA_SUMS_CLOSE = 0,        /* FoldSums::sums_close                                              */
+  RNA_SUMS_ACCESSIBLE = 1,   /* FoldSums::sums_accessible                                         */
+  RNA_SUMS_EXTERNAL = 2,     /* FoldSums::sums_external                                           */
+  RNA_SUMS_RIGHTMOST_EXT = 3,/* FoldSums::sums_rightmost_basepairs_external                       */
+  RNA_SUMS_RIGHTMOST_MB = 4, /* FoldSums::sums_rightmost_basepairs_multibranch (CONTRAfold; else -inf) */
+  RNA_SUMS_MULTIBRANCH = 5,  /* FoldSums::sums_multibranch                                        */
+  RNA_SUMS_1ORMORE = 6,      /* FoldSums::sums_1ormore_basepairs                                  */
+  RNA_SCORES_HAIRPIN = 7,    /* FoldScores::hairpin_scores                                        */
+  RNA_SCORES_MB_CLOSE = 8,   /* FoldScores::multibranch_close_scores                              */
+  RNA_SCORES_ACCESSIBLE = 9, /* FoldScores::accessible_scores                                     */
+  RNA_SUMS_PLANES = 10
+};
+static inline uint64_t rna_sums_len(uint64_t L) { return L * (L + 1) / 2; }
+static inline uint64_t rna_sums_index(uint64_t L, uint64_t i, uint64_t j) { return i * L - i * (i - 1) / 2 + (j - i); }
+int rna_fold_sums_batch(rna_handle *h, const uint8_t *bases, const uint32_t *offsets, uint32_t n_seqs, int model,
+                        int allows_short_hairpins, float *out_sums, const uint64_t *sums_offsets, float *out_logz);
+
 /* ------------------------------------------------------------------------------------------------
  * Single-item convenience wrappers with the reference's per-call granularity.
  * ---------------------------------------------------------------------------------------------- */
@@ -280,6 +318,9 @@ typedef struct {
   float *d_out_expect_acc;
   uint16_t *d_out_pairs;          /* optional [n_gammas][total_len] (i,j) interleaved u16, traceback order */
   uint32_t *d_out_num_pairs;      /* optional [n_gammas][n_seqs] */
+  float *d_out_sums;              /* optional: the planes of rna_fold_sums_batch (reference-exact mode only)   */
+  const uint64_t *d_sums_offsets; /* [n_seqs+1], required with d_out_sums                                      */
+  int inside_only;                /* stop after the inside pass (no BPP / centroid outputs)                    */
 } RnaFoldBatchDev;
 
 int rna_mccaskill_centroid_batch_dev(rna_handle *h, const RnaFoldBatchDev *b, void *stream);
@@ -308,6 +349,54 @@ int rna_validate_fold_lengths(const uint32_t *offsets, uint32_t n_seqs);
  * cost model c(L) = L^3 + 500 L^2 for folding, n*m for pairs).  part_of[u] receives
  * the part index of unit u.  Pure host code, no collective. */
 int rna_partition_lpt(const uint64_t *costs, uint32_t n_units, uint32_t n_parts, uint32_t *part_of);
+
+/* ------------------------------------------------------------------------------------------------
+ * All GPUs of one box behind one object (the reference fans its units out over a thread pool
+ * inside the binary: src/bin/centroid_fold.rs:104-161, src/bin/durbin_algo.rs:56-75).  The units of a call are
+ * partitioned over the devices by longest-processing-time-first on the same cost model as rna_partition_lpt, one
+ * host thread and one rna_handle per device, disjoint output ranges, no collective and no peer traffic.  Same
+ * arguments, outputs and status codes as the single-device entry points; results do not depend on the partition.
+ *   devices / n_devices : CUDA device ordinals (a device may be listed more than once: that many handles share it);
+ *                         n_devices = 0 => every visible device.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct rna_multi rna_multi;
+int rna_multi_create(const int *devices, int n_devices, rna_multi **out);
+int rna_multi_destroy(rna_multi *m);
+int rna_multi_num_devices(const rna_multi *m);
+rna_handle *rna_multi_handle(rna_multi *m, int k);       /* the k-th per-device handle (stats, last error) */
+const char *rna_multi_last_error(const rna_multi *m);
+int rna_multi_set_turner_tables(rna_multi *m, const RnaTurnerTables *t);
+int rna_multi_set_contra_tables(rna_multi *m, const RnaContraTables *t);
+int rna_multi_set_align_tables(rna_multi *m, const RnaAlignTables *t);
+int rna_multi_set_numeric_mode(rna_multi *m, int mode);
+int rna_multi_mccaskill_centroid_batch(rna_multi *m, const uint8_t *bases, const uint32_t *offsets, uint32_t n_seqs,
+                                       int model, int allows_short_hairpins, const float *gammas, uint32_t n_gammas,
+                                       float *out_logz, float *out_bpp, const uint64_t *bpp_offsets,
+                                       uint8_t *out_structs, float *out_expect_acc);
+int rna_multi_durbin_batch(rna_multi *m, const uint8_t *bases, const uint32_t *offsets, uint32_t n_seqs,
+                           const uint32_t *pairs, uint32_t n_pairs, float *out_probs, const uint64_t *prob_offsets);
+/* Busy time (seconds, host clock around the device's share) of every device in the last rna_multi_* batch call, and
+ * the number of units it received: what a caller needs to see the balance of the partition. */
+int rna_multi_last_shares(const rna_multi *m, double *busy_seconds /* [n_devices] */, uint32_t *units /* [n_devices] */);
+
+/* ------------------------------------------------------------------------------------------------
+ * Thread-SAFE front end of one handle for the reference's call granularity.  The reference's callers fold one
+ * sequence per call from the tasks of a thread pool (src/bin/centroid_fold.rs:119-132); one tRNA alone cannot fill a
+ * GPU (one CTA, ~3 ms).  Calls that arrive while a launch is in flight are COALESCED: the first caller becomes the
+ * leader, gathers every request that is pending with the same (model, allows_short_hairpins, threshold) signature
+ * into one rna_mccaskill_centroid_batch call and hands each caller its own results.  Any number of threads may call
+ * rna_queue_* on the same queue concurrently; the wrapped handle must not be used directly while the queue is live.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct rna_queue rna_queue;
+int rna_queue_create(rna_handle *h, rna_queue **out);
+int rna_queue_destroy(rna_queue *q);
+/* mccaskill_algo (+ centroid_fold when out_fold_str / out_expect_accuracy is given) for ONE sequence; blocks until the
+ * caller's results are written.  out_bpp: rna_bpp_len(seq_len) floats or NULL; out_fold_str: seq_len bytes or NULL. */
+int rna_queue_mccaskill_algo(rna_queue *q, const uint8_t *seq, uint32_t seq_len, int uses_contra_model,
+                             int allows_short_hairpins, float *out_bpp, float *out_logz, float centroid_threshold,
+                             uint8_t *out_fold_str, float *out_expect_accuracy);
+/* requests served / batched launches issued since the queue was created */
+int rna_queue_stats(const rna_queue *q, uint64_t *requests, uint64_t *launches);
 
 /* Counters of the last *_batch call on this handle (kernel launches issued, bytes copied). */
 typedef struct {

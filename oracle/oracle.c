@@ -441,6 +441,8 @@ typedef struct FoldSums_ {
   real *mb;     /* sums_multibranch                       init -inf */
   real *m1;     /* sums_1ormore_basepairs                 init -inf */
   real *mbc;    /* fold_scores.multibranch_close_scores (memo, :333-335) */
+  real *hps;    /* fold_scores.hairpin_scores     (-inf = key absent)   */
+  real *accs;   /* fold_scores.accessible_scores  (-inf = key absent)   */
   /* Transposed mirrors (xT[j][i] == x[i][j], written together with x) of the matrices the recurrences walk DOWN A
    * COLUMN (`[k][j]`, k running): the same values read from contiguous memory.  Layout only — no arithmetic differs. */
   real *rbeT, *rbmT, *m1T;
@@ -463,6 +465,8 @@ static void fold_sums_new(FoldSums *f, int L) {
   f->mb = alloc_mat(L, NEG_INF);
   f->m1 = alloc_mat(L, NEG_INF);
   f->mbc = alloc_mat(L, (real)0.);
+  f->hps = alloc_mat(L, NEG_INF);
+  f->accs = alloc_mat(L, NEG_INF);
   f->rbeT = alloc_mat(L, NEG_INF);
   f->rbmT = alloc_mat(L, NEG_INF);
   f->m1T = alloc_mat(L, NEG_INF);
@@ -470,7 +474,7 @@ static void fold_sums_new(FoldSums *f, int L) {
 
 static void fold_sums_free(FoldSums *f) {
   free(f->ext); free(f->rbe); free(f->rbm); free(f->close); free(f->acc); free(f->mb); free(f->m1);
-  free(f->mbc); free(f->rbeT); free(f->rbmT); free(f->m1T);
+  free(f->mbc); free(f->rbeT); free(f->rbmT); free(f->m1T); free(f->hps); free(f->accs);
 }
 
 #define AT(m, i, j) (m)[(size_t)(i) * (size_t)L + (size_t)(j)]
@@ -490,6 +494,7 @@ static void fold_sums_cell(void *vc, int i) {
       real sum = NEG_INF;
       if (j - i + 1 >= MINSPAN && canonical(s[i], s[j])) {
         real hs = hairpin_score(s, i, j, t);
+        AT(f->hps, i, j) = hs;              /* fold_scores.hairpin_scores.insert, :299-301 */
         lse(&sum, hs);
         for (int k = i + 1; k < j - 1; k++) {
           if (k - i - 1 > MAX2) break;
@@ -508,6 +513,7 @@ static void fold_sums_cell(void *vc, int i) {
         real as = accessible_score(s, L, i, j, t);
         if (sum > NEG_INF) {
           AT(f->mbc, i, j) = mbc;
+          AT(f->accs, i, j) = as;
           AT(f->close, i, j) = sum;
           AT(f->acc, i, j) = sum + as;
         }
@@ -567,6 +573,7 @@ static void fold_sums_contra_cell(void *vc, int i) {
       if (canonical(s[i], s[j]) && (allows_short || j - i + 1 >= MINSPAN)) {
         if (j - i - 1 <= MAXL) {
           real hs = c_hairpin_score(s, i, j, t);
+          AT(f->hps, i, j) = hs;            /* :408-410 */
           lse(&sum, hs);
         }
         for (int k = i + 1; k < j - 1; k++) {
@@ -587,6 +594,7 @@ static void fold_sums_contra_cell(void *vc, int i) {
         real as = c_junction(s, L, j, i, t) + (real)t->basepair_scores[s[i]][s[j]];
         if (sum > NEG_INF) {
           AT(f->mbc, i, j) = mbc;
+          AT(f->accs, i, j) = as;
           AT(f->close, i, j) = sum;
           AT(f->acc, i, j) = sum + as;
         }
@@ -851,6 +859,27 @@ static void centroid_cell(void *vc, int i) {
 }
 #undef HAS
 #undef PR
+
+/* get_fold_sums / get_fold_sums_contra stand-alone + the FoldScores memo (src/mccaskill_algo.rs:3-22, 282-516), as dense
+ * L x L planes in the order of include/rna_algos_b200.h RNA_SUMS_*: -inf = key absent (hash-map members). */
+int orc_fold_sums(const uint8_t *seq, int L, int uses_contra_model, int allows_short_hairpins,
+                  const RnaTurnerTables *tt, const RnaContraTables *ct, float *planes) {
+  if (L < 1) return RNA_ERR_EMPTY_SEQ;
+  FoldSums f;
+  fold_sums_new(&f, L);
+  if (uses_contra_model) get_fold_sums_contra(seq, L, allows_short_hairpins, ct, &f);
+  else get_fold_sums(seq, L, tt, &f);
+  const size_t n = (size_t)L * (size_t)L;
+  const real *src[RNA_SUMS_PLANES] = {f.close, f.acc, f.ext, f.rbe, f.rbm, f.mb, f.m1, f.hps, f.mbc, f.accs};
+  for (int p = 0; p < RNA_SUMS_PLANES; p++)
+    for (size_t x = 0; x < n; x++) {
+      float v = (float)src[p][x];
+      if (p == RNA_SCORES_MB_CLOSE && !(f.close[x] > NEG_INF)) v = -INFINITY;   /* inserted with sums_close only */
+      planes[(size_t)p * n + x] = v;
+    }
+  fold_sums_free(&f);
+  return RNA_OK;
+}
 
 /* ---------------------------------------------------------------------------------------------
  * centroid_fold: src/centroid_fold.rs:25-105.  `bpp` is the packed matrix (absent = RNA_BPP_ABSENT).

@@ -26,6 +26,7 @@ STATUS = {
     5: "RNA_ERR_NO_TABLES", 6: "RNA_ERR_BAD_TABLES", 7: "RNA_ERR_CUDA", 8: "RNA_ERR_NO_DEVICE", 9: "RNA_ERR_NOMEM",
 }
 MODEL_TURNER, MODEL_CONTRA = 0, 1
+NUMERIC_REF_EXACT, NUMERIC_FAST_F32, NUMERIC_FAST_F64 = 0, 1, 2
 
 
 class FoldBatchDev(C.Structure):
@@ -38,6 +39,7 @@ class FoldBatchDev(C.Structure):
         ("d_gammas", vp), ("n_gammas", C.c_uint32),
         ("d_out_logz", vp), ("d_out_bpp", vp), ("d_out_structs", vp), ("d_out_expect_acc", vp),
         ("d_out_pairs", vp), ("d_out_num_pairs", vp),
+        ("d_out_sums", vp), ("d_sums_offsets", vp), ("inside_only", C.c_int),
     ]
 
 
@@ -66,12 +68,16 @@ _SIGS = {
     "rna_destroy": (C.c_int, [vp]),
     "rna_last_error": (C.c_char_p, [vp]),
     "rna_device": (C.c_int, [vp]),
+    "rna_set_numeric_mode": (C.c_int, [vp, C.c_int]),
+    "rna_get_numeric_mode": (C.c_int, [vp]),
+    "rna_validate_fold_lengths": (C.c_int, [vp, C.c_uint32]),
     "rna_set_turner_tables": (C.c_int, [vp, C.POINTER(TurnerTables)]),
     "rna_set_contra_tables": (C.c_int, [vp, C.POINTER(ContraTables)]),
     "rna_set_align_tables": (C.c_int, [vp, C.POINTER(AlignTables)]),
     "rna_mccaskill_centroid_batch": (C.c_int, [vp, vp, vp, C.c_uint32, C.c_int, C.c_int, vp, C.c_uint32, vp, vp,
                                                vp, vp, vp]),
     "rna_mccaskill_batch": (C.c_int, [vp, vp, vp, C.c_uint32, C.c_int, C.c_int, vp, vp, vp]),
+    "rna_fold_sums_batch": (C.c_int, [vp, vp, vp, C.c_uint32, C.c_int, C.c_int, vp, vp, vp]),
     "rna_centroid_batch": (C.c_int, [vp, vp, vp, vp, C.c_uint32, vp, C.c_uint32, vp, vp]),
     "rna_durbin_batch": (C.c_int, [vp, vp, vp, C.c_uint32, vp, C.c_uint32, vp, vp]),
     "rna_mccaskill_algo": (C.c_int, [vp, vp, C.c_uint32, C.c_int, C.c_int, vp, vp]),
@@ -82,6 +88,23 @@ _SIGS = {
     "rna_validate_bases": (C.c_int, [vp, vp, C.c_uint32]),
     "rna_partition_lpt": (C.c_int, [vp, C.c_uint32, C.c_uint32, vp]),
     "rna_get_stats": (C.c_int, [vp, C.POINTER(CallStats)]),
+    "rna_queue_create": (C.c_int, [vp, C.POINTER(vp)]),
+    "rna_queue_destroy": (C.c_int, [vp]),
+    "rna_queue_mccaskill_algo": (C.c_int, [vp, vp, C.c_uint32, C.c_int, C.c_int, vp, vp, C.c_float, vp, vp]),
+    "rna_queue_stats": (C.c_int, [vp, u64p, u64p]),
+    "rna_multi_create": (C.c_int, [vp, C.c_int, C.POINTER(vp)]),
+    "rna_multi_destroy": (C.c_int, [vp]),
+    "rna_multi_num_devices": (C.c_int, [vp]),
+    "rna_multi_handle": (vp, [vp, C.c_int]),
+    "rna_multi_last_error": (C.c_char_p, [vp]),
+    "rna_multi_set_turner_tables": (C.c_int, [vp, C.POINTER(TurnerTables)]),
+    "rna_multi_set_contra_tables": (C.c_int, [vp, C.POINTER(ContraTables)]),
+    "rna_multi_set_align_tables": (C.c_int, [vp, C.POINTER(AlignTables)]),
+    "rna_multi_set_numeric_mode": (C.c_int, [vp, C.c_int]),
+    "rna_multi_mccaskill_centroid_batch": (C.c_int, [vp, vp, vp, C.c_uint32, C.c_int, C.c_int, vp, C.c_uint32, vp, vp,
+                                                     vp, vp, vp]),
+    "rna_multi_durbin_batch": (C.c_int, [vp, vp, vp, C.c_uint32, vp, C.c_uint32, vp, vp]),
+    "rna_multi_last_shares": (C.c_int, [vp, vp, vp]),
 }
 
 _lib = None

@@ -142,6 +142,12 @@ class Handle:
         if align is not None:
             self._chk(self.lib.rna_set_align_tables(self.h, C.byref(align)))
 
+    def set_numeric_mode(self, mode) -> None:
+        """"exact" (default: the reference's numerics, bit for bit), "fast" (f32 warp-shuffle reductions, exact math) or
+        "fast64" — include/rna_algos_b200.h RNA_NUMERIC_*."""
+        code = {"exact": 0, "fast": 1, "fast32": 1, "fast64": 2}.get(mode, mode)
+        self._chk(self.lib.rna_set_numeric_mode(self.h, int(code)))
+
     def close(self):
         if getattr(self, "h", None):
             self.lib.rna_destroy(self.h)
@@ -193,6 +199,38 @@ class Handle:
             int(allows_short_hairpins), _p(g) if ng else None, ng, _p(logz), _p(bpp),
             _p(bpp_off) if want_bpp else None, _p(structs) if ng else None, _p(ea) if ng else None))
         return dict(logz=logz, bpp=bpp, bpp_offsets=bpp_off, structs=structs, expect_acc=ea, gammas=g)
+
+    SUMS_PLANES = ("sums_close", "sums_accessible", "sums_external", "sums_rightmost_basepairs_external",
+                   "sums_rightmost_basepairs_multibranch", "sums_multibranch", "sums_1ormore_basepairs",
+                   "hairpin_scores", "multibranch_close_scores", "accessible_scores")
+
+    def fold_sums_batch(self, bases, offsets, uses_contra_model, allows_short_hairpins=False) -> List[Dict[str, np.ndarray]]:
+        """get_fold_sums / get_fold_sums_contra stand-alone + the FoldScores memo (src/mccaskill_algo.rs:3-22, 282-516):
+        per sequence a dict of dense L x L arrays (upper triangle filled; -inf = key absent / never written, except
+        sums_external whose untouched entries are 0.0 like in the reference) and `logz`."""
+        bases = np.ascontiguousarray(bases, dtype=np.uint8)
+        offsets = np.ascontiguousarray(offsets, dtype=np.uint32)
+        n = offsets.shape[0] - 1
+        lens = np.diff(offsets.astype(np.int64))
+        so = np.zeros(n + 1, dtype=np.uint64)
+        so[1:] = np.cumsum(len(self.SUMS_PLANES) * (lens * (lens + 1) // 2))
+        flat = np.empty(int(so[-1]), dtype=np.float32)
+        logz = np.empty(n, dtype=np.float32)
+        self._chk(self.lib.rna_fold_sums_batch(self.h, _p(bases), _p(offsets), n,
+                                               _lib.MODEL_CONTRA if uses_contra_model else _lib.MODEL_TURNER,
+                                               int(allows_short_hairpins), _p(flat), _p(so), _p(logz)))
+        out = []
+        for s in range(n):
+            L = int(lens[s])
+            pl = L * (L + 1) // 2
+            iu = np.triu_indices(L)
+            d = {"logz": logz[s]}
+            for k, name in enumerate(self.SUMS_PLANES):
+                m = np.full((L, L), 0.0 if name == "sums_external" else -np.inf, dtype=np.float32)
+                m[iu] = flat[int(so[s]) + k * pl: int(so[s]) + (k + 1) * pl]
+                d[name] = m
+            out.append(d)
+        return out
 
     def mccaskill_batch(self, bases, offsets, uses_contra_model, allows_short_hairpins=False):
         return self.fold_batch(bases, offsets, uses_contra_model, allows_short_hairpins, gammas=())
@@ -251,6 +289,124 @@ class Handle:
         out = np.empty((a.shape[0] + 2, b.shape[0] + 2), dtype=np.float32)
         self._chk(self.lib.rna_durbin_algo(self.h, _p(a), a.shape[0], _p(b), b.shape[0], _p(out)))
         return out
+
+
+class CallQueue:
+    """Thread-safe front end of a Handle for the reference's call granularity (one sequence per call from a thread
+    pool, src/bin/centroid_fold.rs:119-132): concurrent calls are coalesced into batched launches (rna_queue)."""
+
+    def __init__(self, handle: Handle):
+        self.handle = handle
+        self.lib = handle.lib
+        q = C.c_void_p()
+        rc = self.lib.rna_queue_create(handle.h, C.byref(q))
+        if rc:
+            raise RnaError(rc)
+        self.q = q
+
+    def mccaskill_algo(self, seq, uses_contra_model: bool, allows_short_hairpins: bool = False,
+                       centroid_threshold: Optional[float] = None):
+        """-> (packed bpp, logz) or, with a threshold, (packed bpp, logz, dot-bracket string, expect_accuracy)."""
+        seq = np.ascontiguousarray(seq, dtype=np.uint8)
+        L = seq.shape[0]
+        bpp = np.empty(L * (L - 1) // 2, dtype=np.float32)
+        logz = C.c_float()
+        st = np.empty(L, dtype=np.uint8) if centroid_threshold is not None else None
+        ea = C.c_float()
+        rc = self.lib.rna_queue_mccaskill_algo(self.q, _p(seq), L, int(uses_contra_model), int(allows_short_hairpins), _p(bpp),
+                                               C.byref(logz), C.c_float(centroid_threshold or 0.0), _p(st),
+                                               C.byref(ea) if st is not None else None)
+        if rc:
+            raise RnaError(rc, (self.lib.rna_last_error(self.handle.h) or b"").decode())
+        if st is None:
+            return bpp, np.float32(logz.value)
+        return bpp, np.float32(logz.value), st.tobytes().decode(), np.float32(ea.value)
+
+    def stats(self):
+        r, l = C.c_uint64(), C.c_uint64()
+        self.lib.rna_queue_stats(self.q, C.byref(r), C.byref(l))
+        return dict(requests=int(r.value), launches=int(l.value))
+
+    def close(self):
+        if getattr(self, "q", None):
+            self.lib.rna_queue_destroy(self.q)
+            self.q = None
+
+
+class MultiHandle:
+    """Every GPU of the box behind one object (include/rna_algos_b200.h rna_multi): the units of a call are LPT-
+    partitioned over the devices inside the library, one host thread per device, no collective."""
+
+    def __init__(self, devices: Optional[Sequence[int]] = None, turner=None, contra=None, align=None):
+        self.lib = _lib.load()
+        m = C.c_void_p()
+        devs = np.ascontiguousarray(np.array(list(devices or []), dtype=np.int32))
+        rc = self.lib.rna_multi_create(_p(devs) if len(devs) else None, len(devs), C.byref(m))
+        if rc:
+            raise RnaError(rc, "rna_multi_create: CUDA devices are required (no CPU fallback)")
+        self.m = m
+        if turner is not None:
+            self._chk(self.lib.rna_multi_set_turner_tables(self.m, C.byref(turner)))
+        if contra is not None:
+            self._chk(self.lib.rna_multi_set_contra_tables(self.m, C.byref(contra)))
+        if align is not None:
+            self._chk(self.lib.rna_multi_set_align_tables(self.m, C.byref(align)))
+
+    def _chk(self, rc: int):
+        if rc:
+            raise RnaError(rc, (self.lib.rna_multi_last_error(self.m) or b"").decode())
+
+    @property
+    def num_devices(self) -> int:
+        return int(self.lib.rna_multi_num_devices(self.m))
+
+    def close(self):
+        if getattr(self, "m", None):
+            self.lib.rna_multi_destroy(self.m)
+            self.m = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def shares(self):
+        nd = self.num_devices
+        busy = np.zeros(nd, dtype=np.float64)
+        units = np.zeros(nd, dtype=np.uint32)
+        self.lib.rna_multi_last_shares(self.m, _p(busy), _p(units))
+        return busy, units
+
+    def fold_batch(self, bases, offsets, uses_contra_model, allows_short_hairpins=False, gammas=(), want_bpp=True) -> dict:
+        bases = np.ascontiguousarray(bases, dtype=np.uint8)
+        offsets = np.ascontiguousarray(offsets, dtype=np.uint32)
+        n = offsets.shape[0] - 1
+        g = np.ascontiguousarray(np.array(list(gammas), dtype=np.float32))
+        ng = g.shape[0]
+        total = int(offsets[-1]) if n else 0
+        bpp_off = bpp_offsets_of(offsets)
+        logz = np.empty(n, dtype=np.float32)
+        bpp = np.empty(int(bpp_off[-1]), dtype=np.float32) if want_bpp else None
+        structs = np.empty((ng, total), dtype=np.uint8)
+        ea = np.empty((ng, n), dtype=np.float32)
+        self._chk(self.lib.rna_multi_mccaskill_centroid_batch(
+            self.m, _p(bases), _p(offsets), n, _lib.MODEL_CONTRA if uses_contra_model else _lib.MODEL_TURNER,
+            int(allows_short_hairpins), _p(g) if ng else None, ng, _p(logz), _p(bpp),
+            _p(bpp_off) if want_bpp else None, _p(structs) if ng else None, _p(ea) if ng else None))
+        return dict(logz=logz, bpp=bpp, bpp_offsets=bpp_off, structs=structs, expect_acc=ea, gammas=g)
+
+    def durbin_batch(self, bases, offsets, pairs) -> dict:
+        bases = np.ascontiguousarray(bases, dtype=np.uint8)
+        offsets = np.ascontiguousarray(offsets, dtype=np.uint32)
+        pairs = np.ascontiguousarray(pairs, dtype=np.uint32).reshape(-1, 2)
+        lens = np.diff(offsets.astype(np.int64))
+        po = np.zeros(pairs.shape[0] + 1, dtype=np.uint64)
+        po[1:] = np.cumsum((lens[pairs[:, 0]] + 2) * (lens[pairs[:, 1]] + 2))
+        out = np.empty(int(po[-1]), dtype=np.float32)
+        self._chk(self.lib.rna_multi_durbin_batch(self.m, _p(bases), _p(offsets), offsets.shape[0] - 1, _p(pairs),
+                                                  pairs.shape[0], _p(out), _p(po)))
+        return dict(probs=out, prob_offsets=po)
 
 
 _default: Optional[Handle] = None

@@ -49,6 +49,9 @@ struct FoldArgs {
   uint32_t tcap;             // terms per stream a slot can hold
   long long* dbg;            // optional per-step per-warp cycle counts of CTA 0's first sequence (RNA_FOLD_DBG)
   int no_ml_split;           // cooperative kernel: A/B switch, multiloop chain without the producer warp
+  float* sums;               // optional FoldSums / FoldScores planes (rna_fold_sums_batch), else null
+  const unsigned long long* sums_offsets;
+  int inside_only;           // stop after the inside pass
 };
 
 template <int MODE>

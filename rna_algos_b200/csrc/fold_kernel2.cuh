@@ -86,10 +86,11 @@ __host__ __device__ inline Roles fold2_roles(int Lcap, bool contra, int max_warp
   return r;
 }
 
-// REGS48: a second build of the same kernel under a 48-register cap (1280 resident threads per SM = 5 CTAs of 8
-// warps), used for the buckets whose shared memory allows a fifth CTA.
-template <bool CONTRA, int MODE, bool REGS48 = false>
-__global__ void __launch_bounds__(REGS48 ? 256 : 512, REGS48 ? 5 : 2) fold_kernel2(const FoldArgs a) {
+// SUMS: the build that also exports the FoldSums / FoldScores planes (rna_fold_sums_batch) and can stop after the inside
+// pass; the default build carries none of it (the batch kernel sits at its 64-register cap: measured 10 % slower with
+// the export code compiled in).
+template <bool CONTRA, int MODE, bool SUMS = false>
+__global__ void __launch_bounds__(512, 2) fold_kernel2(const FoldArgs a) {
   typedef typename Model2<CONTRA>::Dev Dev;
   typedef typename Model2<CONTRA>::Small Small;
   typedef typename Model2<CONTRA>::View View;
@@ -178,6 +179,10 @@ __global__ void __launch_bounds__(REGS48 ? 256 : 512, REGS48 ? 5 : 2) fold_kerne
     v.RR = reinterpret_cast<uint8_t*>(v.plist + TRI);
     v.LL = v.RR + L;
     v.tin = nullptr; v.tout = nullptr; v.ccnt = nullptr; v.tcap = a.tcap;
+    float* sums_out = nullptr;   // rna_fold_sums_batch planes of this sequence
+    if constexpr (SUMS) sums_out = a.sums ? a.sums + a.sums_offsets[sidx] : nullptr;
+    v.Mfull = sums_out ? sums_out + (size_t)5 * TRI : nullptr;
+    v.M1rm = nullptr; v.MB = nullptr;
 
     for (int x = tid; x < L; x += nt) s[x] = a.bases[sbeg + x];
     if (tid < 4) { sseq[tid] = 0; s[L + tid] = 0; }
@@ -240,10 +245,10 @@ __global__ void __launch_bounds__(REGS48 ? 256 : 512, REGS48 ? 5 : 2) fold_kerne
       } else if (!helper) {
         const bool isY = warp < a.nXw + a.nYw;
         if (isY) { if constexpr (CONTRA) { if (t - 1 >= d_in0 && t - 1 < L) inside_Y_contra<(MODE == MODE_SMEM ? RNA_Y_CH : 4)>(v, T, lut, t - 1, tid - nXl, nYl); } }
-        else if (t - 2 >= d_in0 && t - 2 < L) inside_Z<CONTRA, (MODE == MODE_SMEM ? RNA_Z_PF : 4)>(v, T, lut, t - 2, tid - nXl - nYl, nZl);
+        else if (t - 2 >= d_in0 && t - 2 < L) inside_Z<CONTRA, (MODE == MODE_SMEM ? RNA_Z_PF : 4), SV, SUMS>(v, T, lut, t - 2, tid - nXl - nYl, nZl);
         asm volatile("bar.sync 1, %0;" ::"r"(nYZl) : "memory");
         if (isY) { if constexpr (CONTRA) { if (t < L) inside_Y_contra<(MODE == MODE_SMEM ? RNA_Y_CH : 4)>(v, T, lut, t, tid - nXl, nYl); } }
-        else if (t - 1 >= d_in0 && t - 1 < L) inside_Z<CONTRA, (MODE == MODE_SMEM ? RNA_Z_PF : 4)>(v, T, lut, t - 1, tid - nXl - nYl, nZl);
+        else if (t - 1 >= d_in0 && t - 1 < L) inside_Z<CONTRA, (MODE == MODE_SMEM ? RNA_Z_PF : 4), SV, SUMS>(v, T, lut, t - 1, tid - nXl - nYl, nZl);
       }
       if (dbg_on && (tid & 31) == 0 && !helper) a.dbg[(size_t)t * 16 + warp] = clock64() - c0;
       __syncthreads();
@@ -256,10 +261,12 @@ __global__ void __launch_bounds__(REGS48 ? 256 : 512, REGS48 ? 5 : 2) fold_kerne
       v.E0[x] = v.E[doff(x, L)];
       v.EL[x] = v.E[doff(L - 1 - x, L) + x];
     }
+    if constexpr (SUMS) { if (sums_out) export_fold_sums<CONTRA>(v, T, P, sums_out, tid, nt); }   // FoldSums / FoldScores (N3)
     __syncthreads();
     const float Z = v.E0[L - 1];
-    for (int x = tid; x < TRI; x += nt) { v.Pm[x] = NEG; v.R[x] = NEG; v.X[x] = NEG; }
     if (tid == 0 && a.out_logz) a.out_logz[sidx] = Z;
+    if constexpr (SUMS) { if (a.inside_only) continue; }
+    for (int x = tid; x < TRI; x += nt) { v.Pm[x] = NEG; v.R[x] = NEG; v.X[x] = NEG; }
     __syncthreads();
     const int d_out0 = v.dout0;
     // pair steps.  phase 1: X = exterior + two-loop parts of log P(d), (d-1)  |  Y = probs_multibranch(2) of d+1, d
@@ -512,6 +519,8 @@ __global__ void __launch_bounds__(256, 1) fold_kernel2_coop(const FoldArgs a) {
     v.tin = nullptr; v.tout = nullptr; v.ccnt = nullptr; v.tcap = a.tcap;
     v.M1rm = a.workspace + fold2_seq_bytes(L, 2, 5) / 4 + 16;   // two more triangular matrices behind the region
     v.MB = v.M1rm + TRI;
+    float* sums_out = a.sums ? a.sums + a.sums_offsets[sidx] : nullptr;
+    v.Mfull = sums_out ? sums_out + (size_t)5 * TRI : nullptr;
 
     long long tk = (a.dbg && gtid == 0) ? clock64() : 0;
     auto mark = [&](int slot) { if (a.dbg && gtid == 0) { const long long now = clock64(); a.dbg[slot] = now - tk; tk = now; } };
@@ -591,12 +600,14 @@ __global__ void __launch_bounds__(256, 1) fold_kernel2_coop(const FoldArgs a) {
       v.E0[x] = v.E[doff(x, L)];
       v.EL[x] = v.E[doff(L - 1 - x, L) + x];
     }
+    if (sums_out) export_fold_sums<CONTRA>(v, T, P, sums_out, gtid, gnt);   // FoldSums / FoldScores (N3)
     grid_sync();
     mark(1);   // inside
     const float Z = v.E0[L - 1];
+    if (gtid == 0 && a.out_logz) a.out_logz[sidx] = Z;
+    if (a.inside_only) continue;
     outside_prep<CONTRA>(v, T, gtid, gnt);   // row-major sums_1ormore, table of multibranch closing scores
     for (size_t x = gtid; x < TRI; x += gnt) { v.Pm[x] = NEG; v.R[x] = NEG; v.X[x] = NEG; }
-    if (gtid == 0 && a.out_logz) a.out_logz[sidx] = Z;
     grid_sync();
     // ---- outside, one diagonal per step: X(d) | Y(d) --------------------------------------------------------------
     const int d_out0 = v.dout0;

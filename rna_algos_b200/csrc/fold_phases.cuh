@@ -70,7 +70,14 @@ struct SeqViewT {
   // cooperative kernel, outside pass only (null elsewhere): ROW-MAJOR triangular copies, index(i,j) = doff(i) + j-i
   float* M1rm;            // sums_1ormore_basepairs, row-major
   float* MB;              // multibranch closing score of every closable (i,j) (0 elsewhere), diagonal-major
+  // optional export of the whole sums_multibranch matrix (only three diagonals are live otherwise): the
+  // RNA_SUMS_MULTIBRANCH plane of rna_fold_sums_batch, row-major upper triangle incl. the diagonal; null = off
+  float* Mfull;
 };
+
+// index of (i,j), i <= j, in a plane of rna_fold_sums_batch (include/rna_algos_b200.h: rna_sums_index)
+RNA_DEV size_t sums_index(int L, int i, int j) { return (size_t)i * L - ((size_t)i * (i - 1)) / 2 + (size_t)(j - i); }
+
 
 RNA_DEV int doff(int d, int L) { return d * L - ((d * (d - 1)) >> 1); }
 
@@ -998,7 +1005,7 @@ RNA_DEV void inside_Y_contra(const SV& v, const ContraView2& T, const float4* lu
 // sums_external, sums_multibranch, sums_1ormore_basepairs (src/mccaskill_algo.rs:344-374, 468-512).
 // Needs: sums_close(d) (role X, previous step), partial R/Rm(d) (role Y, previous step), R/Rm/E/M1 of < d.
 // =========================================================================================================
-template <bool CONTRA, int PF, class SV>
+template <bool CONTRA, int PF, class SV, bool SUMSX = false>
 RNA_DEV void inside_Z(const SV& v, const typename Model2<CONTRA>::View& T, const float4* lut, int d,
                       int lane, int nl) {
   const int L = v.L;
@@ -1099,6 +1106,7 @@ RNA_DEV void inside_Z(const SV& v, const typename Model2<CONTRA>::View& T, const
     }
     v.E[od + i] = sE;
     Mcur[i] = sM;
+    if constexpr (SUMSX) { if (v.Mfull) v.Mfull[sums_index(L, i, j)] = sM; }
     sM1 = lse(sM1, sM, lut);
     v.M1[od + i] = sM1;
   }
@@ -1197,6 +1205,7 @@ RNA_DEV void inside_chain_cell(const SV& v, const typename Model2<CONTRA>::View&
       Mcur[i] = RNA_CHAIN_CALL(coop_chain_fold)(v.X, v.M1, L, d, i, RNA_NEG_INF, 0, 0.f, 0.f, lut);
     else                    // M1[i][k-1] + (R[k][j] + COEFF_NUM_BRANCHES)
       Mcur[i] = RNA_CHAIN_CALL(coop_chain_fold)(v.R, v.M1, L, d, i, RNA_NEG_INF, 3, dev->coeff_num_branches, 0.f, lut);
+    if (v.Mfull) v.Mfull[sums_index(L, i, i + d)] = Mcur[i];
   }
 }
 // Z of a pair step: warp-sized tasks (chain kind x 32 cells) of the diagonals t-2 and t-1, the longer diagonal first;
@@ -1329,6 +1338,49 @@ RNA_DEV void inside_fin_pair(const SV& v, const typename Model2<CONTRA>::View& T
       rm = lse(rm, __fadd_rn(__fadd_rn(acc1, dev->mb_bp), __fmul_rn(dev->mb_unpair, 0.f)), lut);
       v.R[od1 + i] = r;
       v.X[od1 + i] = rm;
+    }
+  }
+}
+
+// =========================================================================================================
+// FoldSums / FoldScores export (rna_fold_sums_batch; src/mccaskill_algo.rs:3-22, 213-245), after the inside pass:
+// lane = any thread of the team.  `out`: RNA_SUMS_PLANES planes of L(L+1)/2 floats; the sums_multibranch plane was
+// written by the chains themselves (Mfull).
+// =========================================================================================================
+template <bool CONTRA, class SV>
+RNA_DEV void export_fold_sums(const SV& v, const typename Model2<CONTRA>::View& T, const ModelParams& P, float* out,
+                              int lane, int nl) {
+  const int L = v.L;
+  const size_t PL = (size_t)L * (L + 1) / 2;
+  const float NEG = RNA_NEG_INF;
+  for (int d = 0; d < L; d++) {
+    const int od = doff(d, L);
+    const bool visited = d >= v.din0;   // (Turner: spans below MIN_SPAN_HAIRPIN_CLOSE are never visited: init values)
+    for (int i = lane; i < L - d; i += nl) {
+      const int j = i + d;
+      const size_t x = sums_index(L, i, j);
+      const float c = v.C[od + i];
+      const bool clos = (get32(v.mask + i * v.W2, j) & 1u) != 0;
+      float hp = NEG, mbc = NEG, acc = NEG, A = NEG;
+      if (clos) {
+        if constexpr (CONTRA) { if (d - 1 <= P.MAX2) hp = c2_hairpin(T, v.s, i, j); }
+        else hp = t_hairpin(T, v.s, i, j);
+        if (c > NEG) {   // (the reference inserts these three only when the pair's sum is finite)
+          mbc = v2_mbclose<CONTRA>(T, v.s, L, i, j);
+          acc = v2_acc<CONTRA>(T, v.s, L, i, j);
+          A = __fadd_rn(c, acc);
+        }
+      }
+      out[0 * PL + x] = c;
+      out[1 * PL + x] = A;
+      out[2 * PL + x] = v.E[od + i];
+      out[3 * PL + x] = v.R[od + i];
+      out[4 * PL + x] = CONTRA ? v.X[od + i] : NEG;
+      if (!visited) out[5 * PL + x] = NEG;
+      out[6 * PL + x] = v.M1[od + i];
+      out[7 * PL + x] = hp;
+      out[8 * PL + x] = mbc;
+      out[9 * PL + x] = acc;
     }
   }
 }

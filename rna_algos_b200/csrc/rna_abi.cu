@@ -14,6 +14,7 @@
 #include "../../include/rna_algos_b200.h"
 #include "dev_tables.h"
 #include "durbin_kernel.cuh"
+#include "fast_kernel.cuh"
 #include "fold_kernel2.cuh"
 #include "table_pack.h"
 
@@ -42,6 +43,8 @@ struct rna_handle {
   DevAlign* d_align = nullptr;
   float *d_hp_ext = nullptr, *d_int11 = nullptr, *d_int12 = nullptr, *d_int22 = nullptr;
   DevBuf ws, counters, order, stream_ws;                           // kernel scratch
+  DevBuf fast_ws, fast_bpp;                                        // FAST numeric mode: matrix slots, internal BPP
+  int numeric_mode = RNA_NUMERIC_REF_EXACT;
   DevBuf b_bases, b_offsets, b_bppoff, b_gammas, b_logz, b_bpp, b_structs, b_ea, b_pairs, b_probs, b_proboff;
   RnaCallStats stats{};
   // cached answers of the CUDA runtime about kernel configurations (kern_prepare)
@@ -121,7 +124,7 @@ extern "C" int rna_destroy(rna_handle* h) {
   if (!h) return RNA_OK;
   cudaSetDevice(h->device);
   cudaStreamSynchronize(h->stream);
-  DevBuf* bufs[] = {&h->ws, &h->counters, &h->order, &h->stream_ws, &h->b_bases, &h->b_offsets, &h->b_bppoff, &h->b_gammas,
+  DevBuf* bufs[] = {&h->ws, &h->counters, &h->order, &h->stream_ws, &h->fast_ws, &h->fast_bpp, &h->b_bases, &h->b_offsets, &h->b_bppoff, &h->b_gammas,
                     &h->b_logz, &h->b_bpp, &h->b_structs, &h->b_ea, &h->b_pairs, &h->b_probs, &h->b_proboff};
   for (DevBuf* b : bufs) free_buf(*b);
   cudaFree(h->d_turner); cudaFree(h->d_contra); cudaFree(h->d_align);
@@ -136,6 +139,12 @@ extern "C" int rna_destroy(rna_handle* h) {
 
 extern "C" const char* rna_last_error(const rna_handle* h) { return h ? h->err.c_str() : "null handle"; }
 extern "C" int rna_device(const rna_handle* h) { return h ? h->device : -1; }
+extern "C" int rna_set_numeric_mode(rna_handle* h, int mode) {
+  if (!h || mode < RNA_NUMERIC_REF_EXACT || mode > RNA_NUMERIC_FAST_F64) return RNA_ERR_BAD_ARG;
+  h->numeric_mode = mode;
+  return RNA_OK;
+}
+extern "C" int rna_get_numeric_mode(const rna_handle* h) { return h ? h->numeric_mode : -1; }
 extern "C" int rna_get_stats(const rna_handle* h, RnaCallStats* out) {
   if (!h || !out) return RNA_ERR_BAD_ARG;
   *out = h->stats;
@@ -335,12 +344,17 @@ static int launch_centroid(rna_handle* h, const RnaFoldBatchDev* b, cudaStream_t
   const int gran = 8;
   int Lsmem = 0;
   for (int L = 16; L <= 1024; L += gran) { if (centroid_ws_floats(L) * 4 + 1024 <= h->smem_optin) Lsmem = L; else break; }
+  // sequences beyond the shared-memory mode: one CTA each when there are many, else one at a time on the whole grid
+  // (a lone 1024-nt sequence takes > 100 ms on one CTA, ~5 ms on the grid)
+  uint32_t n_long = 0;
+  while (n_long < n && len_of(n_long) > Lsmem) n_long++;
+  const int Lcoop_min = (n_long <= 32) ? std::max(Lsmem + 1, 384) : 1025;
   std::vector<Bucket> buckets;
   for (uint32_t pos = 0; pos < n;) {
     const int L = len_of(pos);
     Bucket bk;
     bk.begin = pos;
-    if (L > 1024) {
+    if (L >= Lcoop_min) {
       if (L > RNA_MAX_FOLD_LEN) { h->err = "sequence longer than RNA_MAX_FOLD_LEN (46340 nt)"; return RNA_ERR_TOO_LONG; }
       bk.mode = MODE_COOP; bk.Lcap = L; bk.end = pos + 1;
     } else if (L > Lsmem) {
@@ -415,10 +429,11 @@ static int launch_centroid(rna_handle* h, const RnaFoldBatchDev* b, cudaStream_t
       const int nt = std::min(512, std::max(32, (bk.Lcap + 31) / 32 * 32));
       centroid_kernel<MODE_GLOBAL><<<grid_of[k], nt, 16, st>>>(a, d_bpp_in);
     } else {
-      const int nt = 128;
+      // whole grid: the chunked atomic-max fill has (thresholds x cell groups x chunks) warp tasks per diagonal
+      const int nt = 256;
       int occ = 1;
       TRY(kern_prepare(h, (const void*)centroid_kernel<MODE_COOP>, nt, 16, &occ));
-      const int grid = std::max(1, std::min(std::max(1, occ) * h->sm_count, (bk.Lcap + nt - 1) / nt));
+      const int grid = std::max(1, std::min(occ, 2)) * h->sm_count;
       void* params[] = {(void*)&a, (void*)&d_bpp_in};
       CU(h, cudaLaunchCooperativeKernel((void*)centroid_kernel<MODE_COOP>, dim3(grid), dim3(nt), params, 16, st));
     }
@@ -504,6 +519,7 @@ static void fold_dbg_report(int mode, int Lcap, const FoldArgs& a, long long* d_
 template <bool CONTRA>
 static int launch_fold_model(rna_handle* h, const RnaFoldBatchDev* b, cudaStream_t st) {
   const uint32_t n = b->n_seqs;
+  const bool want_sums = b->d_out_sums != nullptr || b->inside_only;   // (the SUMS build of the batch kernel)
   const uint32_t* ho = b->h_offsets;
   std::vector<uint32_t> order;
   order_by_length(ho, n, order);
@@ -642,7 +658,8 @@ static int launch_fold_model(rna_handle* h, const RnaFoldBatchDev* b, cudaStream
     ro_of[k] = fold2_roles(bk.Lcap, CONTRA, warps);
     const int nt = 32 * warps;
     int occ = 1;
-    TRY(kern_prepare(h, (const void*)fold_kernel2<CONTRA, MODE_SMEM>, nt, smem, &occ));
+    if (want_sums) TRY(kern_prepare(h, (const void*)fold_kernel2<CONTRA, MODE_SMEM, true>, nt, smem, &occ));
+    else TRY(kern_prepare(h, (const void*)fold_kernel2<CONTRA, MODE_SMEM>, nt, smem, &occ));
     occ = std::max(1, std::min(occ, occ_cap));
     nt_of[k] = nt;
     grid_of[k] = (int)std::min<size_t>(bk.end - bk.begin, (size_t)occ * h->sm_count);
@@ -691,6 +708,9 @@ static int launch_fold_model(rna_handle* h, const RnaFoldBatchDev* b, cudaStream
   a.out_ea = b->d_out_expect_acc;
   a.out_pairs = b->d_out_pairs;
   a.out_npairs = b->d_out_num_pairs;
+  a.sums = b->d_out_sums;
+  a.sums_offsets = reinterpret_cast<const unsigned long long*>(b->d_sums_offsets);
+  a.inside_only = b->inside_only;
   a.workspace = (float*)h->ws.p;
   if (nlanes > 1) {
     CU(h, cudaEventRecord(h->ev_fork, st));
@@ -727,11 +747,17 @@ static int launch_fold_model(rna_handle* h, const RnaFoldBatchDev* b, cudaStream
           a.stream_stride = stream_stride_of[k];
           a.stream_ws = (unsigned char*)h->stream_ws.p + (size_t)lane * stream_bytes;
         }
-        fold_kernel2<CONTRA, MODE_SMEM><<<grid_of[k], nt, smem, st>>>(a);
+        if (want_sums) fold_kernel2<CONTRA, MODE_SMEM, true><<<grid_of[k], nt, smem, st>>>(a);
+        else fold_kernel2<CONTRA, MODE_SMEM><<<grid_of[k], nt, smem, st>>>(a);
       } else {
         const size_t smem = fold2_fixed_bytes<CONTRA>(bk.Lcap);
-        TRY(kern_prepare(h, (const void*)fold_kernel2<CONTRA, MODE_GLOBAL>, nt, smem, nullptr));
-        fold_kernel2<CONTRA, MODE_GLOBAL><<<grid_of[k], nt, smem, st>>>(a);
+        if (want_sums) {
+          TRY(kern_prepare(h, (const void*)fold_kernel2<CONTRA, MODE_GLOBAL, true>, nt, smem, nullptr));
+          fold_kernel2<CONTRA, MODE_GLOBAL, true><<<grid_of[k], nt, smem, st>>>(a);
+        } else {
+          TRY(kern_prepare(h, (const void*)fold_kernel2<CONTRA, MODE_GLOBAL>, nt, smem, nullptr));
+          fold_kernel2<CONTRA, MODE_GLOBAL><<<grid_of[k], nt, smem, st>>>(a);
+        }
       }
     } else {
       // long sequence: cooperative grid, roles spread over the SMs
@@ -771,6 +797,115 @@ static int launch_fold_model(rna_handle* h, const RnaFoldBatchDev* b, cudaStream
   return RNA_OK;
 }
 
+// ---------------------------------------------------------------------------------------------------
+// FAST numeric mode (fast_kernel.cuh): sequences up to RNA_FAST_COOP_MIN nt one CTA each, in launches by length class
+// (the slot of a CTA is sized for the class); longer ones one at a time on a cooperative grid.  The centroid
+// estimator then runs on the packed BPP matrices like rna_centroid_batch (it is exact max-plus either way).
+// ---------------------------------------------------------------------------------------------------
+#define RNA_FAST_COOP_MIN 700
+template <bool CONTRA, class real>
+static int launch_fast(rna_handle* h, const RnaFoldBatchDev* b, cudaStream_t st, float* d_bpp) {
+  const uint32_t n = b->n_seqs;
+  const uint32_t* ho = b->h_offsets;
+  std::vector<uint32_t> order;
+  order_by_length(ho, n, order);
+  auto len_of = [&](uint32_t pos) { return (int)(ho[order[pos] + 1] - ho[order[pos]]); };
+  std::vector<Bucket> buckets;
+  for (uint32_t pos = 0; pos < n;) {
+    const int L = len_of(pos);
+    Bucket bk;
+    bk.begin = pos;
+    if (L >= RNA_FAST_COOP_MIN) { bk.mode = MODE_COOP; bk.Lcap = L; bk.end = pos + 1; }
+    else {
+      bk.mode = MODE_GLOBAL;
+      bk.Lcap = L;
+      const int lo = std::max(L / 2, (L > 96) ? 96 : 0);   // a class: lengths in (lo, L] (the shortest class takes all <= 96)
+      uint32_t e = pos;
+      while (e < n && len_of(e) > lo) e++;
+      bk.end = e;
+    }
+    buckets.push_back(bk);
+    pos = bk.end;
+  }
+  TRY(ensure(h, h->order, sizeof(uint32_t) * (size_t)std::max<uint32_t>(n, 1)));
+  TRY(ensure(h, h->counters, sizeof(int) * buckets.size()));
+  CU(h, cudaMemcpyAsync(h->order.p, order.data(), sizeof(uint32_t) * n, cudaMemcpyHostToDevice, st));
+  CU(h, cudaMemsetAsync(h->counters.p, 0, sizeof(int) * buckets.size(), st));
+  h->stats.h2d_bytes += sizeof(uint32_t) * n;
+  int occ_b = 1, occ_c = 1;
+  TRY(kern_prepare(h, (const void*)fast_fold_kernel<CONTRA, false, real>, RNA_FAST_NT_BATCH, 0, &occ_b));
+  TRY(kern_prepare(h, (const void*)fast_fold_kernel<CONTRA, true, real>, RNA_FAST_NT_COOP, 0, &occ_c));
+  size_t freeb = 0, totb = 0;
+  cudaMemGetInfo(&freeb, &totb);
+  const size_t budget = (freeb + h->fast_ws.cap) / 2;
+  size_t ws_bytes = 0;
+  std::vector<int> grid_of(buckets.size(), 0);
+  std::vector<size_t> stride_of(buckets.size(), 0);
+  for (size_t k = 0; k < buckets.size(); k++) {
+    const Bucket& bk = buckets[k];
+    const size_t per = (fast_slot_bytes(bk.Lcap, sizeof(real)) + 255) / 256 * 256;
+    stride_of[k] = per;
+    int g = 1;
+    if (bk.mode != MODE_COOP) {
+      g = (int)std::min<size_t>(bk.end - bk.begin, (size_t)std::max(1, occ_b) * h->sm_count);
+      while (g > 1 && (size_t)g * per > budget) g--;
+    }
+    if ((size_t)g * per > budget) { h->err = "sequence too long for device memory"; return RNA_ERR_NOMEM; }
+    grid_of[k] = g;
+    ws_bytes = std::max(ws_bytes, (size_t)g * per);
+  }
+  TRY(ensure(h, h->fast_ws, ws_bytes));
+  FastArgs a;
+  memset(&a, 0, sizeof a);
+  a.bases = b->d_bases;
+  a.offsets = b->d_offsets;
+  a.tables = CONTRA ? (const void*)h->d_contra : (const void*)h->d_turner;
+  a.allows_short = b->allows_short_hairpins;
+  a.out_logz = b->d_out_logz;
+  a.out_bpp = d_bpp;
+  a.bpp_offsets = b->d_bpp_offsets;
+  a.workspace = h->fast_ws.p;
+  for (size_t k = 0; k < buckets.size(); k++) {
+    const Bucket& bk = buckets[k];
+    a.order = (const uint32_t*)h->order.p + bk.begin;
+    a.n_launch = bk.end - bk.begin;
+    a.work_counter = (int*)h->counters.p + k;
+    a.ws_stride = stride_of[k];
+    if (bk.mode == MODE_COOP) {
+      const int grid = std::max(1, std::min(occ_c, 1)) * h->sm_count;
+      void* params[] = {(void*)&a};
+      CU(h, cudaLaunchCooperativeKernel((void*)fast_fold_kernel<CONTRA, true, real>, dim3(grid), dim3(RNA_FAST_NT_COOP), params, 0, st));
+    } else {
+      fast_fold_kernel<CONTRA, false, real><<<grid_of[k], RNA_FAST_NT_BATCH, 0, st>>>(a);
+    }
+    CU(h, cudaGetLastError());
+    h->stats.kernel_launches++;
+  }
+  return RNA_OK;
+}
+
+static int launch_fast_mode(rna_handle* h, const RnaFoldBatchDev* b, cudaStream_t st) {
+  // the packed BPP matrices feed the centroid kernels: the caller's buffer, or one of the handle's
+  float* d_bpp = b->d_out_bpp;
+  const uint64_t* d_bppoff = b->d_bpp_offsets;
+  RnaFoldBatchDev bb = *b;
+  if (!d_bpp && b->n_gammas) {
+    if (!d_bppoff) { h->err = "d_bpp_offsets required (FAST mode computes the centroid from the packed BPPs)"; return RNA_ERR_BAD_ARG; }
+    uint64_t tot = 0;
+    for (uint32_t s = 0; s < b->n_seqs; s++) tot += rna_bpp_len(b->h_offsets[s + 1] - b->h_offsets[s]);
+    TRY(ensure(h, h->fast_bpp, tot * 4));
+    d_bpp = (float*)h->fast_bpp.p;
+  }
+  const bool f64 = h->numeric_mode == RNA_NUMERIC_FAST_F64;
+  if (b->model == RNA_MODEL_CONTRA) TRY(f64 ? (launch_fast<true, double>(h, b, st, d_bpp)) : (launch_fast<true, float>(h, b, st, d_bpp)));
+  else TRY(f64 ? (launch_fast<false, double>(h, b, st, d_bpp)) : (launch_fast<false, float>(h, b, st, d_bpp)));
+  if (b->n_gammas) {
+    bb.d_out_bpp = d_bpp;
+    TRY(launch_centroid(h, &bb, st, d_bpp));
+  }
+  return RNA_OK;
+}
+
 static int check_fold_args(rna_handle* h, const RnaFoldBatchDev* b) {
   if (!h || !b) return RNA_ERR_BAD_ARG;
   if (b->n_seqs == 0) return RNA_OK;
@@ -780,6 +915,11 @@ static int check_fold_args(rna_handle* h, const RnaFoldBatchDev* b) {
   if (b->model == RNA_MODEL_CONTRA && !h->has_contra) { h->err = "CONTRAfold tables not set"; return RNA_ERR_NO_TABLES; }
   if (b->d_out_bpp && !b->d_bpp_offsets) { h->err = "d_bpp_offsets required"; return RNA_ERR_BAD_ARG; }
   if (b->n_gammas && !b->d_gammas) { h->err = "d_gammas required"; return RNA_ERR_BAD_ARG; }
+  if (b->d_out_sums && !b->d_sums_offsets) { h->err = "d_sums_offsets required"; return RNA_ERR_BAD_ARG; }
+  if ((b->d_out_sums || b->inside_only) && h->numeric_mode != RNA_NUMERIC_REF_EXACT) {
+    h->err = "the FoldSums / FoldScores outputs exist in the reference-exact numeric mode only";
+    return RNA_ERR_BAD_ARG;
+  }
   if (rna_validate_fold_lengths(b->h_offsets, b->n_seqs) != RNA_OK) { h->err = "sequence longer than RNA_MAX_FOLD_LEN (46340 nt)"; return RNA_ERR_TOO_LONG; }
   return RNA_OK;
 }
@@ -790,7 +930,8 @@ extern "C" int rna_mccaskill_centroid_batch_dev(rna_handle* h, const RnaFoldBatc
   CU(h, cudaSetDevice(h->device));
   cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
   TRY(call_begin(h, st));
-  if (b->model == RNA_MODEL_CONTRA) TRY(launch_fold_model<true>(h, b, st));
+  if (h->numeric_mode != RNA_NUMERIC_REF_EXACT) TRY(launch_fast_mode(h, b, st));
+  else if (b->model == RNA_MODEL_CONTRA) TRY(launch_fold_model<true>(h, b, st));
   else TRY(launch_fold_model<false>(h, b, st));
   return call_end(h, st);
 }
@@ -829,7 +970,9 @@ extern "C" int rna_mccaskill_centroid_batch(rna_handle* h, const uint8_t* bases,
   std::vector<uint64_t> own_off;
   uint32_t maxlen = 0;
   for (uint32_t s = 0; s < n_seqs; s++) maxlen = std::max(maxlen, offsets[s + 1] - offsets[s]);
-  if (out_bpp && !bpp_offsets) {
+  // (FAST numeric modes compute the centroid from the packed BPP matrices: offsets are needed even without out_bpp)
+  const bool fast_cent = h->numeric_mode != RNA_NUMERIC_REF_EXACT && n_gammas;
+  if ((out_bpp || fast_cent) && !bpp_offsets) {
     own_off.resize((size_t)n_seqs + 1);
     own_off[0] = 0;
     for (uint32_t s = 0; s < n_seqs; s++) own_off[s + 1] = own_off[s] + rna_bpp_len(offsets[s + 1] - offsets[s]);
@@ -844,6 +987,10 @@ extern "C" int rna_mccaskill_centroid_batch(rna_handle* h, const uint8_t* bases,
   b.d_offsets = (const uint32_t*)h->b_offsets.p;
   size_t bpp_total = 0;
   bool bpp_zero_copy = false;
+  if (fast_cent && !out_bpp) {
+    TRY(h2d(h, h->b_bppoff, bpp_offsets, sizeof(uint64_t) * ((size_t)n_seqs + 1), st));
+    b.d_bpp_offsets = (const uint64_t*)h->b_bppoff.p;
+  }
   if (out_bpp) {
     bpp_total = bpp_offsets[n_seqs];
     TRY(h2d(h, h->b_bppoff, bpp_offsets, sizeof(uint64_t) * ((size_t)n_seqs + 1), st));
@@ -855,7 +1002,8 @@ extern "C" int rna_mccaskill_centroid_batch(rna_handle* h, const uint8_t* bases,
     static const bool no_zc = dev_env("RNA_NO_ZERO_COPY") != nullptr;
     cudaPointerAttributes pat;
     memset(&pat, 0, sizeof pat);
-    if (!no_zc && cudaPointerGetAttributes(&pat, out_bpp) == cudaSuccess && pat.type == cudaMemoryTypeHost && pat.devicePointer) {
+    // (the centroid kernels of the FAST modes re-read the BPPs: staged in HBM)
+    if (!no_zc && !fast_cent && cudaPointerGetAttributes(&pat, out_bpp) == cudaSuccess && pat.type == cudaMemoryTypeHost && pat.devicePointer) {
       // (the whole range must be page-locked: probe its last byte too)
       cudaPointerAttributes pend;
       memset(&pend, 0, sizeof pend);
@@ -890,6 +1038,50 @@ extern "C" int rna_mccaskill_centroid_batch(rna_handle* h, const uint8_t* bases,
   if (out_bpp && bpp_zero_copy) h->stats.d2h_bytes += bpp_total * 4;   // written to host memory by the kernels
   if (n_gammas && out_structs) TRY(d2h(h, out_structs, h->b_structs, (size_t)n_gammas * total, st));
   if (n_gammas && out_expect_acc) TRY(d2h(h, out_expect_acc, h->b_ea, sizeof(float) * (size_t)n_gammas * n_seqs, st));
+  CU(h, cudaStreamSynchronize(st));
+  return RNA_OK;
+}
+
+extern "C" int rna_fold_sums_batch(rna_handle* h, const uint8_t* bases, const uint32_t* offsets, uint32_t n_seqs, int model,
+                                   int allows_short_hairpins, float* out_sums, const uint64_t* sums_offsets, float* out_logz) {
+  if (!h || !out_sums) return RNA_ERR_BAD_ARG;
+  h->stats = RnaCallStats{};
+  if (n_seqs == 0) return RNA_OK;
+  int rc = rna_validate_bases(bases, offsets, n_seqs);
+  if (rc == RNA_OK) rc = rna_validate_fold_lengths(offsets, n_seqs);
+  if (rc != RNA_OK) { h->err = rc == RNA_ERR_TOO_LONG ? "sequence longer than RNA_MAX_FOLD_LEN (46340 nt)" : "input validation failed"; return rc; }
+  if (offsets[0] != 0) { h->err = "offsets[0] must be 0"; return RNA_ERR_BAD_ARG; }
+  CU(h, cudaSetDevice(h->device));
+  cudaStream_t st = h->stream;
+  std::vector<uint64_t> own;
+  if (!sums_offsets) {
+    own.resize((size_t)n_seqs + 1);
+    own[0] = 0;
+    for (uint32_t s = 0; s < n_seqs; s++) own[s + 1] = own[s] + (uint64_t)RNA_SUMS_PLANES * rna_sums_len(offsets[s + 1] - offsets[s]);
+    sums_offsets = own.data();
+  }
+  const size_t tot = sums_offsets[n_seqs];
+  RnaFoldBatchDev b;
+  memset(&b, 0, sizeof b);
+  b.h_offsets = offsets;
+  TRY(h2d(h, h->b_bases, bases, offsets[n_seqs], st));
+  TRY(h2d(h, h->b_offsets, offsets, sizeof(uint32_t) * ((size_t)n_seqs + 1), st));
+  TRY(h2d(h, h->b_proboff, sums_offsets, sizeof(uint64_t) * ((size_t)n_seqs + 1), st));
+  TRY(ensure(h, h->b_probs, tot * 4));
+  if (out_logz) TRY(ensure(h, h->b_logz, sizeof(float) * n_seqs));
+  b.d_bases = (const uint8_t*)h->b_bases.p;
+  b.d_offsets = (const uint32_t*)h->b_offsets.p;
+  b.d_sums_offsets = (const uint64_t*)h->b_proboff.p;
+  b.d_out_sums = (float*)h->b_probs.p;
+  b.d_out_logz = out_logz ? (float*)h->b_logz.p : nullptr;
+  b.n_seqs = n_seqs;
+  b.total_len = offsets[n_seqs];
+  b.model = model;
+  b.allows_short_hairpins = allows_short_hairpins;
+  b.inside_only = 1;
+  TRY(rna_mccaskill_centroid_batch_dev(h, &b, st));
+  TRY(d2h(h, out_sums, h->b_probs, tot * 4, st));
+  if (out_logz) TRY(d2h(h, out_logz, h->b_logz, sizeof(float) * n_seqs, st));
   CU(h, cudaStreamSynchronize(st));
   return RNA_OK;
 }

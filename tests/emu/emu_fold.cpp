@@ -43,7 +43,7 @@ int run(const uint8_t* seq, int L, int allows_short, const typename Model2<CONTR
   v.C = C.data(); v.R = R.data(); v.X = X.data(); v.E = E.data(); v.M1 = M1.data(); v.Mroll = Mroll.data();
   v.E0 = E0.data(); v.EL = EL.data();
   std::vector<float> M1rm(TRI, NEG), MB(TRI, 0.f);
-  v.M1rm = M1rm.data(); v.MB = MB.data();
+  v.M1rm = M1rm.data(); v.MB = MB.data(); v.Mfull = nullptr;
   // log P either aliases sums_external (all-in-one-space modes) or is a matrix of its own (the shared-memory mode
   // keeps C and log P on chip and the dense matrices in its HBM/L2 slot)
   std::vector<float> Pown(TRI, NEG);

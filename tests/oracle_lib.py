@@ -68,6 +68,8 @@ class Oracle:
         L.orc_durbin_batch.argtypes = [u8p, u32p, u32p, C.c_uint32, C.POINTER(AlignTables), f32p, u64p,
                                        C.c_int, u64p]
         L.orc_set_inner_threads.argtypes = [C.c_int]
+        L.orc_fold_sums.restype = C.c_int
+        L.orc_fold_sums.argtypes = [u8p, C.c_int, C.c_int, C.c_int, C.POINTER(TurnerTables), C.POINTER(ContraTables), f32p]
         L.orc_is_exact_flavour.restype = C.c_int
         assert bool(L.orc_is_exact_flavour()) == exact
 
@@ -90,6 +92,16 @@ class Oracle:
         if debug:
             return bpp, float(logz.value), dict(close=dbg[0], external=dbg[1], logprob=dbg[2], m1=dbg[3])
         return bpp, np.float32(logz.value)
+
+    def fold_sums(self, seq: np.ndarray, contra: bool, allows_short: bool, tt, ct) -> np.ndarray:
+        """[RNA_SUMS_PLANES][L][L] dense planes of get_fold_sums(_contra) + FoldScores (-inf = key absent)."""
+        seq = np.ascontiguousarray(seq, dtype=np.uint8)
+        L = int(seq.shape[0])
+        out = np.empty((10, L, L), dtype=np.float32)
+        rc = self.lib.orc_fold_sums(_ptr(seq, u8p), L, int(contra), int(allows_short), C.byref(tt), C.byref(ct),
+                                    _ptr(out, f32p))
+        assert rc == 0, rc
+        return out
 
     def centroid(self, bpp: np.ndarray, L: int, gamma: float):
         bpp = np.ascontiguousarray(bpp, dtype=np.float32)

@@ -343,3 +343,110 @@ def test_zero_copy_bpp_into_pinned_host_buffer(handle, oracle):
         assert (got["structs"] == want["structs"]).all()
     ref = oracle.fold_batch(bases, offsets, True, False, tt, ct, [2.0], n_threads=8)
     assert_bits_equal(got["bpp"], ref["bpp"], "zero-copy BPP vs oracle")
+
+
+@pytest.mark.parametrize("contra", [False, True])
+def test_fold_sums_and_fold_scores_export(handle, oracle, contra):
+    """N3: get_fold_sums(_contra) stand-alone + the FoldScores memo (src/mccaskill_algo.rs:3-22, 213-245, 282-516)
+    through rna_fold_sums_batch: every plane bit-equal to the oracle's, in all three kernel routes (shared-memory
+    batch, HBM-resident one-CTA, cooperative)."""
+    tt, ct, _ = default_tables()
+    seqs = load_trnas()[:3] + random_seqs(5, [1, 4, 5, 31, 300]) + [np.random.default_rng(9).integers(0, 4, 450).astype(np.uint8)]
+    bases, offsets = pack(seqs)
+    got = handle.fold_sums_batch(bases, offsets, contra, False)
+    names = handle.SUMS_PLANES
+    for s, seq in enumerate(seqs):
+        want = oracle.fold_sums(seq, contra, False, tt, ct)
+        iu = np.triu_indices(len(seq))
+        for p, name in enumerate(names):
+            assert_bits_equal(got[s][name][iu], want[p][iu], f"{name} seq {s} (L={len(seq)})")
+        assert_bits_equal(got[s]["logz"], want[2][0, len(seq) - 1], "logZ")
+    # a lone mid-length sequence takes the cooperative route
+    seq = np.random.default_rng(10).integers(0, 4, 500).astype(np.uint8)
+    b1, o1 = pack([seq])
+    g1 = handle.fold_sums_batch(b1, o1, contra, False)[0]
+    want = oracle.fold_sums(seq, contra, False, tt, ct)
+    iu = np.triu_indices(500)
+    for p, name in enumerate(names):
+        assert_bits_equal(g1[name][iu], want[p][iu], f"{name} cooperative route")
+
+
+def test_multi_device_object_partitions_and_scatters(oracle):
+    """rna_multi: LPT partition inside the library, one host thread + handle per device, results scattered into the
+    caller's buffers.  Listing device 0 three times exercises partition / scatter on a one-GPU box; on a multi-GPU
+    box the default (all visible devices) runs too.  Results are bit-identical to the oracle whatever the partition."""
+    import torch
+    from rna_algos_b200.api import MultiHandle
+    tt, ct, at = default_tables()
+    seqs = load_trnas() * 3 + random_seqs(21, [1, 5, 40, 130, 260, 33, 77])
+    bases, offsets = pack(seqs)
+    gammas = [1.0, 4.0]
+    want = oracle.fold_batch(bases, offsets, True, False, tt, ct, gammas, n_threads=8)
+    pairs = np.array([(a, b) for a in range(6) for b in range(a + 1, 6)] + [(20, 3), (24, 24)], dtype=np.uint32)
+    wantd = oracle.durbin_batch(bases, offsets, pairs, at, n_threads=8)
+    configs = [[0, 0, 0]] + ([None] if torch.cuda.device_count() > 1 else [])
+    for devs in configs:
+        m = MultiHandle(devs, tt, ct, at)
+        try:
+            got = m.fold_batch(bases, offsets, True, False, gammas)
+            assert_bits_equal(got["logz"], want["logz"], "logZ")
+            assert_bits_equal(got["bpp"], want["bpp"], "BPP")
+            assert_bits_equal(got["expect_acc"], want["expect_acc"], "expect_accuracy")
+            assert (got["structs"] == want["structs"]).all()
+            busy, units = m.shares()
+            assert units.sum() == len(seqs) and (units > 0).all() and (busy > 0).all()
+            gd = m.durbin_batch(bases, offsets, pairs)
+            assert_bits_equal(gd["probs"], wantd["probs"], "Durbin")
+        finally:
+            m.close()
+
+
+def test_sixteen_threads_of_single_calls_are_coalesced(handle, oracle):
+    """The reference's call granularity (one sequence per call from the tasks of a thread pool,
+    src/bin/centroid_fold.rs:119-132) through rna_queue: 16 threads x single calls are coalesced into batched launches,
+    every caller gets its own bit-exact result, and the rate beats the CPU oracle's on as many threads."""
+    import threading
+    import time
+    from rna_algos_b200.api import CallQueue
+    tt, ct, _ = default_tables()
+    base = load_trnas()
+    n_threads, per_thread = 16, 24
+    work = [[base[(t + k) % 6] for k in range(per_thread)] for t in range(n_threads)]
+    want = {i: oracle.mccaskill(base[i], True, False, tt, ct) for i in range(6)}
+    wantc = {i: oracle.centroid(want[i][0], len(base[i]), 2.0) for i in range(6)}
+    q = CallQueue(handle)
+    errors = []
+
+    def worker(t):
+        try:
+            for k, seq in enumerate(work[t]):
+                i = (t + k) % 6
+                bpp, logz, st, ea = q.mccaskill_algo(seq, True, False, centroid_threshold=2.0)
+                if not ((bpp.view(np.uint32) == want[i][0].view(np.uint32)).all() and st == wantc[i][0]
+                        and np.float32(logz).view(np.uint32) == np.float32(want[i][1]).view(np.uint32)):
+                    errors.append((t, k))
+        except Exception as e:   # noqa: BLE001
+            errors.append(repr(e))
+    for t in range(2):   # warm-up (allocations, first launches)
+        worker(t)
+    th = [threading.Thread(target=worker, args=(t,)) for t in range(n_threads)]
+    t0 = time.perf_counter()
+    for x in th:
+        x.start()
+    for x in th:
+        x.join()
+    dt = time.perf_counter() - t0
+    stats = q.stats()
+    q.close()
+    assert not errors, errors[:3]
+    rate = n_threads * per_thread / dt
+    # the CPU port on the same number of threads, same sequences
+    flat = [s for w in work for s in w]
+    b, o = pack(flat)
+    t0 = time.perf_counter()
+    oracle.fold_batch(b, o, True, False, tt, ct, [2.0], n_threads=n_threads)
+    cpu_rate = len(flat) / (time.perf_counter() - t0)
+    print(f"single calls from {n_threads} threads: {rate:.0f} seq/s in {stats['launches']} launches for {stats['requests']} "
+          f"requests; CPU oracle on {n_threads} threads: {cpu_rate:.0f} seq/s")
+    assert stats["launches"] < stats["requests"] / 2, stats      # coalescing happened
+    assert rate > cpu_rate, (rate, cpu_rate)

@@ -111,3 +111,28 @@ def test_durbin_both_restatements_agree(oracle):
     for a in rs:
         for b in rs:
             assert_bits_equal(TL.durbin_algo((pad(a), pad(b)), rat), oracle.durbin(a, b, rat), "random pair")
+
+
+@pytest.mark.parametrize("contra", [False, True])
+def test_fold_sums_planes_of_both_restatements(oracle, contra):
+    """FoldSums + FoldScores member by member (the oracle's orc_fold_sums planes are what the CUDA path's
+    rna_fold_sums_batch is compared with in tests/test_gpu_parity.py)."""
+    tt, ct, _ = default_tables()
+    seq = load_trnas()[4]
+    L = len(seq)
+    _, scores, sums = TL.mccaskill_algo(seq, contra, False, ct, tt)
+    planes = oracle.fold_sums(seq, contra, False, tt, ct)
+
+    def sparse(d):
+        m = np.full((L, L), -np.inf, dtype=np.float32)
+        for (i, j), v in d.items():
+            m[i, j] = v
+        return m
+    iu = np.triu_indices(L)
+    want = [sparse(sums.sums_close), sparse(sums.sums_accessible), np.array(sums.sums_external, dtype=np.float32),
+            np.array(sums.sums_rightmost_basepairs_external, dtype=np.float32),
+            np.array(sums.sums_rightmost_basepairs_multibranch, dtype=np.float32),
+            np.array(sums.sums_multibranch, dtype=np.float32), np.array(sums.sums_1ormore_basepairs, dtype=np.float32),
+            sparse(scores.hairpin_scores), sparse(scores.multibranch_close_scores), sparse(scores.accessible_scores)]
+    for p, w in enumerate(want):
+        assert_bits_equal(planes[p][iu], w[iu], f"plane {p}")
