@@ -86,6 +86,24 @@ __host__ __device__ inline Roles fold2_roles(int Lcap, bool contra, int max_warp
   return r;
 }
 
+// Roles of the HBM-resident one-CTA mode (sequences beyond the shared-memory mode, up to 1024 nt).  There the dense
+// chains dominate: per sequence the three chains of role Z walk L^3/6 split points, the sparse rightmost-pair chains
+// of role Y (CONTRAfold) ~0.12 L^3 terms, the two-loop chains of role X ~37 L^2 terms (scored on the fly), so the
+// lanes are split in proportion to that work instead of "a lane per closable cell for X".
+__host__ __device__ inline Roles fold2_roles_global(int Lcap, bool contra, int max_warps) {
+  const double L = Lcap;
+  const double wx = 28000.0 * L * L, wz = 50.0 * L * L * L, wy = contra ? 22.0 * L * L * L : 0.0;   // (fitted: 7/3/6 warps at 500 nt)
+  const double tot = wx + wy + wz;
+  Roles r;
+  r.nY = contra ? (int)(max_warps * wy / tot + 0.5) : 0;
+  if (contra && r.nY < 1) r.nY = 1;
+  r.nX = (int)(max_warps * wx / tot + 0.5);
+  if (r.nX < 2) r.nX = 2;
+  r.nZ = max_warps - r.nX - r.nY;
+  if (r.nZ < 2) { r.nZ = 2; r.nX = max_warps - r.nY - r.nZ; }
+  return r;
+}
+
 // SUMS: the build that also exports the FoldSums / FoldScores planes (rna_fold_sums_batch) and can stop after the inside
 // pass; the default build carries none of it (the batch kernel sits at its 64-register cap: measured 10 % slower with
 // the export code compiled in).

@@ -573,9 +573,11 @@ static int launch_fold_model(rna_handle* h, const RnaFoldBatchDev* b, cudaStream
       if (L > RNA_MAX_FOLD_LEN) { h->err = "sequence longer than RNA_MAX_FOLD_LEN (46340 nt)"; return RNA_ERR_TOO_LONG; }
       bk.mode = MODE_COOP; bk.Lcap = L; bk.end = pos + 1;
     } else if (L > Lsmem) {
+      // HBM-resident one-CTA mode, in length classes of 96 nt: the role split and the slot size follow the class
       bk.mode = MODE_GLOBAL; bk.Lcap = L;
+      const int lo = std::max(Lsmem, L - 96);
       uint32_t e = pos;
-      while (e < n && len_of(e) > Lsmem) e++;
+      while (e < n && len_of(e) > lo) e++;
       bk.end = e;
     } else {
       bk.mode = MODE_SMEM;
@@ -736,7 +738,11 @@ static int launch_fold_model(rna_handle* h, const RnaFoldBatchDev* b, cudaStream
     a.Lcap = bk.Lcap;
     a.ws_stride = stride_of[k];
     if (bk.mode != MODE_COOP) {
-      const Roles ro = (bk.mode == MODE_SMEM) ? ro_of[k] : fold2_roles(bk.Lcap, CONTRA, 16);
+      Roles ro = (bk.mode == MODE_SMEM) ? ro_of[k] : fold2_roles_global(bk.Lcap, CONTRA, 16);
+      if (bk.mode != MODE_SMEM && dev_env("RNA_FOLD_ROLES")) {   // A/B: "x,y,z" warps of the HBM-resident one-CTA mode
+        int x = 0, y = 0, z = 0;
+        if (sscanf(dev_env("RNA_FOLD_ROLES"), "%d,%d,%d", &x, &y, &z) == 3 && x > 0 && z > 0 && x + y + z <= 16 && (y > 0) == CONTRA) { ro.nX = x; ro.nY = y; ro.nZ = z; }
+      }
       a.nXw = ro.nX; a.nYw = ro.nY; a.nZw = ro.nZ;
       const int nt = (bk.mode == MODE_SMEM) ? nt_of[k] : 32 * (ro.nX + ro.nY + ro.nZ);
       a.stream_ws = nullptr;

@@ -12,6 +12,11 @@ pub const RNA_MAX_SPECIAL_HAIRPIN_LEN: usize = 12;
 
 #[repr(C)]
 pub struct rna_handle { _private: [u8; 0] }
+#[repr(C)]
+pub struct rna_queue { _private: [u8; 0] }
+#[repr(C)]
+pub struct rna_multi { _private: [u8; 0] }
+pub const RNA_SUMS_PLANES: usize = 10;
 
 #[repr(C)]
 #[derive(Clone, Copy)]
@@ -133,6 +138,24 @@ extern "C" {
         out_fold_str: *mut u8, out_pairs: *mut u16, out_num_pairs: *mut u32, out_expect_accuracy: *mut f32) -> c_int;
     pub fn rna_durbin_algo(h: *mut rna_handle, seq_a: *const u8, len_a: u32, seq_b: *const u8, len_b: u32,
         out_probs: *mut f32) -> c_int;
+    pub fn rna_fold_sums_batch(h: *mut rna_handle, bases: *const u8, offsets: *const u32, n_seqs: u32, model: c_int,
+        allows_short_hairpins: c_int, out_sums: *mut f32, sums_offsets: *const u64, out_logz: *mut f32) -> c_int;
+    pub fn rna_set_numeric_mode(h: *mut rna_handle, mode: c_int) -> c_int;
+    pub fn rna_queue_create(h: *mut rna_handle, out: *mut *mut rna_queue) -> c_int;
+    pub fn rna_queue_destroy(q: *mut rna_queue) -> c_int;
+    pub fn rna_queue_mccaskill_algo(q: *mut rna_queue, seq: *const u8, seq_len: u32, uses_contra_model: c_int,
+        allows_short_hairpins: c_int, out_bpp: *mut f32, out_logz: *mut f32, centroid_threshold: f32,
+        out_fold_str: *mut u8, out_expect_accuracy: *mut f32) -> c_int;
+    pub fn rna_multi_create(devices: *const c_int, n_devices: c_int, out: *mut *mut rna_multi) -> c_int;
+    pub fn rna_multi_destroy(m: *mut rna_multi) -> c_int;
+    pub fn rna_multi_set_turner_tables(m: *mut rna_multi, t: *const RnaTurnerTables) -> c_int;
+    pub fn rna_multi_set_contra_tables(m: *mut rna_multi, t: *const RnaContraTables) -> c_int;
+    pub fn rna_multi_set_align_tables(m: *mut rna_multi, t: *const RnaAlignTables) -> c_int;
+    pub fn rna_multi_mccaskill_centroid_batch(m: *mut rna_multi, bases: *const u8, offsets: *const u32, n_seqs: u32,
+        model: c_int, allows_short_hairpins: c_int, gammas: *const f32, n_gammas: u32, out_logz: *mut f32,
+        out_bpp: *mut f32, bpp_offsets: *const u64, out_structs: *mut u8, out_expect_acc: *mut f32) -> c_int;
+    pub fn rna_multi_durbin_batch(m: *mut rna_multi, bases: *const u8, offsets: *const u32, n_seqs: u32, pairs: *const u32,
+        n_pairs: u32, out_probs: *mut f32, prob_offsets: *const u64) -> c_int;
     pub fn rna_validate_bases(bases: *const u8, offsets: *const u32, n_seqs: u32) -> c_int;
     pub fn rna_partition_lpt(costs: *const u64, n_units: u32, n_parts: u32, part_of: *mut u32) -> c_int;
 }

@@ -7,6 +7,7 @@
 //!
 //! There is no CPU path: `Gpu::new` fails when no CUDA device is usable.
 pub mod ffi;
+pub mod reference_api;   // the reference's own free-function signatures (per-call score sets, coalesced single calls)
 
 use std::collections::HashMap;
 use std::convert::TryFrom;
