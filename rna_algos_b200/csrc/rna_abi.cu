@@ -575,7 +575,8 @@ static int launch_fold_model(rna_handle* h, const RnaFoldBatchDev* b, cudaStream
     } else if (L > Lsmem) {
       // HBM-resident one-CTA mode, in length classes of 96 nt: the role split and the slot size follow the class
       bk.mode = MODE_GLOBAL; bk.Lcap = L;
-      const int lo = std::max(Lsmem, L - 96);
+      static const int cls = dev_env("RNA_GLOBAL_CLASS") ? atoi(dev_env("RNA_GLOBAL_CLASS")) : 96;
+      const int lo = std::max(Lsmem, L - cls);
       uint32_t e = pos;
       while (e < n && len_of(e) > lo) e++;
       bk.end = e;
