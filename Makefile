@@ -1,9 +1,9 @@
 # Builds the product shared library (C ABI + CUDA kernels for sm_100a) in-tree, and the test oracle.
 NVCC ?= nvcc
-NVCCFLAGS := $(EXTRA) -std=c++17 -O3 -gencode arch=compute_100a,code=sm_100a -lineinfo -fmad=false \
+NVCCFLAGS := $(EXTRA) --threads 4 -std=c++17 -O3 -gencode arch=compute_100a,code=sm_100a -lineinfo -fmad=false \
              -Xcompiler -fPIC,-ffp-contract=off,-fno-fast-math -Xptxas -v
 LIB := rna_algos_b200/librna_algos_b200.so
-SRC := rna_algos_b200/csrc/rna_abi.cu rna_algos_b200/csrc/rna_multi.cpp rna_algos_b200/csrc/rna_queue.cpp
+SRC := rna_algos_b200/csrc/rna_abi.cu rna_algos_b200/csrc/fold_fastnum.cu rna_algos_b200/csrc/rna_multi.cpp rna_algos_b200/csrc/rna_queue.cpp
 HDR := $(wildcard rna_algos_b200/csrc/*.cuh rna_algos_b200/csrc/*.h include/*.h)
 
 all: $(LIB) oracle cli peaks

@@ -372,6 +372,22 @@ def config_legs(h, dev, stream, args):
         ms = r.timed(2, 1)
         out[key] = {"seq_s": round(r.n / ms * 1e3), "ms": round(ms, 1), "parity_ok": parity_sample(r, tiled, contra, gam, range(6))}
         del r
+    # the same tRNA batch in the FAST_F32 numeric mode (exact log-space arithmetic, not bit-exact): rate and deviation
+    def fast_leg(r):
+        z0, p0 = r.t["logz"].clone(), r.t["bpp"].clone()
+        h.set_numeric_mode("fast")
+        try:
+            msf = r.timed(2, 1)
+        finally:
+            h.set_numeric_mode("exact")
+        present = p0 >= 0
+        return {"seq_s": round(r.n / msf * 1e3), "ms": round(msf, 1),
+                "max_dlogz": float(f"{(r.t['logz'] - z0).abs().max().item():.3g}"),
+                "max_dbpp": float(f"{(r.t['bpp'] - p0)[present].abs().max().item():.3g}")}
+    r = FoldRunner(h, tiled, True, [1.0], dev, stream)
+    r.timed(1, 0)
+    out["c1_trna_contra_g1_fast_f32"] = fast_leg(r)
+    del r
     # configs[2]: the seeded Rfam-like families (50-500 nt), one GPU's share
     fam_seqs, fam_pairs = family_batch(args.rfam_nseq)
     r = FoldRunner(h, fam_seqs, True, [1.0], dev, stream)
@@ -380,6 +396,7 @@ def config_legs(h, dev, stream, args):
     pick = [int(np.argmax(lens)), int(np.argmin(lens)), 0, len(fam_seqs) // 2, len(fam_seqs) - 1]
     out["c2_rfam_like_contra"] = {"seq_s": round(r.n / ms * 1e3), "ms": round(ms, 1), "n": r.n, "len": [int(lens.min()), int(lens.max())],
                                   "cells_s": round(cells_of(lens) / ms * 1e3), "parity_ok": parity_sample(r, fam_seqs, True, [1.0], pick)}
+    out["c2_rfam_like_contra_fast_f32"] = fast_leg(r)
     del r
     # configs[3]: one random sequence at 1k / 2k / 4k nt, both models; parity at 1024 here, 2048 / 4096 in tests/
     longs = {}

@@ -752,6 +752,7 @@ RNA_DEV float stream_chain(const SV& v, const uint2* __restrict__ st, uint32_t w
                            float Cij, float sum) {
   constexpr int B = RNA_STREAM_BLOCK;
   if (n == 0) return sum;
+  ChainSum cs = chain_begin(sum);
   uint2 nx[B];
 #pragma unroll
   for (int k = 0; k < B; k++) nx[k] = ((uint32_t)k < n) ? RNA_LD_STREAM(&st[wd * k]) : make_uint2(0u, 0u);
@@ -774,9 +775,9 @@ RNA_DEV float stream_chain(const SV& v, const uint2* __restrict__ st, uint32_t w
     }
 #pragma unroll
     for (int k = 0; k < B; k++)
-      sum = lse(sum, term_operand<INSIDE>(c[k], p[k], Cij, __int_as_float((int)cur[k].x)), lut);
+      chain_add(cs, term_operand<INSIDE>(c[k], p[k], Cij, __int_as_float((int)cur[k].x)), lut);
   }
-  return sum;
+  return chain_end(cs);
 }
 
 // The same fold for a view whose sums_close / log P live in HBM/L2 (the cooperative kernel: CoopView): the gathers of
@@ -951,7 +952,7 @@ RNA_DEV void inside_Y_contra(const SV& v, const ContraView2& T, const float4* lu
   const DevContra* dev = T.g;
   for (int i = lane; i < ncell; i += nl) {
     const int j = i + d;
-    float r = NEG, rm = NEG;
+    ChainSum r = chain_begin(NEG), rm = chain_begin(NEG);
     if constexpr (CH <= 1) {
     const uint32_t* row = v.mask + i * v.W2;
     for (int p = i + 1; p <= j - 1 - kskip; p += 32) {
@@ -964,8 +965,8 @@ RNA_DEV void inside_Y_contra(const SV& v, const ContraView2& T, const float4* lu
         const int k = p + t;
         const float av = __fadd_rn(v.C[doff(k - i, L) + i], v2_acc<true>(T, s, L, i, k));
         const float nn = (float)(j - k);
-        r = lse(r, __fadd_rn(__fadd_rn(av, dev->ext_bp), __fmul_rn(dev->ext_unpair, nn)), lut);
-        rm = lse(rm, __fadd_rn(__fadd_rn(av, dev->mb_bp), __fmul_rn(dev->mb_unpair, nn)), lut);
+        chain_add(r, __fadd_rn(__fadd_rn(av, dev->ext_bp), __fmul_rn(dev->ext_unpair, nn)), lut);
+        chain_add(rm, __fadd_rn(__fadd_rn(av, dev->mb_bp), __fmul_rn(dev->mb_unpair, nn)), lut);
       }
     }
     } else {
@@ -989,14 +990,14 @@ RNA_DEV void inside_Y_contra(const SV& v, const ContraView2& T, const float4* lu
           const int k = ka[u];
           const float av = __fadd_rn(ca[u], v2_acc<true>(T, s, L, i, k));
           const float nn = (float)(j - k);
-          r = lse(r, __fadd_rn(__fadd_rn(av, dev->ext_bp), __fmul_rn(dev->ext_unpair, nn)), lut);
-          rm = lse(rm, __fadd_rn(__fadd_rn(av, dev->mb_bp), __fmul_rn(dev->mb_unpair, nn)), lut);
+          chain_add(r, __fadd_rn(__fadd_rn(av, dev->ext_bp), __fmul_rn(dev->ext_unpair, nn)), lut);
+          chain_add(rm, __fadd_rn(__fadd_rn(av, dev->mb_bp), __fmul_rn(dev->mb_unpair, nn)), lut);
         }
       }
     }
     }
-    v.R[od + i] = r;
-    v.X[od + i] = rm;
+    v.R[od + i] = chain_end(r);
+    v.X[od + i] = chain_end(rm);
   }
 }
 
@@ -1029,15 +1030,15 @@ RNA_DEV void inside_Z(const SV& v, const typename Model2<CONTRA>::View& T, const
       v.X[od + i] = Rmij;
     }
     v.R[od + i] = Rij;
-    float sE, sM1, sM = NEG;
+    ChainSum sE, sM1, sM = chain_begin(NEG);
     if constexpr (CONTRA) {
-      sE = __fmul_rn(dev->ext_unpair, (float)(d + 1));
-      sM1 = Rmij;
+      sE = chain_begin(__fmul_rn(dev->ext_unpair, (float)(d + 1)));
+      sM1 = chain_begin(Rmij);
     } else {
-      sE = 0.f;
-      sM1 = __fadd_rn(Rij, dev->coeff_num_branches);
+      sE = chain_begin(0.f);
+      sM1 = chain_begin(__fadd_rn(Rij, dev->coeff_num_branches));
     }
-    sE = lse(sE, __fadd_rn(Rij, 0.f), lut);   // k = i: E[i][i-1] = 0 (lower triangle / literal 0)
+    chain_add(sE, __fadd_rn(Rij, 0.f), lut);   // k = i: E[i][i-1] = 0 (lower triangle / literal 0)
     if constexpr (PF <= 2) {
     // operands two split points ahead are in flight while the three folds of the current one execute
     // (R, Rm, E, M1 may live in HBM/L2: their addresses do not depend on the running sums)
@@ -1057,14 +1058,14 @@ RNA_DEV void inside_Z(const SV& v, const typename Model2<CONTRA>::View& T, const
         r2 = v.R[doff(d - m - 2, L) + i + m + 2]; e2 = v.E[doff(m + 1, L) + i]; q2 = v.M1[doff(m + 1, L) + i];
         if (CONTRA) x2 = v.X[doff(d - m - 2, L) + i + m + 2];
       }
-      sE = lse(sE, __fadd_rn(r, e), lut);
+      chain_add(sE, __fadd_rn(r, e), lut);
       if constexpr (CONTRA) {
-        sM1 = lse(sM1, __fadd_rn(rm, __fmul_rn(dev->mb_unpair, (float)m)), lut);
-        sM = lse(sM, __fadd_rn(m1, rm), lut);
+        chain_add(sM1, __fadd_rn(rm, __fmul_rn(dev->mb_unpair, (float)m)), lut);
+        chain_add(sM, __fadd_rn(m1, rm), lut);
       } else {
         const float xx = __fadd_rn(r, dev->coeff_num_branches);
-        sM1 = lse(sM1, xx, lut);
-        sM = lse(sM, __fadd_rn(m1, xx), lut);
+        chain_add(sM1, xx, lut);
+        chain_add(sM, __fadd_rn(m1, xx), lut);
       }
     }
     } else {
@@ -1091,24 +1092,24 @@ RNA_DEV void inside_Z(const SV& v, const typename Model2<CONTRA>::View& T, const
             pr[u] = v.R[doff(d - mn, L) + i + mn]; pe[u] = v.E[doff(mn - 1, L) + i]; pq[u] = v.M1[doff(mn - 1, L) + i];
             if (CONTRA) px[u] = v.X[doff(d - mn, L) + i + mn];
           }
-          sE = lse(sE, __fadd_rn(r, e), lut);
+          chain_add(sE, __fadd_rn(r, e), lut);
           if constexpr (CONTRA) {
-            sM1 = lse(sM1, __fadd_rn(rm, __fmul_rn(dev->mb_unpair, (float)m)), lut);
-            sM = lse(sM, __fadd_rn(m1, rm), lut);
+            chain_add(sM1, __fadd_rn(rm, __fmul_rn(dev->mb_unpair, (float)m)), lut);
+            chain_add(sM, __fadd_rn(m1, rm), lut);
           } else {
             const float xx = __fadd_rn(r, dev->coeff_num_branches);
-            sM1 = lse(sM1, xx, lut);
-            sM = lse(sM, __fadd_rn(m1, xx), lut);
+            chain_add(sM1, xx, lut);
+            chain_add(sM, __fadd_rn(m1, xx), lut);
           }
         }
       }
     }
     }
-    v.E[od + i] = sE;
-    Mcur[i] = sM;
-    if constexpr (SUMSX) { if (v.Mfull) v.Mfull[sums_index(L, i, j)] = sM; }
-    sM1 = lse(sM1, sM, lut);
-    v.M1[od + i] = sM1;
+    v.E[od + i] = chain_end(sE);
+    const float Mij = chain_end(sM);
+    Mcur[i] = Mij;
+    if constexpr (SUMSX) { if (v.Mfull) v.Mfull[sums_index(L, i, j)] = Mij; }
+    v.M1[od + i] = lse(chain_end(sM1), Mij, lut);
   }
 }
 
@@ -1398,7 +1399,7 @@ RNA_DEV void outside_Y(const SV& v, const typename Model2<CONTRA>::View& T, cons
   const int ncell = L - d, od = doff(d, L);
   for (int i = lane; i < ncell; i += nl) {
     const int j = i + d;
-    float pm = NEG, pm2 = NEG;
+    ChainSum pm = chain_begin(NEG), pm2 = chain_begin(NEG);
     if constexpr (CH <= 1) {
     const uint32_t* row = v.mask + i * v.W2;
     // closable (i,k), k > j ascending; the operands of the next term are fetched before the two folds of the
@@ -1432,9 +1433,9 @@ RNA_DEV void outside_Y(const SV& v, const typename Model2<CONTRA>::View& T, cons
         m11 = (k1 - j >= 2) ? v.M1[doff(k1 - j - 2, L) + j + 1] : NEG;
       }
       const float x = __fsub_rn(__fadd_rn(pv, v2_mbclose<CONTRA>(T, s, L, i, k)), c);
-      pm = lse(pm, __fadd_rn(x, m1), lut);
-      if constexpr (CONTRA) pm2 = lse(pm2, __fadd_rn(x, __fmul_rn(T.g->mb_unpair, (float)(m - 1))), lut);
-      else pm2 = lse(pm2, x, lut);
+      chain_add(pm, __fadd_rn(x, m1), lut);
+      if constexpr (CONTRA) chain_add(pm2, __fadd_rn(x, __fmul_rn(T.g->mb_unpair, (float)(m - 1))), lut);
+      else chain_add(pm2, x, lut);
     }
     } else {
     // closable (i,k), k > j ascending, CH terms at a time; the operands of the next chunk are in flight while
@@ -1465,15 +1466,15 @@ RNA_DEV void outside_Y(const SV& v, const typename Model2<CONTRA>::View& T, cons
         if (ka[u] >= 0) {
           const int k = ka[u], m = k - j;
           const float x = __fsub_rn(__fadd_rn(pa[u], v2_mbclose<CONTRA>(T, s, L, i, k)), ca[u]);
-          pm = lse(pm, __fadd_rn(x, ma[u]), lut);
-          if constexpr (CONTRA) pm2 = lse(pm2, __fadd_rn(x, __fmul_rn(T.g->mb_unpair, (float)(m - 1))), lut);
-          else pm2 = lse(pm2, x, lut);
+          chain_add(pm, __fadd_rn(x, ma[u]), lut);
+          if constexpr (CONTRA) chain_add(pm2, __fadd_rn(x, __fmul_rn(T.g->mb_unpair, (float)(m - 1))), lut);
+          else chain_add(pm2, x, lut);
         }
       }
     }
     }
-    v.R[od + i] = pm;
-    v.X[od + i] = pm2;
+    v.R[od + i] = chain_end(pm);
+    v.X[od + i] = chain_end(pm2);
   }
 }
 
@@ -1507,13 +1508,14 @@ RNA_DEV float outside_cell_partial(const SV& v, const typename Model2<CONTRA>::V
 // enclosing multiloops, k ascending 0..i-1 (needs probs_multibranch(2) of diagonals > j - i)
 template <bool CONTRA, int PF, class SV>
 RNA_DEV float outside_cell_ml(const SV& v, const typename Model2<CONTRA>::View& T, const float4* lut, int i, int j,
-                              float Cij, float sm) {
+                              float Cij, float sm0) {
   const int L = v.L;
   const float NEG = RNA_NEG_INF;
   const typename Model2<CONTRA>::Dev* dev = T.g;
   const float Aij = __fadd_rn(Cij, v2_acc<CONTRA>(T, v.s, L, i, j));
   float sa;
   if constexpr (CONTRA) sa = __fadd_rn(Aij, dev->mb_bp); else sa = __fadd_rn(Aij, dev->coeff_num_branches);
+  ChainSum sm = chain_begin(sm0);
   if constexpr (PF == 2) {
     // operands TWO steps ahead are in flight (explicit registers, no ring): probs_multibranch(2) live in HBM/L2 in
     // the shared-memory mode and one step of three dependent folds is shorter than that latency
@@ -1533,10 +1535,10 @@ RNA_DEV float outside_cell_ml(const SV& v, const typename Model2<CONTRA>::View& 
       const float x1 = ax, p2 = ap, y = ay;
       ax = bx; ap = bp; ay = by;
       fetch(kk + 2, bx, bp, by);
-      sm = lse(sm, __fadd_rn(__fadd_rn(sa, p2), x1), lut);
-      if constexpr (CONTRA) sm = lse(sm, __fadd_rn(__fadd_rn(sa, y), __fmul_rn(dev->mb_unpair, (float)m)), lut);
-      else sm = lse(sm, __fadd_rn(sa, y), lut);
-      sm = lse(sm, __fadd_rn(__fadd_rn(sa, x1), y), lut);
+      chain_add(sm, __fadd_rn(__fadd_rn(sa, p2), x1), lut);
+      if constexpr (CONTRA) chain_add(sm, __fadd_rn(__fadd_rn(sa, y), __fmul_rn(dev->mb_unpair, (float)m)), lut);
+      else chain_add(sm, __fadd_rn(sa, y), lut);
+      chain_add(sm, __fadd_rn(__fadd_rn(sa, x1), y), lut);
     }
   } else if constexpr (PF <= 1) {
     // operands of step kk+1 are loaded before the three dependent logsumexp's of step kk
@@ -1554,10 +1556,10 @@ RNA_DEV float outside_cell_ml(const SV& v, const typename Model2<CONTRA>::View& 
         nx1 = (m - 1 >= 1) ? v.M1[doff(m - 2, L) + kk + 2] : NEG;
         np2 = v.X[q]; ny = v.R[q];
       }
-      sm = lse(sm, __fadd_rn(__fadd_rn(sa, p2), x1), lut);
-      if constexpr (CONTRA) sm = lse(sm, __fadd_rn(__fadd_rn(sa, y), __fmul_rn(dev->mb_unpair, (float)m)), lut);
-      else sm = lse(sm, __fadd_rn(sa, y), lut);
-      sm = lse(sm, __fadd_rn(__fadd_rn(sa, x1), y), lut);
+      chain_add(sm, __fadd_rn(__fadd_rn(sa, p2), x1), lut);
+      if constexpr (CONTRA) chain_add(sm, __fadd_rn(__fadd_rn(sa, y), __fmul_rn(dev->mb_unpair, (float)m)), lut);
+      else chain_add(sm, __fadd_rn(sa, y), lut);
+      chain_add(sm, __fadd_rn(__fadd_rn(sa, x1), y), lut);
     }
   } else {
   // operands PF steps ahead are in flight while the three dependent logsumexp's of a step execute
@@ -1585,15 +1587,15 @@ RNA_DEV float outside_cell_ml(const SV& v, const typename Model2<CONTRA>::View& 
           bx[u] = (mn >= 1) ? v.M1[doff(mn - 1, L) + kn + 1] : NEG;
           bp[u] = v.X[q]; by[u] = v.R[q];
         }
-        sm = lse(sm, __fadd_rn(__fadd_rn(sa, p2), x1), lut);
-        if constexpr (CONTRA) sm = lse(sm, __fadd_rn(__fadd_rn(sa, y), __fmul_rn(dev->mb_unpair, (float)m)), lut);
-        else sm = lse(sm, __fadd_rn(sa, y), lut);
-        sm = lse(sm, __fadd_rn(__fadd_rn(sa, x1), y), lut);
+        chain_add(sm, __fadd_rn(__fadd_rn(sa, p2), x1), lut);
+        if constexpr (CONTRA) chain_add(sm, __fadd_rn(__fadd_rn(sa, y), __fmul_rn(dev->mb_unpair, (float)m)), lut);
+        else chain_add(sm, __fadd_rn(sa, y), lut);
+        chain_add(sm, __fadd_rn(__fadd_rn(sa, x1), y), lut);
       }
     }
   }
   }
-  return sm;
+  return chain_end(sm);
 }
 // X, phase 1 of outside step st: exterior term + enclosing two-loops of log P for the diagonals d and d-1 of the
 // step: both only need log P of diagonals >= d+1.

@@ -8,6 +8,12 @@
 namespace rna {
 
 #define RNA_NEG_INF (__int_as_float(0xff800000))
+// RNA_FASTNUM = 1: the FAST_F32 numeric mode's build of the batch kernel (csrc/fold_fastnum.cu) — same phases, roles
+// and data layout, but logsumexp / exp in exact log-space arithmetic (MUFU ex2 / lg2) instead of the reference's
+// piecewise polynomials, and the long chains accumulate in linear space (fold_phases.cuh ChainSum).
+#ifndef RNA_FASTNUM
+#define RNA_FASTNUM 0
+#endif
 #define RNA_LSE_THRESHOLD 11.862479f
 
 // Coefficient table of ln_exp_1p: 8 segments x {a, b, c, d}, poly = ((a*x + b)*x + c)*x + d.
@@ -58,6 +64,13 @@ RNA_DEV bool is_finite(float x) { return fabsf(x) < __int_as_float(0x7f800000); 
 //   both -inf          z = NaN, (z < inf) is false        -> max = -inf
 RNA_DEV float lse(float sum, float x, const float4* __restrict__ lut) {
   x = (x > RNA_NEG_INF) ? x : RNA_NEG_INF;
+#if RNA_FASTNUM
+  {   // exact log-space arithmetic on the MUFU pipe: max + log(1 + exp(min - max)); both -inf stays -inf
+    const float mx = fmaxf(sum, x);
+    const float r = __fadd_rn(mx, __logf(__fadd_rn(1.f, __expf(__fsub_rn(fminf(sum, x), mx)))));
+    return (mx > RNA_NEG_INF) ? r : RNA_NEG_INF;
+  }
+#endif
   const float y = fminf(sum, x);
   const float mx = fmaxf(sum, x);
   const float z = __fsub_rn(mx, y);
@@ -106,6 +119,36 @@ RNA_DEV float lse_lat(float sum, float x) {
 // logsumexp into an EMPTY sum (sum == -inf): the reference takes x if it is finite (src/utils.rs:581-586)
 RNA_DEV float lse_init(float x) { return (x > RNA_NEG_INF) ? x : RNA_NEG_INF; }
 
+// Running sum of a long chain (the two-loop streams, the dense split-point chains, the rightmost-pair chains).
+// Reference-exact build: the log-space value itself, folded with lse() term by term in the reference's order.
+// FAST build: a LINEAR-space accumulator relative to a reference exponent — value = ref + log(s) — so a step is one
+// ex2 off the dependency chain plus one dependent FADD; the reference moves only when a term exceeds it by e^60
+// (that also handles the first finite term: ref = -inf), so s stays far inside the f32 range.
+#if RNA_FASTNUM
+struct ChainSum { float s, ref; };
+RNA_DEV ChainSum chain_begin(float sumlog) {
+  ChainSum c;
+  c.ref = sumlog;
+  c.s = (sumlog > RNA_NEG_INF) ? 1.f : 0.f;
+  return c;
+}
+RNA_DEV void chain_add(ChainSum& c, float x, const float4* __restrict__) {
+  // branch-free.  t = +inf: the first finite term (ref = -inf); t = NaN: -inf - -inf or a NaN operand (skipped)
+  const float t = __fsub_rn(x, c.ref);
+  const bool lead = t > 60.f;
+  const float e = __expf(lead ? -t : t);
+  const float sn = lead ? fmaf(c.s, e, 1.f) : __fadd_rn(c.s, e);
+  c.s = (t == t) ? sn : c.s;
+  c.ref = lead ? x : c.ref;
+}
+RNA_DEV float chain_end(const ChainSum& c) { return (c.s > 0.f) ? __fadd_rn(c.ref, __logf(c.s)) : RNA_NEG_INF; }
+#else
+typedef float ChainSum;
+RNA_DEV float chain_begin(float sumlog) { return sumlog; }
+RNA_DEV void chain_add(float& c, float x, const float4* __restrict__ lut) { c = lse(c, x, lut); }
+RNA_DEV float chain_end(float c) { return c; }
+#endif
+
 // lse with a per-lane enable predicate (disabled lanes keep `sum`).
 RNA_DEV float lse_if(bool on, float sum, float x, const float4* __restrict__ lut) {
   return lse(sum, on ? x : RNA_NEG_INF, lut);
@@ -115,6 +158,9 @@ RNA_DEV float lse_if(bool on, float sum, float x, const float4* __restrict__ lut
 // and rounded once to f32, which equals the correctly rounded f32 result (and glibc's <1-ULP expf)
 // except for ~1e-8 of inputs (DESIGN.md "numerics").
 RNA_DEV float approx_expf(float x) {
+#if RNA_FASTNUM
+  return expf(x);
+#endif
   if (x < -2.4915035f) {
     if (x < -5.8622823f) {
       if (x < -9.91152f) return 0.f;

@@ -311,14 +311,17 @@ struct Bucket {
 };
 
 // sequence indices by length, longest first (LPT inside each launch's work queue); stable, O(n + max length)
-static void order_by_length(const uint32_t* ho, uint32_t n, std::vector<uint32_t>& order) {
+// Sequences (all, or the ones listed in `subset`) in order of decreasing length (counting sort, stable).
+static void order_by_length(const uint32_t* ho, uint32_t n, std::vector<uint32_t>& order, const std::vector<uint32_t>* subset = nullptr) {
+  const uint32_t m = subset ? (uint32_t)subset->size() : n;
+  auto id = [&](uint32_t x) { return subset ? (*subset)[x] : x; };
   uint32_t maxlen = 0;
-  for (uint32_t i = 0; i < n; i++) maxlen = std::max(maxlen, ho[i + 1] - ho[i]);
+  for (uint32_t x = 0; x < m; x++) maxlen = std::max(maxlen, ho[id(x) + 1] - ho[id(x)]);
   std::vector<uint32_t> start((size_t)maxlen + 2, 0);
-  for (uint32_t i = 0; i < n; i++) start[maxlen - (ho[i + 1] - ho[i]) + 1]++;
+  for (uint32_t x = 0; x < m; x++) start[maxlen - (ho[id(x) + 1] - ho[id(x)]) + 1]++;
   for (size_t x = 1; x < start.size(); x++) start[x] += start[x - 1];
-  order.resize(n);
-  for (uint32_t i = 0; i < n; i++) order[start[maxlen - (ho[i + 1] - ho[i])]++] = i;
+  order.resize(m);
+  for (uint32_t x = 0; x < m; x++) order[start[maxlen - (ho[id(x) + 1] - ho[id(x)])]++] = id(x);
 }
 
 // Every call of a handle uses the same scratch (workspace, work counters, order array): calls are stream-ordered
@@ -335,11 +338,12 @@ static int call_end(rna_handle* h, cudaStream_t st) {
 
 // centroid_fold over packed BPP matrices (rna_centroid_batch): buckets by length, one CTA per sequence; sequences
 // beyond 1024 nt one at a time on the whole grid
-static int launch_centroid(rna_handle* h, const RnaFoldBatchDev* b, cudaStream_t st, const float* d_bpp_in) {
-  const uint32_t n = b->n_seqs;
+static int launch_centroid(rna_handle* h, const RnaFoldBatchDev* b, cudaStream_t st, const float* d_bpp_in,
+                           const std::vector<uint32_t>* subset = nullptr) {
   const uint32_t* ho = b->h_offsets;
   std::vector<uint32_t> order;
-  order_by_length(ho, n, order);
+  order_by_length(ho, b->n_seqs, order, subset);
+  const uint32_t n = (uint32_t)order.size();   // sequences of this launch
   auto len_of = [&](uint32_t pos) { return (int)(ho[order[pos] + 1] - ho[order[pos]]); };
   const int gran = 8;
   int Lsmem = 0;
@@ -401,7 +405,7 @@ static int launch_centroid(rna_handle* h, const RnaFoldBatchDev* b, cudaStream_t
   FoldArgs a;
   memset(&a, 0, sizeof a);
   a.offsets = b->d_offsets;
-  a.n_seqs = n;
+  a.n_seqs = b->n_seqs;
   a.total_len = b->total_len;
   a.gammas = b->d_gammas;
   a.n_gammas = b->n_gammas;
@@ -516,13 +520,18 @@ static void fold_dbg_report(int mode, int Lcap, const FoldArgs& a, long long* d_
 }
 #endif
 
+// fastnum: the FAST_F32 build of the batch kernel (fold_fastnum.cu); its caller passes sequences <= 1024 nt only
+extern "C" const void* rna_fastnum_fold_kernel(int contra, int hbm_mode);
+extern "C" unsigned long rna_fastnum_sizeof_fold_args();
 template <bool CONTRA>
-static int launch_fold_model(rna_handle* h, const RnaFoldBatchDev* b, cudaStream_t st) {
-  const uint32_t n = b->n_seqs;
+static int launch_fold_model(rna_handle* h, const RnaFoldBatchDev* b, cudaStream_t st, const std::vector<uint32_t>* subset = nullptr,
+                             bool fastnum = false) {
   const bool want_sums = b->d_out_sums != nullptr || b->inside_only;   // (the SUMS build of the batch kernel)
   const uint32_t* ho = b->h_offsets;
   std::vector<uint32_t> order;
-  order_by_length(ho, n, order);
+  order_by_length(ho, b->n_seqs, order, subset);
+  const uint32_t n = (uint32_t)order.size();   // sequences of this launch
+  if (fastnum && rna_fastnum_sizeof_fold_args() != sizeof(FoldArgs)) { h->err = "FoldArgs image mismatch"; return RNA_ERR_CUDA; }
   auto len_of = [&](uint32_t pos) { return (int)(ho[order[pos] + 1] - ho[order[pos]]); };
   const size_t smem_cap = h->smem_optin;
   const int gran = 4;                                     // bucket width in nt
@@ -536,7 +545,8 @@ static int launch_fold_model(rna_handle* h, const RnaFoldBatchDev* b, cudaStream
   // Sequences beyond 1024 nt get the whole grid, one at a time.  So do the few sequences that are too long for the
   // shared-memory mode when there are not enough of them to occupy the GPU one CTA each.
   int Lcoop_min = 1025;
-  {
+  if (fastnum) Lcoop_min = 0x7fffffff;   // (long sequences of the FAST mode run on fast_fold_kernel's cooperative grid)
+  else {
     uint32_t n_long = 0;
     while (n_long < n && len_of(n_long) > Lsmem) n_long++;
     // Cost model from B200 measurements (CONTRAfold; Turner is alike): a cooperative run takes ~230 ms x (L/1024)^2
@@ -661,7 +671,8 @@ static int launch_fold_model(rna_handle* h, const RnaFoldBatchDev* b, cudaStream
     ro_of[k] = fold2_roles(bk.Lcap, CONTRA, warps);
     const int nt = 32 * warps;
     int occ = 1;
-    if (want_sums) TRY(kern_prepare(h, (const void*)fold_kernel2<CONTRA, MODE_SMEM, true>, nt, smem, &occ));
+    if (fastnum) TRY(kern_prepare(h, rna_fastnum_fold_kernel(CONTRA, 0), nt, smem, &occ));
+    else if (want_sums) TRY(kern_prepare(h, (const void*)fold_kernel2<CONTRA, MODE_SMEM, true>, nt, smem, &occ));
     else TRY(kern_prepare(h, (const void*)fold_kernel2<CONTRA, MODE_SMEM>, nt, smem, &occ));
     occ = std::max(1, std::min(occ, occ_cap));
     nt_of[k] = nt;
@@ -698,7 +709,7 @@ static int launch_fold_model(rna_handle* h, const RnaFoldBatchDev* b, cudaStream
   memset(&a, 0, sizeof a);
   a.bases = b->d_bases;
   a.offsets = b->d_offsets;
-  a.n_seqs = n;
+  a.n_seqs = b->n_seqs;
   a.total_len = b->total_len;
   a.allows_short = b->allows_short_hairpins;
   a.tables = CONTRA ? (const void*)h->d_contra : (const void*)h->d_turner;
@@ -754,11 +765,17 @@ static int launch_fold_model(rna_handle* h, const RnaFoldBatchDev* b, cudaStream
           a.stream_stride = stream_stride_of[k];
           a.stream_ws = (unsigned char*)h->stream_ws.p + (size_t)lane * stream_bytes;
         }
-        if (want_sums) fold_kernel2<CONTRA, MODE_SMEM, true><<<grid_of[k], nt, smem, st>>>(a);
+        void* params[] = {(void*)&a};
+        if (fastnum) CU(h, cudaLaunchKernel(rna_fastnum_fold_kernel(CONTRA, 0), dim3(grid_of[k]), dim3(nt), params, smem, st));
+        else if (want_sums) fold_kernel2<CONTRA, MODE_SMEM, true><<<grid_of[k], nt, smem, st>>>(a);
         else fold_kernel2<CONTRA, MODE_SMEM><<<grid_of[k], nt, smem, st>>>(a);
       } else {
         const size_t smem = fold2_fixed_bytes<CONTRA>(bk.Lcap);
-        if (want_sums) {
+        if (fastnum) {
+          void* params[] = {(void*)&a};
+          TRY(kern_prepare(h, rna_fastnum_fold_kernel(CONTRA, 1), nt, smem, nullptr));
+          CU(h, cudaLaunchKernel(rna_fastnum_fold_kernel(CONTRA, 1), dim3(grid_of[k]), dim3(nt), params, smem, st));
+        } else if (want_sums) {
           TRY(kern_prepare(h, (const void*)fold_kernel2<CONTRA, MODE_GLOBAL, true>, nt, smem, nullptr));
           fold_kernel2<CONTRA, MODE_GLOBAL, true><<<grid_of[k], nt, smem, st>>>(a);
         } else {
@@ -810,19 +827,20 @@ static int launch_fold_model(rna_handle* h, const RnaFoldBatchDev* b, cudaStream
 // estimator then runs on the packed BPP matrices like rna_centroid_batch (it is exact max-plus either way).
 // ---------------------------------------------------------------------------------------------------
 #define RNA_FAST_COOP_MIN 700
+#define RNA_FASTNUM_WAVE_MS 5500.0   // a full wave of one-CTA sequences of 1024 nt on the FAST batch kernel (measured)
 template <bool CONTRA, class real>
-static int launch_fast(rna_handle* h, const RnaFoldBatchDev* b, cudaStream_t st, float* d_bpp) {
-  const uint32_t n = b->n_seqs;
+static int launch_fast(rna_handle* h, const RnaFoldBatchDev* b, cudaStream_t st, float* d_bpp, const std::vector<uint32_t>* subset = nullptr) {
   const uint32_t* ho = b->h_offsets;
   std::vector<uint32_t> order;
-  order_by_length(ho, n, order);
+  order_by_length(ho, b->n_seqs, order, subset);
+  const uint32_t n = (uint32_t)order.size();   // sequences of this launch
   auto len_of = [&](uint32_t pos) { return (int)(ho[order[pos] + 1] - ho[order[pos]]); };
   std::vector<Bucket> buckets;
   for (uint32_t pos = 0; pos < n;) {
     const int L = len_of(pos);
     Bucket bk;
     bk.begin = pos;
-    if (L >= RNA_FAST_COOP_MIN) { bk.mode = MODE_COOP; bk.Lcap = L; bk.end = pos + 1; }
+    if (L >= RNA_FAST_COOP_MIN || subset) { bk.mode = MODE_COOP; bk.Lcap = L; bk.end = pos + 1; }   // (a subset = the sequences chosen for the cooperative grid)
     else {
       bk.mode = MODE_GLOBAL;
       bk.Lcap = L;
@@ -891,24 +909,65 @@ static int launch_fast(rna_handle* h, const RnaFoldBatchDev* b, cudaStream_t st,
   return RNA_OK;
 }
 
+// FAST_F64 runs everything on fast_fold_kernel (f64 state: the accuracy mode).  FAST_F32 is the speed mode: the few
+// long sequences that would otherwise each wait for one CTA go one at a time to fast_fold_kernel's cooperative grid
+// (warp-shuffle reductions: 36 / 85 / 317 ms at 1 / 2 / 4 k nt), everything else to the FAST build of the batch kernel
+// (fold_fastnum.cu), which is several times faster than fast_fold_kernel's one-CTA-per-sequence launch on batches.
 static int launch_fast_mode(rna_handle* h, const RnaFoldBatchDev* b, cudaStream_t st) {
-  // the packed BPP matrices feed the centroid kernels: the caller's buffer, or one of the handle's
+  const bool f64 = h->numeric_mode == RNA_NUMERIC_FAST_F64;
+  const bool contra = b->model == RNA_MODEL_CONTRA;
+  const uint32_t n = b->n_seqs;
+  const uint32_t* ho = b->h_offsets;
+  std::vector<uint32_t> sel_coop, sel_batch;
+  if (!f64) {
+    std::vector<uint32_t> order;
+    order_by_length(ho, n, order);
+    auto len_of = [&](uint32_t pos) { return (int)(ho[order[pos] + 1] - ho[order[pos]]); };
+    uint32_t n_long = 0, forced = 0;
+    while (n_long < n && len_of(n_long) > 220) n_long++;          // (beyond the shared-memory mode)
+    while (forced < n_long && len_of(forced) > 1024) forced++;    // (beyond the one-CTA modes)
+    // cost model from B200 measurements, like launch_fold_model's: the longest c long sequences go to the cooperative grid
+    auto coop_ms = [](int L) { const double r = L / 1024.0; return 36.0 * (r <= 1.0 ? r * std::sqrt(r) : r * r); };
+    auto wave_ms = [&](int Lmax, uint32_t cnt) {
+      if (cnt == 0) return 0.0;
+      const double r = Lmax / 1024.0, per_wave = 2.0 * h->sm_count;
+      return RNA_FASTNUM_WAVE_MS * r * r * r * std::max(0.5, cnt / per_wave);
+    };
+    double best = 1e300, prefix = 0;
+    uint32_t best_c = forced;
+    for (uint32_t c = 0; c <= std::min<uint32_t>(n_long, forced + 256); c++) {
+      if (c >= forced) {
+        const double cost = prefix + (c < n_long ? wave_ms(len_of(c), n_long - c) : 0.0);
+        if (cost < best) { best = cost; best_c = c; }
+      }
+      if (c < n_long) prefix += coop_ms(len_of(c));
+    }
+    sel_coop.assign(order.begin(), order.begin() + best_c);
+    sel_batch.assign(order.begin() + best_c, order.end());
+  }
+  const bool all_fast_kernel = f64;
+  // the packed BPP matrices feed the centroid kernels of the fast_fold_kernel part: the caller's buffer, or one of the handle's
   float* d_bpp = b->d_out_bpp;
-  const uint64_t* d_bppoff = b->d_bpp_offsets;
   RnaFoldBatchDev bb = *b;
-  if (!d_bpp && b->n_gammas) {
-    if (!d_bppoff) { h->err = "d_bpp_offsets required (FAST mode computes the centroid from the packed BPPs)"; return RNA_ERR_BAD_ARG; }
+  if (!d_bpp && b->n_gammas && (all_fast_kernel || !sel_coop.empty())) {
+    if (!b->d_bpp_offsets) { h->err = "d_bpp_offsets required (FAST mode computes the centroid from the packed BPPs)"; return RNA_ERR_BAD_ARG; }
     uint64_t tot = 0;
     for (uint32_t s = 0; s < b->n_seqs; s++) tot += rna_bpp_len(b->h_offsets[s + 1] - b->h_offsets[s]);
     TRY(ensure(h, h->fast_bpp, tot * 4));
     d_bpp = (float*)h->fast_bpp.p;
   }
-  const bool f64 = h->numeric_mode == RNA_NUMERIC_FAST_F64;
-  if (b->model == RNA_MODEL_CONTRA) TRY(f64 ? (launch_fast<true, double>(h, b, st, d_bpp)) : (launch_fast<true, float>(h, b, st, d_bpp)));
-  else TRY(f64 ? (launch_fast<false, double>(h, b, st, d_bpp)) : (launch_fast<false, float>(h, b, st, d_bpp)));
-  if (b->n_gammas) {
-    bb.d_out_bpp = d_bpp;
-    TRY(launch_centroid(h, &bb, st, d_bpp));
+  bb.d_out_bpp = d_bpp;
+  if (all_fast_kernel) {
+    if (contra) TRY((launch_fast<true, double>(h, b, st, d_bpp))); else TRY((launch_fast<false, double>(h, b, st, d_bpp)));
+    if (b->n_gammas) TRY(launch_centroid(h, &bb, st, d_bpp));
+    return RNA_OK;
+  }
+  if (!sel_coop.empty()) {
+    if (contra) TRY((launch_fast<true, float>(h, b, st, d_bpp, &sel_coop))); else TRY((launch_fast<false, float>(h, b, st, d_bpp, &sel_coop)));
+    if (b->n_gammas) TRY(launch_centroid(h, &bb, st, d_bpp, &sel_coop));
+  }
+  if (!sel_batch.empty()) {
+    if (contra) TRY(launch_fold_model<true>(h, b, st, &sel_batch, true)); else TRY(launch_fold_model<false>(h, b, st, &sel_batch, true));
   }
   return RNA_OK;
 }

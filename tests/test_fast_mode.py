@@ -100,3 +100,36 @@ def test_fast_long_sequence_cooperative(handle, exact, contra):
     g32 = run_mode(handle, "fast", bases, offsets, contra, [2.0])
     ez, ep = errors(g32, want)
     assert ez < 5e-6 and ep < 5e-3, (ez, ep)
+
+
+@pytest.mark.parametrize("contra", [False, True])
+def test_fast_f32_mixed_batch_hybrid_dispatch(handle, exact, contra):
+    """FAST_F32 sends the few long sequences of a call to fast_fold_kernel's cooperative grid (centroid from the packed
+    BPPs, on that subset) and everything else to the FAST build of the batch kernel (shared-memory and HBM-resident
+    modes, centroid in the kernel): one ragged call covers all of it.  State against exact math; structures must be
+    centroid_fold of the returned BPPs whichever kernel produced them."""
+    import os
+    tt, ct, _ = default_tables()
+    seqs = random_seqs(21, [1100, 400, 150, 89, 30, 5, 1, 260])
+    bases, offsets = pack(seqs)
+    gammas = [1.0, 8.0]
+    want = exact.fold_batch(bases, offsets, contra, False, tt, ct, gammas, inner_threads=max(2, os.cpu_count() or 2))
+    got = run_mode(handle, "fast", bases, offsets, contra, gammas)
+    ez, ep = errors(got, want)
+    assert ez < 5e-6 and ep < 5e-3, (ez, ep)
+    f32o = Oracle()
+    for s_ in range(len(seqs)):
+        L = len(seqs[s_])
+        lo = int(got["bpp_offsets"][s_])
+        for gi, g in enumerate(gammas):
+            st, _, ea = f32o.centroid(got["bpp"][lo:lo + L * (L - 1) // 2], L, g)
+            assert bytes(got["structs"][gi, offsets[s_]:offsets[s_ + 1]]).decode() == st, (s_, L, g)
+            assert np.float32(ea) == got["expect_acc"][gi, s_]
+    # same call without the BPP output: the structures must not change (the cooperative part then stages its BPPs in
+    # a buffer of the handle)
+    handle.set_numeric_mode("fast")
+    try:
+        nob = handle.fold_batch(bases, offsets, contra, False, gammas, want_bpp=False)
+    finally:
+        handle.set_numeric_mode("exact")
+    assert (nob["structs"] == got["structs"]).all() and (nob["logz"] == got["logz"]).all()
