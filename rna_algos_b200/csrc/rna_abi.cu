@@ -643,6 +643,21 @@ static int launch_fold_model(rna_handle* h, const RnaFoldBatchDev* b, cudaStream
   std::vector<int> nt_of(buckets.size(), 0);
   std::vector<Roles> ro_of(buckets.size());
   size_t stream_bytes = 0;
+  // Several long sequences: the cooperative kernel keeps one chain per warp, so a sequence of L nt occupies
+  // coop_warps(L) warps = that many / 8 SMs' worth of CTAs and the rest of the GPU idles (1024 nt: 43 of 148 SMs).
+  // Up to kLanes of them run side by side, each on its own cooperative grid of sm_count / c CTAs (one CTA per SM:
+  // the kernel takes the whole register file of an SM), sized for the longest one.
+  auto coop_warps = [](int L) { const int full = (L + 31) / 32; return (3 * L / 4 + 31) / 32 + 6 * full + (CONTRA ? 4 * full : 0); };
+  uint32_t n_coop = 0;
+  while (n_coop < buckets.size() && buckets[n_coop].mode == MODE_COOP) n_coop++;   // (sorted longest first: they lead)
+  static const int force_coop_lanes = dev_env("RNA_COOP_LANES") ? atoi(dev_env("RNA_COOP_LANES")) : 0;
+  int coop_lanes = 1;
+  if (n_coop > 1) {
+    const int sms_needed = std::max(1, (coop_warps(buckets[0].Lcap) + 7) / 8);
+    // (measured: a grid 15 % short of its lanes costs nothing — 8 x 1024 nt on 4 grids, 4 x 2048 nt on 2 — a grid 40 % short does)
+    coop_lanes = std::max(1, std::min<int>({(int)rna_handle::kLanes, (int)n_coop, (int)(h->sm_count / (0.85 * sms_needed))}));
+    if (force_coop_lanes > 0) coop_lanes = std::min<int>({force_coop_lanes, (int)rna_handle::kLanes, (int)n_coop});
+  }
   for (size_t k = 0; k < buckets.size(); k++) {
     const Bucket& bk = buckets[k];
     if (bk.mode == MODE_COOP && !no_streams) {
@@ -651,7 +666,7 @@ static int launch_fold_model(rna_handle* h, const RnaFoldBatchDev* b, cudaStream
       const size_t Tc = (size_t)bk.Lcap * (bk.Lcap + 1) / 2;
       meminfo();
       size_t cap = std::min<size_t>(96 * Tc, (size_t)0xfffffff0u);
-      const size_t budget = (freeb + h->stream_ws.cap) / 3;
+      const size_t budget = (freeb + h->stream_ws.cap) / 3 / (size_t)coop_lanes;
       if (cap * 16 > budget) cap = budget / 16;
       tcap_of[k] = (uint32_t)cap;
       stream_stride_of[k] = fold2_stream_bytes(bk.Lcap, tcap_of[k]);
@@ -697,9 +712,10 @@ static int launch_fold_model(rna_handle* h, const RnaFoldBatchDev* b, cudaStream
   for (size_t k = 0; k < buckets.size(); k++)
     if (buckets[k].mode != MODE_COOP) batch_buckets++;
   static const int force_lanes = dev_env("RNA_FOLD_LANES") ? atoi(dev_env("RNA_FOLD_LANES")) : 0;
+  if (serial) coop_lanes = 1;
   const int nlanes = serial ? 1
-                     : (int)std::max<size_t>(1, std::min<size_t>(force_lanes > 0 ? (size_t)std::min(force_lanes, (int)rna_handle::kLanes)
-                                                                              : (size_t)rna_handle::kLanes, batch_buckets));
+                     : std::max(coop_lanes, (int)std::max<size_t>(1, std::min<size_t>(force_lanes > 0 ? (size_t)std::min(force_lanes, (int)rna_handle::kLanes)
+                                                                                               : (size_t)rna_handle::kLanes, batch_buckets)));
   ws_floats = (ws_floats + 63) / 64 * 64;
   stream_bytes = (stream_bytes + 255) / 256 * 256;
   if (stream_bytes) TRY(ensure(h, h->stream_ws, stream_bytes * nlanes));
@@ -736,13 +752,15 @@ static int launch_fold_model(rna_handle* h, const RnaFoldBatchDev* b, cudaStream
   if (dbg_roles) { cudaMalloc(&d_dbg, (size_t)(1 << 20) * 8); cudaMemset(d_dbg, 0, (size_t)(1 << 20) * 8); a.dbg = d_dbg; }
   for (size_t k = 0; k < buckets.size(); k++) {
     const Bucket& bk = buckets[k];
-    const int lane = (nlanes > 1 && bk.mode != MODE_COOP) ? (int)(k % nlanes) : 0;
-    if (nlanes > 1 && bk.mode == MODE_COOP) {   // a cooperative grid wants the whole GPU: join, run it on the main stream
+    // cooperative grids first (the long sequences lead the order), coop_lanes of them side by side; then a join, so
+    // that the one-CTA buckets never hold SMs a cooperative grid is waiting for
+    const int lane = nlanes <= 1 ? 0 : (bk.mode == MODE_COOP ? (int)(k % coop_lanes) : (int)(k % nlanes));
+    if (nlanes > 1 && k == n_coop && n_coop > 0) {
       for (int x = 0; x < nlanes; x++) { CU(h, cudaEventRecord(h->ev_join[x], h->aux[x])); CU(h, cudaStreamWaitEvent(st_main, h->ev_join[x], 0)); }
       CU(h, cudaEventRecord(h->ev_fork, st_main));
       for (int x = 0; x < nlanes; x++) CU(h, cudaStreamWaitEvent(h->aux[x], h->ev_fork, 0));
     }
-    st = (nlanes > 1 && bk.mode != MODE_COOP) ? h->aux[lane] : st_main;
+    st = nlanes > 1 ? h->aux[lane] : st_main;
     a.workspace = (float*)h->ws.p + (size_t)lane * ws_floats;
     a.order = (const uint32_t*)h->order.p + bk.begin;
     a.n_launch = bk.end - bk.begin;
@@ -791,7 +809,7 @@ static int launch_fold_model(rna_handle* h, const RnaFoldBatchDev* b, cudaStream
       a.no_ml_split = no_split ? 1 : 0;
       int occ = 1;
       TRY(kern_prepare(h, (const void*)fold_kernel2_coop<CONTRA>, nt, smem, &occ));
-      const int grid = std::max(1, std::min(occ, 2)) * h->sm_count;
+      const int grid = std::max(1, std::max(1, std::min(occ, 2)) * h->sm_count / coop_lanes);
       const int W = grid * (nt / 32);
       // inside pair steps: X = closable cells of two diagonals, Y = all cells of two diagonals, Z = three chains per
       // cell of two diagonals (one lane each)
@@ -803,7 +821,7 @@ static int launch_fold_model(rna_handle* h, const RnaFoldBatchDev* b, cudaStream
       if (stream_stride_of[k]) {
         a.tcap = tcap_of[k];
         a.stream_stride = stream_stride_of[k];
-        a.stream_ws = (unsigned char*)h->stream_ws.p;
+        a.stream_ws = (unsigned char*)h->stream_ws.p + (size_t)lane * stream_bytes;
       }
       void* params[] = {(void*)&a};
       CU(h, cudaLaunchCooperativeKernel((void*)fold_kernel2_coop<CONTRA>, dim3(grid), dim3(nt), params, smem, st));

@@ -269,6 +269,30 @@ def test_mixed_long_and_mid_routing(handle, oracle):
     check_fold(handle, oracle, seqs[1:], False, False, [2.0], tt, ct)
 
 
+@pytest.mark.parametrize("contra", [False, True])
+def test_several_long_sequences_run_on_concurrent_cooperative_grids(handle, oracle, contra):
+    """Several > 1024-nt sequences in one call: the launcher runs up to four cooperative grids side by side, each on its
+    share of the SMs with scratch of its own.  Bit parity with the oracle on two of them, and every sequence
+    bit-identical to the same sequence folded alone (the whole-GPU grid that test_config3 pins against the oracle)."""
+    import os
+    tt, ct, _ = default_tables()
+    seqs = random_seqs(64, [1100, 1090, 1061, 1040, 1030, 1026, 700, 90])
+    bases, offsets = pack(seqs)
+    gammas = [1.0, 4.0]
+    got = handle.fold_batch(bases, offsets, contra, False, gammas)
+    bo = got["bpp_offsets"]
+    for s_ in range(len(seqs)):
+        b1, o1 = pack([seqs[s_]])
+        if s_ in (1, 4):
+            alone = oracle.fold_batch(b1, o1, contra, False, tt, ct, gammas, inner_threads=max(2, os.cpu_count() or 2))
+        else:
+            alone = handle.fold_batch(b1, o1, contra, False, gammas)
+        assert_bits_equal(got["logz"][s_:s_ + 1], alone["logz"], f"logZ seq {s_}")
+        assert_bits_equal(got["bpp"][int(bo[s_]):int(bo[s_ + 1])], alone["bpp"], f"BPP seq {s_}")
+        assert_bits_equal(got["expect_acc"][:, s_], alone["expect_acc"][:, 0], f"expect_accuracy seq {s_}")
+        assert (got["structs"][:, offsets[s_]:offsets[s_ + 1]] == alone["structs"]).all(), f"structures seq {s_}"
+
+
 def test_long_cooperative_edge_lengths(handle, oracle):
     """The cooperative kernel is also the route for a lone mid-length sequence: odd/even lengths around the warp and
     pair-step boundaries (the last pair step handles one or two diagonals)."""
