@@ -549,16 +549,25 @@ static int launch_fold_model(rna_handle* h, const RnaFoldBatchDev* b, cudaStream
   else {
     uint32_t n_long = 0;
     while (n_long < n && len_of(n_long) > Lsmem) n_long++;
-    // Cost model from B200 measurements (CONTRAfold; Turner is alike): a cooperative run takes ~230 ms x (L/1024)^2
-    // (latency-bound, one sequence at a time); a wave of up to 2 x SM-count one-CTA sequences takes ~5.5 s x
-    // (L/1024)^3 when full and about half of that when nearly empty.  Sequences are sorted longest first: give the
-    // longest c of the long ones to the cooperative kernel, c chosen to minimise the sum.
-    auto coop_ms = [](int L) { const double r = L / 1024.0; return 230.0 * r * r; };
+    // Cost model from B200 measurements (CONTRAfold; Turner is alike).  A cooperative run alone takes ~140 ms x
+    // (L/1024)^1.7 up to 1024 nt (29 / 78 / 139 ms at 400 / 700 / 1000 nt) and x (L/1024)^2 beyond (300 / 487 ms at
+    // 1500 / 2048); up to four run side by side (coop_lanes below) at ~0.8 of the speed-up their share of the SMs
+    // allows (4 x 700 nt: 77 ms; 8 x 1024 nt: 442 ms).  A wave of up to 2 x SM-count one-CTA sequences takes ~2.3 s x
+    // (L/1024)^3 when full and ~0.55 of that when nearly empty.  Sequences are sorted longest first: give the longest c
+    // of the long ones to the cooperative kernel, c chosen to minimise the sum.
+    auto coop_ms = [](int L) { const double r = L / 1024.0; return 140.0 * (r <= 1.0 ? std::pow(r, 1.7) : r * r); };
+    auto coop_conc = [&](uint32_t c) {
+      if (c < 2) return 1.0;
+      const int Lmax = len_of(0), full = (Lmax + 31) / 32;
+      const double sms_needed = std::max(1, ((3 * Lmax / 4 + 31) / 32 + 6 * full + (CONTRA ? 4 * full : 0) + 7) / 8);
+      const int lanes = std::max(1, std::min<int>({(int)rna_handle::kLanes, (int)c, (int)(h->sm_count / (0.85 * sms_needed))}));
+      return std::max(1.0, 0.8 * std::min<double>(lanes, h->sm_count / sms_needed));
+    };
     auto wave_ms = [&](int Lmax, uint32_t cnt) {
       if (cnt == 0) return 0.0;
       const double r = Lmax / 1024.0, per_wave = 2.0 * h->sm_count;
       const double waves = cnt / per_wave;
-      return 5500.0 * r * r * r * std::max(0.5, waves);
+      return 2300.0 * r * r * r * std::max(waves, std::min(1.0, 0.55 + 0.65 * waves));
     };
     uint32_t forced = 0;
     while (forced < n_long && len_of(forced) > 1024) forced++;
@@ -566,7 +575,7 @@ static int launch_fold_model(rna_handle* h, const RnaFoldBatchDev* b, cudaStream
     uint32_t best_c = forced;
     for (uint32_t c = 0; c <= std::min<uint32_t>(n_long, forced + 64); c++) {
       if (c >= forced) {
-        const double cost = prefix + (c < n_long ? wave_ms(len_of(c), n_long - c) : 0.0);
+        const double cost = prefix / coop_conc(c) + (c < n_long ? wave_ms(len_of(c), n_long - c) : 0.0);
         if (cost < best) { best = cost; best_c = c; }
       }
       if (c < n_long) prefix += coop_ms(len_of(c));
@@ -845,7 +854,7 @@ static int launch_fold_model(rna_handle* h, const RnaFoldBatchDev* b, cudaStream
 // estimator then runs on the packed BPP matrices like rna_centroid_batch (it is exact max-plus either way).
 // ---------------------------------------------------------------------------------------------------
 #define RNA_FAST_COOP_MIN 700
-#define RNA_FASTNUM_WAVE_MS 5500.0   // a full wave of one-CTA sequences of 1024 nt on the FAST batch kernel (measured)
+#define RNA_FASTNUM_WAVE_MS 2300.0   // a full wave of one-CTA sequences of 1024 nt on the FAST batch kernel (measured)
 template <bool CONTRA, class real>
 static int launch_fast(rna_handle* h, const RnaFoldBatchDev* b, cudaStream_t st, float* d_bpp, const std::vector<uint32_t>* subset = nullptr) {
   const uint32_t* ho = b->h_offsets;
@@ -949,7 +958,8 @@ static int launch_fast_mode(rna_handle* h, const RnaFoldBatchDev* b, cudaStream_
     auto wave_ms = [&](int Lmax, uint32_t cnt) {
       if (cnt == 0) return 0.0;
       const double r = Lmax / 1024.0, per_wave = 2.0 * h->sm_count;
-      return RNA_FASTNUM_WAVE_MS * r * r * r * std::max(0.5, cnt / per_wave);
+      const double waves = cnt / per_wave;
+      return RNA_FASTNUM_WAVE_MS * r * r * r * std::max(waves, std::min(1.0, 0.55 + 0.65 * waves));
     };
     double best = 1e300, prefix = 0;
     uint32_t best_c = forced;
