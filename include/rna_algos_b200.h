@@ -55,9 +55,12 @@ enum { RNA_MODEL_TURNER = 0, RNA_MODEL_CONTRA = 1 };
 /* Numeric modes of the McCaskill passes (rna_set_numeric_mode).
  *   RNA_NUMERIC_REF_EXACT  (default) every fold in the reference's order with its piecewise-cubic logsumexp / expf
  *                          (src/utils.rs:579-655): results bit-identical to the reference algorithm.
- *   RNA_NUMERIC_FAST_F32   the same recurrences in exact log-space arithmetic, re-associated into warp-shuffle
- *                          max / sum-of-exp reductions (ex2.approx / lg2.approx), f32 state.
- *   RNA_NUMERIC_FAST_F64   the same with f64 state and libdevice exp / log.
+ *   RNA_NUMERIC_FAST_F32   the speed mode: the same recurrences in exact log-space arithmetic (ex2.approx /
+ *                          lg2.approx, f32 state).  The few long sequences of a call run one at a time on a cooperative
+ *                          grid with warp-shuffle max / sum-of-exp reductions (3-8x faster than REF_EXACT at 1-4 k nt);
+ *                          everything else runs on a second build of the batch kernel whose chains keep linear-space
+ *                          sums (1.1x REF_EXACT on tRNA-length batches).
+ *   RNA_NUMERIC_FAST_F64   the accuracy mode: f64 state and libdevice exp / log, warp-shuffle reductions throughout.
  * The FAST modes do NOT reproduce the reference's approximation error (<= 7.6e-6 per logsumexp): they agree with an
  * exact-math evaluation to the tolerances of DESIGN.md §2 and with the reference only to ~1e-3 in a probability. */
 enum { RNA_NUMERIC_REF_EXACT = 0, RNA_NUMERIC_FAST_F32 = 1, RNA_NUMERIC_FAST_F64 = 2 };
