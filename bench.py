@@ -412,7 +412,7 @@ def config_legs(h, dev, stream, args):
                 exact_logz = float(r.t["logz"][0])
                 h.set_numeric_mode("fast")
                 try:
-                    ent["fast_ms"] = round(r.timed(1, 1), 1)
+                    ent["fast_ms"] = round(min(r.timed(1, 1), r.timed(1, 0), r.timed(1, 0)), 1)   # (best of three single calls)
                     ent["fast_dlogz"] = float(f"{abs(float(r.t['logz'][0]) - exact_logz):.3g}")
                 finally:
                     h.set_numeric_mode("exact")
@@ -448,9 +448,12 @@ def config_legs(h, dev, stream, args):
     ev1.record(stream)
     torch.cuda.synchronize()
     dms = ev0.elapsed_time(ev1)
-    res = h.durbin_batch(b, o, fam_pairs)
+    # end to end from host buffers; the match-probability matrices (GBs) land in a page-locked buffer, which the kernels
+    # write directly over PCIe (a pageable buffer takes the staged path and is several times slower)
+    pinned_out = torch.empty(int(po[-1]), dtype=torch.float32, pin_memory=True).numpy()
+    res = h.durbin_batch(b, o, fam_pairs, out=pinned_out)
     t1 = time.perf_counter()
-    res = h.durbin_batch(b, o, fam_pairs)
+    res = h.durbin_batch(b, o, fam_pairs, out=pinned_out)
     torch.cuda.synchronize()
     dt = time.perf_counter() - t1
     k = min(len(fam_pairs), 48)
@@ -459,6 +462,7 @@ def config_legs(h, dev, stream, args):
     dev_ok = bool((d["out"][:hi].cpu().numpy().view(np.uint32) == want["probs"].view(np.uint32)).all())
     out["c4_durbin_family_pairs"] = {"pairs_s": round(len(fam_pairs) / dms * 1e3), "ms": round(dms, 1), "n": int(len(fam_pairs)),
                                      "cells_s": round(int(sizes.sum()) / dms * 1e3), "e2e_pairs_s": round(len(fam_pairs) / dt),
+                                     "e2e_out_bytes": int(po[-1]) * 4,
                                      "parity_ok": dev_ok and bool((res["probs"][:hi].view(np.uint32) == want["probs"].view(np.uint32)).all())}
     return out
 
