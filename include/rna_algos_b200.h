@@ -279,6 +279,19 @@ static inline uint64_t rna_sums_index(uint64_t L, uint64_t i, uint64_t j) { retu
 int rna_fold_sums_batch(rna_handle *h, const uint8_t *bases, const uint32_t *offsets, uint32_t n_seqs, int model,
                         int allows_short_hairpins, float *out_sums, const uint64_t *sums_offsets, float *out_logz);
 
+/* FoldScores::twoloop_scores (src/mccaskill_algo.rs:16, filled at :320 / :431): the 4-D memo of two-loop scores, as a
+ * flat list in the reference's insertion order — closing pairs (i,j) by span then i ascending, their partners (k,l)
+ * with a sums_close entry by k ascending, l descending — value = get_2loop_score(seq, (i,j), (k,l)) bit for bit.
+ * One sequence per call (the reference's granularity).  *out_count receives the number of entries; at most `capacity`
+ * of them are written (call with capacity 0 to size the buffer: RNA_OK either way).  Reference-exact mode only;
+ * lengths up to RNA_MAX_SEQ_LEN (positions are u16 like the reference's HashIndex) and RNA_MAX_FOLD_LEN. */
+typedef struct RnaTwoloopScore {
+  uint16_t i, j, k, l;
+  float score;
+} RnaTwoloopScore;
+int rna_twoloop_scores(rna_handle *h, const uint8_t *seq, uint32_t seq_len, int model, int allows_short_hairpins,
+                       RnaTwoloopScore *out, uint64_t capacity, uint64_t *out_count);
+
 /* ------------------------------------------------------------------------------------------------
  * Single-item convenience wrappers with the reference's per-call granularity.
  * ---------------------------------------------------------------------------------------------- */

@@ -78,6 +78,7 @@ _SIGS = {
                                                vp, vp, vp]),
     "rna_mccaskill_batch": (C.c_int, [vp, vp, vp, C.c_uint32, C.c_int, C.c_int, vp, vp, vp]),
     "rna_fold_sums_batch": (C.c_int, [vp, vp, vp, C.c_uint32, C.c_int, C.c_int, vp, vp, vp]),
+    "rna_twoloop_scores": (C.c_int, [vp, vp, C.c_uint32, C.c_int, C.c_int, vp, C.c_uint64, vp]),
     "rna_centroid_batch": (C.c_int, [vp, vp, vp, vp, C.c_uint32, vp, C.c_uint32, vp, vp]),
     "rna_durbin_batch": (C.c_int, [vp, vp, vp, C.c_uint32, vp, C.c_uint32, vp, vp]),
     "rna_mccaskill_algo": (C.c_int, [vp, vp, C.c_uint32, C.c_int, C.c_int, vp, vp]),

@@ -232,6 +232,21 @@ class Handle:
             out.append(d)
         return out
 
+    TWOLOOP_DTYPE = np.dtype([("i", np.uint16), ("j", np.uint16), ("k", np.uint16), ("l", np.uint16), ("score", np.float32)])
+
+    def twoloop_scores(self, seq: np.ndarray, uses_contra_model: bool, allows_short_hairpins: bool = False) -> np.ndarray:
+        """FoldScores::twoloop_scores (src/mccaskill_algo.rs:16,320,431) of one sequence: structured array of
+        (i, j, k, l, score) in the reference's insertion order."""
+        seq = np.ascontiguousarray(seq, dtype=np.uint8)
+        model = _lib.MODEL_CONTRA if uses_contra_model else _lib.MODEL_TURNER
+        cnt = C.c_uint64(0)
+        self._chk(self.lib.rna_twoloop_scores(self.h, _p(seq), seq.shape[0], model, int(allows_short_hairpins), None, 0, C.byref(cnt)))
+        out = np.empty(cnt.value, dtype=self.TWOLOOP_DTYPE)
+        if cnt.value:
+            self._chk(self.lib.rna_twoloop_scores(self.h, _p(seq), seq.shape[0], model, int(allows_short_hairpins),
+                                                  _p(out), cnt.value, C.byref(cnt)))
+        return out
+
     def mccaskill_batch(self, bases, offsets, uses_contra_model, allows_short_hairpins=False):
         return self.fold_batch(bases, offsets, uses_contra_model, allows_short_hairpins, gammas=())
 

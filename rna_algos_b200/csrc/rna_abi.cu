@@ -17,6 +17,7 @@
 #include "fast_kernel.cuh"
 #include "fold_kernel2.cuh"
 #include "table_pack.h"
+#include "twoloop_export.cuh"
 
 using namespace rna;
 
@@ -1176,6 +1177,80 @@ extern "C" int rna_fold_sums_batch(rna_handle* h, const uint8_t* bases, const ui
   TRY(rna_mccaskill_centroid_batch_dev(h, &b, st));
   TRY(d2h(h, out_sums, h->b_probs, tot * 4, st));
   if (out_logz) TRY(d2h(h, out_logz, h->b_logz, sizeof(float) * n_seqs, st));
+  CU(h, cudaStreamSynchronize(st));
+  return RNA_OK;
+}
+
+// FoldScores::twoloop_scores of one sequence (twoloop_export.cuh): inside pass for the sums_close keys, count, scan, fill.
+extern "C" int rna_twoloop_scores(rna_handle* h, const uint8_t* seq, uint32_t seq_len, int model, int allows_short_hairpins,
+                                  RnaTwoloopScore* out, uint64_t capacity, uint64_t* out_count) {
+  if (!h || !seq || !out_count || (capacity && !out)) return RNA_ERR_BAD_ARG;
+  if (seq_len == 0) return RNA_ERR_EMPTY_SEQ;
+  if (seq_len > RNA_MAX_SEQ_LEN) { h->err = "sequence longer than RNA_MAX_SEQ_LEN (positions are u16)"; return RNA_ERR_TOO_LONG; }
+  if (h->numeric_mode != RNA_NUMERIC_REF_EXACT) { h->err = "the FoldSums / FoldScores outputs exist in the reference-exact numeric mode only"; return RNA_ERR_BAD_ARG; }
+  const uint32_t offsets[2] = {0, seq_len};
+  const int L = (int)seq_len;
+  const size_t ncell = (size_t)L * ((size_t)L + 1) / 2;
+  // inside pass: the planes stay on the device (h->b_probs), only sums_close is read
+  {
+    int rc = rna_validate_bases(seq, offsets, 1);
+    if (rc == RNA_OK) rc = rna_validate_fold_lengths(offsets, 1);
+    if (rc != RNA_OK) { h->err = rc == RNA_ERR_TOO_LONG ? "sequence longer than RNA_MAX_FOLD_LEN (46340 nt)" : "input validation failed"; return rc; }
+  }
+  h->stats = RnaCallStats{};
+  CU(h, cudaSetDevice(h->device));
+  cudaStream_t st = h->stream;
+  const uint64_t sums_offsets[2] = {0, (uint64_t)RNA_SUMS_PLANES * rna_sums_len(seq_len)};
+  RnaFoldBatchDev b;
+  memset(&b, 0, sizeof b);
+  b.h_offsets = offsets;
+  TRY(h2d(h, h->b_bases, seq, seq_len, st));
+  TRY(h2d(h, h->b_offsets, offsets, sizeof offsets, st));
+  TRY(h2d(h, h->b_proboff, sums_offsets, sizeof sums_offsets, st));
+  TRY(ensure(h, h->b_probs, sums_offsets[1] * 4));
+  b.d_bases = (const uint8_t*)h->b_bases.p;
+  b.d_offsets = (const uint32_t*)h->b_offsets.p;
+  b.d_sums_offsets = (const uint64_t*)h->b_proboff.p;
+  b.d_out_sums = (float*)h->b_probs.p;
+  b.n_seqs = 1;
+  b.total_len = seq_len;
+  b.model = model;
+  b.allows_short_hairpins = allows_short_hairpins;
+  b.inside_only = 1;
+  TRY(rna_mccaskill_centroid_batch_dev(h, &b, st));
+  // codes, counts
+  TRY(ensure(h, h->b_pairs, 3 * ((size_t)L + 16)));
+  TRY(ensure(h, h->b_bppoff, sizeof(unsigned long long) * ncell));
+  TwoloopArgs a;
+  memset(&a, 0, sizeof a);
+  uint8_t* codes = (uint8_t*)h->b_pairs.p;
+  a.sq = codes + 4; a.RR = codes + (L + 16); a.LL = codes + 2 * ((size_t)L + 16);
+  a.L = L;
+  a.tables = model == RNA_MODEL_CONTRA ? (const void*)h->d_contra : (const void*)h->d_turner;
+  a.allows_short = allows_short_hairpins;
+  a.close = (const float*)h->b_probs.p + (size_t)RNA_SUMS_CLOSE * rna_sums_len(seq_len);
+  a.offsets = (unsigned long long*)h->b_bppoff.p;
+  const int nt = 128, grid = (int)std::min<size_t>((ncell + nt - 1) / nt, (size_t)h->sm_count * 16);
+  twoloop_codes_kernel<<<std::max(1, (L + 8 + 255) / 256), 256, 0, st>>>((const uint8_t*)h->b_bases.p, L, codes, const_cast<uint8_t*>(a.RR), const_cast<uint8_t*>(a.LL));
+  if (model == RNA_MODEL_CONTRA) twoloop_kernel<true, false><<<grid, nt, 0, st>>>(a); else twoloop_kernel<false, false><<<grid, nt, 0, st>>>(a);
+  CU(h, cudaGetLastError());
+  std::vector<unsigned long long> cnt(ncell);
+  CU(h, cudaMemcpyAsync(cnt.data(), a.offsets, sizeof(unsigned long long) * ncell, cudaMemcpyDeviceToHost, st));
+  CU(h, cudaStreamSynchronize(st));
+  unsigned long long run = 0;
+  for (size_t c = 0; c < ncell; c++) { const unsigned long long n = cnt[c]; cnt[c] = run; run += n; }
+  *out_count = run;
+  h->stats.kernel_launches += 2;
+  const uint64_t nwrite = std::min<uint64_t>(run, capacity);
+  if (nwrite == 0) return RNA_OK;
+  CU(h, cudaMemcpyAsync(a.offsets, cnt.data(), sizeof(unsigned long long) * ncell, cudaMemcpyHostToDevice, st));
+  TRY(ensure(h, h->b_bpp, nwrite * sizeof(RnaTwoloopScore)));
+  a.out = (RnaTwoloopScore*)h->b_bpp.p;
+  a.capacity = nwrite;
+  if (model == RNA_MODEL_CONTRA) twoloop_kernel<true, true><<<grid, nt, 0, st>>>(a); else twoloop_kernel<false, true><<<grid, nt, 0, st>>>(a);
+  CU(h, cudaGetLastError());
+  h->stats.kernel_launches++;
+  TRY(d2h(h, out, h->b_bpp, nwrite * sizeof(RnaTwoloopScore), st));
   CU(h, cudaStreamSynchronize(st));
   return RNA_OK;
 }

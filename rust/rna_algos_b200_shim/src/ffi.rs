@@ -109,6 +109,11 @@ pub struct RnaAlignTables {
     pub match_scores: [[f32; 4]; 4],
 }
 
+/// include/rna_algos_b200.h RnaTwoloopScore: one entry of FoldScores::twoloop_scores
+#[repr(C)]
+#[derive(Clone, Copy, Default)]
+pub struct RnaTwoloopScore { pub i: u16, pub j: u16, pub k: u16, pub l: u16, pub score: f32 }
+
 extern "C" {
     pub fn rna_create(device: c_int, out: *mut *mut rna_handle) -> c_int;
     pub fn rna_destroy(h: *mut rna_handle) -> c_int;
@@ -140,6 +145,8 @@ extern "C" {
         out_probs: *mut f32) -> c_int;
     pub fn rna_fold_sums_batch(h: *mut rna_handle, bases: *const u8, offsets: *const u32, n_seqs: u32, model: c_int,
         allows_short_hairpins: c_int, out_sums: *mut f32, sums_offsets: *const u64, out_logz: *mut f32) -> c_int;
+    pub fn rna_twoloop_scores(h: *mut rna_handle, seq: *const u8, seq_len: u32, model: c_int, allows_short_hairpins: c_int,
+        out: *mut RnaTwoloopScore, capacity: u64, out_count: *mut u64) -> c_int;
     pub fn rna_set_numeric_mode(h: *mut rna_handle, mode: c_int) -> c_int;
     pub fn rna_queue_create(h: *mut rna_handle, out: *mut *mut rna_queue) -> c_int;
     pub fn rna_queue_destroy(q: *mut rna_queue) -> c_int;

@@ -32,8 +32,7 @@ pub type FoldScoreSets = ffi::RnaContraTables;
 /// src/durbin_algo.rs:4-14
 pub type AlignScores = ffi::RnaAlignTables;
 
-/// src/mccaskill_algo.rs:13-22.  `twoloop_scores` (up to 496 entries per pair) is left empty: it is a pure function of
-/// the sequence (utils::get_2loop_score*) that no in-tree caller of the reference reads.
+/// src/mccaskill_algo.rs:13-22: all four members are filled (`twoloop_scores` through rna_twoloop_scores).
 pub struct FoldScores<T: Hash + Eq> {
     pub hairpin_scores: SparseScoreMat<T>,
     pub twoloop_scores: ScoreMat4d<T>,
@@ -100,6 +99,23 @@ pub fn mccaskill_algo<T: HashIndex>(seq: SeqSlice, uses_contra_model: bool, allo
             if planes[9 * pl + x] > f32::NEG_INFINITY { fs.accessible_scores.insert((a, b), planes[9 * pl + x]); }
         }
     }}
+    // twoloop_scores: the 4-D memo (src/mccaskill_algo.rs:320, 431), sized by a first call with capacity 0
+    let model = if uses_contra_model { ffi::RNA_MODEL_CONTRA } else { ffi::RNA_MODEL_TURNER };
+    let mut cnt = 0u64;
+    let rc = unsafe { ffi::rna_twoloop_scores(h, bases.as_ptr(), l as u32, model, allows_short_hairpins as i32,
+        std::ptr::null_mut(), 0, &mut cnt) };
+    assert_eq!(rc, ffi::RNA_OK, "rna_twoloop_scores failed");
+    let mut ent = vec![ffi::RnaTwoloopScore::default(); cnt as usize];
+    if cnt > 0 {
+        let rc = unsafe { ffi::rna_twoloop_scores(h, bases.as_ptr(), l as u32, model, allows_short_hairpins as i32,
+            ent.as_mut_ptr(), cnt, &mut cnt) };
+        assert_eq!(rc, ffi::RNA_OK, "rna_twoloop_scores failed");
+    }
+    for e in &ent {
+        if let (Ok(a), Ok(b), Ok(c), Ok(d)) = (T::try_from(e.i as usize), T::try_from(e.j as usize), T::try_from(e.k as usize), T::try_from(e.l as usize)) {
+            fs.twoloop_scores.insert((a, b, c, d), e.score);
+        }
+    }
     (probs, fs)
 }
 

@@ -103,6 +103,34 @@ class Oracle:
         assert rc == 0, rc
         return out
 
+    def twoloop_scores(self, seq: np.ndarray, contra: bool, allows_short: bool, tt, ct):
+        """FoldScores::twoloop_scores in the reference's insertion order (src/mccaskill_algo.rs:290-324, 395-435):
+        list of (i, j, k, l, f32 score).  The visited pairs and the partners' sums_close keys come from fold_sums()."""
+        seq = np.ascontiguousarray(seq, dtype=np.uint8)
+        L = int(seq.shape[0])
+        close = self.fold_sums(seq, contra, allows_short, tt, ct)[0]
+        has = close > -np.inf
+        canon = {(0, 3), (1, 2), (2, 1), (2, 3), (3, 0), (3, 2)}
+        max2 = ct.max_loop_len if contra else tt.max_2loop_len
+        minspan = ct.min_span_hairpin_close if contra else tt.min_span_hairpin_close
+        sp = _ptr(seq, u8p)
+        out = []
+        for span in range(2 if (contra and allows_short) else minspan, L + 1):
+            for i in range(0, L - span + 1):
+                j = i + span - 1
+                if (int(seq[i]), int(seq[j])) not in canon:
+                    continue
+                for k in range(i + 1, j - 1):
+                    if k - i - 1 > max2:
+                        break
+                    for l in range(j - 1, k, -1):
+                        if (j - l - 1) + (k - i - 1) > max2:
+                            break
+                        if has[k, l]:
+                            sc = self.lib.orc_score_twoloop(sp, L, i, j, k, l, int(contra), C.byref(tt), C.byref(ct))
+                            out.append((i, j, k, l, np.float32(sc)))
+        return out
+
     def centroid(self, bpp: np.ndarray, L: int, gamma: float):
         bpp = np.ascontiguousarray(bpp, dtype=np.float32)
         s = np.empty(L, dtype=np.uint8)

@@ -395,6 +395,30 @@ def test_fold_sums_and_fold_scores_export(handle, oracle, contra):
         assert_bits_equal(g1[name][iu], want[p][iu], f"{name} cooperative route")
 
 
+@pytest.mark.parametrize("contra", [False, True])
+def test_twoloop_scores_export(handle, oracle, contra):
+    """N3: FoldScores::twoloop_scores through rna_twoloop_scores — every (i,j,k,l) key in the reference's insertion
+    order with its score bit-equal to the oracle's get_2loop_score; sizing call, truncated capacity, short hairpins."""
+    import ctypes as C
+    tt, ct, _ = default_tables()
+    for seq, short in ((load_trnas()[4], False), (random_seqs(8, [37])[0], bool(contra)), (random_seqs(8, [4])[0], False)):
+        want = oracle.twoloop_scores(seq, contra, short, tt, ct)
+        got = handle.twoloop_scores(seq, contra, short)
+        assert got.shape[0] == len(want)
+        if want:
+            w = np.array([(i, j, k, l) for (i, j, k, l, _) in want], dtype=np.uint16)
+            assert (np.stack([got["i"], got["j"], got["k"], got["l"]], axis=1) == w).all(), "keys / order"
+            assert_bits_equal(got["score"], np.array([sc for (*_, sc) in want], dtype=np.float32), "two-loop scores")
+    # capacity smaller than the count: the count is still reported, the prefix is written
+    seq = load_trnas()[0]
+    full = handle.twoloop_scores(seq, contra)
+    part = np.zeros(10, dtype=handle.TWOLOOP_DTYPE)
+    cnt = C.c_uint64(0)
+    rc = handle.lib.rna_twoloop_scores(handle.h, seq.ctypes.data_as(C.c_void_p), seq.shape[0], int(contra), 0,
+                                       part.ctypes.data_as(C.c_void_p), 10, C.byref(cnt))
+    assert rc == 0 and cnt.value == full.shape[0] and (part == full[:10]).all()
+
+
 def test_multi_device_object_partitions_and_scatters(oracle):
     """rna_multi: LPT partition inside the library, one host thread + handle per device, results scattered into the
     caller's buffers.  Listing device 0 three times exercises partition / scatter on a one-GPU box; on a multi-GPU

@@ -136,3 +136,16 @@ def test_fold_sums_planes_of_both_restatements(oracle, contra):
             sparse(scores.hairpin_scores), sparse(scores.multibranch_close_scores), sparse(scores.accessible_scores)]
     for p, w in enumerate(want):
         assert_bits_equal(planes[p][iu], w[iu], f"plane {p}")
+
+
+@pytest.mark.parametrize("contra", [False, True])
+def test_twoloop_scores_memo_of_both_restatements(oracle, contra):
+    """FoldScores::twoloop_scores (the 4-D memo): the oracle-side enumeration that the CUDA export is compared with
+    (tests/oracle_lib.py twoloop_scores) against the transliteration's dict — same keys, same f32 values."""
+    tt, ct, _ = default_tables()
+    for seq, short in ((load_trnas()[3], False), (random_seqs(3, [40])[0], True)):
+        scores = TL.mccaskill_algo(seq, contra, short, ct, tt)[1]
+        lst = oracle.twoloop_scores(seq, contra, short, tt, ct)
+        assert len(lst) == len(scores.twoloop_scores) and len(lst) > 100
+        for (i, j, k, l, sc) in lst:
+            assert np.float32(scores.twoloop_scores[(i, j, k, l)]).view(np.uint32) == sc.view(np.uint32), (i, j, k, l)
