@@ -638,7 +638,8 @@ static int launch_fold_model(rna_handle* h, const RnaFoldBatchDev* b, cudaStream
     } else {
       meminfo();
       const size_t budget = (freeb + h->ws.cap) / 2;
-      int g = (int)std::min<size_t>(bk.end - bk.begin, (size_t)h->sm_count * 2);
+      static const int gocc = dev_env("RNA_GLOBAL_OCC") ? atoi(dev_env("RNA_GLOBAL_OCC")) : 2;   // CTAs per SM of the HBM-resident mode
+      int g = (int)std::min<size_t>(bk.end - bk.begin, (size_t)h->sm_count * gocc);
       while (g > 1 && (size_t)g * per * 4 > budget) g--;
       if ((size_t)g * per * 4 > budget) { h->err = "sequence too long for device memory"; return RNA_ERR_NOMEM; }
       grid_of[k] = g;

@@ -293,6 +293,22 @@ def test_several_long_sequences_run_on_concurrent_cooperative_grids(handle, orac
         assert (got["structs"][:, offsets[s_]:offsets[s_ + 1]] == alone["structs"]).all(), f"structures seq {s_}"
 
 
+@pytest.mark.parametrize("seed,contra", [(301, True), (302, False), (303, True)])
+def test_random_ragged_batches_through_every_route(handle, oracle, seed, contra):
+    """Seeded ragged batches whose lengths straddle every routing boundary of the launcher at once — the 4-nt
+    shared-memory buckets, the 96-nt classes of the HBM-resident mode, the cooperative / one-CTA cost model and the
+    concurrent cooperative grids — in shuffled order: results must be bit-identical whatever route a sequence takes."""
+    import os
+    tt, ct, _ = default_tables()
+    rng = np.random.default_rng(seed)
+    lens = [int(x) for x in rng.integers(1, 230, size=24)] + [int(x) for x in rng.integers(221, 720, size=10 if seed != 303 else 3)]
+    if seed == 303:
+        lens += [1040, 1031]
+    rng.shuffle(lens)
+    seqs = random_seqs(seed, lens)
+    check_fold(handle, oracle, seqs, contra, bool(contra and seed == 303), [1.0, 6.0], tt, ct, threads=max(8, os.cpu_count() or 8))
+
+
 def test_long_cooperative_edge_lengths(handle, oracle):
     """The cooperative kernel is also the route for a lone mid-length sequence: odd/even lengths around the warp and
     pair-step boundaries (the last pair step handles one or two diagonals)."""
