@@ -92,6 +92,17 @@ __device__ __forceinline__ real warp_lse(LseAcc<real> a) {
   }
   return a.value();
 }
+// the lanes' partial sums merged (every lane holds the result), not yet a logarithm
+template <class real>
+__device__ __forceinline__ LseAcc<real> warp_merge(LseAcc<real> a) {
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) {
+    const real m2 = __shfl_xor_sync(0xffffffffu, a.m, off);
+    const real s2 = __shfl_xor_sync(0xffffffffu, a.s, off);
+    a.merge(m2, s2);
+  }
+  return a;
+}
 template <class real>
 __device__ __forceinline__ real lse2(real a, real b) {
   LseAcc<real> x;
@@ -125,8 +136,6 @@ __global__ void __launch_bounds__(COOP ? RNA_FAST_NT_COOP : RNA_FAST_NT_BATCH, C
   const real NEG = FM::ninf();
   const int tid = threadIdx.x, lane = tid & 31;
   // warps of the team that works on one sequence: the CTA (batch) or the whole grid (cooperative)
-  const int wid = COOP ? (tid >> 5) * (int)gridDim.x + (int)blockIdx.x : (tid >> 5);
-  const int nw = COOP ? (int)(gridDim.x * (blockDim.x >> 5)) : (int)(blockDim.x >> 5);
   const int gtid = COOP ? (int)(blockIdx.x * blockDim.x + tid) : tid;
   const int gnt = COOP ? (int)(gridDim.x * blockDim.x) : (int)blockDim.x;
   unsigned bar_target = 0;
@@ -136,6 +145,13 @@ __global__ void __launch_bounds__(COOP ? RNA_FAST_NT_COOP : RNA_FAST_NT_BATCH, C
   auto ld = [](const real* p) -> real { if constexpr (COOP) return __ldcg(p); else return *p; };
   __shared__ int s_work;
   __shared__ uint8_t cand[2 * 496];             // (a, b) of the interior-loop enumeration, a + b <= MAX2 <= 30
+  // A diagonal with fewer cells than the team has warps (the LONG diagonals, whose cells carry the longest reductions)
+  // gives each cell S warps of ONE CTA: every warp reduces its share of the split points / candidates, the partial
+  // (max, sum) pairs meet in shared memory and the first warp of the cell finishes it.  Cells go round-robin over the
+  // CTAs of the team (cell c: CTA c % G, slot c / G), so all CTAs see the same number of slots and rounds.
+  __shared__ real s_red[(COOP ? RNA_FAST_NT_COOP : RNA_FAST_NT_BATCH) / 32][4][2];
+  const int G = COOP ? (int)gridDim.x : 1, cta = COOP ? (int)blockIdx.x : 0;
+  const int WPC = (int)(blockDim.x >> 5), wic = tid >> 5;
   int ncand = 0;
   for (int aa = 0; aa <= P.MAX2; aa++) ncand += P.MAX2 - aa + 1;
   for (int x = tid; x < ncand; x += blockDim.x) {
@@ -204,19 +220,21 @@ __global__ void __launch_bounds__(COOP ? RNA_FAST_NT_COOP : RNA_FAST_NT_BATCH, C
     for (int d = d_in0; d < L; d++) {
       real* Sprev = (d & 1) ? vS0 : vS1;   // S of diagonal d-1 (by column j)
       real* Scur = (d & 1) ? vS1 : vS0;
-      for (int i = wid; i < L - d; i += nw) {
-        const int j = i + d;
-        // (1) sums_close: hairpin (+) interior loops (+) multiloop closing
-        real Cij = NEG;
-        if (closable(i, j)) {
-          LseAcc<real> acc;
-          if (lane == 0) {
-            if constexpr (CONTRA) { if (d - 1 <= P.MAX2) acc.add((real)c2_hairpin(T, sq, i, j)); }
-            else acc.add((real)t_hairpin(T, sq, i, j));
-            if (d >= 2) acc.add(ld(&mM[(size_t)(i + 1) * L + (j - 1)]) + (real)v2_mbclose<CONTRA>(T, sq, L, i, j));
-          }
+      const int ncell = L - d, cpc = (ncell + G - 1) / G;
+      int S = 1;
+      while (S * 2 * cpc <= WPC) S *= 2;                    // warps per cell (1 while the diagonal has cells for every warp)
+      const int spr = WPC / S, rounds = (cpc + spr - 1) / spr;   // slots per round, rounds (identical in every CTA)
+      const int part = wic % S;
+      for (int rd = 0; rd < rounds; rd++) {
+        const int slot = rd * spr + wic / S;
+        const int i = slot * G + cta, j = i + d;
+        const bool active = slot < cpc && i < ncell;
+        const bool clos = active && closable(i, j);
+        // ---- partial sums of this warp's share: interior-loop candidates, the two O(span) reductions ----
+        LseAcc<real> acc, e, m;
+        if (clos) {
           const typename LoopOf<CONTRA, true>::type lp = make_loop<CONTRA, true>(v, T, i, j);
-          for (int c0 = lane; c0 < ncand; c0 += 128) {   // four candidates per lane in flight
+          for (int c0 = lane + 128 * part; c0 < ncand; c0 += 128 * S) {   // four candidates per lane in flight
             real ck[4];
             int ca[4], cb[4];
 #pragma unroll
@@ -239,8 +257,56 @@ __global__ void __launch_bounds__(COOP ? RNA_FAST_NT_COOP : RNA_FAST_NT_BATCH, C
               }
             }
           }
-          Cij = warp_lse(acc);
-          if (lane == 0) mC[(size_t)i * L + j] = Cij;
+        }
+        if (active) {
+          const real* rowE = mE + (size_t)i * L;
+          const real* rowM1 = mM1 + (size_t)i * L;
+          const real* colR = mRT + (size_t)j * L;
+          const real* colX = mXT + (size_t)j * L;
+          for (int k0 = i + 1 + lane + 128 * part; k0 <= j - 1; k0 += 128 * S) {   // four split points per lane in flight
+            real r[4], ee[4], mm[4], xx[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+              const int k = k0 + 32 * u;
+              r[u] = NEG; ee[u] = NEG; mm[u] = NEG; xx[u] = NEG;
+              if (k <= j - 1) {
+                r[u] = ld(&colR[k]); ee[u] = ld(&rowE[k - 1]); mm[u] = ld(&rowM1[k - 1]);
+                if constexpr (CONTRA) xx[u] = ld(&colX[k]);
+              }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+              e.add(r[u] + ee[u]);
+              if constexpr (CONTRA) m.add(mm[u] + xx[u]);
+              else m.add(mm[u] + (r[u] + (real)cnb));
+            }
+          }
+        }
+        acc = warp_merge(acc); e = warp_merge(e); m = warp_merge(m);
+        if (S > 1) {   // (uniform in the CTA)
+          if (lane == 0) {
+            s_red[wic][0][0] = acc.m; s_red[wic][0][1] = acc.s; s_red[wic][1][0] = e.m; s_red[wic][1][1] = e.s;
+            s_red[wic][2][0] = m.m; s_red[wic][2][1] = m.s;
+          }
+          __syncthreads();
+          if (part == 0) {
+            for (int q = 1; q < S; q++) {
+              acc.merge(s_red[wic + q][0][0], s_red[wic + q][0][1]);
+              e.merge(s_red[wic + q][1][0], s_red[wic + q][1][1]);
+              m.merge(s_red[wic + q][2][0], s_red[wic + q][2][1]);
+            }
+          }
+          __syncthreads();
+        }
+        if (!active || part != 0) continue;
+        // ---- the cell's first warp finishes it (every lane computes the same scalars, lane 0 stores) ----
+        // (1) sums_close: hairpin (+) interior loops (+) multiloop closing
+        real Cij = NEG;
+        if (clos) {
+          if constexpr (CONTRA) { if (d - 1 <= P.MAX2) acc.add((real)c2_hairpin(T, sq, i, j)); }
+          else acc.add((real)t_hairpin(T, sq, i, j));
+          if (d >= 2) acc.add(ld(&mM[(size_t)(i + 1) * L + (j - 1)]) + (real)v2_mbclose<CONTRA>(T, sq, L, i, j));
+          Cij = acc.value();
         }
         // (2) rightmost-pair sums by their one-term recurrences
         const real Aij = (Cij > NEG) ? Cij + (real)v2_acc<CONTRA>(T, sq, L, i, j) : NEG;
@@ -253,41 +319,17 @@ __global__ void __launch_bounds__(COOP ? RNA_FAST_NT_COOP : RNA_FAST_NT_BATCH, C
         } else {
           Rij = lse2<real>(Rprev, Aij);
         }
-        // (3) sums_external, (4) sums_multibranch: the two O(span) reductions, lanes over the split point k
-        LseAcc<real> e, m;
-        if (lane == 0) {
-          e.add(CONTRA ? (real)eu * (real)(d + 1) : (real)0);
-          e.add(Rij);                                     // k = i: E[i][i-1] = 0
-        }
-        const real* rowE = mE + (size_t)i * L;
-        const real* rowM1 = mM1 + (size_t)i * L;
-        const real* colR = mRT + (size_t)j * L;
-        const real* colX = mXT + (size_t)j * L;
-        for (int k0 = i + 1 + lane; k0 <= j - 1; k0 += 128) {   // four split points per lane in flight
-          real r[4], ee[4], mm[4], xx[4];
-#pragma unroll
-          for (int u = 0; u < 4; u++) {
-            const int k = k0 + 32 * u;
-            r[u] = NEG; ee[u] = NEG; mm[u] = NEG; xx[u] = NEG;
-            if (k <= j - 1) {
-              r[u] = ld(&colR[k]); ee[u] = ld(&rowE[k - 1]); mm[u] = ld(&rowM1[k - 1]);
-              if constexpr (CONTRA) xx[u] = ld(&colX[k]);
-            }
-          }
-#pragma unroll
-          for (int u = 0; u < 4; u++) {
-            e.add(r[u] + ee[u]);
-            if constexpr (CONTRA) m.add(mm[u] + xx[u]);
-            else m.add(mm[u] + (r[u] + (real)cnb));
-          }
-        }
-        const real Eij = warp_lse(e), Mij = warp_lse(m);
+        // (3) sums_external, (4) sums_multibranch: the split-point reductions plus the k = i terms
+        e.add(CONTRA ? (real)eu * (real)(d + 1) : (real)0);
+        e.add(Rij);                                     // k = i: E[i][i-1] = 0
+        const real Eij = e.value(), Mij = m.value();
         // first chain of the 1-or-more sum by its recurrence down the column
         real Sij;
         if constexpr (CONTRA) Sij = lse2<real>(Rmij, (real)mu + ld(&Sprev[j]));
         else Sij = lse2<real>(Rij, ld(&Sprev[j]));
         const real M1ij = lse2<real>(CONTRA ? Sij : Sij + (real)cnb, Mij);
         if (lane == 0) {
+          if (clos) mC[(size_t)i * L + j] = Cij;
           mRT[(size_t)j * L + i] = Rij;
           if constexpr (CONTRA) mXT[(size_t)j * L + i] = Rmij;
           mE[(size_t)i * L + j] = Eij;
@@ -315,39 +357,37 @@ __global__ void __launch_bounds__(COOP ? RNA_FAST_NT_COOP : RNA_FAST_NT_BATCH, C
     for (int d = L - 1; d >= d_out0; d--) {
       real* Tprev = (d & 1) ? vS0 : vS1;   // T2 of diagonal d+1 (by column j)
       real* Tcur = (d & 1) ? vS1 : vS0;
-      for (int i = wid; i < L - d; i += nw) {
-        const int j = i + d;
-        // probs_multibranch2 by its recurrence, probs_multibranch by a reduction over k > j
-        real pm2 = NEG;
-        if (j + 1 < L) pm2 = lse2<real>(ld(&mPM2T[(size_t)(j + 1) * L + i]) + (real)mu, ld(&mXQ[(size_t)i * L + (j + 1)]));
-        LseAcc<real> pmacc;
-        const real* rowXQ = mXQ + (size_t)i * L;
-        const real* rowM1 = mM1 + (size_t)(j + 1) * L;
-        for (int k0 = j + 2 + lane; k0 < L; k0 += 128) {
-          real xq4[4], m14[4];
+      const int ncell = L - d, cpc = (ncell + G - 1) / G;
+      int S = 1;
+      while (S * 2 * cpc <= WPC) S *= 2;
+      const int spr = WPC / S, rounds = (cpc + spr - 1) / spr;
+      const int part = wic % S;
+      for (int rd = 0; rd < rounds; rd++) {
+        const int slot = rd * spr + wic / S;
+        const int i = slot * G + cta, j = i + d;
+        const bool active = slot < cpc && i < ncell;
+        const real Cij = active ? ld(&mC[(size_t)i * L + j]) : NEG;
+        const bool clos = Cij > NEG;
+        // ---- partial sums of this warp's share ----
+        LseAcc<real> pmacc, acc, t1acc, t3acc;
+        if (active) {   // probs_multibranch: reduction over k > j
+          const real* rowXQ = mXQ + (size_t)i * L;
+          const real* rowM1 = mM1 + (size_t)(j + 1) * L;
+          for (int k0 = j + 2 + lane + 128 * part; k0 < L; k0 += 128 * S) {
+            real xq4[4], m14[4];
 #pragma unroll
-          for (int u = 0; u < 4; u++) {
-            const int k = k0 + 32 * u;
-            xq4[u] = NEG; m14[u] = NEG;
-            if (k < L) { xq4[u] = ld(&rowXQ[k]); m14[u] = ld(&rowM1[k - 1]); }
+            for (int u = 0; u < 4; u++) {
+              const int k = k0 + 32 * u;
+              xq4[u] = NEG; m14[u] = NEG;
+              if (k < L) { xq4[u] = ld(&rowXQ[k]); m14[u] = ld(&rowM1[k - 1]); }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; u++) pmacc.add(xq4[u] + m14[u]);
           }
-#pragma unroll
-          for (int u = 0; u < 4; u++) pmacc.add(xq4[u] + m14[u]);
         }
-        const real pm = warp_lse(pmacc);
-        // T2[i][j] = lse over k < i of probs_multibranch[k][j] + unpair * (i - k - 1)
-        real t2 = NEG;
-        if (i >= 1) t2 = lse2<real>(ld(&mPMT[(size_t)j * L + (i - 1)]), (real)mu + ld(&Tprev[j]));
-        // log P(i,j)
-        const real Cij = ld(&mC[(size_t)i * L + j]);
-        real Pij = NEG, xq = NEG;
-        if (Cij > NEG) {
-          const real Aij = Cij + (real)v2_acc<CONTRA>(T, sq, L, i, j);
-          const real El = (i < 1) ? (real)0 : ld(&vE0[i - 1]), Er = (j > L - 2) ? (real)0 : ld(&vEL[j + 1]);
-          LseAcc<real> acc;
-          if (lane == 0) acc.add(CONTRA ? El + Er + Aij + (real)ebp - Z : El + Aij + Er - Z);
+        if (clos) {
           const typename LoopOf<CONTRA, false>::type lp = make_loop<CONTRA, false>(v, T, i, j);
-          for (int c0 = lane; c0 < ncand; c0 += 128) {
+          for (int c0 = lane + 128 * part; c0 < ncand; c0 += 128 * S) {
             real ck[4], pk[4];
             int ca[4], cb[4];
 #pragma unroll
@@ -371,12 +411,11 @@ __global__ void __launch_bounds__(COOP ? RNA_FAST_NT_COOP : RNA_FAST_NT_BATCH, C
             }
           }
           // enclosing multiloops: T1 = lse_k PM2[k][j] + M1[k+1][i-1], T3 = lse_k PM[k][j] + M1[k+1][i-1], k <= i-2
-          LseAcc<real> t1acc, t3acc;
           if (i >= 2) {
             const real* colPM2 = mPM2T + (size_t)j * L;
             const real* colPM = mPMT + (size_t)j * L;
             const real* colM1 = mM1T + (size_t)(i - 1) * L;
-            for (int k0 = lane; k0 <= i - 2; k0 += 128) {
+            for (int k0 = lane + 128 * part; k0 <= i - 2; k0 += 128 * S) {
               real x14[4], p24[4], p4[4];
 #pragma unroll
               for (int u = 0; u < 4; u++) {
@@ -388,10 +427,42 @@ __global__ void __launch_bounds__(COOP ? RNA_FAST_NT_COOP : RNA_FAST_NT_BATCH, C
               for (int u = 0; u < 4; u++) { t1acc.add(p24[u] + x14[u]); t3acc.add(p4[u] + x14[u]); }
             }
           }
+        }
+        pmacc = warp_merge(pmacc); acc = warp_merge(acc); t1acc = warp_merge(t1acc); t3acc = warp_merge(t3acc);
+        if (S > 1) {
+          if (lane == 0) {
+            s_red[wic][0][0] = pmacc.m; s_red[wic][0][1] = pmacc.s; s_red[wic][1][0] = acc.m; s_red[wic][1][1] = acc.s;
+            s_red[wic][2][0] = t1acc.m; s_red[wic][2][1] = t1acc.s; s_red[wic][3][0] = t3acc.m; s_red[wic][3][1] = t3acc.s;
+          }
+          __syncthreads();
+          if (part == 0) {
+            for (int q = 1; q < S; q++) {
+              pmacc.merge(s_red[wic + q][0][0], s_red[wic + q][0][1]);
+              acc.merge(s_red[wic + q][1][0], s_red[wic + q][1][1]);
+              t1acc.merge(s_red[wic + q][2][0], s_red[wic + q][2][1]);
+              t3acc.merge(s_red[wic + q][3][0], s_red[wic + q][3][1]);
+            }
+          }
+          __syncthreads();
+        }
+        if (!active || part != 0) continue;
+        // ---- the cell's first warp finishes it ----
+        // probs_multibranch2 by its recurrence, probs_multibranch from the reduction
+        real pm2 = NEG;
+        if (j + 1 < L) pm2 = lse2<real>(ld(&mPM2T[(size_t)(j + 1) * L + i]) + (real)mu, ld(&mXQ[(size_t)i * L + (j + 1)]));
+        const real pm = pmacc.value();
+        // T2[i][j] = lse over k < i of probs_multibranch[k][j] + unpair * (i - k - 1)
+        real t2 = NEG;
+        if (i >= 1) t2 = lse2<real>(ld(&mPMT[(size_t)j * L + (i - 1)]), (real)mu + ld(&Tprev[j]));
+        // log P(i,j)
+        real Pij = NEG, xq = NEG;
+        if (clos) {
+          const real Aij = Cij + (real)v2_acc<CONTRA>(T, sq, L, i, j);
+          const real El = (i < 1) ? (real)0 : ld(&vE0[i - 1]), Er = (j > L - 2) ? (real)0 : ld(&vEL[j + 1]);
+          acc.add(CONTRA ? El + Er + Aij + (real)ebp - Z : El + Aij + Er - Z);
           const real sa = Aij + (CONTRA ? (real)mbp : (real)cnb);
-          const real T1 = warp_lse(t1acc), T3 = warp_lse(t3acc);
-          if (lane == 0) { acc.add(sa + T1); acc.add(sa + t2); acc.add(sa + T3); }
-          Pij = warp_lse(acc);
+          acc.add(sa + t1acc.value()); acc.add(sa + t2); acc.add(sa + t3acc.value());
+          Pij = acc.value();
           xq = Pij + (real)v2_mbclose<CONTRA>(T, sq, L, i, j) - Cij;
         }
         if (lane == 0) {

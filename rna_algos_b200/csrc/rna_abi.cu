@@ -292,7 +292,9 @@ static int kern_prepare(rna_handle* h, const void* fn, int nt, size_t smem, int*
   bool attr_done = false;
   for (const void* f : h->attr_set) attr_done = attr_done || f == fn;
   if (!attr_done) {
-    CU(h, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_optin - 1024));   // (static shared memory comes out of the same budget)
+    cudaFuncAttributes fa;
+    CU(h, cudaFuncGetAttributes(&fa, fn));   // (static shared memory comes out of the same opt-in budget)
+    CU(h, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_optin - (int)std::max<size_t>(1024, fa.sharedSizeBytes)));
     h->attr_set.push_back(fn);
   }
   if (!occ_out) return RNA_OK;
@@ -940,7 +942,7 @@ static int launch_fast(rna_handle* h, const RnaFoldBatchDev* b, cudaStream_t st,
 
 // FAST_F64 runs everything on fast_fold_kernel (f64 state: the accuracy mode).  FAST_F32 is the speed mode: the few
 // long sequences that would otherwise each wait for one CTA go one at a time to fast_fold_kernel's cooperative grid
-// (warp-shuffle reductions: 36 / 85 / 317 ms at 1 / 2 / 4 k nt), everything else to the FAST build of the batch kernel
+// (warp-shuffle reductions: 29 / 77 / 307 ms at 1 / 2 / 4 k nt), everything else to the FAST build of the batch kernel
 // (fold_fastnum.cu), which is several times faster than fast_fold_kernel's one-CTA-per-sequence launch on batches.
 static int launch_fast_mode(rna_handle* h, const RnaFoldBatchDev* b, cudaStream_t st) {
   const bool f64 = h->numeric_mode == RNA_NUMERIC_FAST_F64;
@@ -956,7 +958,7 @@ static int launch_fast_mode(rna_handle* h, const RnaFoldBatchDev* b, cudaStream_
     while (n_long < n && len_of(n_long) > 220) n_long++;          // (beyond the shared-memory mode)
     while (forced < n_long && len_of(forced) > 1024) forced++;    // (beyond the one-CTA modes)
     // cost model from B200 measurements, like launch_fold_model's: the longest c long sequences go to the cooperative grid
-    auto coop_ms = [](int L) { const double r = L / 1024.0; return 36.0 * (r <= 1.0 ? r * std::sqrt(r) : r * r); };
+    auto coop_ms = [](int L) { const double r = L / 1024.0; return 29.0 * (r <= 1.0 ? r * std::sqrt(r) : r * r); };
     auto wave_ms = [&](int Lmax, uint32_t cnt) {
       if (cnt == 0) return 0.0;
       const double r = Lmax / 1024.0, per_wave = 2.0 * h->sm_count;
