@@ -150,6 +150,7 @@ __global__ void __launch_bounds__(COOP ? RNA_FAST_NT_COOP : RNA_FAST_NT_BATCH, C
   // (max, sum) pairs meet in shared memory and the first warp of the cell finishes it.  Cells go round-robin over the
   // CTAs of the team (cell c: CTA c % G, slot c / G), so all CTAs see the same number of slots and rounds.
   __shared__ real s_red[(COOP ? RNA_FAST_NT_COOP : RNA_FAST_NT_BATCH) / 32][4][2];
+  constexpr int UR = COOP ? 8 : 4;   // split points per lane in flight (the cooperative launch has 128 registers per thread)
   const int G = COOP ? (int)gridDim.x : 1, cta = COOP ? (int)blockIdx.x : 0;
   const int WPC = (int)(blockDim.x >> 5), wic = tid >> 5;
   int ncand = 0;
@@ -263,10 +264,10 @@ __global__ void __launch_bounds__(COOP ? RNA_FAST_NT_COOP : RNA_FAST_NT_BATCH, C
           const real* rowM1 = mM1 + (size_t)i * L;
           const real* colR = mRT + (size_t)j * L;
           const real* colX = mXT + (size_t)j * L;
-          for (int k0 = i + 1 + lane + 128 * part; k0 <= j - 1; k0 += 128 * S) {   // four split points per lane in flight
-            real r[4], ee[4], mm[4], xx[4];
+          for (int k0 = i + 1 + lane + 32 * UR * part; k0 <= j - 1; k0 += 32 * UR * S) {   // UR split points per lane in flight
+            real r[UR], ee[UR], mm[UR], xx[UR];
 #pragma unroll
-            for (int u = 0; u < 4; u++) {
+            for (int u = 0; u < UR; u++) {
               const int k = k0 + 32 * u;
               r[u] = NEG; ee[u] = NEG; mm[u] = NEG; xx[u] = NEG;
               if (k <= j - 1) {
@@ -275,7 +276,7 @@ __global__ void __launch_bounds__(COOP ? RNA_FAST_NT_COOP : RNA_FAST_NT_BATCH, C
               }
             }
 #pragma unroll
-            for (int u = 0; u < 4; u++) {
+            for (int u = 0; u < UR; u++) {
               e.add(r[u] + ee[u]);
               if constexpr (CONTRA) m.add(mm[u] + xx[u]);
               else m.add(mm[u] + (r[u] + (real)cnb));
@@ -373,16 +374,16 @@ __global__ void __launch_bounds__(COOP ? RNA_FAST_NT_COOP : RNA_FAST_NT_BATCH, C
         if (active) {   // probs_multibranch: reduction over k > j
           const real* rowXQ = mXQ + (size_t)i * L;
           const real* rowM1 = mM1 + (size_t)(j + 1) * L;
-          for (int k0 = j + 2 + lane + 128 * part; k0 < L; k0 += 128 * S) {
-            real xq4[4], m14[4];
+          for (int k0 = j + 2 + lane + 32 * UR * part; k0 < L; k0 += 32 * UR * S) {
+            real xq4[UR], m14[UR];
 #pragma unroll
-            for (int u = 0; u < 4; u++) {
+            for (int u = 0; u < UR; u++) {
               const int k = k0 + 32 * u;
               xq4[u] = NEG; m14[u] = NEG;
               if (k < L) { xq4[u] = ld(&rowXQ[k]); m14[u] = ld(&rowM1[k - 1]); }
             }
 #pragma unroll
-            for (int u = 0; u < 4; u++) pmacc.add(xq4[u] + m14[u]);
+            for (int u = 0; u < UR; u++) pmacc.add(xq4[u] + m14[u]);
           }
         }
         if (clos) {
@@ -415,16 +416,16 @@ __global__ void __launch_bounds__(COOP ? RNA_FAST_NT_COOP : RNA_FAST_NT_BATCH, C
             const real* colPM2 = mPM2T + (size_t)j * L;
             const real* colPM = mPMT + (size_t)j * L;
             const real* colM1 = mM1T + (size_t)(i - 1) * L;
-            for (int k0 = lane + 128 * part; k0 <= i - 2; k0 += 128 * S) {
-              real x14[4], p24[4], p4[4];
+            for (int k0 = lane + 32 * UR * part; k0 <= i - 2; k0 += 32 * UR * S) {
+              real x14[UR], p24[UR], p4[UR];
 #pragma unroll
-              for (int u = 0; u < 4; u++) {
+              for (int u = 0; u < UR; u++) {
                 const int k = k0 + 32 * u;
                 x14[u] = NEG; p24[u] = NEG; p4[u] = NEG;
                 if (k <= i - 2) { x14[u] = ld(&colM1[k + 1]); p24[u] = ld(&colPM2[k]); p4[u] = ld(&colPM[k]); }
               }
 #pragma unroll
-              for (int u = 0; u < 4; u++) { t1acc.add(p24[u] + x14[u]); t3acc.add(p4[u] + x14[u]); }
+              for (int u = 0; u < UR; u++) { t1acc.add(p24[u] + x14[u]); t3acc.add(p4[u] + x14[u]); }
             }
           }
         }

@@ -942,7 +942,7 @@ static int launch_fast(rna_handle* h, const RnaFoldBatchDev* b, cudaStream_t st,
 
 // FAST_F64 runs everything on fast_fold_kernel (f64 state: the accuracy mode).  FAST_F32 is the speed mode: the few
 // long sequences that would otherwise each wait for one CTA go one at a time to fast_fold_kernel's cooperative grid
-// (warp-shuffle reductions: 29 / 77 / 307 ms at 1 / 2 / 4 k nt), everything else to the FAST build of the batch kernel
+// (warp-shuffle reductions: 29 / 76 / 284 ms at 1 / 2 / 4 k nt), everything else to the FAST build of the batch kernel
 // (fold_fastnum.cu), which is several times faster than fast_fold_kernel's one-CTA-per-sequence launch on batches.
 static int launch_fast_mode(rna_handle* h, const RnaFoldBatchDev* b, cudaStream_t st) {
   const bool f64 = h->numeric_mode == RNA_NUMERIC_FAST_F64;
