@@ -52,6 +52,8 @@ struct FoldArgs {
   float* sums;               // optional FoldSums / FoldScores planes (rna_fold_sums_batch), else null
   const unsigned long long* sums_offsets;
   int inside_only;           // stop after the inside pass
+  unsigned ring_bytes;          // HBM-resident mode: bytes of the dense chains' shared-memory operand ring (0 = none)
+  int nXw_out;                  // warps of role X in the outside pass (0 = as in the inside pass); the rest fold role Y
 };
 
 template <int MODE>

@@ -92,7 +92,8 @@ __host__ __device__ inline Roles fold2_roles(int Lcap, bool contra, int max_warp
 // lanes are split in proportion to that work instead of "a lane per closable cell for X".
 __host__ __device__ inline Roles fold2_roles_global(int Lcap, bool contra, int max_warps) {
   const double L = Lcap;
-  const double wx = 28000.0 * L * L, wz = 50.0 * L * L * L, wy = contra ? 22.0 * L * L * L : 0.0;   // (fitted: 7/3/6 warps at 500 nt)
+  // (fitted to the role timers with the shared-memory operand rings: 6/4/6 warps at 460 nt)
+  const double wx = 21500.0 * L * L, wz = 50.0 * L * L * L, wy = contra ? 30.0 * L * L * L : 0.0;
   const double tot = wx + wy + wz;
   Roles r;
   r.nY = contra ? (int)(max_warps * wy / tot + 0.5) : 0;
@@ -102,6 +103,22 @@ __host__ __device__ inline Roles fold2_roles_global(int Lcap, bool contra, int m
   r.nZ = max_warps - r.nX - r.nY;
   if (r.nZ < 2) { r.nZ = 2; r.nX = max_warps - r.nY - r.nZ; }
   return r;
+}
+// X warps of the OUTSIDE pass in the HBM-resident mode.  Phase 1 runs X (exterior + enclosing two-loops, scored on the
+// fly: ~L^2) beside Y (probs_multibranch(2): ~L^3) on the other warps; phase 2 is X alone (the multiloop chain: ~L^3).
+__host__ __device__ inline int fold2_xwarps_outside_global(int Lcap, int max_warps) {
+  const double L = Lcap;
+  // (X's two-loop chains stop scaling once every closable cell of a step has a lane, so the fit is deliberately biased
+  // towards Y: 8 of 16 warps at 460 nt, 9 at 300 nt measured best; 9-12 X warps at 460 nt are 1-5 % slower)
+  const double wx = 3.08e-3 * L * L, wy = 7.49e-6 * L * L * L, wm = 3.88e-6 * L * L * L;
+  int best = 2;
+  double bt = 1e300;
+  for (int nx = 2; nx <= max_warps - 2; nx++) {
+    const double p1 = wx / nx > wy / (max_warps - nx) ? wx / nx : wy / (max_warps - nx);
+    const double t = p1 + wm / nx;
+    if (t < bt) { bt = t; best = nx; }
+  }
+  return best;
 }
 
 // SUMS: the build that also exports the FoldSums / FoldScores planes (rna_fold_sums_batch) and can stop after the inside
@@ -140,6 +157,9 @@ __global__ void __launch_bounds__(512, 2) fold_kernel2(const FoldArgs a) {
   const float NEG = RNA_NEG_INF;
   const int warp = tid >> 5;
   const int nXl = a.nXw * 32, nYl = a.nYw * 32, nZl = a.nZw * 32;
+  // HBM-resident mode: shared memory is free there, the dense chains keep their operands in flight in it (fold_phases.cuh)
+  float4* const zring = (MODE == MODE_GLOBAL && a.ring_bytes) ? reinterpret_cast<float4*>(sregion) : nullptr;
+  float4* const yring = zring ? zring + RNA_Z_RING * nZl : nullptr;   // (inside pass: Y and Z fold side by side)
   __syncthreads();
 
   for (;;) {
@@ -262,11 +282,11 @@ __global__ void __launch_bounds__(512, 2) fold_kernel2(const FoldArgs a) {
         inside_X<CONTRA>(v, T, lut, P, st, tid, nXl);
       } else if (!helper) {
         const bool isY = warp < a.nXw + a.nYw;
-        if (isY) { if constexpr (CONTRA) { if (t - 1 >= d_in0 && t - 1 < L) inside_Y_contra<(MODE == MODE_SMEM ? RNA_Y_CH : 4)>(v, T, lut, t - 1, tid - nXl, nYl); } }
-        else if (t - 2 >= d_in0 && t - 2 < L) inside_Z<CONTRA, (MODE == MODE_SMEM ? RNA_Z_PF : 4), SV, SUMS>(v, T, lut, t - 2, tid - nXl - nYl, nZl);
+        if (isY) { if constexpr (CONTRA) { if (t - 1 >= d_in0 && t - 1 < L) inside_Y_contra<(MODE == MODE_SMEM ? RNA_Y_CH : 4)>(v, T, lut, t - 1, tid - nXl, nYl, 0, yring); } }
+        else if (t - 2 >= d_in0 && t - 2 < L) inside_Z<CONTRA, (MODE == MODE_SMEM ? RNA_Z_PF : 4), SV, SUMS>(v, T, lut, t - 2, tid - nXl - nYl, nZl, zring);
         asm volatile("bar.sync 1, %0;" ::"r"(nYZl) : "memory");
-        if (isY) { if constexpr (CONTRA) { if (t < L) inside_Y_contra<(MODE == MODE_SMEM ? RNA_Y_CH : 4)>(v, T, lut, t, tid - nXl, nYl); } }
-        else if (t - 1 >= d_in0 && t - 1 < L) inside_Z<CONTRA, (MODE == MODE_SMEM ? RNA_Z_PF : 4), SV, SUMS>(v, T, lut, t - 1, tid - nXl - nYl, nZl);
+        if (isY) { if constexpr (CONTRA) { if (t < L) inside_Y_contra<(MODE == MODE_SMEM ? RNA_Y_CH : 4)>(v, T, lut, t, tid - nXl, nYl, 0, yring); } }
+        else if (t - 1 >= d_in0 && t - 1 < L) inside_Z<CONTRA, (MODE == MODE_SMEM ? RNA_Z_PF : 4), SV, SUMS>(v, T, lut, t - 1, tid - nXl - nYl, nZl, zring);
       }
       if (dbg_on && (tid & 31) == 0 && !helper) a.dbg[(size_t)t * 16 + warp] = clock64() - c0;
       __syncthreads();
@@ -289,20 +309,23 @@ __global__ void __launch_bounds__(512, 2) fold_kernel2(const FoldArgs a) {
     const int d_out0 = v.dout0;
     // pair steps.  phase 1: X = exterior + two-loop parts of log P(d), (d-1)  |  Y = probs_multibranch(2) of d+1, d
     //             phase 2: X = multiloop parts
+    // (the outside pass may split the role warps differently: its X role also scores / streams the enclosing two-loops
+    // AND folds the multiloop chain, its Y role takes all the other role warps)
+    const int nXo = a.nXw_out > 0 ? a.nXw_out : a.nXw, nXol = nXo * 32, nYZol = nXl + nYZl - nXol;
     for (int st = 0; L - 1 - 2 * st >= d_out0; st++) {
       const int d = L - 1 - 2 * st;
       const long long c0 = dbg_on ? clock64() : 0;
-      if (warp < a.nXw) {
-        outside_X<CONTRA>(v, T, lut, P, Z, st, tid, nXl);
+      if (warp < nXo) {
+        outside_X<CONTRA>(v, T, lut, P, Z, st, tid, nXol);
       } else if (!helper) {
-        if (d + 1 < L) outside_Y<CONTRA, (MODE == MODE_SMEM ? RNA_Y_CH : 4)>(v, T, lut, d + 1, tid - nXl, nYZl);
-        outside_Y<CONTRA, (MODE == MODE_SMEM ? RNA_Y_CH : 4)>(v, T, lut, d, tid - nXl, nYZl);
+        if (d + 1 < L) outside_Y<CONTRA, (MODE == MODE_SMEM ? RNA_Y_CH : 4)>(v, T, lut, d + 1, tid - nXol, nYZol, zring);
+        outside_Y<CONTRA, (MODE == MODE_SMEM ? RNA_Y_CH : 4)>(v, T, lut, d, tid - nXol, nYZol, zring);
       }
       if (dbg_on && (tid & 31) == 0 && !helper) a.dbg[(size_t)(1024 + d) * 16 + warp] = clock64() - c0;
       __syncthreads();
       const long long c1 = dbg_on ? clock64() : 0;
-      if (warp < a.nXw) outside_X_ml<CONTRA, (MODE == MODE_SMEM ? RNA_ML_PF : 3)>(v, T, lut, st, tid, nXl);
-      if (dbg_on && (tid & 31) == 0 && warp < a.nXw) a.dbg[(size_t)(1024 + d) * 16 + 8 + warp] = clock64() - c1;
+      if (warp < nXo) outside_X_ml<CONTRA, (MODE == MODE_SMEM ? RNA_ML_PF : 3)>(v, T, lut, st, tid, nXol, zring);
+      if (dbg_on && (tid & 31) == 0 && warp < nXo) a.dbg[(size_t)(1024 + d) * 16 + 8 + warp] = clock64() - c1;
       __syncthreads();
     }
 

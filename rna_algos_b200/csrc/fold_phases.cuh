@@ -747,6 +747,9 @@ RNA_DEV void stream_fill_task(const SV& v, const typename Model2<CONTRA>::View& 
 #ifndef RNA_STREAM_PF_DIST
 #define RNA_STREAM_PF_DIST 32
 #endif
+#ifndef RNA_Z_RING
+#define RNA_Z_RING 8      // split points in flight per lane of the dense chains in the HBM-resident mode (power of two)
+#endif
 template <bool INSIDE, class SV>
 RNA_DEV float stream_chain(const SV& v, const uint2* __restrict__ st, uint32_t wd, uint32_t n, const float4* lut,
                            float Cij, float sum) {
@@ -944,7 +947,7 @@ struct RowBits {
 // =========================================================================================================
 template <int CH, class SV>
 RNA_DEV void inside_Y_contra(const SV& v, const ContraView2& T, const float4* lut, int d, int lane, int nl,
-                                int kskip = 0) {   // kskip: leave the last kskip values of k (j-1, ...) to a later phase
+                                int kskip = 0, float4* ring = nullptr) {   // kskip: leave the last kskip values of k (j-1, ...) to a later phase
   const int L = v.L;
   const uint8_t* s = v.s;
   const float NEG = RNA_NEG_INF;
@@ -953,6 +956,41 @@ RNA_DEV void inside_Y_contra(const SV& v, const ContraView2& T, const float4* lu
   for (int i = lane; i < ncell; i += nl) {
     const int j = i + d;
     ChainSum r = chain_begin(NEG), rm = chain_begin(NEG);
+#ifdef __CUDACC__
+    if (ring) {
+    // HBM-resident mode: the sums_close gathers of RNA_Z_RING terms are in flight in the lane's shared-memory ring
+    // ({value, k}: the bit-matrix iterator runs that many terms ahead of the folds)
+    constexpr int D = RNA_Z_RING;
+    float4* my = ring + lane;
+    RowBits it(v.mask + i * v.W2, i + 1, j - 1 - kskip);
+    auto issue = [&](int slot) -> bool {
+      const int k = it.next();
+      if (k < 0) return false;
+      float* dst = reinterpret_cast<float*>(my + slot * nl);
+      RNA_CP_ASYNC4(dst, &v.C[doff(k - i, L) + i]);
+      reinterpret_cast<int*>(dst)[1] = k;
+      return true;
+    };
+    int pending = 0;
+#pragma unroll 1
+    for (int sl = 0; sl < D; sl++) { if (issue(sl)) pending++; RNA_CP_COMMIT(); }
+#pragma unroll 1
+    for (int n = 0; pending > 0; n++) {
+      RNA_CP_WAIT(RNA_Z_RING - 1);
+      const int slot = n & (D - 1);
+      const float4 o = my[slot * nl];
+      pending--;
+      if (issue(slot)) pending++;
+      RNA_CP_COMMIT();
+      const int k = __float_as_int(o.y);
+      const float av = __fadd_rn(o.x, v2_acc<true>(T, s, L, i, k));
+      const float nn = (float)(j - k);
+      chain_add(r, __fadd_rn(__fadd_rn(av, dev->ext_bp), __fmul_rn(dev->ext_unpair, nn)), lut);
+      chain_add(rm, __fadd_rn(__fadd_rn(av, dev->mb_bp), __fmul_rn(dev->mb_unpair, nn)), lut);
+    }
+    RNA_CP_WAIT(0);
+    } else
+#endif
     if constexpr (CH <= 1) {
     const uint32_t* row = v.mask + i * v.W2;
     for (int p = i + 1; p <= j - 1 - kskip; p += 32) {
@@ -1008,7 +1046,7 @@ RNA_DEV void inside_Y_contra(const SV& v, const ContraView2& T, const float4* lu
 // =========================================================================================================
 template <bool CONTRA, int PF, class SV, bool SUMSX = false>
 RNA_DEV void inside_Z(const SV& v, const typename Model2<CONTRA>::View& T, const float4* lut, int d,
-                      int lane, int nl) {
+                      int lane, int nl, float4* ring = nullptr) {
   const int L = v.L;
   const uint8_t* s = v.s;
   const float NEG = RNA_NEG_INF;
@@ -1039,6 +1077,43 @@ RNA_DEV void inside_Z(const SV& v, const typename Model2<CONTRA>::View& T, const
       sM1 = chain_begin(__fadd_rn(Rij, dev->coeff_num_branches));
     }
     chain_add(sE, __fadd_rn(Rij, 0.f), lut);   // k = i: E[i][i-1] = 0 (lower triangle / literal 0)
+#ifdef __CUDACC__
+    if (ring) {
+    // HBM-resident mode: the operands of RNA_Z_RING split points are in flight per lane as 4-byte asynchronous copies
+    // into a shared-memory ring of the lane's own (slot-major: conflict-free float4 rows) — DRAM / L2 latency is a few
+    // thousand cycles under load there, far more than four split points of folds, and no register is held meanwhile
+    constexpr int D = RNA_Z_RING;
+    float4* my = ring + lane;
+    auto issue = [&](int m, int slot) {
+      float* dst = reinterpret_cast<float*>(my + slot * nl);
+      RNA_CP_ASYNC4(dst + 0, &v.R[doff(d - m, L) + i + m]);
+      RNA_CP_ASYNC4(dst + 1, &v.E[doff(m - 1, L) + i]);
+      RNA_CP_ASYNC4(dst + 2, &v.M1[doff(m - 1, L) + i]);
+      if (CONTRA) RNA_CP_ASYNC4(dst + 3, &v.X[doff(d - m, L) + i + m]);
+    };
+#pragma unroll 1
+    for (int sl = 0; sl < D; sl++) { if (1 + sl < d) issue(1 + sl, sl); RNA_CP_COMMIT(); }
+#pragma unroll 1
+    for (int m = 1; m < d; m++) {
+      RNA_CP_WAIT(RNA_Z_RING - 1);
+      const int slot = (m - 1) & (D - 1);
+      const float4 o = my[slot * nl];
+      if (m + D < d) issue(m + D, slot);
+      RNA_CP_COMMIT();
+      const float r = o.x, e = o.y, m1 = o.z, rm = o.w;
+      chain_add(sE, __fadd_rn(r, e), lut);
+      if constexpr (CONTRA) {
+        chain_add(sM1, __fadd_rn(rm, __fmul_rn(dev->mb_unpair, (float)m)), lut);
+        chain_add(sM, __fadd_rn(m1, rm), lut);
+      } else {
+        const float xx = __fadd_rn(r, dev->coeff_num_branches);
+        chain_add(sM1, xx, lut);
+        chain_add(sM, __fadd_rn(m1, xx), lut);
+      }
+    }
+    RNA_CP_WAIT(0);
+    } else
+#endif
     if constexpr (PF <= 2) {
     // operands two split points ahead are in flight while the three folds of the current one execute
     // (R, Rm, E, M1 may live in HBM/L2: their addresses do not depend on the running sums)
@@ -1392,7 +1467,7 @@ RNA_DEV void export_fold_sums(const SV& v, const typename Model2<CONTRA>::View& 
 // =========================================================================================================
 template <bool CONTRA, int CH, class SV>
 RNA_DEV void outside_Y(const SV& v, const typename Model2<CONTRA>::View& T, const float4* lut, int d,
-                       int lane, int nl) {
+                       int lane, int nl, float4* ring = nullptr) {
   const int L = v.L;
   const uint8_t* s = v.s;
   const float NEG = RNA_NEG_INF;
@@ -1400,6 +1475,44 @@ RNA_DEV void outside_Y(const SV& v, const typename Model2<CONTRA>::View& T, cons
   for (int i = lane; i < ncell; i += nl) {
     const int j = i + d;
     ChainSum pm = chain_begin(NEG), pm2 = chain_begin(NEG);
+#ifdef __CUDACC__
+    if (ring) {
+    // HBM-resident mode: {sums_close, log P, sums_1ormore} of RNA_Z_RING terms in flight in the lane's ring, k alongside
+    constexpr int D = RNA_Z_RING;
+    float4* my = ring + lane;
+    RowBits it(v.mask + i * v.W2, j + 1, L - 1);
+    auto issue = [&](int slot) -> bool {
+      const int k = it.next();
+      if (k < 0) return false;
+      float* dst = reinterpret_cast<float*>(my + slot * nl);
+      const int q = doff(k - i, L) + i;
+      RNA_CP_ASYNC4(dst + 0, &v.C[q]);
+      RNA_CP_ASYNC4(dst + 1, &v.Pm[q]);
+      if (k - j >= 2) RNA_CP_ASYNC4(dst + 2, &v.M1[doff(k - j - 2, L) + j + 1]);
+      reinterpret_cast<int*>(dst)[3] = k;
+      return true;
+    };
+    int pending = 0;
+#pragma unroll 1
+    for (int sl = 0; sl < D; sl++) { if (issue(sl)) pending++; RNA_CP_COMMIT(); }
+#pragma unroll 1
+    for (int n = 0; pending > 0; n++) {
+      RNA_CP_WAIT(RNA_Z_RING - 1);
+      const int slot = n & (D - 1);
+      const float4 o = my[slot * nl];
+      pending--;
+      if (issue(slot)) pending++;
+      RNA_CP_COMMIT();
+      const int k = __float_as_int(o.w), m = k - j;
+      const float m1 = (m >= 2) ? o.z : NEG;
+      const float x = __fsub_rn(__fadd_rn(o.y, v2_mbclose<CONTRA>(T, s, L, i, k)), o.x);
+      chain_add(pm, __fadd_rn(x, m1), lut);
+      if constexpr (CONTRA) chain_add(pm2, __fadd_rn(x, __fmul_rn(T.g->mb_unpair, (float)(m - 1))), lut);
+      else chain_add(pm2, x, lut);
+    }
+    RNA_CP_WAIT(0);
+    } else
+#endif
     if constexpr (CH <= 1) {
     const uint32_t* row = v.mask + i * v.W2;
     // closable (i,k), k > j ascending; the operands of the next term are fetched before the two folds of the
@@ -1508,7 +1621,7 @@ RNA_DEV float outside_cell_partial(const SV& v, const typename Model2<CONTRA>::V
 // enclosing multiloops, k ascending 0..i-1 (needs probs_multibranch(2) of diagonals > j - i)
 template <bool CONTRA, int PF, class SV>
 RNA_DEV float outside_cell_ml(const SV& v, const typename Model2<CONTRA>::View& T, const float4* lut, int i, int j,
-                              float Cij, float sm0) {
+                              float Cij, float sm0, float4* ring = nullptr, int rstride = 0) {
   const int L = v.L;
   const float NEG = RNA_NEG_INF;
   const typename Model2<CONTRA>::Dev* dev = T.g;
@@ -1516,6 +1629,35 @@ RNA_DEV float outside_cell_ml(const SV& v, const typename Model2<CONTRA>::View& 
   float sa;
   if constexpr (CONTRA) sa = __fadd_rn(Aij, dev->mb_bp); else sa = __fadd_rn(Aij, dev->coeff_num_branches);
   ChainSum sm = chain_begin(sm0);
+#ifdef __CUDACC__
+  if (ring) {
+    // HBM-resident mode: operands of RNA_Z_RING steps in flight in the lane's shared-memory ring (see inside_Z)
+    constexpr int D = RNA_Z_RING;
+    auto issue = [&](int kk, int slot) {
+      float* dst = reinterpret_cast<float*>(ring + slot * rstride);
+      const int m = i - 1 - kk, q = doff(j - kk, L) + kk;
+      if (m >= 1) RNA_CP_ASYNC4(dst + 0, &v.M1[doff(m - 1, L) + kk + 1]);
+      RNA_CP_ASYNC4(dst + 1, &v.X[q]);
+      RNA_CP_ASYNC4(dst + 2, &v.R[q]);
+    };
+#pragma unroll 1
+    for (int sl = 0; sl < D; sl++) { if (sl < i) issue(sl, sl); RNA_CP_COMMIT(); }
+#pragma unroll 1
+    for (int kk = 0; kk < i; kk++) {
+      RNA_CP_WAIT(RNA_Z_RING - 1);
+      const int slot = kk & (D - 1), m = i - 1 - kk;
+      const float4 o = ring[slot * rstride];
+      if (kk + D < i) issue(kk + D, slot);
+      RNA_CP_COMMIT();
+      const float x1 = (m >= 1) ? o.x : NEG, p2 = o.y, y = o.z;
+      chain_add(sm, __fadd_rn(__fadd_rn(sa, p2), x1), lut);
+      if constexpr (CONTRA) chain_add(sm, __fadd_rn(__fadd_rn(sa, y), __fmul_rn(dev->mb_unpair, (float)m)), lut);
+      else chain_add(sm, __fadd_rn(sa, y), lut);
+      chain_add(sm, __fadd_rn(__fadd_rn(sa, x1), y), lut);
+    }
+    RNA_CP_WAIT(0);
+  } else
+#endif
   if constexpr (PF == 2) {
     // operands TWO steps ahead are in flight (explicit registers, no ring): probs_multibranch(2) live in HBM/L2 in
     // the shared-memory mode and one step of three dependent folds is shorter than that latency
@@ -1618,7 +1760,7 @@ RNA_DEV void outside_X(const SV& v, const typename Model2<CONTRA>::View& T, cons
 // X, phase 2: enclosing multiloops (needs probs_multibranch(2) of diagonals >= d resp. d+1)
 template <bool CONTRA, int PF, class SV>
 RNA_DEV void outside_X_ml(const SV& v, const typename Model2<CONTRA>::View& T, const float4* lut, int st, int lane,
-                          int nl) {
+                          int nl, float4* ring = nullptr) {
   const int L = v.L;
   const StepCells sc = step_cells<false>(v, st);
   for (int x = lane; x < sc.cA + sc.cB; x += nl) {
@@ -1627,7 +1769,7 @@ RNA_DEV void outside_X_ml(const SV& v, const typename Model2<CONTRA>::View& T, c
     const int od = doff(dd, L), i = v.plist[od + r];
     const float Cij = v.C[od + i];
     if (!(Cij > RNA_NEG_INF)) continue;
-    v.Pm[od + i] = outside_cell_ml<CONTRA, PF>(v, T, lut, i, i + dd, Cij, v.Pm[od + i]);
+    v.Pm[od + i] = outside_cell_ml<CONTRA, PF>(v, T, lut, i, i + dd, Cij, v.Pm[od + i], ring ? ring + lane : nullptr, nl);
   }
 }
 // X of a ONE-diagonal step (grid-wide wavefront): the whole fold of log P(i,j); needs log P, probs_multibranch(2)

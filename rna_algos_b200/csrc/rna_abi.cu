@@ -497,7 +497,8 @@ static void fold_dbg_report(int mode, int Lcap, const FoldArgs& a, long long* d_
         for (int t = 0; t < 1000; t++) {
           long long m[3] = {0, 0, 0};
           for (int wv = 0; wv < 16; wv++) {
-            const int r = wv < a.nXw ? 0 : wv < a.nXw + a.nYw ? 1 : 2;
+            const int nxo = (pass == 1 && a.nXw_out > 0) ? a.nXw_out : a.nXw;   // (the outside pass may split differently: X | Y)
+            const int r = pass == 1 ? (wv < nxo ? 0 : 1) : (wv < a.nXw ? 0 : wv < a.nXw + a.nYw ? 1 : 2);
             m[r] = std::max(m[r], hd[(size_t)(pass * 1024 + t) * 16 + wv]);
           }
           const long long mx = std::max(m[0], std::max(m[1], m[2]));
@@ -787,6 +788,11 @@ static int launch_fold_model(rna_handle* h, const RnaFoldBatchDev* b, cudaStream
         if (sscanf(dev_env("RNA_FOLD_ROLES"), "%d,%d,%d", &x, &y, &z) == 3 && x > 0 && z > 0 && x + y + z <= 16 && (y > 0) == CONTRA) { ro.nX = x; ro.nY = y; ro.nZ = z; }
       }
       a.nXw = ro.nX; a.nYw = ro.nY; a.nZw = ro.nZ;
+      a.nXw_out = 0;
+      if (bk.mode != MODE_SMEM) {
+        a.nXw_out = fold2_xwarps_outside_global(bk.Lcap, ro.nX + ro.nY + ro.nZ);
+        if (dev_env("RNA_FOLD_XOUT")) a.nXw_out = std::max(1, std::min(atoi(dev_env("RNA_FOLD_XOUT")), ro.nX + ro.nY + ro.nZ - 1));
+      }
       const int nt = (bk.mode == MODE_SMEM) ? nt_of[k] : 32 * (ro.nX + ro.nY + ro.nZ);
       a.stream_ws = nullptr;
       if (bk.mode == MODE_SMEM) {
@@ -801,7 +807,9 @@ static int launch_fold_model(rna_handle* h, const RnaFoldBatchDev* b, cudaStream
         else if (want_sums) fold_kernel2<CONTRA, MODE_SMEM, true><<<grid_of[k], nt, smem, st>>>(a);
         else fold_kernel2<CONTRA, MODE_SMEM><<<grid_of[k], nt, smem, st>>>(a);
       } else {
-        const size_t smem = fold2_fixed_bytes<CONTRA>(bk.Lcap);
+        static const bool no_ring = dev_env("RNA_NO_ZRING") != nullptr;
+        a.ring_bytes = no_ring ? 0u : (unsigned)((size_t)std::max(std::max(ro.nX, a.nXw_out), std::max(ro.nY + ro.nZ, ro.nX + ro.nY + ro.nZ - a.nXw_out)) * 32 * RNA_Z_RING * sizeof(float4));   // a ring column per lane of the widest role
+        const size_t smem = fold2_fixed_bytes<CONTRA>(bk.Lcap) + a.ring_bytes;
         if (fastnum) {
           void* params[] = {(void*)&a};
           TRY(kern_prepare(h, rna_fastnum_fold_kernel(CONTRA, 1), nt, smem, nullptr));
