@@ -157,9 +157,6 @@ __global__ void __launch_bounds__(512, 2) fold_kernel2(const FoldArgs a) {
   const float NEG = RNA_NEG_INF;
   const int warp = tid >> 5;
   const int nXl = a.nXw * 32, nYl = a.nYw * 32, nZl = a.nZw * 32;
-  // HBM-resident mode: shared memory is free there, the dense chains keep their operands in flight in it (fold_phases.cuh)
-  float4* const zring = (MODE == MODE_GLOBAL && a.ring_bytes) ? reinterpret_cast<float4*>(sregion) : nullptr;
-  float4* const yring = zring ? zring + RNA_Z_RING * nZl : nullptr;   // (inside pass: Y and Z fold side by side)
   __syncthreads();
 
   for (;;) {
@@ -282,11 +279,30 @@ __global__ void __launch_bounds__(512, 2) fold_kernel2(const FoldArgs a) {
         inside_X<CONTRA>(v, T, lut, P, st, tid, nXl);
       } else if (!helper) {
         const bool isY = warp < a.nXw + a.nYw;
-        if (isY) { if constexpr (CONTRA) { if (t - 1 >= d_in0 && t - 1 < L) inside_Y_contra<(MODE == MODE_SMEM ? RNA_Y_CH : 4)>(v, T, lut, t - 1, tid - nXl, nYl, 0, yring); } }
-        else if (t - 2 >= d_in0 && t - 2 < L) inside_Z<CONTRA, (MODE == MODE_SMEM ? RNA_Z_PF : 4), SV, SUMS>(v, T, lut, t - 2, tid - nXl - nYl, nZl, zring);
+        if constexpr (MODE == MODE_GLOBAL) {
+          // HBM-resident mode: shared memory is free, the chains keep their operands in flight in it (ring variants of
+          // fold_phases.cuh; inside pass: the Z lanes' ring columns first, then the Y lanes')
+          float4* const zring = a.ring_bytes ? reinterpret_cast<float4*>(sregion) : nullptr;
+          float4* const yring = zring ? zring + RNA_Z_RING * nZl : nullptr;
+          for (int half = 0; half < 2; half++) {
+            const int dy = t - 1 + half, dz = t - 2 + half;
+            if (isY) {
+              if constexpr (CONTRA) {
+                if (dy >= d_in0 && dy < L) { if (yring) inside_Y_contra_ring(v, T, lut, dy, tid - nXl, nYl, 0, yring); else inside_Y_contra<4>(v, T, lut, dy, tid - nXl, nYl); }
+              }
+            } else if (dz >= d_in0 && dz < L) {
+              if (zring) inside_Z_ring<CONTRA, SV, SUMS>(v, T, lut, dz, tid - nXl - nYl, nZl, zring);
+              else inside_Z<CONTRA, 4, SV, SUMS>(v, T, lut, dz, tid - nXl - nYl, nZl);
+            }
+            if (half == 0) asm volatile("bar.sync 1, %0;" ::"r"(nYZl) : "memory");
+          }
+        } else {
+        if (isY) { if constexpr (CONTRA) { if (t - 1 >= d_in0 && t - 1 < L) inside_Y_contra<(MODE == MODE_SMEM ? RNA_Y_CH : 4)>(v, T, lut, t - 1, tid - nXl, nYl); } }
+        else if (t - 2 >= d_in0 && t - 2 < L) inside_Z<CONTRA, (MODE == MODE_SMEM ? RNA_Z_PF : 4), SV, SUMS>(v, T, lut, t - 2, tid - nXl - nYl, nZl);
         asm volatile("bar.sync 1, %0;" ::"r"(nYZl) : "memory");
-        if (isY) { if constexpr (CONTRA) { if (t < L) inside_Y_contra<(MODE == MODE_SMEM ? RNA_Y_CH : 4)>(v, T, lut, t, tid - nXl, nYl, 0, yring); } }
-        else if (t - 1 >= d_in0 && t - 1 < L) inside_Z<CONTRA, (MODE == MODE_SMEM ? RNA_Z_PF : 4), SV, SUMS>(v, T, lut, t - 1, tid - nXl - nYl, nZl, zring);
+        if (isY) { if constexpr (CONTRA) { if (t < L) inside_Y_contra<(MODE == MODE_SMEM ? RNA_Y_CH : 4)>(v, T, lut, t, tid - nXl, nYl); } }
+        else if (t - 1 >= d_in0 && t - 1 < L) inside_Z<CONTRA, (MODE == MODE_SMEM ? RNA_Z_PF : 4), SV, SUMS>(v, T, lut, t - 1, tid - nXl - nYl, nZl);
+        }
       }
       if (dbg_on && (tid & 31) == 0 && !helper) a.dbg[(size_t)t * 16 + warp] = clock64() - c0;
       __syncthreads();
@@ -309,24 +325,51 @@ __global__ void __launch_bounds__(512, 2) fold_kernel2(const FoldArgs a) {
     const int d_out0 = v.dout0;
     // pair steps.  phase 1: X = exterior + two-loop parts of log P(d), (d-1)  |  Y = probs_multibranch(2) of d+1, d
     //             phase 2: X = multiloop parts
-    // (the outside pass may split the role warps differently: its X role also scores / streams the enclosing two-loops
-    // AND folds the multiloop chain, its Y role takes all the other role warps)
-    const int nXo = a.nXw_out > 0 ? a.nXw_out : a.nXw, nXol = nXo * 32, nYZol = nXl + nYZl - nXol;
+    if constexpr (MODE == MODE_GLOBAL) {
+      // HBM-resident mode: its own split of the role warps for this pass (X also folds the multiloop chain here, Y takes
+      // all the other role warps) and the ring variants of the chains
+      float4* const zring = a.ring_bytes ? reinterpret_cast<float4*>(sregion) : nullptr;
+      const int nXo = a.nXw_out > 0 ? a.nXw_out : a.nXw, nXol = nXo * 32, nYZol = nXl + nYZl - nXol;
+      for (int st = 0; L - 1 - 2 * st >= d_out0; st++) {
+        const int d = L - 1 - 2 * st;
+        const long long c0 = dbg_on ? clock64() : 0;
+        if (warp < nXo) {
+          outside_X<CONTRA>(v, T, lut, P, Z, st, tid, nXol);
+        } else if (!helper) {
+          for (int dd = d + 1; dd >= d; dd--) {
+            if (dd >= L) continue;
+            if (zring) outside_Y_ring<CONTRA>(v, T, lut, dd, tid - nXol, nYZol, zring);
+            else outside_Y<CONTRA, 4>(v, T, lut, dd, tid - nXol, nYZol);
+          }
+        }
+        if (dbg_on && (tid & 31) == 0 && !helper) a.dbg[(size_t)(1024 + d) * 16 + warp] = clock64() - c0;
+        __syncthreads();
+        const long long c1 = dbg_on ? clock64() : 0;
+        if (warp < nXo) {
+          if (zring) outside_X_ml_ring<CONTRA>(v, T, lut, st, tid, nXol, zring);
+          else outside_X_ml<CONTRA, 3>(v, T, lut, st, tid, nXol);
+        }
+        if (dbg_on && (tid & 31) == 0 && warp < nXo) a.dbg[(size_t)(1024 + d) * 16 + 8 + warp] = clock64() - c1;
+        __syncthreads();
+      }
+    } else {
     for (int st = 0; L - 1 - 2 * st >= d_out0; st++) {
       const int d = L - 1 - 2 * st;
       const long long c0 = dbg_on ? clock64() : 0;
-      if (warp < nXo) {
-        outside_X<CONTRA>(v, T, lut, P, Z, st, tid, nXol);
+      if (warp < a.nXw) {
+        outside_X<CONTRA>(v, T, lut, P, Z, st, tid, nXl);
       } else if (!helper) {
-        if (d + 1 < L) outside_Y<CONTRA, (MODE == MODE_SMEM ? RNA_Y_CH : 4)>(v, T, lut, d + 1, tid - nXol, nYZol, zring);
-        outside_Y<CONTRA, (MODE == MODE_SMEM ? RNA_Y_CH : 4)>(v, T, lut, d, tid - nXol, nYZol, zring);
+        if (d + 1 < L) outside_Y<CONTRA, (MODE == MODE_SMEM ? RNA_Y_CH : 4)>(v, T, lut, d + 1, tid - nXl, nYZl);
+        outside_Y<CONTRA, (MODE == MODE_SMEM ? RNA_Y_CH : 4)>(v, T, lut, d, tid - nXl, nYZl);
       }
       if (dbg_on && (tid & 31) == 0 && !helper) a.dbg[(size_t)(1024 + d) * 16 + warp] = clock64() - c0;
       __syncthreads();
       const long long c1 = dbg_on ? clock64() : 0;
-      if (warp < nXo) outside_X_ml<CONTRA, (MODE == MODE_SMEM ? RNA_ML_PF : 3)>(v, T, lut, st, tid, nXol, zring);
-      if (dbg_on && (tid & 31) == 0 && warp < nXo) a.dbg[(size_t)(1024 + d) * 16 + 8 + warp] = clock64() - c1;
+      if (warp < a.nXw) outside_X_ml<CONTRA, (MODE == MODE_SMEM ? RNA_ML_PF : 3)>(v, T, lut, st, tid, nXl);
+      if (dbg_on && (tid & 31) == 0 && warp < a.nXw) a.dbg[(size_t)(1024 + d) * 16 + 8 + warp] = clock64() - c1;
       __syncthreads();
+    }
+
     }
 
     const long long tpost0 = dbg_on ? clock64() : 0;

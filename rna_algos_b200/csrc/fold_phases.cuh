@@ -747,9 +747,6 @@ RNA_DEV void stream_fill_task(const SV& v, const typename Model2<CONTRA>::View& 
 #ifndef RNA_STREAM_PF_DIST
 #define RNA_STREAM_PF_DIST 32
 #endif
-#ifndef RNA_Z_RING
-#define RNA_Z_RING 8      // split points in flight per lane of the dense chains in the HBM-resident mode (power of two)
-#endif
 template <bool INSIDE, class SV>
 RNA_DEV float stream_chain(const SV& v, const uint2* __restrict__ st, uint32_t wd, uint32_t n, const float4* lut,
                            float Cij, float sum) {
@@ -947,7 +944,7 @@ struct RowBits {
 // =========================================================================================================
 template <int CH, class SV>
 RNA_DEV void inside_Y_contra(const SV& v, const ContraView2& T, const float4* lut, int d, int lane, int nl,
-                                int kskip = 0, float4* ring = nullptr) {   // kskip: leave the last kskip values of k (j-1, ...) to a later phase
+                                int kskip = 0) {   // kskip: leave the last kskip values of k (j-1, ...) to a later phase
   const int L = v.L;
   const uint8_t* s = v.s;
   const float NEG = RNA_NEG_INF;
@@ -956,41 +953,6 @@ RNA_DEV void inside_Y_contra(const SV& v, const ContraView2& T, const float4* lu
   for (int i = lane; i < ncell; i += nl) {
     const int j = i + d;
     ChainSum r = chain_begin(NEG), rm = chain_begin(NEG);
-#ifdef __CUDACC__
-    if (ring) {
-    // HBM-resident mode: the sums_close gathers of RNA_Z_RING terms are in flight in the lane's shared-memory ring
-    // ({value, k}: the bit-matrix iterator runs that many terms ahead of the folds)
-    constexpr int D = RNA_Z_RING;
-    float4* my = ring + lane;
-    RowBits it(v.mask + i * v.W2, i + 1, j - 1 - kskip);
-    auto issue = [&](int slot) -> bool {
-      const int k = it.next();
-      if (k < 0) return false;
-      float* dst = reinterpret_cast<float*>(my + slot * nl);
-      RNA_CP_ASYNC4(dst, &v.C[doff(k - i, L) + i]);
-      reinterpret_cast<int*>(dst)[1] = k;
-      return true;
-    };
-    int pending = 0;
-#pragma unroll 1
-    for (int sl = 0; sl < D; sl++) { if (issue(sl)) pending++; RNA_CP_COMMIT(); }
-#pragma unroll 1
-    for (int n = 0; pending > 0; n++) {
-      RNA_CP_WAIT(RNA_Z_RING - 1);
-      const int slot = n & (D - 1);
-      const float4 o = my[slot * nl];
-      pending--;
-      if (issue(slot)) pending++;
-      RNA_CP_COMMIT();
-      const int k = __float_as_int(o.y);
-      const float av = __fadd_rn(o.x, v2_acc<true>(T, s, L, i, k));
-      const float nn = (float)(j - k);
-      chain_add(r, __fadd_rn(__fadd_rn(av, dev->ext_bp), __fmul_rn(dev->ext_unpair, nn)), lut);
-      chain_add(rm, __fadd_rn(__fadd_rn(av, dev->mb_bp), __fmul_rn(dev->mb_unpair, nn)), lut);
-    }
-    RNA_CP_WAIT(0);
-    } else
-#endif
     if constexpr (CH <= 1) {
     const uint32_t* row = v.mask + i * v.W2;
     for (int p = i + 1; p <= j - 1 - kskip; p += 32) {
@@ -1046,7 +1008,7 @@ RNA_DEV void inside_Y_contra(const SV& v, const ContraView2& T, const float4* lu
 // =========================================================================================================
 template <bool CONTRA, int PF, class SV, bool SUMSX = false>
 RNA_DEV void inside_Z(const SV& v, const typename Model2<CONTRA>::View& T, const float4* lut, int d,
-                      int lane, int nl, float4* ring = nullptr) {
+                      int lane, int nl) {
   const int L = v.L;
   const uint8_t* s = v.s;
   const float NEG = RNA_NEG_INF;
@@ -1077,43 +1039,6 @@ RNA_DEV void inside_Z(const SV& v, const typename Model2<CONTRA>::View& T, const
       sM1 = chain_begin(__fadd_rn(Rij, dev->coeff_num_branches));
     }
     chain_add(sE, __fadd_rn(Rij, 0.f), lut);   // k = i: E[i][i-1] = 0 (lower triangle / literal 0)
-#ifdef __CUDACC__
-    if (ring) {
-    // HBM-resident mode: the operands of RNA_Z_RING split points are in flight per lane as 4-byte asynchronous copies
-    // into a shared-memory ring of the lane's own (slot-major: conflict-free float4 rows) — DRAM / L2 latency is a few
-    // thousand cycles under load there, far more than four split points of folds, and no register is held meanwhile
-    constexpr int D = RNA_Z_RING;
-    float4* my = ring + lane;
-    auto issue = [&](int m, int slot) {
-      float* dst = reinterpret_cast<float*>(my + slot * nl);
-      RNA_CP_ASYNC4(dst + 0, &v.R[doff(d - m, L) + i + m]);
-      RNA_CP_ASYNC4(dst + 1, &v.E[doff(m - 1, L) + i]);
-      RNA_CP_ASYNC4(dst + 2, &v.M1[doff(m - 1, L) + i]);
-      if (CONTRA) RNA_CP_ASYNC4(dst + 3, &v.X[doff(d - m, L) + i + m]);
-    };
-#pragma unroll 1
-    for (int sl = 0; sl < D; sl++) { if (1 + sl < d) issue(1 + sl, sl); RNA_CP_COMMIT(); }
-#pragma unroll 1
-    for (int m = 1; m < d; m++) {
-      RNA_CP_WAIT(RNA_Z_RING - 1);
-      const int slot = (m - 1) & (D - 1);
-      const float4 o = my[slot * nl];
-      if (m + D < d) issue(m + D, slot);
-      RNA_CP_COMMIT();
-      const float r = o.x, e = o.y, m1 = o.z, rm = o.w;
-      chain_add(sE, __fadd_rn(r, e), lut);
-      if constexpr (CONTRA) {
-        chain_add(sM1, __fadd_rn(rm, __fmul_rn(dev->mb_unpair, (float)m)), lut);
-        chain_add(sM, __fadd_rn(m1, rm), lut);
-      } else {
-        const float xx = __fadd_rn(r, dev->coeff_num_branches);
-        chain_add(sM1, xx, lut);
-        chain_add(sM, __fadd_rn(m1, xx), lut);
-      }
-    }
-    RNA_CP_WAIT(0);
-    } else
-#endif
     if constexpr (PF <= 2) {
     // operands two split points ahead are in flight while the three folds of the current one execute
     // (R, Rm, E, M1 may live in HBM/L2: their addresses do not depend on the running sums)
@@ -1467,7 +1392,7 @@ RNA_DEV void export_fold_sums(const SV& v, const typename Model2<CONTRA>::View& 
 // =========================================================================================================
 template <bool CONTRA, int CH, class SV>
 RNA_DEV void outside_Y(const SV& v, const typename Model2<CONTRA>::View& T, const float4* lut, int d,
-                       int lane, int nl, float4* ring = nullptr) {
+                       int lane, int nl) {
   const int L = v.L;
   const uint8_t* s = v.s;
   const float NEG = RNA_NEG_INF;
@@ -1475,44 +1400,6 @@ RNA_DEV void outside_Y(const SV& v, const typename Model2<CONTRA>::View& T, cons
   for (int i = lane; i < ncell; i += nl) {
     const int j = i + d;
     ChainSum pm = chain_begin(NEG), pm2 = chain_begin(NEG);
-#ifdef __CUDACC__
-    if (ring) {
-    // HBM-resident mode: {sums_close, log P, sums_1ormore} of RNA_Z_RING terms in flight in the lane's ring, k alongside
-    constexpr int D = RNA_Z_RING;
-    float4* my = ring + lane;
-    RowBits it(v.mask + i * v.W2, j + 1, L - 1);
-    auto issue = [&](int slot) -> bool {
-      const int k = it.next();
-      if (k < 0) return false;
-      float* dst = reinterpret_cast<float*>(my + slot * nl);
-      const int q = doff(k - i, L) + i;
-      RNA_CP_ASYNC4(dst + 0, &v.C[q]);
-      RNA_CP_ASYNC4(dst + 1, &v.Pm[q]);
-      if (k - j >= 2) RNA_CP_ASYNC4(dst + 2, &v.M1[doff(k - j - 2, L) + j + 1]);
-      reinterpret_cast<int*>(dst)[3] = k;
-      return true;
-    };
-    int pending = 0;
-#pragma unroll 1
-    for (int sl = 0; sl < D; sl++) { if (issue(sl)) pending++; RNA_CP_COMMIT(); }
-#pragma unroll 1
-    for (int n = 0; pending > 0; n++) {
-      RNA_CP_WAIT(RNA_Z_RING - 1);
-      const int slot = n & (D - 1);
-      const float4 o = my[slot * nl];
-      pending--;
-      if (issue(slot)) pending++;
-      RNA_CP_COMMIT();
-      const int k = __float_as_int(o.w), m = k - j;
-      const float m1 = (m >= 2) ? o.z : NEG;
-      const float x = __fsub_rn(__fadd_rn(o.y, v2_mbclose<CONTRA>(T, s, L, i, k)), o.x);
-      chain_add(pm, __fadd_rn(x, m1), lut);
-      if constexpr (CONTRA) chain_add(pm2, __fadd_rn(x, __fmul_rn(T.g->mb_unpair, (float)(m - 1))), lut);
-      else chain_add(pm2, x, lut);
-    }
-    RNA_CP_WAIT(0);
-    } else
-#endif
     if constexpr (CH <= 1) {
     const uint32_t* row = v.mask + i * v.W2;
     // closable (i,k), k > j ascending; the operands of the next term are fetched before the two folds of the
@@ -1621,7 +1508,7 @@ RNA_DEV float outside_cell_partial(const SV& v, const typename Model2<CONTRA>::V
 // enclosing multiloops, k ascending 0..i-1 (needs probs_multibranch(2) of diagonals > j - i)
 template <bool CONTRA, int PF, class SV>
 RNA_DEV float outside_cell_ml(const SV& v, const typename Model2<CONTRA>::View& T, const float4* lut, int i, int j,
-                              float Cij, float sm0, float4* ring = nullptr, int rstride = 0) {
+                              float Cij, float sm0) {
   const int L = v.L;
   const float NEG = RNA_NEG_INF;
   const typename Model2<CONTRA>::Dev* dev = T.g;
@@ -1629,35 +1516,6 @@ RNA_DEV float outside_cell_ml(const SV& v, const typename Model2<CONTRA>::View& 
   float sa;
   if constexpr (CONTRA) sa = __fadd_rn(Aij, dev->mb_bp); else sa = __fadd_rn(Aij, dev->coeff_num_branches);
   ChainSum sm = chain_begin(sm0);
-#ifdef __CUDACC__
-  if (ring) {
-    // HBM-resident mode: operands of RNA_Z_RING steps in flight in the lane's shared-memory ring (see inside_Z)
-    constexpr int D = RNA_Z_RING;
-    auto issue = [&](int kk, int slot) {
-      float* dst = reinterpret_cast<float*>(ring + slot * rstride);
-      const int m = i - 1 - kk, q = doff(j - kk, L) + kk;
-      if (m >= 1) RNA_CP_ASYNC4(dst + 0, &v.M1[doff(m - 1, L) + kk + 1]);
-      RNA_CP_ASYNC4(dst + 1, &v.X[q]);
-      RNA_CP_ASYNC4(dst + 2, &v.R[q]);
-    };
-#pragma unroll 1
-    for (int sl = 0; sl < D; sl++) { if (sl < i) issue(sl, sl); RNA_CP_COMMIT(); }
-#pragma unroll 1
-    for (int kk = 0; kk < i; kk++) {
-      RNA_CP_WAIT(RNA_Z_RING - 1);
-      const int slot = kk & (D - 1), m = i - 1 - kk;
-      const float4 o = ring[slot * rstride];
-      if (kk + D < i) issue(kk + D, slot);
-      RNA_CP_COMMIT();
-      const float x1 = (m >= 1) ? o.x : NEG, p2 = o.y, y = o.z;
-      chain_add(sm, __fadd_rn(__fadd_rn(sa, p2), x1), lut);
-      if constexpr (CONTRA) chain_add(sm, __fadd_rn(__fadd_rn(sa, y), __fmul_rn(dev->mb_unpair, (float)m)), lut);
-      else chain_add(sm, __fadd_rn(sa, y), lut);
-      chain_add(sm, __fadd_rn(__fadd_rn(sa, x1), y), lut);
-    }
-    RNA_CP_WAIT(0);
-  } else
-#endif
   if constexpr (PF == 2) {
     // operands TWO steps ahead are in flight (explicit registers, no ring): probs_multibranch(2) live in HBM/L2 in
     // the shared-memory mode and one step of three dependent folds is shorter than that latency
@@ -1760,7 +1618,7 @@ RNA_DEV void outside_X(const SV& v, const typename Model2<CONTRA>::View& T, cons
 // X, phase 2: enclosing multiloops (needs probs_multibranch(2) of diagonals >= d resp. d+1)
 template <bool CONTRA, int PF, class SV>
 RNA_DEV void outside_X_ml(const SV& v, const typename Model2<CONTRA>::View& T, const float4* lut, int st, int lane,
-                          int nl, float4* ring = nullptr) {
+                          int nl) {
   const int L = v.L;
   const StepCells sc = step_cells<false>(v, st);
   for (int x = lane; x < sc.cA + sc.cB; x += nl) {
@@ -1769,7 +1627,7 @@ RNA_DEV void outside_X_ml(const SV& v, const typename Model2<CONTRA>::View& T, c
     const int od = doff(dd, L), i = v.plist[od + r];
     const float Cij = v.C[od + i];
     if (!(Cij > RNA_NEG_INF)) continue;
-    v.Pm[od + i] = outside_cell_ml<CONTRA, PF>(v, T, lut, i, i + dd, Cij, v.Pm[od + i], ring ? ring + lane : nullptr, nl);
+    v.Pm[od + i] = outside_cell_ml<CONTRA, PF>(v, T, lut, i, i + dd, Cij, v.Pm[od + i]);
   }
 }
 // X of a ONE-diagonal step (grid-wide wavefront): the whole fold of log P(i,j); needs log P, probs_multibranch(2)
@@ -1951,5 +1809,248 @@ RNA_DEV void outside_X_diag_rm(const SV& v, const typename Model2<CONTRA>::View&
     v.Pm[od + i] = outside_cell_ml_rm<CONTRA, PF>(v, T, lut, i, j, Cij, sm);
   }
 }
+
+
+// =========================================================================================================
+// HBM-resident mode (fold_kernel2<.., MODE_GLOBAL>): the same chains with their operands in flight through per-lane
+// cp.async rings in shared memory.  Separate functions on purpose: the shared-memory-mode kernel sits at its
+// 64-register cap and its code generation reacts to anything that touches the functions it instantiates (a dead
+// `if (ring)` branch in them cost it 3 % on the default bench), so that kernel keeps the functions above untouched.
+// =========================================================================================================
+#ifdef __CUDACC__
+#ifndef RNA_Z_RING
+#define RNA_Z_RING 8      // split points / terms in flight per lane (power of two)
+#endif
+template <bool CONTRA, class SV, bool SUMSX = false>
+RNA_DEV void inside_Z_ring(const SV& v, const typename Model2<CONTRA>::View& T, const float4* lut, int d,
+                      int lane, int nl, float4* ring) {
+  const int L = v.L;
+  const uint8_t* s = v.s;
+  const float NEG = RNA_NEG_INF;
+  const int ncell = L - d, od = doff(d, L);
+  const typename Model2<CONTRA>::Dev* dev = T.g;
+  float* Mcur = v.Mroll + (d % 3) * L;
+  for (int i = lane; i < ncell; i += nl) {
+    const int j = i + d;
+    const float c = v.C[od + i];
+    const float accv = (c > NEG) ? __fadd_rn(c, v2_acc<CONTRA>(T, s, L, i, j)) : NEG;
+    float Rij, Rmij = NEG;
+    if constexpr (!CONTRA) {
+      // prefix property of the left-to-right fold: R[i][j] = R[i][j-1] (+) A(i,j)
+      const float prev = (d >= 1) ? v.R[doff(d - 1, L) + i] : NEG;
+      Rij = lse(prev, accv, lut);
+    } else {
+      Rij = lse(v.R[od + i], __fadd_rn(__fadd_rn(accv, dev->ext_bp), __fmul_rn(dev->ext_unpair, 0.f)), lut);
+      Rmij = lse(v.X[od + i], __fadd_rn(__fadd_rn(accv, dev->mb_bp), __fmul_rn(dev->mb_unpair, 0.f)), lut);
+      v.X[od + i] = Rmij;
+    }
+    v.R[od + i] = Rij;
+    ChainSum sE, sM1, sM = chain_begin(NEG);
+    if constexpr (CONTRA) {
+      sE = chain_begin(__fmul_rn(dev->ext_unpair, (float)(d + 1)));
+      sM1 = chain_begin(Rmij);
+    } else {
+      sE = chain_begin(0.f);
+      sM1 = chain_begin(__fadd_rn(Rij, dev->coeff_num_branches));
+    }
+    chain_add(sE, __fadd_rn(Rij, 0.f), lut);   // k = i: E[i][i-1] = 0 (lower triangle / literal 0)
+    {
+    // HBM-resident mode: the operands of RNA_Z_RING split points are in flight per lane as 4-byte asynchronous copies
+    // into a shared-memory ring of the lane's own (slot-major: conflict-free float4 rows) — DRAM / L2 latency is a few
+    // thousand cycles under load there, far more than four split points of folds, and no register is held meanwhile
+    constexpr int D = RNA_Z_RING;
+    float4* my = ring + lane;
+    auto issue = [&](int m, int slot) {
+      float* dst = reinterpret_cast<float*>(my + slot * nl);
+      RNA_CP_ASYNC4(dst + 0, &v.R[doff(d - m, L) + i + m]);
+      RNA_CP_ASYNC4(dst + 1, &v.E[doff(m - 1, L) + i]);
+      RNA_CP_ASYNC4(dst + 2, &v.M1[doff(m - 1, L) + i]);
+      if (CONTRA) RNA_CP_ASYNC4(dst + 3, &v.X[doff(d - m, L) + i + m]);
+    };
+#pragma unroll 1
+    for (int sl = 0; sl < D; sl++) { if (1 + sl < d) issue(1 + sl, sl); RNA_CP_COMMIT(); }
+#pragma unroll 1
+    for (int m = 1; m < d; m++) {
+      RNA_CP_WAIT(RNA_Z_RING - 1);
+      const int slot = (m - 1) & (D - 1);
+      const float4 o = my[slot * nl];
+      if (m + D < d) issue(m + D, slot);
+      RNA_CP_COMMIT();
+      const float r = o.x, e = o.y, m1 = o.z, rm = o.w;
+      chain_add(sE, __fadd_rn(r, e), lut);
+      if constexpr (CONTRA) {
+        chain_add(sM1, __fadd_rn(rm, __fmul_rn(dev->mb_unpair, (float)m)), lut);
+        chain_add(sM, __fadd_rn(m1, rm), lut);
+      } else {
+        const float xx = __fadd_rn(r, dev->coeff_num_branches);
+        chain_add(sM1, xx, lut);
+        chain_add(sM, __fadd_rn(m1, xx), lut);
+      }
+    }
+    RNA_CP_WAIT(0);
+    }
+    v.E[od + i] = chain_end(sE);
+    const float Mij = chain_end(sM);
+    Mcur[i] = Mij;
+    if constexpr (SUMSX) { if (v.Mfull) v.Mfull[sums_index(L, i, j)] = Mij; }
+    v.M1[od + i] = lse(chain_end(sM1), Mij, lut);
+  }
+}
+
+template <class SV>
+RNA_DEV void inside_Y_contra_ring(const SV& v, const ContraView2& T, const float4* lut, int d, int lane, int nl,
+                                int kskip = 0, float4* ring = nullptr) {   // kskip: leave the last kskip values of k (j-1, ...) to a later phase
+  const int L = v.L;
+  const uint8_t* s = v.s;
+  const float NEG = RNA_NEG_INF;
+  const int ncell = L - d, od = doff(d, L);
+  const DevContra* dev = T.g;
+  for (int i = lane; i < ncell; i += nl) {
+    const int j = i + d;
+    ChainSum r = chain_begin(NEG), rm = chain_begin(NEG);
+    {
+    // HBM-resident mode: the sums_close gathers of RNA_Z_RING terms are in flight in the lane's shared-memory ring
+    // ({value, k}: the bit-matrix iterator runs that many terms ahead of the folds)
+    constexpr int D = RNA_Z_RING;
+    float4* my = ring + lane;
+    RowBits it(v.mask + i * v.W2, i + 1, j - 1 - kskip);
+    auto issue = [&](int slot) -> bool {
+      const int k = it.next();
+      if (k < 0) return false;
+      float* dst = reinterpret_cast<float*>(my + slot * nl);
+      RNA_CP_ASYNC4(dst, &v.C[doff(k - i, L) + i]);
+      reinterpret_cast<int*>(dst)[1] = k;
+      return true;
+    };
+    int pending = 0;
+#pragma unroll 1
+    for (int sl = 0; sl < D; sl++) { if (issue(sl)) pending++; RNA_CP_COMMIT(); }
+#pragma unroll 1
+    for (int n = 0; pending > 0; n++) {
+      RNA_CP_WAIT(RNA_Z_RING - 1);
+      const int slot = n & (D - 1);
+      const float4 o = my[slot * nl];
+      pending--;
+      if (issue(slot)) pending++;
+      RNA_CP_COMMIT();
+      const int k = __float_as_int(o.y);
+      const float av = __fadd_rn(o.x, v2_acc<true>(T, s, L, i, k));
+      const float nn = (float)(j - k);
+      chain_add(r, __fadd_rn(__fadd_rn(av, dev->ext_bp), __fmul_rn(dev->ext_unpair, nn)), lut);
+      chain_add(rm, __fadd_rn(__fadd_rn(av, dev->mb_bp), __fmul_rn(dev->mb_unpair, nn)), lut);
+    }
+    RNA_CP_WAIT(0);
+    }
+    v.R[od + i] = chain_end(r);
+    v.X[od + i] = chain_end(rm);
+  }
+}
+
+template <bool CONTRA, class SV>
+RNA_DEV void outside_Y_ring(const SV& v, const typename Model2<CONTRA>::View& T, const float4* lut, int d,
+                       int lane, int nl, float4* ring = nullptr) {
+  const int L = v.L;
+  const uint8_t* s = v.s;
+  const float NEG = RNA_NEG_INF;
+  const int ncell = L - d, od = doff(d, L);
+  for (int i = lane; i < ncell; i += nl) {
+    const int j = i + d;
+    ChainSum pm = chain_begin(NEG), pm2 = chain_begin(NEG);
+    {
+    // HBM-resident mode: {sums_close, log P, sums_1ormore} of RNA_Z_RING terms in flight in the lane's ring, k alongside
+    constexpr int D = RNA_Z_RING;
+    float4* my = ring + lane;
+    RowBits it(v.mask + i * v.W2, j + 1, L - 1);
+    auto issue = [&](int slot) -> bool {
+      const int k = it.next();
+      if (k < 0) return false;
+      float* dst = reinterpret_cast<float*>(my + slot * nl);
+      const int q = doff(k - i, L) + i;
+      RNA_CP_ASYNC4(dst + 0, &v.C[q]);
+      RNA_CP_ASYNC4(dst + 1, &v.Pm[q]);
+      if (k - j >= 2) RNA_CP_ASYNC4(dst + 2, &v.M1[doff(k - j - 2, L) + j + 1]);
+      reinterpret_cast<int*>(dst)[3] = k;
+      return true;
+    };
+    int pending = 0;
+#pragma unroll 1
+    for (int sl = 0; sl < D; sl++) { if (issue(sl)) pending++; RNA_CP_COMMIT(); }
+#pragma unroll 1
+    for (int n = 0; pending > 0; n++) {
+      RNA_CP_WAIT(RNA_Z_RING - 1);
+      const int slot = n & (D - 1);
+      const float4 o = my[slot * nl];
+      pending--;
+      if (issue(slot)) pending++;
+      RNA_CP_COMMIT();
+      const int k = __float_as_int(o.w), m = k - j;
+      const float m1 = (m >= 2) ? o.z : NEG;
+      const float x = __fsub_rn(__fadd_rn(o.y, v2_mbclose<CONTRA>(T, s, L, i, k)), o.x);
+      chain_add(pm, __fadd_rn(x, m1), lut);
+      if constexpr (CONTRA) chain_add(pm2, __fadd_rn(x, __fmul_rn(T.g->mb_unpair, (float)(m - 1))), lut);
+      else chain_add(pm2, x, lut);
+    }
+    RNA_CP_WAIT(0);
+    }
+    v.R[od + i] = chain_end(pm);
+    v.X[od + i] = chain_end(pm2);
+  }
+}
+
+template <bool CONTRA, class SV>
+RNA_DEV float outside_cell_ml_ring(const SV& v, const typename Model2<CONTRA>::View& T, const float4* lut, int i, int j,
+                              float Cij, float sm0, float4* ring = nullptr, int rstride = 0) {
+  const int L = v.L;
+  const float NEG = RNA_NEG_INF;
+  const typename Model2<CONTRA>::Dev* dev = T.g;
+  const float Aij = __fadd_rn(Cij, v2_acc<CONTRA>(T, v.s, L, i, j));
+  float sa;
+  if constexpr (CONTRA) sa = __fadd_rn(Aij, dev->mb_bp); else sa = __fadd_rn(Aij, dev->coeff_num_branches);
+  ChainSum sm = chain_begin(sm0);
+  {
+    // HBM-resident mode: operands of RNA_Z_RING steps in flight in the lane's shared-memory ring (see inside_Z)
+    constexpr int D = RNA_Z_RING;
+    auto issue = [&](int kk, int slot) {
+      float* dst = reinterpret_cast<float*>(ring + slot * rstride);
+      const int m = i - 1 - kk, q = doff(j - kk, L) + kk;
+      if (m >= 1) RNA_CP_ASYNC4(dst + 0, &v.M1[doff(m - 1, L) + kk + 1]);
+      RNA_CP_ASYNC4(dst + 1, &v.X[q]);
+      RNA_CP_ASYNC4(dst + 2, &v.R[q]);
+    };
+#pragma unroll 1
+    for (int sl = 0; sl < D; sl++) { if (sl < i) issue(sl, sl); RNA_CP_COMMIT(); }
+#pragma unroll 1
+    for (int kk = 0; kk < i; kk++) {
+      RNA_CP_WAIT(RNA_Z_RING - 1);
+      const int slot = kk & (D - 1), m = i - 1 - kk;
+      const float4 o = ring[slot * rstride];
+      if (kk + D < i) issue(kk + D, slot);
+      RNA_CP_COMMIT();
+      const float x1 = (m >= 1) ? o.x : NEG, p2 = o.y, y = o.z;
+      chain_add(sm, __fadd_rn(__fadd_rn(sa, p2), x1), lut);
+      if constexpr (CONTRA) chain_add(sm, __fadd_rn(__fadd_rn(sa, y), __fmul_rn(dev->mb_unpair, (float)m)), lut);
+      else chain_add(sm, __fadd_rn(sa, y), lut);
+      chain_add(sm, __fadd_rn(__fadd_rn(sa, x1), y), lut);
+    }
+    RNA_CP_WAIT(0);
+  }
+  return chain_end(sm);
+}
+
+template <bool CONTRA, class SV>
+RNA_DEV void outside_X_ml_ring(const SV& v, const typename Model2<CONTRA>::View& T, const float4* lut, int st, int lane,
+                          int nl, float4* ring) {
+  const int L = v.L;
+  const StepCells sc = step_cells<false>(v, st);
+  for (int x = lane; x < sc.cA + sc.cB; x += nl) {
+    int dd, r;
+    step_cell(sc, x, dd, r);
+    const int od = doff(dd, L), i = v.plist[od + r];
+    const float Cij = v.C[od + i];
+    if (!(Cij > RNA_NEG_INF)) continue;
+    v.Pm[od + i] = outside_cell_ml_ring<CONTRA, SV>(v, T, lut, i, i + dd, Cij, v.Pm[od + i], ring ? ring + lane : nullptr, nl);
+  }
+}
+#endif   // __CUDACC__
 
 }  // namespace rna
