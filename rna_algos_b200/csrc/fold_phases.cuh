@@ -1860,21 +1860,28 @@ RNA_DEV void inside_Z_ring(const SV& v, const typename Model2<CONTRA>::View& T, 
     // thousand cycles under load there, far more than four split points of folds, and no register is held meanwhile
     constexpr int D = RNA_Z_RING;
     float4* my = ring + lane;
-    auto issue = [&](int m, int slot) {
-      float* dst = reinterpret_cast<float*>(my + slot * nl);
-      RNA_CP_ASYNC4(dst + 0, &v.R[doff(d - m, L) + i + m]);
-      RNA_CP_ASYNC4(dst + 1, &v.E[doff(m - 1, L) + i]);
-      RNA_CP_ASYNC4(dst + 2, &v.M1[doff(m - 1, L) + i]);
-      if (CONTRA) RNA_CP_ASYNC4(dst + 3, &v.X[doff(d - m, L) + i + m]);
+    // split points are issued in ascending m: the matrix offsets advance incrementally (diagonal-major layout:
+    // off(d - m) + i + m moves by d - m - L per step, off(m - 1) + i by L - m + 1), the ring slot is a 32-bit shared address
+    const unsigned sbase = (unsigned)__cvta_generic_to_shared(my);
+    int oR = doff(d - 1, L) + i + 1, oE = doff(0, L) + i, mi = 1;   // offsets of the next split point to issue (mi)
+    auto issue = [&](int slot) {
+      const unsigned dst = sbase + (unsigned)(slot * nl) * 16u;
+      RNA_CP_ASYNC4_S(dst + 0u, v.R + oR);
+      RNA_CP_ASYNC4_S(dst + 4u, v.E + oE);
+      RNA_CP_ASYNC4_S(dst + 8u, v.M1 + oE);
+      if (CONTRA) RNA_CP_ASYNC4_S(dst + 12u, v.X + oR);
+      oR += d - mi - L;
+      oE += L - mi + 1;
+      mi++;
     };
 #pragma unroll 1
-    for (int sl = 0; sl < D; sl++) { if (1 + sl < d) issue(1 + sl, sl); RNA_CP_COMMIT(); }
+    for (int sl = 0; sl < D; sl++) { if (1 + sl < d) issue(sl); RNA_CP_COMMIT(); }
 #pragma unroll 1
     for (int m = 1; m < d; m++) {
       RNA_CP_WAIT(RNA_Z_RING - 1);
       const int slot = (m - 1) & (D - 1);
       const float4 o = my[slot * nl];
-      if (m + D < d) issue(m + D, slot);
+      if (m + D < d) issue(slot);
       RNA_CP_COMMIT();
       const float r = o.x, e = o.y, m1 = o.z, rm = o.w;
       chain_add(sE, __fadd_rn(r, e), lut);
@@ -2010,21 +2017,26 @@ RNA_DEV float outside_cell_ml_ring(const SV& v, const typename Model2<CONTRA>::V
   {
     // HBM-resident mode: operands of RNA_Z_RING steps in flight in the lane's shared-memory ring (see inside_Z)
     constexpr int D = RNA_Z_RING;
-    auto issue = [&](int kk, int slot) {
-      float* dst = reinterpret_cast<float*>(ring + slot * rstride);
-      const int m = i - 1 - kk, q = doff(j - kk, L) + kk;
-      if (m >= 1) RNA_CP_ASYNC4(dst + 0, &v.M1[doff(m - 1, L) + kk + 1]);
-      RNA_CP_ASYNC4(dst + 1, &v.X[q]);
-      RNA_CP_ASYNC4(dst + 2, &v.R[q]);
+    // steps are issued in ascending k: q = off(j - k) + k advances by j - k - L, off(i - 2 - k) + k + 1 by i - k - 2 - L
+    const unsigned sbase = (unsigned)__cvta_generic_to_shared(ring);
+    int oq = doff(j, L), oM = (i >= 2) ? doff(i - 2, L) + 1 : 0, ki = 0;   // offsets of the next step to issue (ki)
+    auto issue = [&](int slot) {
+      const unsigned dst = sbase + (unsigned)(slot * rstride) * 16u;
+      if (i - 1 - ki >= 1) RNA_CP_ASYNC4_S(dst + 0u, v.M1 + oM);
+      RNA_CP_ASYNC4_S(dst + 4u, v.X + oq);
+      RNA_CP_ASYNC4_S(dst + 8u, v.R + oq);
+      oq += j - ki - L;
+      oM += i - ki - 2 - L;
+      ki++;
     };
 #pragma unroll 1
-    for (int sl = 0; sl < D; sl++) { if (sl < i) issue(sl, sl); RNA_CP_COMMIT(); }
+    for (int sl = 0; sl < D; sl++) { if (sl < i) issue(sl); RNA_CP_COMMIT(); }
 #pragma unroll 1
     for (int kk = 0; kk < i; kk++) {
       RNA_CP_WAIT(RNA_Z_RING - 1);
       const int slot = kk & (D - 1), m = i - 1 - kk;
       const float4 o = ring[slot * rstride];
-      if (kk + D < i) issue(kk + D, slot);
+      if (kk + D < i) issue(slot);
       RNA_CP_COMMIT();
       const float x1 = (m >= 1) ? o.x : NEG, p2 = o.y, y = o.z;
       chain_add(sm, __fadd_rn(__fadd_rn(sa, p2), x1), lut);

@@ -15,6 +15,8 @@
 #define RNA_PREFETCH_L2(p) asm volatile("prefetch.global.L2 [%0];" ::"l"(p))
 // 4-byte asynchronous copy global -> shared (no register holds the value in flight), commit / wait of this thread's groups
 #define RNA_CP_ASYNC4(sptr, gptr) asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((unsigned)__cvta_generic_to_shared(sptr)), "l"(gptr) : "memory")
+// (the same with a 32-bit shared-memory address computed by the caller)
+#define RNA_CP_ASYNC4_S(saddr, gptr) asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(saddr), "l"(gptr) : "memory")
 #define RNA_CP_COMMIT() asm volatile("cp.async.commit_group;" ::: "memory")
 #define RNA_CP_WAIT(n) asm volatile("cp.async.wait_group %0;" ::"n"(n) : "memory")
 // the two-loop term streams (st.global.cs / ld.global.cs measured 9 % SLOWER on the default bench: plain accesses)
